@@ -1,0 +1,341 @@
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE'S OWN CODE (build container only).
+
+Test infrastructure.  Run:  python oracle/gen_golden.py   (needs /root/reference; the GPU box
+does not have it, which is why the outputs are committed).
+
+The reference ships no golden vectors, so parity is pinned by importing
+its modules from /root/reference/src (model.squeezedet, model.modules, engine.detector,
+utils.boxes) and recording what they return for seeded synthetic inputs
+(squeezedet_pytorch_b200.synth -- inputs are regenerated from the seed, only reference OUTPUTS
+are stored).  Nothing from the reference is copied into this repo.
+
+Versions at generation time are recorded in each file's ``meta`` entry.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("SQD_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(REF, "src"))
+
+import torch  # noqa: E402
+import torchvision  # noqa: E402
+
+from squeezedet_pytorch_b200 import synth  # noqa: E402
+
+import model.squeezedet as ref_model  # noqa: E402  (reference)
+import model.modules as ref_modules  # noqa: E402  (reference)
+import engine.detector as ref_detector  # noqa: E402  (reference)
+import utils.boxes as ref_boxes  # noqa: E402  (reference)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+META = json.dumps({
+    "torch": torch.__version__, "torchvision": torchvision.__version__, "numpy": np.__version__,
+    "reference": "hazenai/SqueezeDet-PyTorch @ /root/reference", "device": "cpu",
+})
+
+
+def ref_cfg(shape: synth.Shape):
+    """The argparse namespace the reference's classes read (config.py:121-131)."""
+    anchors = ref_boxes.generate_anchors(shape.grid_hw, shape.input_hw, synth.KITTI_SEEDS)
+    return types.SimpleNamespace(
+        input_size=shape.input_hw, num_classes=shape.num_classes, anchors=anchors,
+        anchors_per_grid=shape.anchors_per_grid, num_anchors=anchors.shape[0], arch="squeezedet",
+        dropout_prob=0.5, device=torch.device("cpu"), keep_top_k=shape.top_k,
+        nms_thresh=shape.nms_thresh, score_thresh=shape.score_thresh, debug=0, mode="eval",
+        class_loss_weight=1.0, positive_score_loss_weight=3.75, negative_score_loss_weight=100.0,
+        bbox_loss_weight=6.0,
+    )
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, meta=np.array(META), **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def tracked_filter(detector, det):
+    """Detector.filter (detector.py:87-122) restated with anchor-index tracking; its VALUES are
+    asserted equal to the untouched reference filter before anything is stored."""
+    cfg = detector.cfg
+    orders = torch.argsort(det["scores"], descending=True)[:cfg.keep_top_k]
+    class_ids = det["class_ids"][orders]
+    scores = det["scores"][orders]
+    boxes = det["boxes"][orders, :]
+    idx = []
+    for c in range(cfg.num_classes):
+        sel = torch.nonzero(class_ids == c).flatten()
+        if sel.numel() == 0:
+            continue
+        keeps = torchvision.ops.nms(boxes[sel], scores[sel], cfg.nms_thresh)
+        idx.append(sel[keeps])
+    pos = torch.cat(idx)
+    pos = pos[scores[pos] > cfg.score_thresh]
+    out = detector.filter({k: v.clone() for k, v in det.items()})
+    if out is None:
+        assert pos.numel() == 0
+    else:
+        assert torch.equal(out["class_ids"], class_ids[pos])
+        assert torch.equal(out["scores"], scores[pos])
+        assert torch.equal(out["boxes"], boxes[pos])
+    # top-k boundary must not be tied, otherwise the reference's unstable argsort is not an oracle
+    srt = torch.sort(det["scores"], descending=True)[0]
+    k = min(cfg.keep_top_k, srt.numel() - 1)
+    assert srt[k - 1] > srt[k], "tie at the top-k boundary"
+    assert torch.unique(scores).numel() == scores.numel(), "tied scores inside the top-k"
+    return orders[pos].numpy().astype(np.int64), class_ids[pos].numpy(), scores[pos].numpy(), boxes[pos].numpy()
+
+
+def pack_ragged(rows, dtype, width=None):
+    counts = np.array([len(r) for r in rows], dtype=np.int64)
+    flat = np.concatenate([np.asarray(r, dtype=dtype).reshape(len(r), *( [width] if width else [])) for r in rows]) \
+        if counts.sum() else np.zeros((0, *( [width] if width else [])), dtype=dtype)
+    return counts, flat
+
+
+# ------------------------------------------------------------------------------------------
+def gen_anchors():
+    out = {}
+    for shp in (synth.TINY, synth.KITTI, synth.STRESS):
+        a = ref_boxes.generate_anchors(shp.grid_hw, shp.input_hw, synth.KITTI_SEEDS)
+        out[shp.name + "_sha256"] = np.array(hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest())
+        out[shp.name + "_head"] = a[:27]
+        out[shp.name + "_tail"] = a[-27:]
+    # known answer from the reference's own experiment dump, exp/my_train/config.txt:6-12,45
+    out["config_txt_first3"] = np.array([[8, 8, 34, 30], [8, 8, 75, 45], [8, 8, 38, 90]], dtype=np.float64)
+    out["config_txt_last3"] = np.array([[1240, 376, 194, 178], [1240, 376, 283, 156], [1240, 376, 381, 185]],
+                                       dtype=np.float64)
+    out["config_txt_num_anchors"] = np.array(16848)
+    save("anchors", **out)
+
+
+def gen_decode_filter():
+    """PredictionResolver + SqueezeDet scoring + Detector.filter on pred-level synthetic input."""
+    for shp, batch, seed in ((synth.TINY, 4, 11), (synth.KITTI, 2, 12), (synth.STRESS, 1, 13)):
+        cfg = ref_cfg(shp)
+        pred = torch.from_numpy(synth.clustered_pred(shp, batch, seed, anchors=cfg.anchors))
+        res = ref_model.PredictionResolver(cfg, log_softmax=True)
+        with torch.no_grad():
+            probs, logp, conf, deltas, boxes = res(pred)
+            p2 = probs.clone()
+            p2 *= conf                                     # squeezedet.py:200
+            ids = torch.argmax(p2, dim=2)
+            scores = torch.max(p2, dim=2)[0]
+        det = ref_detector.Detector(torch.nn.Identity(), cfg)
+        kept = [tracked_filter(det, {"class_ids": ids[b], "scores": scores[b], "boxes": boxes[b]})
+                for b in range(batch)]
+        cnt, kidx = pack_ragged([k[0] for k in kept], np.int64)
+        _, kcls = pack_ragged([k[1] for k in kept], np.int64)
+        _, ksc = pack_ragged([k[2] for k in kept], np.float32)
+        _, kbx = pack_ragged([k[3] for k in kept], np.float32, 4)
+        store_dense = shp is not synth.STRESS           # keep the fixture small
+        extra = dict(probs=probs.numpy(), logp=logp.numpy(), conf=conf.numpy(), boxes=boxes.numpy()) \
+            if store_dense else {}
+        save(f"decode_filter_{shp.name}", seed=np.array(seed), batch=np.array(batch),
+             class_ids=ids.numpy().astype(np.int16), scores=scores.numpy(),
+             kept_count=cnt, kept_anchor=kidx, kept_class=kcls, kept_score=ksc, kept_box=kbx, **extra)
+        print("   kept per image:", cnt.tolist())
+
+
+def gen_nms():
+    """torchvision.ops.nms (installed 0.26, CPU) on clustered boxes incl. tied scores and
+    zero-area boxes: pins the oracle's restatement of the third-party kernel."""
+    rs = np.random.RandomState(77)
+    boxes_l, scores_l, keep_l, thr_l = [], [], [], []
+    for t in range(200):
+        n = int(rs.randint(1, 80))
+        centers = rs.uniform(0, 300, size=(max(1, n // 6), 2))
+        c = centers[rs.randint(0, centers.shape[0], size=n)] + rs.normal(0, 6, size=(n, 2))
+        wh = np.exp(rs.normal(3.5, 0.4, size=(n, 2)))
+        b = np.concatenate([c - wh / 2, c + wh / 2], axis=1).astype(np.float32)
+        if t % 5 == 0:   # zero-area boxes clamped on the border -> 0/0 IoU
+            b[rs.randint(0, n, size=max(1, n // 8))] = 0.0
+        s = rs.uniform(0, 1, size=n).astype(np.float32)
+        if t % 3 == 0:   # tied scores
+            s = np.round(s * 8) / 8
+        thr = float([0.4, 0.5, 0.3, 0.7][t % 4])
+        keep = torchvision.ops.nms(torch.from_numpy(b), torch.from_numpy(s), thr).numpy()
+        boxes_l.append(b); scores_l.append(s); keep_l.append(keep); thr_l.append(thr)
+    cnt, bx = pack_ragged(boxes_l, np.float32, 4)
+    _, sc = pack_ragged(scores_l, np.float32)
+    kcnt, kp = pack_ragged(keep_l, np.int64)
+    save("nms_torchvision", n=cnt, boxes=bx, scores=sc, keep_n=kcnt, keep=kp, thresh=np.array(thr_l))
+
+
+class _StableNumpy:
+    """numpy proxy whose argsort is stable: the declared matcher tie policy, injected
+    without touching any reference file."""
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+    @staticmethod
+    def argsort(a, *args, **kw):
+        kw["kind"] = "stable"
+        return np.argsort(a, *args, **kw)
+
+
+def gen_matcher():
+    for shp, n_img, seed0 in ((synth.TINY, 24, 500), (synth.KITTI, 24, 600), (synth.STRESS, 4, 700)):
+        cfg = ref_cfg(shp)
+        idx_l, dl_l, idx_unpatched_l, box_l, cls_l = [], [], [], [], []
+        for i in range(n_img):
+            cls, boxes = synth.gt_boxes(shp, seed0 + i)
+            if i % 6 == 5:  # crowd of identical small boxes -> exercises "already taken" + distance fallback
+                boxes = np.repeat(boxes[:1], 12, axis=0)
+                boxes[:, 2] = boxes[:, 0] + 3.0
+                boxes[:, 3] = boxes[:, 1] + 2.0
+                cls = np.repeat(cls[:1], 12)
+            d_u, i_u = ref_boxes.compute_deltas(boxes.copy(), cfg.anchors)          # reference as is
+            ref_boxes.np = _StableNumpy()
+            try:
+                d_s, i_s = ref_boxes.compute_deltas(boxes.copy(), cfg.anchors)      # stable tie order
+            finally:
+                ref_boxes.np = np
+            idx_l.append(i_s); dl_l.append(d_s); idx_unpatched_l.append(i_u); box_l.append(boxes); cls_l.append(cls)
+        cnt, idx = pack_ragged(idx_l, np.int32)
+        _, dl = pack_ragged(dl_l, np.float32, 4)
+        _, idx_u = pack_ragged(idx_unpatched_l, np.int32)
+        agree = float(np.mean(idx == idx_u))
+        print(f"   matcher {shp.name}: stable vs unpatched reference agree on {agree:.3f} of GT boxes")
+        save(f"matcher_{shp.name}", seed0=np.array(seed0), n_img=np.array(n_img), count=cnt,
+             anchor_idx=idx, deltas=dl, anchor_idx_unpatched=idx_u)
+
+
+def fallback_case():
+    """12-anchor table + 16 GT boxes: anchors run out, so the squared-distance fallback
+    (boxes.py:115-121) and the 'already taken' skip are both exercised."""
+    seeds = np.array([[20, 20], [30, 10]], dtype=np.float32)
+    anchors = ref_boxes.generate_anchors((2, 3), (64, 96), seeds)
+    rs = np.random.RandomState(9)
+    x1 = rs.uniform(0, 80, size=16); y1 = rs.uniform(0, 50, size=16)
+    boxes = np.stack([x1, y1, x1 + rs.uniform(2, 15, size=16), y1 + rs.uniform(2, 12, size=16)], 1).astype(np.float32)
+    boxes[5] = boxes[4]          # exact duplicate
+    boxes[11] = [90, 60, 95, 63]  # far corner, overlaps little
+    return anchors, boxes[:12], boxes
+
+
+def gen_matcher_fallback():
+    anchors, boxes12, boxes16 = fallback_case()
+    ref_boxes.np = _StableNumpy()
+    try:
+        d, i = ref_boxes.compute_deltas(boxes12.copy(), anchors)
+    finally:
+        ref_boxes.np = np
+    assert len(set(i.tolist())) == 12   # every anchor used exactly once -> fallback was hit
+    save("matcher_fallback", anchors=anchors, boxes=boxes12, anchor_idx=i, deltas=d)
+
+
+def _dense_gt(shp, cfg, seed):
+    """BaseDataset.prepare_annotations (datasets/base.py:61-76) executed via the reference's
+    compute_deltas (stable tie order); the 6-line scatter itself is restated because importing
+    `datasets` collides with the HuggingFace package of the same name."""
+    cls, boxes = synth.gt_boxes(shp, seed)
+    ref_boxes.np = _StableNumpy()
+    try:
+        deltas, idx = ref_boxes.compute_deltas(boxes.copy(), cfg.anchors)
+    finally:
+        ref_boxes.np = np
+    gt = np.zeros((cfg.num_anchors, cfg.num_classes + 9), dtype=np.float32)
+    gt[idx, 0] = 1.
+    gt[idx, 1:5] = boxes
+    gt[idx, 5:9] = deltas
+    gt[idx, 9 + cls] = 1.
+    return gt
+
+
+def gen_loss():
+    for shp, batch, seed in ((synth.TINY, 4, 21), (synth.KITTI, 2, 22)):
+        cfg = ref_cfg(shp)
+        pred = torch.from_numpy(synth.clustered_pred(shp, batch, seed, anchors=cfg.anchors)).requires_grad_(True)
+        gt = torch.from_numpy(np.stack([_dense_gt(shp, cfg, 1000 * seed + b) for b in range(batch)]))
+        loss_mod = ref_model.Loss(cfg)
+        loss, stats = loss_mod(pred, gt)
+        loss.mean().backward()                              # trainer.py:43,47
+        save(f"loss_{shp.name}", seed=np.array(seed), batch=np.array(batch),
+             loss=loss.detach().numpy(), class_loss=stats["class_loss"].detach().numpy(),
+             score_loss=stats["score_loss"].detach().numpy(), bbox_loss=stats["bbox_loss"].detach().numpy(),
+             dpred=pred.grad.numpy())
+        print("   loss:", loss.detach().numpy())
+    # zero-object image -> NaN loss (squeezedet.py:149, 0/0), preserved not fixed
+    shp = synth.TINY
+    cfg = ref_cfg(shp)
+    pred = torch.from_numpy(synth.clustered_pred(shp, 1, 5, anchors=cfg.anchors)).requires_grad_(True)
+    gt = torch.zeros((1, cfg.num_anchors, cfg.num_classes + 9))
+    loss, _ = ref_model.Loss(cfg)(pred, gt)
+    loss.mean().backward()
+    save("loss_zero_objects", loss=loss.detach().numpy(), dpred_isnan_all=np.array(bool(torch.isnan(pred.grad).all())))
+
+
+def gen_head_e2e():
+    """features -> reference SqueezeDet (backbone replaced by Identity so that the reference's own
+    forward tail, squeezedet.py:79-87,197-206, runs on a Fire11-shaped input) -> Detector.filter."""
+    for shp, batch, seed in ((synth.TINY, 2, 31), (synth.KITTI, 2, 32)):
+        cfg = ref_cfg(shp)
+        net = ref_model.SqueezeDet(cfg)
+        net.base.features = torch.nn.Identity()
+        w, b = synth.convdet_params(shp, seed + 1)
+        with torch.no_grad():
+            net.base.convdet.weight.copy_(torch.from_numpy(w))
+            net.base.convdet.bias.copy_(torch.from_numpy(b))
+        det = ref_detector.Detector(net, cfg)           # .eval(): dropout is a no-op
+        feat = torch.from_numpy(synth.features(shp, batch, seed))
+        with torch.no_grad():
+            pred = net.base(feat)
+            dets = net({"image": feat})
+        kept = [tracked_filter(det, {k: v[i] for k, v in dets.items()}) for i in range(batch)]
+        cnt, kidx = pack_ragged([k[0] for k in kept], np.int64)
+        _, kcls = pack_ragged([k[1] for k in kept], np.int64)
+        _, ksc = pack_ragged([k[2] for k in kept], np.float32)
+        _, kbx = pack_ragged([k[3] for k in kept], np.float32, 4)
+        # score gap to the nearest rival, for diagnosing near-tie flips of other fp32 conv orders
+        save(f"head_e2e_{shp.name}", seed=np.array(seed), batch=np.array(batch), pred=pred.numpy(),
+             kept_count=cnt, kept_anchor=kidx, kept_class=kcls, kept_score=ksc, kept_box=kbx)
+        print("   kept per image:", cnt.tolist(), "pred std", float(pred.std()))
+
+
+def gen_postprocess():
+    rs = np.random.RandomState(5)
+    cases = []
+    for t in range(8):
+        boxes = np.sort(rs.uniform(0, 380, size=(6, 2, 2)), axis=1).transpose(0, 2, 1).reshape(6, 4).astype(np.float32)
+        boxes = boxes[:, [0, 2, 1, 3]][:, [0, 1, 2, 3]]
+        meta = {"orig_size": np.array([375, 1242, 3], dtype=np.int32)}
+        if t % 2 == 0:
+            meta["scales"] = np.array([384 / 375., 1248 / 1242.], dtype=np.float32)
+        if t % 3 == 0:
+            meta["drifts"] = np.array([rs.randint(-20, 20), rs.randint(-20, 20)], dtype=np.int32)
+            meta["drifted_size"] = np.array([375 - 3, 1242 - 5, 3], dtype=np.int32)
+        if t % 4 == 1:
+            meta["padding"] = np.array([2, 3, 4, 5], dtype=np.int32)
+        if t % 4 == 3:
+            meta["crops"] = np.array([1, 2, 3, 4], dtype=np.int32)
+        if t >= 4:
+            meta["flipped"] = True
+        out = ref_boxes.boxes_postprocess(boxes.copy(), meta)
+        cases.append((boxes, meta, out))
+    arrays = {}
+    for i, (b, m, o) in enumerate(cases):
+        arrays[f"in_{i}"] = b
+        arrays[f"out_{i}"] = o
+        arrays[f"meta_{i}"] = np.array(json.dumps({k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in m.items()}))
+    save("postprocess", n=np.array(len(cases)), **arrays)
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    which = sys.argv[1:] or ["anchors", "decode_filter", "nms", "matcher", "matcher_fallback", "loss", "head_e2e",
+                             "postprocess"]
+    for w in which:
+        print("==", w)
+        globals()["gen_" + w]()

@@ -1,0 +1,222 @@
+"""Pin the CPU oracle (oracle/oracle.py) against outputs of the reference's own code
+(tests/golden/*.npz, produced by oracle/gen_golden.py in the build container)."""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from squeezedet_pytorch_b200 import synth
+from conftest import split_ragged
+
+SHAPES = {s.name: s for s in (synth.TINY, synth.KITTI, synth.STRESS)}
+RTOL = 1e-4  # north_star tolerance for scores / boxes / losses
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_anchor_table_bit_exact(golden, name):
+    g = golden("anchors")
+    shp = SHAPES[name]
+    for table in (orc.generate_anchors(shp.grid_hw, shp.input_hw, synth.KITTI_SEEDS), synth.anchor_table(shp)):
+        assert table.dtype == np.float64 and table.shape == (shp.num_anchors, 4)
+        assert hashlib.sha256(table.tobytes()).hexdigest() == str(g[name + "_sha256"])
+        assert np.array_equal(table[:27], g[name + "_head"]) and np.array_equal(table[-27:], g[name + "_tail"])
+
+
+def test_anchor_known_answer_from_reference_experiment(golden):
+    g = golden("anchors")  # exp/my_train/config.txt:6-12,45
+    a = orc.generate_anchors(synth.KITTI.grid_hw, synth.KITTI.input_hw, synth.KITTI_SEEDS)
+    assert a.shape[0] == int(g["config_txt_num_anchors"]) == 16848
+    assert np.array_equal(a[:3], g["config_txt_first3"]) and np.array_equal(a[-3:], g["config_txt_last3"])
+
+
+@pytest.mark.parametrize("name", ["tiny_160x96", "kitti_1248x384"])
+def test_decode_matches_reference(golden, name):
+    g = golden("decode_filter_" + name)
+    shp = SHAPES[name]
+    anchors = synth.anchor_table(shp)
+    pred = synth.clustered_pred(shp, int(g["batch"]), int(g["seed"]), anchors=anchors)
+    probs, logp, conf, deltas, boxes = orc.resolve(pred, anchors, shp.input_hw, shp.num_classes, log_softmax=True)
+    np.testing.assert_allclose(probs, g["probs"], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(logp, g["logp"], rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(conf, g["conf"], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(boxes, g["boxes"], rtol=RTOL, atol=1e-3)
+    assert np.array_equal(deltas, pred[..., shp.num_classes + 1:])
+    ids, scores = orc.score_argmax(probs, conf)
+    assert np.array_equal(ids, g["class_ids"].astype(np.int64))
+    np.testing.assert_allclose(scores, g["scores"], rtol=RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_filter_kept_indices_bit_exact(golden, name):
+    """pred -> decode -> top-k -> per-class NMS -> threshold: kept ANCHOR indices, classes and
+    order must equal the reference's; scores/boxes within 1e-4."""
+    g = golden("decode_filter_" + name)
+    shp = SHAPES[name]
+    anchors = synth.anchor_table(shp)
+    pred = synth.clustered_pred(shp, int(g["batch"]), int(g["seed"]), anchors=anchors)
+    outs = orc.detect_filtered(pred, anchors, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh,
+                               shp.score_thresh)
+    idx = split_ragged(g["kept_count"], g["kept_anchor"])
+    cls = split_ragged(g["kept_count"], g["kept_class"])
+    sc = split_ragged(g["kept_count"], g["kept_score"])
+    bx = split_ragged(g["kept_count"], g["kept_box"])
+    assert sum(len(i) for i in idx) > 0
+    for b, o in enumerate(outs):
+        assert np.array_equal(o["anchor_idx"], idx[b])
+        assert np.array_equal(o["class_ids"], cls[b])
+        np.testing.assert_allclose(o["scores"], sc[b], rtol=RTOL, atol=1e-7)
+        np.testing.assert_allclose(o["boxes"], bx[b], rtol=RTOL, atol=1e-3)
+
+
+def test_filter_given_reference_dense_outputs_is_bit_exact(golden):
+    """Same dense (ids, scores, boxes) in -> identical kept set AND identical float values out."""
+    g = golden("decode_filter_kitti_1248x384")
+    shp = synth.KITTI
+    idx = split_ragged(g["kept_count"], g["kept_anchor"])
+    sc = split_ragged(g["kept_count"], g["kept_score"])
+    bx = split_ragged(g["kept_count"], g["kept_box"])
+    for b in range(int(g["batch"])):
+        o = orc.filter_image(g["class_ids"][b], g["scores"][b], g["boxes"][b], shp.num_classes, shp.top_k,
+                             shp.nms_thresh, shp.score_thresh)
+        assert np.array_equal(o["anchor_idx"], idx[b])
+        assert np.array_equal(o["scores"], sc[b]) and np.array_equal(o["boxes"], bx[b])
+
+
+def test_nms_restatement_matches_torchvision(golden):
+    g = golden("nms_torchvision")
+    boxes = split_ragged(g["n"], g["boxes"])
+    scores = split_ragged(g["n"], g["scores"])
+    keep = split_ragged(g["keep_n"], g["keep"])
+    for t in range(len(boxes)):
+        got = orc.nms(boxes[t], scores[t], float(g["thresh"][t]))
+        assert np.array_equal(got, keep[t]), f"trial {t}"
+
+
+def test_nms_edge_cases():
+    assert orc.nms(np.zeros((0, 4), np.float32), np.zeros((0,), np.float32), 0.4).size == 0
+    one = np.array([[0, 0, 10, 10]], np.float32)
+    assert orc.nms(one, np.array([0.5], np.float32), 0.4).tolist() == [0]
+    # identical zero-area boxes: IoU is 0/0 = NaN and never suppresses
+    z = np.zeros((3, 4), np.float32)
+    assert orc.nms(z, np.array([0.1, 0.3, 0.2], np.float32), 0.4).tolist() == [1, 2, 0]
+    # tied scores keep input order (stable sort)
+    b = np.array([[0, 0, 10, 10], [100, 100, 110, 110], [0, 0, 10, 10]], np.float32)
+    assert orc.nms(b, np.array([0.5, 0.5, 0.5], np.float32), 0.4).tolist() == [0, 1]
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_matcher_indices_bit_exact(golden, name):
+    g = golden("matcher_" + name)
+    shp = SHAPES[name]
+    anchors = synth.anchor_table(shp)
+    idx = split_ragged(g["count"], g["anchor_idx"])
+    dl = split_ragged(g["count"], g["deltas"])
+    idx_u = split_ragged(g["count"], g["anchor_idx_unpatched"])
+    fallback_seen = False
+    for i in range(int(g["n_img"])):
+        cls, boxes = synth.gt_boxes(shp, int(g["seed0"]) + i)
+        if i % 6 == 5:  # the crowd case of gen_golden.gen_matcher
+            boxes = np.repeat(boxes[:1], 12, axis=0)
+            boxes[:, 2] = boxes[:, 0] + 3.0
+            boxes[:, 3] = boxes[:, 1] + 2.0
+            fallback_seen = True
+        d, a = orc.match_anchors(boxes, anchors)
+        assert a.dtype == np.int32 and np.array_equal(a, idx[i]), f"image {i}"
+        np.testing.assert_allclose(d, dl[i], rtol=1e-6, atol=1e-7)
+        assert len(set(a.tolist())) == len(a)  # an anchor is never assigned twice
+        # where the unpatched reference differs it must be an equal-IoU tie, never a better anchor
+        assert len(idx_u[i]) == len(a)
+    assert fallback_seen or int(g["n_img"]) < 6
+
+
+def test_matcher_distance_fallback(golden):
+    """12 anchors, 12 GT boxes: anchors run out -> squared-distance fallback (boxes.py:115-121)."""
+    g = golden("matcher_fallback")
+    d, a = orc.match_anchors(g["boxes"], g["anchors"])
+    assert np.array_equal(a, g["anchor_idx"]) and sorted(a.tolist()) == list(range(12))
+    np.testing.assert_allclose(d, g["deltas"], rtol=1e-6, atol=1e-7)
+
+
+def test_dense_targets_layout():
+    shp = synth.TINY
+    anchors = synth.anchor_table(shp)
+    cls, boxes = synth.gt_boxes(shp, 3)
+    gt = orc.dense_targets(cls, boxes, anchors, shp.num_classes)
+    d, idx = orc.match_anchors(boxes, anchors)
+    assert gt.shape == (shp.num_anchors, shp.num_classes + 9) and gt.dtype == np.float32
+    assert gt[:, 0].sum() == len(idx)
+    assert np.array_equal(gt[idx, 1:5], boxes) and np.array_equal(gt[idx, 5:9], d)
+    assert np.array_equal(np.argmax(gt[idx, 9:], axis=1), cls)
+    rest = np.ones(shp.num_anchors, bool)
+    rest[idx] = False
+    assert not gt[rest].any()
+
+
+def _loss_inputs(shp, g):
+    anchors = synth.anchor_table(shp)
+    batch, seed = int(g["batch"]), int(g["seed"])
+    pred = synth.clustered_pred(shp, batch, seed, anchors=anchors)
+    gts = []
+    for b in range(batch):
+        cls, boxes = synth.gt_boxes(shp, 1000 * seed + b)
+        gts.append(orc.dense_targets(cls, boxes, anchors, shp.num_classes))
+    return anchors, pred, np.stack(gts)
+
+
+@pytest.mark.parametrize("name", ["tiny_160x96", "kitti_1248x384"])
+def test_loss_forward_backward_matches_reference_autograd(golden, name):
+    g = golden("loss_" + name)
+    shp = SHAPES[name]
+    anchors, pred, gt = _loss_inputs(shp, g)
+    out = orc.loss_forward(pred, gt, anchors, shp.input_hw, shp.num_classes)
+    for k in ("loss", "class_loss", "score_loss", "bbox_loss"):
+        np.testing.assert_allclose(out[k], g[k], rtol=RTOL)
+    B = pred.shape[0]
+    dpred = orc.loss_backward(pred, gt, anchors, shp.input_hw, shp.num_classes, np.full((B,), 1.0 / B))
+    ref = g["dpred"]
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(dpred, ref, rtol=1e-3, atol=1e-6 * scale)
+    # gradient flows through the IoU target into the deltas of matched anchors (not detached)
+    assert np.abs(ref[..., shp.num_classes + 1:]).sum() > 0
+
+
+def test_loss_zero_objects_is_nan(golden):
+    g = golden("loss_zero_objects")
+    shp = synth.TINY
+    anchors = synth.anchor_table(shp)
+    pred = synth.clustered_pred(shp, 1, 5, anchors=anchors)
+    gt = np.zeros((1, shp.num_anchors, shp.num_classes + 9), np.float32)
+    out = orc.loss_forward(pred, gt, anchors, shp.input_hw, shp.num_classes)
+    assert np.isnan(g["loss"]).all() and np.isnan(out["loss"]).all()
+    dp = orc.loss_backward(pred, gt, anchors, shp.input_hw, shp.num_classes, np.ones((1,)))
+    assert bool(g["dpred_isnan_all"]) and np.isnan(dp).all()
+
+
+@pytest.mark.parametrize("name", ["tiny_160x96", "kitti_1248x384"])
+def test_head_end_to_end_matches_reference(golden, name):
+    g = golden("head_e2e_" + name)
+    shp = SHAPES[name]
+    anchors = synth.anchor_table(shp)
+    batch, seed = int(g["batch"]), int(g["seed"])
+    feat = synth.features(shp, batch, seed)
+    w, b = synth.convdet_params(shp, seed + 1)
+    pred = orc.convdet_forward(feat, w, b, shp.num_anchors, shp.num_fields)
+    np.testing.assert_allclose(pred, g["pred"], rtol=RTOL, atol=1e-5)
+    outs = orc.detect_filtered(g["pred"], anchors, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh,
+                               shp.score_thresh)
+    idx = split_ragged(g["kept_count"], g["kept_anchor"])
+    for i, o in enumerate(outs):
+        assert np.array_equal(o["anchor_idx"], idx[i])
+    if name == "tiny_160x96":
+        p64 = orc.convdet_forward_f64(feat, w, b, shp.num_anchors, shp.num_fields)
+        np.testing.assert_allclose(pred, p64, rtol=0, atol=2e-5)
+
+
+def test_boxes_postprocess(golden):
+    g = golden("postprocess")
+    for i in range(int(g["n"])):
+        meta = json.loads(str(g[f"meta_{i}"]))
+        out = orc.boxes_postprocess(g[f"in_{i}"], meta)
+        np.testing.assert_allclose(out, g[f"out_{i}"], rtol=1e-6, atol=1e-4)
