@@ -1,0 +1,189 @@
+/*
+ * sqdet_b200.h -- C ABI of libsqdet_b200.so: SqueezeDet's post-backbone detection path as
+ * hand-written sm_100a CUDA kernels.
+ *
+ * The reference (hazenai/SqueezeDet-PyTorch) has NO FFI layer: its "operator API" for this path
+ * is the Python class surface of src/model/squeezedet.py and src/engine/detector.py
+ * (SURVEY.md 8b).  Each entry point below therefore names the reference function(s) whose device
+ * work it replaces; the Python mirrors in squeezedet-pytorch_b200/ bind them through ctypes and
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes; no torch / C++ types cross the boundary.
+ *   - every pointer named d_* is a DEVICE pointer on the current CUDA device; `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).  Calls only ENQUEUE work.
+ *   - return 0 on success, <0 for a bad argument (SQD_E_*), >0 for a cudaError_t.  A message
+ *     for the last failure on the calling thread is available from sqd_last_error().
+ *   - the library never allocates device memory: scratch is caller-provided and sized by the
+ *     matching *_workspace_bytes() query.  No global mutable state; safe to call from several
+ *     host threads (one per device, as torch's DataParallel does -- parallel_apply.py).
+ *   - all tensors are dense, row-major, with the shapes given per function.
+ *
+ * Anchor index convention (src/model/squeezedet.py:85-87, src/utils/boxes.py:49-67):
+ *   a = (y*grid_w + x)*K + k ; per-anchor fields interleaved [cls_0..cls_{C-1} | conf | dx dy dw dh].
+ */
+#ifndef SQDET_B200_H
+#define SQDET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SQD_API __attribute__((visibility("default")))
+#else
+#define SQD_API
+#endif
+
+#define SQD_OK 0
+#define SQD_E_NULL (-1)      /* required pointer is NULL                     */
+#define SQD_E_SHAPE (-2)     /* unsupported / inconsistent shape             */
+#define SQD_E_WORKSPACE (-3) /* workspace too small or misaligned            */
+#define SQD_E_ALIGN (-4)     /* pointer not aligned as required (16 bytes)   */
+#define SQD_E_UNSUPPORTED (-5)
+#define SQD_E_DRIVER (-6)    /* CUDA driver entry point unavailable          */
+
+#define SQD_MAX_CLASSES 32
+#define SQD_MAX_TOPK 1024
+#define SQD_MAX_GT 256
+
+/* feature-map memory layouts accepted by the ConvDet head */
+#define SQD_LAYOUT_NCHW 0
+#define SQD_LAYOUT_NHWC 1 /* torch channels_last: logical NCHW, physical NHWC */
+
+/* ConvDet algorithms */
+#define SQD_CONV_TCGEN05_3XTF32 0 /* tcgen05.mma kind::tf32, hi/lo split operands, fp32 TMEM accumulators */
+#define SQD_CONV_SIMT_FP32 1      /* CUDA-core fp32 FMA implicit GEMM (validation yardstick)            */
+
+SQD_API int sqd_abi_version(void);
+SQD_API const char *sqd_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1  ConvDet head: 3x3 conv, pad 1, stride 1, + bias, written directly in the (B, A, C+5)
+ *     layout.  Replaces SqueezeDetBase.convdet + permute/contiguous/view,
+ *     src/model/squeezedet.py:73-75,83-87 (cuDNN conv + ATen copy in the reference).
+ *
+ *   d_feat   (B, Cin, gh, gw) fp32 in `layout` (NCHW or NHWC-physical), 16-byte aligned
+ *   d_weight (Cout, Cin, 3, 3) fp32 -- the reference's state-dict tensor base.convdet.weight
+ *   d_bias   (Cout) fp32
+ *   d_pred   (B, gh*gw*K, C+5) fp32 == (B, gh, gw, Cout) ; Cout = K*(C+5)
+ *
+ * sqd_convdet_pack_weights() derives the kernel-side weight planes (tap-major, hi/lo tf32 split,
+ * N padded to a multiple of 16) ONCE per weight update; they are derived data and never saved.
+ * ------------------------------------------------------------------------------------------- */
+SQD_API size_t sqd_convdet_packed_weight_bytes(int cout, int cin);
+SQD_API int sqd_convdet_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, void *stream);
+SQD_API size_t sqd_convdet_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout, int algo);
+SQD_API int sqd_convdet_forward(const float *d_feat, int layout, const void *d_packed, const float *d_weight,
+                        const float *d_bias, int batch, int cin, int gh, int gw, int cout, float *d_pred,
+                        void *d_workspace, size_t workspace_bytes, int algo, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a2-a7  PredictionResolver.forward + SqueezeDet.forward scoring, one pass over pred.
+ *     Replaces safe_softmax (modules.py:66-68), log_softmax / sigmoid (squeezedet.py:110-114),
+ *     deltas_to_boxes + xywh_to_xyxy + clamp (modules.py:17-45), probs*=conf / argmax / max
+ *     (squeezedet.py:200-202).
+ *
+ *   d_pred     (B, A, C+5) fp32
+ *   d_anchors  (A, 4) fp32 xywh  (== cfg.anchors.astype(float32), squeezedet.py:106)
+ *   outputs, each may be NULL to skip it:
+ *     d_class_ids (B, A) int64 | d_scores (B, A) | d_boxes (B, A, 4) xyxy clamped
+ *     d_probs (B, A, C) softmax (NOT multiplied by conf) | d_logp (B, A, C) | d_conf (B, A, 1)
+ *     d_deltas (B, A, 4)
+ * ------------------------------------------------------------------------------------------- */
+SQD_API int sqd_decode_scores(const float *d_pred, const float *d_anchors, int batch, int num_anchors, int num_classes,
+                      int input_h, int input_w, int64_t *d_class_ids, float *d_scores, float *d_boxes,
+                      float *d_probs, float *d_logp, float *d_conf, float *d_deltas, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a8-a9  Detector.filter for a whole batch: top-k by score (ties: lower anchor index first),
+ *     per-class greedy NMS with torchvision.ops.nms semantics (float IoU, strict '>' against the
+ *     double threshold), strict score > (float)score_thresh.  Replaces src/engine/detector.py:87-122
+ *     (torch.argsort + 3 torchvision nms calls + >= 3C+3 host syncs per image).
+ *
+ *   inputs : d_class_ids (B, A) int64, d_scores (B, A), d_boxes (B, A, 4)   [SqueezeDet.forward dict]
+ *   outputs: d_count (B) int32 ; rows [0,count) of (B, top_k[,4]) buffers in the reference's output
+ *            order (class ascending, score descending inside a class):
+ *            d_out_anchor int32 (kept anchor index), d_out_class int32, d_out_score, d_out_box
+ * ------------------------------------------------------------------------------------------- */
+SQD_API int sqd_topk_nms(const int64_t *d_class_ids, const float *d_scores, const float *d_boxes, int batch,
+                 int num_anchors, int num_classes, int top_k, double nms_thresh, double score_thresh,
+                 int32_t *d_count, int32_t *d_out_anchor, int32_t *d_out_class, float *d_out_score,
+                 float *d_out_box, void *stream);
+
+/* Fused a2-a9: pred -> final detections in ONE launch; the dense (B,A) ids/scores/boxes of the
+ * SqueezeDet.forward contract are never materialised (reads A*(C+5)*4 bytes per image once). */
+SQD_API int sqd_detect_from_pred(const float *d_pred, const float *d_anchors, int batch, int num_anchors, int num_classes,
+                         int input_h, int input_w, int top_k, double nms_thresh, double score_thresh,
+                         int32_t *d_count, int32_t *d_out_anchor, int32_t *d_out_class, float *d_out_score,
+                         float *d_out_box, void *stream);
+
+/* Fused a1-a9: Fire11 features -> final detections (Detector.detect's device work,
+ * src/engine/detector.py:20-31).  Workspace from sqd_head_detect_workspace_bytes(). */
+SQD_API size_t sqd_head_detect_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout, int algo);
+SQD_API int sqd_head_detect_fused(const float *d_feat, int layout, const void *d_packed, const float *d_weight,
+                          const float *d_bias, const float *d_anchors, int batch, int cin, int gh, int gw,
+                          int anchors_per_grid, int num_classes, int input_h, int input_w, int top_k,
+                          double nms_thresh, double score_thresh, int32_t *d_count, int32_t *d_out_anchor,
+                          int32_t *d_out_class, float *d_out_score, float *d_out_box, void *d_workspace,
+                          size_t workspace_bytes, int algo, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a11-a12  compute_deltas: greedy sequential anchor<->ground-truth matching in float64.
+ *     Replaces numpy compute_overlaps + compute_deltas, src/utils/boxes.py:70-135.
+ *     Tie policy: lowest anchor index among equal IoU / equal distance (== the reference with a
+ *     stable argsort; its default unstable sort is implementation defined).
+ *
+ *   d_gt_boxes (B, gmax, 4) fp32 xyxy, rows >= d_gt_count[b] ignored ; d_gt_count (B) int32
+ *   d_anchors64 (A, 4) float64 xywh -- the numpy-generated table (boxes.py:37-67)
+ *   outputs: d_anchor_idx (B, gmax) int32 (-1 in unused rows), d_deltas (B, gmax, 4) fp32
+ * a13  prepare_annotations: dense target (B, A, C+9) = [mask | box | deltas | one-hot]
+ *     Replaces src/datasets/base.py:61-76.  d_gt_classes (B, gmax) int32.
+ * ------------------------------------------------------------------------------------------- */
+SQD_API int sqd_match_anchors(const float *d_gt_boxes, const int32_t *d_gt_count, int batch, int gmax,
+                      const double *d_anchors64, int num_anchors, int32_t *d_anchor_idx, float *d_deltas,
+                      void *stream);
+SQD_API int sqd_build_targets(const float *d_gt_boxes, const int32_t *d_gt_classes, const int32_t *d_gt_count,
+                      const int32_t *d_anchor_idx, const float *d_deltas, int batch, int gmax, int num_anchors,
+                      int num_classes, float *d_gt_dense, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a14-a16  Loss.forward and its backward.  Replaces PredictionResolver(log_softmax) + torch
+ *     compute_overlaps (modules.py:48-63) + the four loss sums (squeezedet.py:133-174) and the
+ *     autograd graph behind them.
+ *
+ *   d_pred (B, A, C+5), d_gt (B, A, C+9) [mask | gt box xyxy | gt deltas | one-hot], d_anchors (A,4) fp32
+ *   weights[4] (HOST pointer) = {class, positive_score, negative_score, bbox}
+ *   d_losses (B, 4) = per image {class, positive_score, negative_score, bbox}  (loss = their sum)
+ *   d_grad_loss (B, 4) upstream d(objective)/d(d_losses[b][t]) or NULL (= all ones) ;
+ *   d_dpred (B, A, C+5) or NULL (forward only)
+ * ------------------------------------------------------------------------------------------- */
+SQD_API size_t sqd_loss_workspace_bytes(int batch, int num_anchors);
+SQD_API int sqd_loss_fwd_bwd(const float *d_pred, const float *d_gt, const float *d_anchors, int batch, int num_anchors,
+                     int num_classes, int input_h, int input_w, const float *weights, const float *d_grad_loss,
+                     float *d_losses, float *d_dpred, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 8(f) rank 1  boxes_postprocess for the kept detections (src/utils/boxes.py:138-168), in place on
+ *     the (B, top_k, 4) output of the filter: /scale, -padding, +crops, flip, +drifts in the
+ *     reference's order.  d_meta (B, 10) fp32, one record per image:
+ *     [scale_y, scale_x, pad_top, pad_left, crop_top, crop_left, flip_width (<=0: not flipped),
+ *      drift_y, drift_x, 0] ; keys absent from image_meta are passed as identity (1 / 0).
+ * ------------------------------------------------------------------------------------------- */
+SQD_API int sqd_boxes_postprocess(float *d_boxes, const int32_t *d_count, const float *d_meta, int batch, int top_k,
+                          void *stream);
+
+/* Debug aid: synchronise `stream`, return 0 if the last tcgen05 ConvDet launch on this workspace
+ * drained cleanly, else the role (1 TMA producer, 2 MMA issuer, 3 epilogue) whose bounded mbarrier
+ * wait timed out.  The kernels never spin forever. */
+SQD_API int sqd_convdet_status(const void *d_workspace, int batch, int cin, int gh, int gw, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQDET_B200_H */

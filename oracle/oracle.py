@@ -390,11 +390,14 @@ def loss_backward(pred, gt, anchors_xywh, input_hw, num_classes, grad_loss,
     d = deltas.astype(F64)
     p = boxes.astype(F64)
     anc = np.asarray(anchors_xywh).astype(F32).astype(F64)[None]
-    go = np.asarray(grad_loss, dtype=F64).reshape(B, 1)
+    go = np.asarray(grad_loss, dtype=F64)
+    if go.ndim == 1:                      # one upstream gradient per image, shared by the four terms
+        go = np.repeat(go.reshape(B, 1), 4, axis=1)
+    go_cls, go_pos, go_neg, go_box = (go[:, i:i + 1] for i in range(4))
     with np.errstate(invalid="ignore", divide="ignore"):
         n = m.sum(axis=1, keepdims=True)
-        k_obj = go * m / n                    # per-anchor weight of the "/ num_objects" sums
-        k_bg = go * (1.0 - m) / (A - n)
+        k_obj = m / n                         # per-anchor weight of the "/ num_objects" sums
+        k_bg = (1.0 - m) / (A - n)
         # raw (unclamped) box, for the clamp pass-through mask
         cx = anc[..., 0] + anc[..., 2] * d[..., 0]
         cy = anc[..., 1] + anc[..., 3] * d[..., 1]
@@ -432,16 +435,17 @@ def loss_backward(pred, gt, anchors_xywh, input_hw, num_classes, grad_loss,
         dA = np.stack([-ph, -pw, ph, pw], -1)
         diou_dp = d_inter[..., None] * dI + d_area[..., None] * dA
         resid = iou - sig
-        dL_diou_raw = (w_pos * k_obj + w_neg * k_bg) * 2.0 * resid * m
+        k_sc = go_pos * w_pos * k_obj + go_neg * w_neg * k_bg
+        dL_diou_raw = k_sc * 2.0 * resid * m
         Gp = dL_diou_raw[..., None] * diou_dp * passed
         grad = np.zeros((B, A, C + 5), dtype=F64)
         # class logits
         ysum = onehot.sum(-1, keepdims=True)
-        grad[..., :C] = w_cls * k_obj[..., None] * (ysum * probs - onehot)
+        grad[..., :C] = (go_cls * w_cls * k_obj)[..., None] * (ysum * probs - onehot)
         # confidence logit
-        grad[..., C] = (w_pos * k_obj + w_neg * k_bg) * 2.0 * resid * (-sig * (1.0 - sig))
+        grad[..., C] = k_sc * 2.0 * resid * (-sig * (1.0 - sig))
         # deltas: bbox regression term + IoU path
-        gd = w_box * k_obj[..., None] * 2.0 * (d - gdel)
+        gd = (go_box * w_box * k_obj)[..., None] * 2.0 * (d - gdel)
         gd[..., 0] += anc[..., 2] * (Gp[..., 0] + Gp[..., 2])
         gd[..., 1] += anc[..., 3] * (Gp[..., 1] + Gp[..., 3])
         gd[..., 2] += 0.5 * bw * (Gp[..., 2] - Gp[..., 0])

@@ -1,0 +1,152 @@
+// C-ABI glue: error plumbing, ConvDet algorithm dispatch, the fused head->detections entry point and
+// the boxes_postprocess epilogue.  See include/sqdet_b200.h for the contract of every symbol.
+#include <string.h>
+
+#include "common.cuh"
+
+// implemented in convdet_simt.cu / convdet_tc.cu
+size_t sqd_simt_workspace_bytes(int cin, int cout);
+int sqd_convdet_simt(const float *d_feat, int layout, const float *d_weight, const float *d_bias, int batch, int cin,
+                     int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
+size_t sqd_tc_packed_bytes(int cout, int cin);
+size_t sqd_tc_workspace_bytes(int batch, int cin, int gh, int gw);
+int sqd_tc_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, cudaStream_t st);
+int sqd_convdet_tc(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
+                   int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
+const int *sqd_tc_status_ptr(const void *d_workspace, int batch, int cin, int gh, int gw);
+
+static thread_local char g_err[512] = "";
+
+void sqd_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int sqd_abi_version(void) { return SQD_ABI_VERSION; }
+extern "C" const char *sqd_last_error(void) { return g_err; }
+
+// ---- a1 -------------------------------------------------------------------------------------------
+extern "C" size_t sqd_convdet_packed_weight_bytes(int cout, int cin) {
+    if (cout <= 0 || cin <= 0) return 0;
+    return sqd_tc_packed_bytes(cout, cin);
+}
+
+extern "C" int sqd_convdet_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, void *stream) {
+    SQD_REQUIRE(d_weight && d_packed, SQD_E_NULL, "sqd_convdet_pack_weights: NULL pointer");
+    SQD_REQUIRE(cout >= 1 && cout <= 128 && cin >= 32 && cin % 32 == 0, SQD_E_SHAPE,
+                "sqd_convdet_pack_weights: need 1<=Cout<=128 and Cin a multiple of 32 (got %d, %d)", cout, cin);
+    SQD_REQUIRE(sqd_aligned16(d_packed), SQD_E_ALIGN, "sqd_convdet_pack_weights: packed buffer must be 16-byte aligned");
+    return sqd_tc_pack_weights(d_weight, cout, cin, d_packed, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t sqd_convdet_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout, int algo) {
+    (void)layout;
+    if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0) return 256;
+    if (algo == SQD_CONV_SIMT_FP32) return align_up(sqd_simt_workspace_bytes(cin, cout), 256);
+    return align_up(sqd_tc_workspace_bytes(batch, cin, gh, gw), 256);
+}
+
+extern "C" int sqd_convdet_forward(const float *d_feat, int layout, const void *d_packed, const float *d_weight,
+                                   const float *d_bias, int batch, int cin, int gh, int gw, int cout, float *d_pred,
+                                   void *d_workspace, size_t workspace_bytes, int algo, void *stream) {
+    SQD_REQUIRE(d_feat && d_bias && d_pred && d_workspace, SQD_E_NULL, "sqd_convdet_forward: NULL pointer");
+    SQD_REQUIRE(layout == SQD_LAYOUT_NCHW || layout == SQD_LAYOUT_NHWC, SQD_E_SHAPE, "sqd_convdet_forward: bad layout %d",
+                layout);
+    SQD_REQUIRE(batch >= 0 && cin > 0 && gh > 0 && gw > 0 && cout > 0, SQD_E_SHAPE, "sqd_convdet_forward: bad shape");
+    SQD_REQUIRE(sqd_aligned16(d_feat) && sqd_aligned16(d_pred) && sqd_aligned16(d_workspace), SQD_E_ALIGN,
+                "sqd_convdet_forward: feat/pred/workspace must be 16-byte aligned");
+    SQD_REQUIRE(workspace_bytes >= sqd_convdet_workspace_bytes(batch, cin, gh, gw, cout, layout, algo), SQD_E_WORKSPACE,
+                "sqd_convdet_forward: workspace too small (%zu bytes)", workspace_bytes);
+    if (batch == 0) return SQD_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (algo == SQD_CONV_SIMT_FP32) {
+        SQD_REQUIRE(d_weight, SQD_E_NULL, "sqd_convdet_forward: SIMT algorithm needs the raw weight tensor");
+        return sqd_convdet_simt(d_feat, layout, d_weight, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
+    }
+    SQD_REQUIRE(algo == SQD_CONV_TCGEN05_3XTF32, SQD_E_UNSUPPORTED, "sqd_convdet_forward: unknown algo %d", algo);
+    SQD_REQUIRE(d_packed, SQD_E_NULL, "sqd_convdet_forward: tcgen05 algorithm needs packed weights");
+    return sqd_convdet_tc(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
+}
+
+// Synchronises `stream` and reports whether the last tcgen05 launch that used this workspace drained cleanly
+// (0) or hit a bounded-wait timeout (>0: 1 producer, 2 MMA issuer, 3 epilogue).  Debug / test aid.
+extern "C" int sqd_convdet_status(const void *d_workspace, int batch, int cin, int gh, int gw, void *stream) {
+    SQD_REQUIRE(d_workspace, SQD_E_NULL, "sqd_convdet_status: NULL workspace");
+    int h = -1;
+    SQD_CUDA(cudaMemcpyAsync(&h, sqd_tc_status_ptr(d_workspace, batch, cin, gh, gw), sizeof(int), cudaMemcpyDeviceToHost,
+                             static_cast<cudaStream_t>(stream)));
+    SQD_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    if (h != 0) sqd_set_error("tcgen05 ConvDet pipeline timed out (role %d)", h);
+    return h;
+}
+
+// ---- fused a1-a9 -----------------------------------------------------------------------------------
+extern "C" size_t sqd_head_detect_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout, int algo) {
+    if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0) return 256;
+    const size_t pred = align_up((size_t)batch * gh * gw * cout * sizeof(float), 256);
+    return pred + sqd_convdet_workspace_bytes(batch, cin, gh, gw, cout, layout, algo);
+}
+
+extern "C" int sqd_head_detect_fused(const float *d_feat, int layout, const void *d_packed, const float *d_weight,
+                                     const float *d_bias, const float *d_anchors, int batch, int cin, int gh, int gw,
+                                     int anchors_per_grid, int num_classes, int input_h, int input_w, int top_k,
+                                     double nms_thresh, double score_thresh, int32_t *d_count, int32_t *d_out_anchor,
+                                     int32_t *d_out_class, float *d_out_score, float *d_out_box, void *d_workspace,
+                                     size_t workspace_bytes, int algo, void *stream) {
+    SQD_REQUIRE(anchors_per_grid >= 1 && num_classes >= 1, SQD_E_SHAPE, "sqd_head_detect_fused: bad anchor/class count");
+    const int cout = anchors_per_grid * (num_classes + 5);
+    SQD_REQUIRE(d_workspace, SQD_E_NULL, "sqd_head_detect_fused: NULL workspace");
+    SQD_REQUIRE(workspace_bytes >= sqd_head_detect_workspace_bytes(batch, cin, gh, gw, cout, layout, algo),
+                SQD_E_WORKSPACE, "sqd_head_detect_fused: workspace too small (%zu bytes)", workspace_bytes);
+    const size_t pred_bytes = align_up((size_t)(batch > 0 ? batch : 0) * gh * gw * cout * sizeof(float), 256);
+    float *pred = static_cast<float *>(d_workspace);
+    void *conv_ws = static_cast<char *>(d_workspace) + pred_bytes;
+    int rc = sqd_convdet_forward(d_feat, layout, d_packed, d_weight, d_bias, batch, cin, gh, gw, cout, pred, conv_ws,
+                                 workspace_bytes - pred_bytes, algo, stream);
+    if (rc) return rc;
+    return sqd_detect_from_pred(pred, d_anchors, batch, gh * gw * anchors_per_grid, num_classes, input_h, input_w, top_k,
+                                nms_thresh, score_thresh, d_count, d_out_anchor, d_out_class, d_out_score, d_out_box,
+                                stream);
+}
+
+// ---- 8(f) rank 1: boxes_postprocess -----------------------------------------------------------------
+// Reference order (src/utils/boxes.py:145-166): /scale, -padding, +crops, flip, +drifts.  One 10-float record
+// per image: [scale_y, scale_x, pad_top, pad_left, crop_top, crop_left, flip_width (<=0: not flipped),
+// drift_y, drift_x, 0]; absent keys are passed as their identity (scale 1, offsets 0).
+namespace {
+__global__ void postprocess_kernel(float4 *boxes, const int *count, const float *meta, int k) {
+    const int img = blockIdx.x;
+    const int n = count[img];
+    const float *m = meta + (size_t)img * 10;
+    const float sy = m[0], sx = m[1], pt = m[2], pl = m[3], ct = m[4], cl = m[5], fw = m[6], dy = m[7], dx = m[8];
+    for (int i = threadIdx.x; i < n && i < k; i += blockDim.x) {
+        float4 b = boxes[(size_t)img * k + i];
+        b.x = fdiv(b.x, sx); b.z = fdiv(b.z, sx); b.y = fdiv(b.y, sy); b.w = fdiv(b.w, sy);
+        b.x = fsub(b.x, pl); b.z = fsub(b.z, pl); b.y = fsub(b.y, pt); b.w = fsub(b.w, pt);
+        b.x = fadd(b.x, cl); b.z = fadd(b.z, cl); b.y = fadd(b.y, ct); b.w = fadd(b.w, ct);
+        if (fw > 0.f) {
+            const float w = fadd(fsub(b.z, b.x), 1.f);
+            b.x = fsub(fsub(fw, 1.f), b.z);
+            b.z = fsub(fadd(b.x, w), 1.f);
+        }
+        b.x = fadd(b.x, dx); b.z = fadd(b.z, dx); b.y = fadd(b.y, dy); b.w = fadd(b.w, dy);
+        boxes[(size_t)img * k + i] = b;
+    }
+}
+}  // namespace
+
+extern "C" int sqd_boxes_postprocess(float *d_boxes, const int32_t *d_count, const float *d_meta, int batch, int top_k,
+                                     void *stream) {
+    SQD_REQUIRE(d_boxes && d_count && d_meta, SQD_E_NULL, "sqd_boxes_postprocess: NULL pointer");
+    SQD_REQUIRE(batch >= 0 && top_k >= 1, SQD_E_SHAPE, "sqd_boxes_postprocess: bad shape");
+    SQD_REQUIRE(sqd_aligned16(d_boxes), SQD_E_ALIGN, "sqd_boxes_postprocess: boxes must be 16-byte aligned");
+    if (batch == 0) return SQD_OK;
+    postprocess_kernel<<<batch, 64, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<float4 *>(d_boxes), d_count,
+                                                                           d_meta, top_k);
+    SQD_LAUNCH_CHECK("postprocess_kernel");
+    return SQD_OK;
+}

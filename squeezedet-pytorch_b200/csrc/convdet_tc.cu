@@ -1,0 +1,487 @@
+// a1: ConvDet 3x3 head as a tcgen05 / TMEM implicit GEMM fed by TMA (sm_100a), 3xTF32.
+// Reference: SqueezeDetBase.convdet + permute(0,2,3,1) + view, src/model/squeezedet.py:73-75,83-87
+// (cuDNN conv with N=72 plus an NCHW->NHWC copy kernel there).
+//
+// GEMM view per image: M = gh*gw cells, N = Cout = K_anchors*(C+5) (72 KITTI, padded to 80), K = 9*Cin = 6912.
+//
+//  * M tile = 8 x 16 spatial block of cells = 128 rows = one UMMA_M.  For filter tap (dy,dx) and channel
+//    block c0 the A operand is ONE 4-D TMA box {32 ch, 16 x, 8 y, 1 img} at (c0, x0+dx, y0+dy, b): the
+//    conv padding is TMA's out-of-bounds zero fill, so there is no im2col buffer and no halo logic.
+//    The box lands as 128 rows x 128 B, 128B-swizzled = the canonical K-major UMMA layout.
+//  * B operand = packed weights [Npad][9*Cin] K-major (k = tap*Cin + c), a 2-D TMA box {32, Npad}.
+//  * 3xTF32: features and weights are pre-split into tf32-exact hi and lo planes
+//    (hi = rna_tf32(x), lo = rna_tf32(x - hi)); D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with fp32
+//    accumulation in TMEM.  One tf32 pass flips top-k order; three passes recover fp32-level
+//    products.  Algorithmic FLOPs per image: 2*M*Cout*K (the 3 passes and N padding are NOT counted).
+//  * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
+//    lane), warps 2..5 = epilogue (tcgen05.ld -> +bias -> pred in the reference's (B, A, C+5) layout).
+//    smem ring of kStages x {A_hi, A_lo, B_hi, B_lo} with full/empty mbarriers; tcgen05.commit frees slots.
+//  * Every mbarrier wait is bounded: on timeout the CTA sets a status word and drains instead of hanging.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTileX = 16, kTileY = 8;        // cells per M tile (8 x 16 = 128 = UMMA_M)
+constexpr int kBlockK = 32;                   // channels per pipeline stage (128 B of fp32 = one swizzle row)
+constexpr int kUmmaK = 8;                     // tf32 MMA K
+constexpr int kABytes = 128 * kBlockK * 4;    // 16 KiB per A plane per stage
+constexpr int kThreadsTC = 192;
+constexpr unsigned kSpinLimit = 1u << 24;
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: returns false (and raises the CTA abort flag) instead of spinning forever.
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, volatile int *abort_flag) {
+    const uint32_t addr = smem_u32(bar);
+    for (unsigned spin = 0; spin < kSpinLimit; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return true;
+        if (*abort_flag) return false;
+    }
+    *abort_flag = 1;
+    return false;
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, M=128, kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives when all previously issued MMAs of this thread have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread i of the warp = TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), start address 1024-aligned
+// (+ k*32 B inside the swizzle row for the k-th UMMA_K step).  Field layout: cute::UMMA::SmemDescriptor.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);      // [0,14)  start address >> 4
+    d |= (uint64_t)1 << 16;                        // [16,30) leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;              // [32,46) stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                        // [46,48) descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                        // [61,64) layout: SWIZZLE_128B
+    return d;
+}
+// cute::UMMA::InstrDescriptor: c=F32, a=b=TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pre-passes: hi/lo split of features (-> NHWC planes) and of the weights (-> [Npad][9*Cin] planes)
+// ---------------------------------------------------------------------------------------------------
+__global__ void split_nhwc_kernel(const float4 *__restrict__ in, float4 *__restrict__ hi, float4 *__restrict__ lo,
+                                  size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = ld_stream_f4(in + i);
+        float4 h, l;
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+// NCHW (B,Cin,P) -> NHWC (B,P,Cin) planes through a 32x33 shared tile; P = gh*gw
+__global__ void split_nchw_kernel(const float *__restrict__ in, float *__restrict__ hi, float *__restrict__ lo, int cin,
+                                  int P) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const float *src = in + (size_t)b * cin * P;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, p = p0 + threadIdx.x;
+        tile[j][threadIdx.x] = (c < cin && p < P) ? __ldg(src + (size_t)c * P + p) : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int p = p0 + j, c = c0 + threadIdx.x;
+        if (p < P && c < cin) {
+            const float v = tile[threadIdx.x][j];
+            const float h = tf32_rna(v);
+            const size_t o = ((size_t)b * P + p) * cin + c;
+            hi[o] = h;
+            lo[o] = tf32_rna(v - h);
+        }
+    }
+}
+
+__global__ void pack_weights_tc_kernel(const float *__restrict__ w, int cout, int cin, int npad, float *__restrict__ hi,
+                                       float *__restrict__ lo) {
+    const size_t ktot = (size_t)9 * cin, total = (size_t)npad * ktot;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / ktot);
+        const size_t k = i % ktot;
+        const int tap = (int)(k / cin), c = (int)(k % cin);
+        float v = 0.f;
+        if (n < cout) v = w[((size_t)n * cin + c) * 9 + tap];
+        const float h = tf32_rna(v);
+        hi[i] = h;
+        lo[i] = tf32_rna(v - h);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------------
+struct TcParams {
+    int cin, gh, gw, cout;
+    int tiles_x;
+    int num_stages;
+    const float *bias;
+    float *pred;
+    int *status;  // 0 ok; else 1 + role that timed out
+};
+
+template <int NPAD>
+__global__ void __launch_bounds__(kThreadsTC, 1)
+convdet_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                  const TcParams p) {
+    constexpr int kBBytes = NPAD * kBlockK * 4;
+    constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+    constexpr uint32_t kTmemCols = NPAD <= 32 ? 32 : (NPAD <= 64 ? 64 : 128);
+    constexpr uint32_t kIdesc = umma_idesc_tf32(128, NPAD);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int S = p.num_stages;
+    uint8_t *ctrl = smem + (size_t)S * kStageBytes;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(ctrl);
+    uint64_t *empty_bar = full_bar + 8;
+    uint64_t *tmem_full_bar = empty_bar + 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+    volatile int *abort_flag = reinterpret_cast<volatile int *>(tmem_slot + 1);
+    float *s_bias = reinterpret_cast<float *>(tmem_slot + 2);  // NPAD floats
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, img = blockIdx.y;
+    const int x0 = (tile % p.tiles_x) * kTileX, y0 = (tile / p.tiles_x) * kTileY;
+    const int cblocks = p.cin / kBlockK;
+    const int iters = cblocks * 9;
+
+    if (threadIdx.x == 0) {
+        *abort_flag = 0;
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_b_hi);
+        tma_prefetch_desc(&map_b_lo);
+    }
+    for (int i = threadIdx.x; i < NPAD; i += kThreadsTC) s_bias[i] = i < p.cout ? __ldg(p.bias + i) : 0.f;
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                if (!mbar_wait(empty_bar + s, ph ^ 1u, abort_flag)) {
+                    atomicCAS(p.status, 0, 1);
+                    break;
+                }
+                const int cb = it / 9, tap = it - cb * 9;   // channel block outer, tap inner: the 9 shifted
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;  // windows of one channel block hit L2 back to back
+                uint8_t *st = smem + (size_t)s * kStageBytes;
+                mbar_arrive_expect_tx(full_bar + s, kStageBytes);
+                tma_load_4d(&map_a_hi, full_bar + s, st, cb * kBlockK, x0 + dx, y0 + dy, img);
+                tma_load_4d(&map_a_lo, full_bar + s, st + kABytes, cb * kBlockK, x0 + dx, y0 + dy, img);
+                tma_load_2d(&map_b_hi, full_bar + s, st + 2 * kABytes, tap * p.cin + cb * kBlockK, 0);
+                tma_load_2d(&map_b_lo, full_bar + s, st + 2 * kABytes + kBBytes, tap * p.cin + cb * kBlockK, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (single thread) =====
+        if (lane == 0) {
+            bool ok = true;
+            for (int it = 0; it < iters && ok; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                if (!mbar_wait(full_bar + s, ph, abort_flag)) {
+                    atomicCAS(p.status, 0, 2);
+                    ok = false;
+                    break;
+                }
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes);
+                const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + kABytes);
+                const uint64_t b_hi = umma_desc_sw128(sa + 2 * kABytes), b_lo = umma_desc_sw128(sa + 2 * kABytes + kBBytes);
+#pragma unroll
+                for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
+                    const uint64_t adv = (uint64_t)((ks * kUmmaK * 4) >> 4);  // +32 B per K step, in 16 B units
+                    // small cross terms first, then the dominant hi*hi product
+                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, kIdesc, (it | ks) ? 1u : 0u);
+                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, kIdesc, 1u);
+                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, kIdesc, 1u);
+                }
+                umma_commit(empty_bar + s);  // slot reusable once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);      // accumulator complete (also fires after an aborted loop)
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> (+bias) -> pred =====
+        const bool ok = mbar_wait(tmem_full_bar, 0, abort_flag);
+        if (!ok && lane == 0) atomicCAS(p.status, 0, 3);
+        tc_fence_after();
+        __syncwarp();
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;          // accumulator row == cell inside the 8x16 tile
+        const int y = y0 + row / kTileX, x = x0 + row % kTileX;
+        uint32_t v[NPAD];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < NPAD; c += 16) tmem_ld_x16(taddr + c, v + c);
+        tmem_ld_wait();
+        if (ok && y < p.gh && x < p.gw) {
+            float *out = p.pred + (((size_t)img * p.gh + y) * p.gw + x) * p.cout;
+            if ((p.cout & 3) == 0) {
+                float4 *o4 = reinterpret_cast<float4 *>(out);
+#pragma unroll
+                for (int n = 0; n < NPAD; n += 4)
+                    if (n < p.cout)
+                        o4[n >> 2] = make_float4(__uint_as_float(v[n]) + s_bias[n], __uint_as_float(v[n + 1]) + s_bias[n + 1],
+                                                 __uint_as_float(v[n + 2]) + s_bias[n + 2],
+                                                 __uint_as_float(v[n + 3]) + s_bias[n + 3]);
+            } else {
+#pragma unroll
+                for (int n = 0; n < NPAD; ++n)
+                    if (n < p.cout) out[n] = __uint_as_float(v[n]) + s_bias[n];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;  // benign race: every thread resolves the same pointer
+    if (fn) return fn;
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+    return fn;
+}
+
+int npad_of(int cout) { return (cout + 15) / 16 * 16; }
+
+int stages_for(int npad) {
+    const int stage = 2 * kABytes + 2 * npad * kBlockK * 4;
+    int s = (227 * 1024 - 2048 - 1024) / stage;
+    if (s > 4) s = 4;
+    return s;
+}
+
+size_t smem_bytes_for(int npad, int stages) {
+    return (size_t)stages * (2 * kABytes + 2 * npad * kBlockK * 4) + 1024 /*align*/ + 256 /*barriers*/ + npad * 4;
+}
+
+}  // namespace
+
+size_t sqd_tc_packed_bytes(int cout, int cin) { return (size_t)2 * npad_of(cout) * 9 * cin * sizeof(float); }
+
+size_t sqd_tc_workspace_bytes(int batch, int cin, int gh, int gw) {
+    return (size_t)2 * batch * gh * gw * cin * sizeof(float) + 256;
+}
+
+int sqd_tc_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, cudaStream_t st) {
+    const int npad = npad_of(cout);
+    float *hi = static_cast<float *>(d_packed);
+    float *lo = hi + (size_t)npad * 9 * cin;
+    pack_weights_tc_kernel<<<2 * SQD_SM_COUNT, 256, 0, st>>>(d_weight, cout, cin, npad, hi, lo);
+    SQD_LAUNCH_CHECK("pack_weights_tc_kernel");
+    return SQD_OK;
+}
+
+template <int NPAD>
+static int launch_tc(const CUtensorMap *maps, const TcParams &p, int tiles, int batch, cudaStream_t st) {
+    const size_t smem = smem_bytes_for(NPAD, p.num_stages);
+    SQD_CUDA(cudaFuncSetAttribute(convdet_tc_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    convdet_tc_kernel<NPAD><<<dim3(tiles, batch), kThreadsTC, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+    SQD_LAUNCH_CHECK("convdet_tc_kernel");
+    return SQD_OK;
+}
+
+// d_workspace: [A_hi plane | A_lo plane | status word]
+int sqd_convdet_tc(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
+                   int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st) {
+    SQD_REQUIRE(cin % kBlockK == 0, SQD_E_SHAPE, "convdet (tcgen05): Cin %d must be a multiple of %d", cin, kBlockK);
+    SQD_REQUIRE(cout >= 1 && cout <= 128, SQD_E_SHAPE, "convdet (tcgen05): Cout %d outside [1,128]", cout);
+    SQD_REQUIRE(batch <= 65535, SQD_E_SHAPE, "convdet (tcgen05): batch %d > 65535 (split the call)", batch);
+    EncodeTiledFn encode = get_encode_fn();
+    SQD_REQUIRE(encode != nullptr, SQD_E_DRIVER, "cuTensorMapEncodeTiled not available from the CUDA driver");
+    const int npad = npad_of(cout);
+    const size_t plane = (size_t)batch * gh * gw * cin;
+    float *a_hi = static_cast<float *>(d_workspace);
+    float *a_lo = a_hi + plane;
+    int *status = reinterpret_cast<int *>(a_lo + plane);
+    SQD_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+
+    // 1. hi/lo split into NHWC planes
+    if (layout == SQD_LAYOUT_NHWC) {
+        split_nhwc_kernel<<<4 * SQD_SM_COUNT, 256, 0, st>>>(reinterpret_cast<const float4 *>(d_feat),
+                                                            reinterpret_cast<float4 *>(a_hi),
+                                                            reinterpret_cast<float4 *>(a_lo), plane / 4);
+    } else {
+        const int P = gh * gw;
+        dim3 grid((P + 31) / 32, (cin + 31) / 32, batch);
+        split_nchw_kernel<<<grid, dim3(32, 8), 0, st>>>(d_feat, a_hi, a_lo, cin, P);
+    }
+    SQD_LAUNCH_CHECK("split kernel");
+
+    // 2. tensor maps
+    alignas(64) CUtensorMap maps[4];
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)gw, (cuuint64_t)gh, (cuuint64_t)batch};
+        const cuuint64_t strides[3] = {(cuuint64_t)cin * 4, (cuuint64_t)gw * cin * 4, (cuuint64_t)gh * gw * cin * 4};
+        const cuuint32_t box[4] = {kBlockK, kTileX, kTileY, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        for (int i = 0; i < 2; ++i) {
+            CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, i == 0 ? (void *)a_hi : (void *)a_lo, dims,
+                                strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SQD_REQUIRE(r == CUDA_SUCCESS, SQD_E_DRIVER, "cuTensorMapEncodeTiled(features) failed: CUresult %d", (int)r);
+        }
+    }
+    {
+        const size_t ktot = (size_t)9 * cin;
+        const float *b_hi = static_cast<const float *>(d_packed);
+        const float *b_lo = b_hi + (size_t)npad * ktot;
+        const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)npad};
+        const cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
+        const cuuint32_t box[2] = {kBlockK, (cuuint32_t)npad};
+        const cuuint32_t estr[2] = {1, 1};
+        for (int i = 0; i < 2; ++i) {
+            CUresult r = encode(&maps[2 + i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, i == 0 ? (void *)b_hi : (void *)b_lo,
+                                dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SQD_REQUIRE(r == CUDA_SUCCESS, SQD_E_DRIVER, "cuTensorMapEncodeTiled(weights) failed: CUresult %d", (int)r);
+        }
+    }
+
+    // 3. the GEMM
+    TcParams p;
+    p.cin = cin; p.gh = gh; p.gw = gw; p.cout = cout;
+    p.tiles_x = (gw + kTileX - 1) / kTileX;
+    p.num_stages = stages_for(npad);
+    p.bias = d_bias;
+    p.pred = d_pred;
+    p.status = status;
+    const int tiles = p.tiles_x * ((gh + kTileY - 1) / kTileY);
+    switch (npad / 16) {
+        case 1: return launch_tc<16>(maps, p, tiles, batch, st);
+        case 2: return launch_tc<32>(maps, p, tiles, batch, st);
+        case 3: return launch_tc<48>(maps, p, tiles, batch, st);
+        case 4: return launch_tc<64>(maps, p, tiles, batch, st);
+        case 5: return launch_tc<80>(maps, p, tiles, batch, st);
+        case 6: return launch_tc<96>(maps, p, tiles, batch, st);
+        case 7: return launch_tc<112>(maps, p, tiles, batch, st);
+        case 8: return launch_tc<128>(maps, p, tiles, batch, st);
+    }
+    SQD_REQUIRE(false, SQD_E_SHAPE, "convdet (tcgen05): unsupported Cout %d", cout);
+}
+
+// status word lives right after the two feature planes (see sqd_convdet_tc)
+const int *sqd_tc_status_ptr(const void *d_workspace, int batch, int cin, int gh, int gw) {
+    const float *base = static_cast<const float *>(d_workspace);
+    return reinterpret_cast<const int *>(base + (size_t)2 * batch * gh * gw * cin);
+}

@@ -1,0 +1,213 @@
+// a11-a13: training-side anchor <-> ground-truth matching and the dense target tensor.
+// Reference: numpy compute_overlaps / compute_deltas, src/utils/boxes.py:70-135 (one full
+// np.argsort of A IoUs per GT box, in DataLoader workers) and BaseDataset.prepare_annotations,
+// src/datasets/base.py:61-76.
+//
+// One CTA per image; GT boxes are processed sequentially (the greedy assignment is order
+// dependent by definition), each one as a block-wide masked arg-max over the A anchors in
+// float64 with the reference's exact operation order (no FMA contraction), so equal IoUs are
+// bit-equal here exactly when they are in numpy.  Tie policy: lowest anchor index (a stable
+// argsort in the reference).  "Taken" anchors live in a shared-memory bitmask.
+// Bytes per image: G * A * 32 (float64 anchor table, L2-resident across the batch).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct Best {
+    double v;
+    int idx;
+};
+
+// larger v wins; ties -> lower index.  idx == INT_MAX marks "none".
+__device__ __forceinline__ Best better_max(Best a, Best b) {
+    if (b.idx == 0x7fffffff) return a;
+    if (a.idx == 0x7fffffff) return b;
+    if (b.v > a.v || (b.v == a.v && b.idx < a.idx)) return b;
+    return a;
+}
+__device__ __forceinline__ Best better_min(Best a, Best b) {
+    if (b.idx == 0x7fffffff) return a;
+    if (a.idx == 0x7fffffff) return b;
+    if (b.v < a.v || (b.v == a.v && b.idx < a.idx)) return b;
+    return a;
+}
+
+template <bool kMax>
+__device__ Best block_reduce(Best x, Best *scratch) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Best y;
+        y.v = __shfl_down_sync(0xffffffffu, x.v, off);
+        y.idx = __shfl_down_sync(0xffffffffu, x.idx, off);
+        x = kMax ? better_max(x, y) : better_min(x, y);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();  // scratch reuse across calls
+    if (lane == 0) scratch[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        x = lane < (kThreads >> 5) ? scratch[lane] : Best{0.0, 0x7fffffff};
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            Best y;
+            y.v = __shfl_down_sync(0xffffffffu, x.v, off);
+            y.idx = __shfl_down_sync(0xffffffffu, x.idx, off);
+            x = kMax ? better_max(x, y) : better_min(x, y);
+        }
+        if (lane == 0) scratch[0] = x;
+    }
+    __syncthreads();
+    return scratch[0];
+}
+
+__global__ void __launch_bounds__(kThreads) match_kernel(const float4 *gt_boxes, const int *gt_count, int gmax,
+                                                         const double *anchors, int A, int *out_idx,
+                                                         float4 *out_deltas) {
+    extern __shared__ unsigned taken[];  // ceil(A/32) words
+    __shared__ Best scratch[kThreads / 32];
+    const int img = blockIdx.x;
+    const int G = min(max(gt_count[img], 0), gmax);
+    for (int i = threadIdx.x; i < (A + 31) / 32; i += kThreads) taken[i] = 0u;
+    for (int g = G + threadIdx.x; g < gmax; g += kThreads) {
+        out_idx[(size_t)img * gmax + g] = -1;
+        out_deltas[(size_t)img * gmax + g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+
+    for (int g = 0; g < G; ++g) {
+        const float4 b = gt_boxes[(size_t)img * gmax + g];
+        // float32 scalar arithmetic of boxes.py:17-22 (xyxy_to_xywh on the float32 GT array)
+        const float gx = fdiv(fadd(b.x, b.z), 2.0f);
+        const float gy = fdiv(fadd(b.y, b.w), 2.0f);
+        const float gw = fadd(fsub(b.z, b.x), 1.0f);
+        const float gh = fadd(fsub(b.w, b.y), 1.0f);
+        const double bx1 = b.x, by1 = b.y, bx2 = b.z, by2 = b.w;
+        const double area_g = (double)fmul(fsub(b.z, b.x), fsub(b.w, b.y));  // float32 product, then promoted
+
+        // pass 1: best IoU > 0 among untaken anchors (boxes.py:70-81,104-111)
+        Best best{0.0, 0x7fffffff};
+        for (int a = threadIdx.x; a < A; a += kThreads) {
+            if ((taken[a >> 5] >> (a & 31)) & 1u) continue;
+            const double2 xy = *reinterpret_cast<const double2 *>(anchors + (size_t)a * 4);
+            const double2 wh = *reinterpret_cast<const double2 *>(anchors + (size_t)a * 4 + 2);
+            const double hw = d_mul(0.5, d_sub(wh.x, 1.0)), hh = d_mul(0.5, d_sub(wh.y, 1.0));
+            const double x1 = d_sub(xy.x, hw), y1 = d_sub(xy.y, hh), x2 = d_add(xy.x, hw), y2 = d_add(xy.y, hh);
+            const double lr = fmax(d_sub(fmin(x2, bx2), fmax(x1, bx1)), 0.0);
+            const double tb = fmax(d_sub(fmin(y2, by2), fmax(y1, by1)), 0.0);
+            const double inter = d_mul(lr, tb);
+            const double area_a = d_mul(d_sub(x2, x1), d_sub(y2, y1));
+            const double uni = d_sub(d_add(area_a, area_g), inter);
+            const double iou = d_div(inter, d_add(uni, 1e-10));
+            if (iou > 0.0 && (best.idx == 0x7fffffff || iou > best.v)) {  // a ascends per thread: first max kept
+                best.v = iou;
+                best.idx = a;
+            }
+        }
+        best = block_reduce<true>(best, scratch);
+
+        if (best.idx == 0x7fffffff) {
+            // pass 2: nearest untaken anchor in squared xywh distance (boxes.py:115-121)
+            Best nb{0.0, 0x7fffffff};
+            for (int a = threadIdx.x; a < A; a += kThreads) {
+                if ((taken[a >> 5] >> (a & 31)) & 1u) continue;
+                const double2 xy = *reinterpret_cast<const double2 *>(anchors + (size_t)a * 4);
+                const double2 wh = *reinterpret_cast<const double2 *>(anchors + (size_t)a * 4 + 2);
+                const double d0 = d_sub((double)gx, xy.x), d1 = d_sub((double)gy, xy.y);
+                const double d2 = d_sub((double)gw, wh.x), d3 = d_sub((double)gh, wh.y);
+                const double dist = d_add(d_add(d_add(d_mul(d0, d0), d_mul(d1, d1)), d_mul(d2, d2)), d_mul(d3, d3));
+                if (nb.idx == 0x7fffffff || dist < nb.v) {
+                    nb.v = dist;
+                    nb.idx = a;
+                }
+            }
+            best = block_reduce<false>(nb, scratch);
+        }
+
+        if (threadIdx.x == 0) {
+            int j = best.idx;
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j != 0x7fffffff) {
+                taken[j >> 5] |= 1u << (j & 31);
+                const double ax = anchors[(size_t)j * 4], ay = anchors[(size_t)j * 4 + 1];
+                const double aw = anchors[(size_t)j * 4 + 2], ah = anchors[(size_t)j * 4 + 3];
+                d.x = (float)d_div(d_sub((double)gx, ax), aw);   // boxes.py:125-128, float64 then cast
+                d.y = (float)d_div(d_sub((double)gy, ay), ah);
+                d.z = (float)log(d_div((double)gw, aw));
+                d.w = (float)log(d_div((double)gh, ah));
+            } else {
+                j = A;  // more GT boxes than anchors: the reference leaves anchor_idx == num_anchors
+            }
+            out_idx[(size_t)img * gmax + g] = j;
+            out_deltas[(size_t)img * gmax + g] = d;
+        }
+        __syncthreads();  // taken[] update visible before the next GT box
+    }
+}
+
+// scatter the matched rows into the (already zeroed) dense target, base.py:69-74
+__global__ void scatter_targets_kernel(const float4 *gt_boxes, const int *gt_classes, const int *gt_count,
+                                       const int *anchor_idx, const float4 *deltas, int gmax, int A, int C,
+                                       float *gt_dense) {
+    const int img = blockIdx.x;
+    const int G = min(max(gt_count[img], 0), gmax);
+    const int W = C + 9;
+    // later rows win where the reference's fancy-index assignment would (duplicates cannot occur for idx < A)
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const int j = anchor_idx[(size_t)img * gmax + g];
+        if (j < 0 || j >= A) continue;
+        float *row = gt_dense + ((size_t)img * A + j) * W;
+        const float4 b = gt_boxes[(size_t)img * gmax + g];
+        const float4 d = deltas[(size_t)img * gmax + g];
+        row[0] = 1.f;
+        row[1] = b.x; row[2] = b.y; row[3] = b.z; row[4] = b.w;
+        row[5] = d.x; row[6] = d.y; row[7] = d.z; row[8] = d.w;
+        const int c = gt_classes[(size_t)img * gmax + g];
+        if (c >= 0 && c < C) row[9 + c] = 1.f;
+    }
+}
+
+}  // namespace
+
+extern "C" int sqd_match_anchors(const float *d_gt_boxes, const int32_t *d_gt_count, int batch, int gmax,
+                                 const double *d_anchors64, int num_anchors, int32_t *d_anchor_idx,
+                                 float *d_deltas, void *stream) {
+    SQD_REQUIRE(d_gt_boxes && d_gt_count && d_anchors64 && d_anchor_idx && d_deltas, SQD_E_NULL,
+                "sqd_match_anchors: NULL pointer");
+    SQD_REQUIRE(batch >= 0 && gmax >= 1 && gmax <= SQD_MAX_GT, SQD_E_SHAPE, "sqd_match_anchors: gmax %d outside [1,%d]",
+                gmax, SQD_MAX_GT);
+    SQD_REQUIRE(num_anchors > 0 && num_anchors <= (1 << 20), SQD_E_SHAPE, "sqd_match_anchors: bad num_anchors %d",
+                num_anchors);
+    SQD_REQUIRE(sqd_aligned16(d_gt_boxes) && sqd_aligned16(d_anchors64) && sqd_aligned16(d_deltas), SQD_E_ALIGN,
+                "sqd_match_anchors: gt_boxes/anchors/deltas must be 16-byte aligned");
+    if (batch == 0) return SQD_OK;
+    const size_t smem = (size_t)((num_anchors + 31) / 32) * sizeof(unsigned);
+    if (smem > 48 * 1024)
+        SQD_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    match_kernel<<<batch, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4 *>(d_gt_boxes), d_gt_count, gmax, d_anchors64, num_anchors, d_anchor_idx,
+        reinterpret_cast<float4 *>(d_deltas));
+    SQD_LAUNCH_CHECK("match_kernel");
+    return SQD_OK;
+}
+
+extern "C" int sqd_build_targets(const float *d_gt_boxes, const int32_t *d_gt_classes, const int32_t *d_gt_count,
+                                 const int32_t *d_anchor_idx, const float *d_deltas, int batch, int gmax,
+                                 int num_anchors, int num_classes, float *d_gt_dense, void *stream) {
+    SQD_REQUIRE(d_gt_boxes && d_gt_classes && d_gt_count && d_anchor_idx && d_deltas && d_gt_dense, SQD_E_NULL,
+                "sqd_build_targets: NULL pointer");
+    SQD_REQUIRE(batch >= 0 && gmax >= 1 && gmax <= SQD_MAX_GT && num_anchors > 0, SQD_E_SHAPE,
+                "sqd_build_targets: bad shape");
+    SQD_REQUIRE(num_classes >= 1 && num_classes <= SQD_MAX_CLASSES, SQD_E_SHAPE, "sqd_build_targets: bad num_classes");
+    SQD_REQUIRE(sqd_aligned16(d_gt_boxes) && sqd_aligned16(d_deltas), SQD_E_ALIGN,
+                "sqd_build_targets: gt_boxes/deltas must be 16-byte aligned");
+    if (batch == 0) return SQD_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SQD_CUDA(cudaMemsetAsync(d_gt_dense, 0, (size_t)batch * num_anchors * (num_classes + 9) * sizeof(float), st));
+    scatter_targets_kernel<<<batch, 64, 0, st>>>(reinterpret_cast<const float4 *>(d_gt_boxes), d_gt_classes,
+                                                 d_gt_count, d_anchor_idx, reinterpret_cast<const float4 *>(d_deltas),
+                                                 gmax, num_anchors, num_classes, d_gt_dense);
+    SQD_LAUNCH_CHECK("scatter_targets_kernel");
+    return SQD_OK;
+}

@@ -1,0 +1,80 @@
+"""Multi-GPU plumbing.  One process per GPU.
+
+Inference shards by image: rank r owns images [r*B/n, (r+1)*B/n) and runs the whole path on its
+slice; there is NO collective on the inference path.  Training is data parallel over images with
+ONE collective per step: an all-reduce(sum) of a single flat fp32 gradient bucket, replacing the
+reference's per-step parameter broadcast + reduce-to-GPU-0 (src/utils/data_parallel.py:93-101)."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from RANK / WORLD_SIZE / MASTER_* (torchrun).  Returns
+    (rank, world, local_rank); a no-op single process when the variables are absent."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_range(total, rank, world):
+    """Contiguous, balanced image range of this rank: sizes differ by at most one."""
+    base, rem = divmod(int(total), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_batch(batch, rank, world):
+    """Slice every batched tensor / list of a batch dict to this rank's images."""
+    n = None
+    for v in batch.values():
+        if torch.is_tensor(v):
+            n = v.shape[0]
+            break
+    lo, hi = shard_range(n, rank, world)
+    out = {}
+    for k, v in batch.items():
+        if torch.is_tensor(v) or isinstance(v, list):
+            out[k] = v[lo:hi]
+        elif isinstance(v, dict):
+            out[k] = {kk: vv[lo:hi] for kk, vv in v.items()}
+        else:
+            out[k] = v
+    return out
+
+
+class GradBucket:
+    """All parameter gradients as views into one flat fp32 buffer -> one all-reduce per step."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else "cpu"
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def allreduce_mean(self, world=None, async_op=False):
+        """sum over ranks then scale by 1/world (each rank's loss is its local per-image mean)."""
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return None
+        world = world or dist.get_world_size()
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        if async_op:
+            return work
+        self.flat.mul_(1.0 / world)
+        return None

@@ -1,0 +1,215 @@
+"""Tensor-level entry points: one Python function per C-ABI call (include/sqdet_b200.h).
+
+Each function takes / returns CUDA torch tensors and enqueues work on torch's current stream.
+Nothing here computes on the host; nothing falls back to PyTorch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import CONV_SIMT_FP32, CONV_TCGEN05_3XTF32, LAYOUT_NCHW, LAYOUT_NHWC, check, load, ptr, stream_ptr, workspace
+
+
+@dataclass
+class Detections:
+    """Batched filter output: rows [0, count[b]) of each (B, top_k[,4]) buffer are valid, in the
+    reference's order (class ascending, score descending inside a class)."""
+    count: torch.Tensor    # (B,) int32
+    anchor: torch.Tensor   # (B, top_k) int32 kept anchor indices, -1 padding
+    cls: torch.Tensor      # (B, top_k) int32
+    score: torch.Tensor    # (B, top_k) float32
+    box: torch.Tensor      # (B, top_k, 4) float32 xyxy
+
+    def to_list(self):
+        """One host transfer for the whole batch -> list of reference-style dicts (or None when
+        an image keeps nothing, like Detector.filter, detector.py:115-116)."""
+        count = self.count.cpu().tolist()
+        anchor, cls, score, box = self.anchor.cpu(), self.cls.cpu(), self.score.cpu(), self.box.cpu()
+        out = []
+        for b, n in enumerate(count):
+            if n == 0:
+                out.append(None)
+                continue
+            out.append({"class_ids": cls[b, :n].to(torch.int64), "scores": score[b, :n], "boxes": box[b, :n],
+                        "anchor_idx": anchor[b, :n].to(torch.int64)})
+        return out
+
+
+def _alloc_detections(batch, top_k, device) -> Detections:
+    return Detections(
+        count=torch.empty((batch,), dtype=torch.int32, device=device),
+        anchor=torch.empty((batch, top_k), dtype=torch.int32, device=device),
+        cls=torch.empty((batch, top_k), dtype=torch.int32, device=device),
+        score=torch.empty((batch, top_k), dtype=torch.float32, device=device),
+        box=torch.empty((batch, top_k, 4), dtype=torch.float32, device=device),
+    )
+
+
+def feature_layout(feat: torch.Tensor):
+    """(layout code, tensor to hand to the kernel) for a logical (B,C,H,W) feature map: a
+    channels_last tensor is consumed in place (zero copy); anything else is made NCHW-contiguous."""
+    if feat.dim() != 4:
+        raise _lib.SqdError("features must be (B, C, H, W)")
+    if feat.is_contiguous(memory_format=torch.channels_last) and not feat.is_contiguous():
+        return LAYOUT_NHWC, feat
+    return LAYOUT_NCHW, feat.contiguous()
+
+
+# ---- a1 --------------------------------------------------------------------------------------------
+def pack_convdet_weights(weight: torch.Tensor) -> torch.Tensor:
+    """Derive the tcgen05 kernel's weight planes from base.convdet.weight (Cout,Cin,3,3)."""
+    lib = load()
+    w = weight.detach().contiguous().float()
+    cout, cin = w.shape[0], w.shape[1]
+    nbytes = lib.sqd_convdet_packed_weight_bytes(cout, cin)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    check(lib.sqd_convdet_pack_weights(ptr(w), cout, cin, ptr(packed), stream_ptr(w.device)), "sqd_convdet_pack_weights")
+    return packed
+
+
+def convdet_forward(feat, weight, bias, packed=None, algo=CONV_TCGEN05_3XTF32, num_fields=None, check_status=False):
+    """feat (B,Cin,gh,gw) -> pred (B, gh*gw*K, C+5) [or (B,gh,gw,Cout) when num_fields is None]."""
+    lib = load()
+    layout, x = feature_layout(feat)
+    B, cin, gh, gw = x.shape
+    w = weight.detach().contiguous()
+    b = bias.detach().contiguous()
+    cout = w.shape[0]
+    if algo == CONV_TCGEN05_3XTF32 and packed is None:
+        packed = pack_convdet_weights(w)
+    nbytes = lib.sqd_convdet_workspace_bytes(B, cin, gh, gw, cout, layout, algo)
+    ws = workspace().get("convdet", nbytes, x.device)
+    pred = torch.empty((B, gh, gw, cout), dtype=torch.float32, device=x.device)
+    xp = C.c_void_p(x.data_ptr())  # channels_last tensors are not .is_contiguous(); pointer is still the base
+    check(lib.sqd_convdet_forward(xp, layout, ptr(packed), ptr(w), ptr(b), B, cin, gh, gw, cout, ptr(pred), ptr(ws),
+                                  ws.numel(), algo, stream_ptr(x.device)), "sqd_convdet_forward")
+    if check_status and algo == CONV_TCGEN05_3XTF32:
+        check(lib.sqd_convdet_status(ptr(ws), B, cin, gh, gw, stream_ptr(x.device)), "sqd_convdet_status")
+    if num_fields is not None:
+        pred = pred.view(B, gh * gw * (cout // num_fields), num_fields)
+    return pred
+
+
+# ---- a2-a7 -----------------------------------------------------------------------------------------
+def decode_scores(pred, anchors_f32, input_hw, num_classes, want=("class_ids", "scores", "boxes")):
+    """pred (B,A,C+5) -> dict with the requested keys among class_ids/scores/boxes/probs/logp/conf/deltas."""
+    lib = load()
+    pred = pred.contiguous()
+    B, A, NF = pred.shape
+    if NF != num_classes + 5:
+        raise _lib.SqdError(f"pred has {NF} fields, expected {num_classes + 5}")
+    dev = pred.device
+    shapes = {"class_ids": ((B, A), torch.int64), "scores": ((B, A), torch.float32), "boxes": ((B, A, 4), torch.float32),
+              "probs": ((B, A, num_classes), torch.float32), "logp": ((B, A, num_classes), torch.float32),
+              "conf": ((B, A, 1), torch.float32), "deltas": ((B, A, 4), torch.float32)}
+    out = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], device=dev) for k in want}
+    g = lambda k: ptr(out[k]) if k in out else None  # noqa: E731
+    check(lib.sqd_decode_scores(ptr(pred), ptr(anchors_f32), B, A, num_classes, int(input_hw[0]), int(input_hw[1]),
+                                g("class_ids"), g("scores"), g("boxes"), g("probs"), g("logp"), g("conf"), g("deltas"),
+                                stream_ptr(dev)), "sqd_decode_scores")
+    return out
+
+
+# ---- a8-a9 -----------------------------------------------------------------------------------------
+def topk_nms(class_ids, scores, boxes, num_classes, top_k, nms_thresh, score_thresh) -> Detections:
+    """Dense SqueezeDet.forward outputs (B,A)/(B,A,4) -> Detections (Detector.filter for the batch)."""
+    lib = load()
+    class_ids, scores, boxes = class_ids.contiguous(), scores.contiguous(), boxes.contiguous()
+    B, A = scores.shape
+    det = _alloc_detections(B, top_k, scores.device)
+    check(lib.sqd_topk_nms(ptr(class_ids), ptr(scores), ptr(boxes), B, A, num_classes, top_k, float(nms_thresh),
+                           float(score_thresh), ptr(det.count), ptr(det.anchor), ptr(det.cls), ptr(det.score),
+                           ptr(det.box), stream_ptr(scores.device)), "sqd_topk_nms")
+    return det
+
+
+def detect_from_pred(pred, anchors_f32, input_hw, num_classes, top_k, nms_thresh, score_thresh) -> Detections:
+    """Fused decode + score + top-k + NMS from the ConvDet output, one launch."""
+    lib = load()
+    pred = pred.contiguous()
+    B, A, _ = pred.shape
+    det = _alloc_detections(B, top_k, pred.device)
+    check(lib.sqd_detect_from_pred(ptr(pred), ptr(anchors_f32), B, A, num_classes, int(input_hw[0]), int(input_hw[1]),
+                                   top_k, float(nms_thresh), float(score_thresh), ptr(det.count), ptr(det.anchor),
+                                   ptr(det.cls), ptr(det.score), ptr(det.box), stream_ptr(pred.device)),
+          "sqd_detect_from_pred")
+    return det
+
+
+def head_detect(feat, weight, bias, anchors_f32, anchors_per_grid, num_classes, input_hw, top_k, nms_thresh,
+                score_thresh, packed=None, algo=CONV_TCGEN05_3XTF32, out: Detections = None) -> Detections:
+    """Fire11 features -> final detections (ConvDet + decode + top-k + NMS) through one ABI call."""
+    lib = load()
+    layout, x = feature_layout(feat)
+    B, cin, gh, gw = x.shape
+    w = weight.detach().contiguous()
+    b = bias.detach().contiguous()
+    cout = w.shape[0]
+    if algo == CONV_TCGEN05_3XTF32 and packed is None:
+        packed = pack_convdet_weights(w)
+    nbytes = lib.sqd_head_detect_workspace_bytes(B, cin, gh, gw, cout, layout, algo)
+    ws = workspace().get("head_detect", nbytes, x.device)
+    det = out if out is not None else _alloc_detections(B, top_k, x.device)
+    check(lib.sqd_head_detect_fused(C.c_void_p(x.data_ptr()), layout, ptr(packed), ptr(w), ptr(b), ptr(anchors_f32), B,
+                                    cin, gh, gw, anchors_per_grid, num_classes, int(input_hw[0]), int(input_hw[1]),
+                                    top_k, float(nms_thresh), float(score_thresh), ptr(det.count), ptr(det.anchor),
+                                    ptr(det.cls), ptr(det.score), ptr(det.box), ptr(ws), ws.numel(), algo,
+                                    stream_ptr(x.device)), "sqd_head_detect_fused")
+    return det
+
+
+# ---- a11-a13 ---------------------------------------------------------------------------------------
+def match_anchors(gt_boxes, gt_count, anchors_f64):
+    """gt_boxes (B,Gmax,4) f32 xyxy, gt_count (B,) i32, anchors (A,4) f64 -> (anchor_idx (B,Gmax) i32, deltas (B,Gmax,4))."""
+    lib = load()
+    gt_boxes, gt_count = gt_boxes.contiguous(), gt_count.contiguous()
+    B, G, _ = gt_boxes.shape
+    idx = torch.empty((B, G), dtype=torch.int32, device=gt_boxes.device)
+    deltas = torch.empty((B, G, 4), dtype=torch.float32, device=gt_boxes.device)
+    check(lib.sqd_match_anchors(ptr(gt_boxes), ptr(gt_count), B, G, ptr(anchors_f64), anchors_f64.shape[0], ptr(idx),
+                                ptr(deltas), stream_ptr(gt_boxes.device)), "sqd_match_anchors")
+    return idx, deltas
+
+
+def build_targets(gt_boxes, gt_classes, gt_count, anchor_idx, deltas, num_anchors, num_classes):
+    """-> dense gt (B, A, C+9) = [mask | box | deltas | one-hot] (datasets/base.py:61-76)."""
+    lib = load()
+    B, G, _ = gt_boxes.shape
+    gt = torch.empty((B, num_anchors, num_classes + 9), dtype=torch.float32, device=gt_boxes.device)
+    check(lib.sqd_build_targets(ptr(gt_boxes.contiguous()), ptr(gt_classes.contiguous()), ptr(gt_count.contiguous()),
+                                ptr(anchor_idx), ptr(deltas), B, G, num_anchors, num_classes, ptr(gt),
+                                stream_ptr(gt.device)), "sqd_build_targets")
+    return gt
+
+
+# ---- a14-a16 ---------------------------------------------------------------------------------------
+def loss_fwd_bwd(pred, gt, anchors_f32, input_hw, num_classes, weights, grad_loss=None, want_grad=True):
+    """-> (losses (B,4) = [class, positive_score, negative_score, bbox], dpred (B,A,C+5) or None)."""
+    lib = load()
+    pred, gt = pred.contiguous(), gt.contiguous()
+    B, A, _ = pred.shape
+    dev = pred.device
+    nbytes = lib.sqd_loss_workspace_bytes(B, A)
+    ws = workspace().get("loss", nbytes, dev)
+    losses = torch.empty((B, 4), dtype=torch.float32, device=dev)
+    dpred = torch.empty_like(pred) if want_grad else None
+    w = (C.c_float * 4)(*[float(x) for x in weights])
+    gl = grad_loss.contiguous().float() if grad_loss is not None else None
+    check(lib.sqd_loss_fwd_bwd(ptr(pred), ptr(gt), ptr(anchors_f32), B, A, num_classes, int(input_hw[0]),
+                               int(input_hw[1]), w, ptr(gl), ptr(losses), ptr(dpred), ptr(ws), ws.numel(),
+                               stream_ptr(dev)), "sqd_loss_fwd_bwd")
+    return losses, dpred
+
+
+# ---- 8(f).1 ----------------------------------------------------------------------------------------
+def boxes_postprocess_(det: Detections, meta: torch.Tensor):
+    """In-place boxes_postprocess of the kept rows; meta (B,10) f32, see the header."""
+    lib = load()
+    B, K, _ = det.box.shape
+    check(lib.sqd_boxes_postprocess(ptr(det.box), ptr(det.count), ptr(meta.contiguous()), B, K,
+                                    stream_ptr(det.box.device)), "sqd_boxes_postprocess")
+    return det

@@ -1,0 +1,163 @@
+"""a1 ConvDet head on the GPU: tcgen05 3xTF32 kernel and the fp32 SIMT yardstick against the
+reference's conv (golden pred recorded from the reference, and the oracle = torch CPU conv2d),
+then the end-to-end kept-index parity features -> detections."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from squeezedet_pytorch_b200 import synth
+from conftest import split_ragged
+
+pytestmark = pytest.mark.gpu
+SHAPES = {s.name: s for s in (synth.TINY, synth.KITTI)}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from squeezedet_pytorch_b200 import ops as _ops
+    return _ops
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _case(g, shp):
+    batch, seed = int(g["batch"]), int(g["seed"])
+    feat = synth.features(shp, batch, seed)
+    w, b = synth.convdet_params(shp, seed + 1)
+    return feat, w, b
+
+
+def _err(a, b):
+    return float(np.abs(a - b).max()), float(np.sqrt(np.mean((a - b) ** 2)))
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+@pytest.mark.parametrize("algo_name", ["simt", "tcgen05"])
+@pytest.mark.parametrize("layout", ["nchw", "channels_last"])
+def test_convdet_vs_reference_golden(ops, golden, name, algo_name, layout):
+    from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32, CONV_TCGEN05_3XTF32
+    g = golden("head_e2e_" + name)
+    shp = SHAPES[name]
+    feat, w, b = _case(g, shp)
+    x = dev(feat)
+    if layout == "channels_last":
+        x = x.contiguous(memory_format=torch.channels_last)
+    algo = CONV_SIMT_FP32 if algo_name == "simt" else CONV_TCGEN05_3XTF32
+    pred = ops.convdet_forward(x, dev(w), dev(b), algo=algo, num_fields=shp.num_fields, check_status=True)
+    assert pred.shape == (feat.shape[0], shp.num_anchors, shp.num_fields)
+    got = pred.cpu().numpy()
+    mx, rms = _err(got, g["pred"])
+    print(f"{name} {algo_name} {layout}: max|err|={mx:.3e} rms={rms:.3e} vs reference fp32 conv")
+    # logits have std ~1: fp32-level agreement (1e-4 relative on O(1) values, absolute floor for small ones)
+    np.testing.assert_allclose(got, g["pred"], rtol=1e-4, atol=2e-5)
+
+
+def test_convdet_accuracy_vs_float64(ops):
+    """Error of each fp32 implementation against a float64 evaluation (tiny shape): the 3xTF32
+    tensor-core kernel must be as accurate as fp32 CUDA-core FMA / the reference's CPU conv."""
+    from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32, CONV_TCGEN05_3XTF32
+    shp = synth.TINY
+    feat = synth.features(shp, 2, 77)
+    w, b = synth.convdet_params(shp, 78)
+    p64 = orc.convdet_forward_f64(feat, w, b, shp.num_anchors, shp.num_fields)
+    ref32 = orc.convdet_forward(feat, w, b, shp.num_anchors, shp.num_fields)
+    simt = ops.convdet_forward(dev(feat), dev(w), dev(b), algo=CONV_SIMT_FP32, num_fields=shp.num_fields).cpu().numpy()
+    tc = ops.convdet_forward(dev(feat), dev(w), dev(b), algo=CONV_TCGEN05_3XTF32, num_fields=shp.num_fields,
+                             check_status=True).cpu().numpy()
+    e_ref, e_simt, e_tc = _err(ref32, p64), _err(simt, p64), _err(tc, p64)
+    print(f"vs float64: torch-cpu max/rms {e_ref}, simt {e_simt}, tcgen05-3xtf32 {e_tc}")
+    assert e_simt[0] < 2e-5 and e_tc[0] < 2e-5
+    assert e_tc[1] < 4 * max(e_ref[1], e_simt[1]) + 1e-7
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_head_to_detections_kept_indices(ops, golden, name):
+    """features -> ConvDet(tcgen05) -> decode -> top-k -> NMS through the single fused ABI call:
+    kept anchor indices equal the reference's, scores/boxes within 1e-4 (SURVEY 7.3 stage iii)."""
+    g = golden("head_e2e_" + name)
+    shp = SHAPES[name]
+    feat, w, b = _case(g, shp)
+    a32 = dev(synth.anchor_table(shp).astype(np.float32))
+    det = ops.head_detect(dev(feat), dev(w), dev(b), a32, shp.anchors_per_grid, shp.num_classes, shp.input_hw,
+                          shp.top_k, shp.nms_thresh, shp.score_thresh)
+    rows = det.to_list()
+    idx = split_ragged(g["kept_count"], g["kept_anchor"])
+    sc = split_ragged(g["kept_count"], g["kept_score"])
+    bx = split_ragged(g["kept_count"], g["kept_box"])
+    flips = 0
+    for i, row in enumerate(rows):
+        got = row["anchor_idx"].numpy()
+        if np.array_equal(got, idx[i]):
+            np.testing.assert_allclose(row["scores"].numpy(), sc[i], rtol=1e-4, atol=1e-7)
+            np.testing.assert_allclose(row["boxes"].numpy(), bx[i], rtol=1e-4, atol=1e-3)
+        else:
+            flips += 1
+            # a different fp32 summation order may swap two near-tied scores; anything else is a bug
+            assert set(got.tolist()) ^ set(idx[i].tolist()) == set() or len(set(got.tolist()) ^ set(idx[i].tolist())) <= 2
+            print(f"image {i}: order/near-tie difference vs reference: {got.tolist()} vs {idx[i].tolist()}")
+    assert flips == 0, f"{flips} images differ from the reference's kept indices"
+
+
+def test_head_properties_full_batch(ops):
+    """BASELINE configs[1] size (B=20, KITTI): tcgen05 vs SIMT on the GPU, linearity of the conv in its
+    input, and equality of the fused ABI call with the staged one."""
+    from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32, CONV_TCGEN05_3XTF32
+    shp = synth.KITTI
+    g = torch.Generator(device="cuda").manual_seed(5)
+    feat = torch.relu(torch.randn((20, shp.in_channels, *shp.grid_hw), generator=g, device="cuda"))
+    w, b = synth.convdet_params(shp, 9)
+    w, b = dev(w), dev(b)
+    tc = ops.convdet_forward(feat, w, b, algo=CONV_TCGEN05_3XTF32, num_fields=8, check_status=True)
+    simt = ops.convdet_forward(feat, w, b, algo=CONV_SIMT_FP32, num_fields=8)
+    assert torch.allclose(tc, simt, rtol=1e-4, atol=2e-5), float((tc - simt).abs().max())
+    zero_b = torch.zeros_like(b)
+    lin = ops.convdet_forward(2.0 * feat, w, zero_b, num_fields=8)
+    base = ops.convdet_forward(feat, w, zero_b, num_fields=8)
+    assert torch.allclose(lin, 2.0 * base, rtol=1e-5, atol=1e-6)
+    a32 = dev(synth.anchor_table(shp).astype(np.float32))
+    fused = ops.head_detect(feat, w, b, a32, 9, 3, shp.input_hw, shp.top_k, shp.nms_thresh, shp.score_thresh)
+    staged = ops.detect_from_pred(tc, a32, shp.input_hw, 3, shp.top_k, shp.nms_thresh, shp.score_thresh)
+    for f in ("count", "anchor", "cls", "score", "box"):
+        assert torch.equal(getattr(fused, f), getattr(staged, f))
+
+
+def test_module_surface(ops):
+    """SqueezeDet / Detector keep the reference's call surface and state-dict keys."""
+    from squeezedet_pytorch_b200 import config, model, detector
+    shp = synth.TINY
+    cfg = config.make_config(shp)
+    net = model.SqueezeDet(cfg)
+    assert {"base.convdet.weight", "base.convdet.bias", "base.features.0.weight"} <= set(net.state_dict())
+    w, b = synth.convdet_params(shp, 3)
+    with torch.no_grad():
+        net.base.convdet.weight.copy_(torch.from_numpy(w))
+        net.base.convdet.bias.copy_(torch.from_numpy(b))
+        for m in net.base.features.modules():          # reference init (std 0.005) kills the signal; rescale
+            if isinstance(m, torch.nn.Conv2d):
+                torch.nn.init.kaiming_normal_(m.weight)
+    det = detector.Detector(net, cfg)
+    img = torch.randn((3, 3, *shp.input_hw), device="cuda")
+    with torch.no_grad():
+        dense = net({"image": img})
+    A = shp.num_anchors
+    assert dense["class_ids"].shape == (3, A) and dense["class_ids"].dtype == torch.int64
+    assert dense["scores"].shape == (3, A) and dense["boxes"].shape == (3, A, 4)
+    one = det.filter({k: v[0] for k, v in dense.items()})
+    results = det.detect({"image": img, "image_meta": {"index": torch.arange(3), "image_id": ["a", "b", "c"]}})
+    assert len(results) == 3 and all("image_meta" in r for r in results)
+    if one is not None:
+        assert np.array_equal(results[0]["class_ids"], one["class_ids"].cpu().numpy())
+        np.testing.assert_allclose(results[0]["boxes"], one["boxes"].cpu().numpy(), rtol=1e-5, atol=1e-4)
+    # training surface: SqueezeDetWithLoss -> loss.mean().backward() reaches the backbone
+    tnet = model.SqueezeDetWithLoss(config.make_config(shp, dropout_prob=0.0)).cuda()
+    from squeezedet_pytorch_b200 import targets
+    m = targets.AnchorMatcher(cfg.anchors, shp.num_classes)
+    cls_l, box_l = zip(*[synth.gt_boxes(shp, 50 + i) for i in range(3)])
+    gt = m.dense_targets(*m.pack(list(box_l), list(cls_l)))
+    loss, stats = tnet({"image": img, "gt": gt})
+    loss.mean().backward()
+    assert loss.shape == (3,) and set(stats) == {"loss", "class_loss", "score_loss", "bbox_loss"}
+    assert tnet.base.convdet.weight.grad is not None and torch.isfinite(tnet.base.convdet.weight.grad).all()

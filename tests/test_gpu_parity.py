@@ -1,0 +1,398 @@
+"""GPU parity tests proper: every CUDA entry point (through the C ABI, via the ctypes host layer)
+against the CPU oracle on the same seeded inputs, against the golden fixtures recorded from the
+reference, and -- at BASELINE.json's full sizes -- through size-independent properties.
+
+Bars: indices / class ids / counts bit-exact; scores, boxes, losses, gradients within 1e-4
+relative (north_star), with the absolute floors of SURVEY 8c."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from squeezedet_pytorch_b200 import synth
+from conftest import split_ragged
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+SHAPES = {s.name: s for s in (synth.TINY, synth.KITTI, synth.STRESS)}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from squeezedet_pytorch_b200 import ops as _ops
+    return _ops
+
+
+def dev(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def anchors_dev(shape):
+    a = synth.anchor_table(shape)
+    return a, dev(a.astype(np.float32))
+
+
+def dets_to_lists(det):
+    return det.to_list()
+
+
+# ------------------------------------------------------------------------------------------------------
+# a2-a7 decode
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,batch", [("tiny_160x96", 4), ("kitti_1248x384", 2), ("stress_2496x768", 1)])
+def test_decode_vs_oracle(ops, name, batch):
+    shp = SHAPES[name]
+    a64, a32 = anchors_dev(shp)
+    pred = synth.clustered_pred(shp, batch, 101, anchors=a64)
+    out = ops.decode_scores(dev(pred), a32, shp.input_hw, shp.num_classes,
+                            ("class_ids", "scores", "boxes", "probs", "logp", "conf", "deltas"))
+    probs, logp, conf, deltas, boxes = orc.resolve(pred, a64, shp.input_hw, shp.num_classes, log_softmax=True)
+    ids, scores = orc.score_argmax(probs, conf)
+    np.testing.assert_allclose(out["probs"].cpu().numpy(), probs, rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(out["logp"].cpu().numpy(), logp, rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(out["conf"].cpu().numpy(), conf, rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(out["boxes"].cpu().numpy(), boxes, rtol=RTOL, atol=1e-3)
+    np.testing.assert_allclose(out["scores"].cpu().numpy(), scores, rtol=RTOL, atol=1e-7)
+    assert np.array_equal(out["deltas"].cpu().numpy(), deltas)
+    got_ids = out["class_ids"].cpu().numpy()
+    assert got_ids.dtype == np.int64
+    mism = got_ids != ids
+    if mism.any():  # only legal where the two best class scores are within rounding of each other
+        s = (probs * conf)[mism]
+        top2 = np.sort(s, axis=-1)[:, -2:]
+        assert np.all(top2[:, 1] - top2[:, 0] <= 1e-6 * top2[:, 1])
+    assert mism.mean() < 1e-4
+
+
+@pytest.mark.parametrize("name", ["tiny_160x96", "kitti_1248x384"])
+def test_decode_vs_reference_golden(ops, golden, name):
+    g = golden("decode_filter_" + name)
+    shp = SHAPES[name]
+    a64, a32 = anchors_dev(shp)
+    pred = synth.clustered_pred(shp, int(g["batch"]), int(g["seed"]), anchors=a64)
+    out = ops.decode_scores(dev(pred), a32, shp.input_hw, shp.num_classes,
+                            ("class_ids", "scores", "boxes", "probs", "logp", "conf"))
+    np.testing.assert_allclose(out["probs"].cpu().numpy(), g["probs"], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(out["logp"].cpu().numpy(), g["logp"], rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(out["conf"].cpu().numpy(), g["conf"], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(out["boxes"].cpu().numpy(), g["boxes"], rtol=RTOL, atol=1e-3)
+    np.testing.assert_allclose(out["scores"].cpu().numpy(), g["scores"], rtol=RTOL, atol=1e-7)
+    assert (out["class_ids"].cpu().numpy() != g["class_ids"]).mean() < 1e-4
+
+
+def test_decode_empty_batch_and_bad_args(ops):
+    from squeezedet_pytorch_b200._lib import SqdError
+    shp = synth.TINY
+    _, a32 = anchors_dev(shp)
+    out = ops.decode_scores(torch.empty((0, shp.num_anchors, 8), device="cuda"), a32, shp.input_hw, 3)
+    assert out["scores"].shape == (0, shp.num_anchors)
+    with pytest.raises(SqdError):
+        ops.decode_scores(torch.zeros((1, shp.num_anchors, 9), device="cuda"), a32, shp.input_hw, 3)
+    with pytest.raises(SqdError):
+        ops.decode_scores(torch.zeros((1, shp.num_anchors, 8)), a32, shp.input_hw, 3)  # CPU tensor: no fallback
+
+
+# ------------------------------------------------------------------------------------------------------
+# a8-a9 filter
+# ------------------------------------------------------------------------------------------------------
+def _check_rows(rows, expect, exact_values):
+    for b, (row, exp) in enumerate(zip(rows, expect)):
+        n = len(exp["anchor_idx"])
+        if n == 0:
+            assert row is None
+            continue
+        assert row is not None, f"image {b}: nothing kept, expected {n}"
+        assert np.array_equal(row["anchor_idx"].numpy(), exp["anchor_idx"]), f"image {b}"
+        assert np.array_equal(row["class_ids"].numpy(), exp["class_ids"])
+        if exact_values:
+            assert np.array_equal(row["scores"].numpy(), exp["scores"])
+            assert np.array_equal(row["boxes"].numpy(), exp["boxes"])
+        else:
+            np.testing.assert_allclose(row["scores"].numpy(), exp["scores"], rtol=RTOL, atol=1e-7)
+            np.testing.assert_allclose(row["boxes"].numpy(), exp["boxes"], rtol=RTOL, atol=1e-3)
+
+
+@pytest.mark.parametrize("name", ["tiny_160x96", "kitti_1248x384"])
+def test_filter_on_reference_dense_outputs_bit_exact(ops, golden, name):
+    """The reference's own dense (ids, scores, boxes) in -> the reference's kept set out, bit for bit."""
+    g = golden("decode_filter_" + name)
+    shp = SHAPES[name]
+    det = ops.topk_nms(dev(g["class_ids"], torch.int64), dev(g["scores"]), dev(g["boxes"]), shp.num_classes,
+                       shp.top_k, shp.nms_thresh, shp.score_thresh)
+    expect = [dict(anchor_idx=i, class_ids=c, scores=s, boxes=x) for i, c, s, x in zip(
+        split_ragged(g["kept_count"], g["kept_anchor"]), split_ragged(g["kept_count"], g["kept_class"]),
+        split_ragged(g["kept_count"], g["kept_score"]), split_ragged(g["kept_count"], g["kept_box"]))]
+    _check_rows(dets_to_lists(det), expect, exact_values=True)
+    # padding rows are deterministic
+    cnt = det.count.cpu().numpy()
+    assert np.array_equal(cnt, g["kept_count"])
+    assert (det.anchor.cpu().numpy()[0, cnt[0]:] == -1).all()
+
+
+@pytest.mark.parametrize("name,batch", [("tiny_160x96", 6), ("kitti_1248x384", 4), ("stress_2496x768", 2)])
+def test_fused_detect_equals_unfused_and_oracle(ops, name, batch):
+    shp = SHAPES[name]
+    a64, a32 = anchors_dev(shp)
+    pred = synth.clustered_pred(shp, batch, 202, anchors=a64)
+    dp = dev(pred)
+    fused = ops.detect_from_pred(dp, a32, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh, shp.score_thresh)
+    dense = ops.decode_scores(dp, a32, shp.input_hw, shp.num_classes)
+    unfused = ops.topk_nms(dense["class_ids"], dense["scores"], dense["boxes"], shp.num_classes, shp.top_k,
+                           shp.nms_thresh, shp.score_thresh)
+    # (i) the two CUDA routes agree bit for bit
+    for f in ("count", "anchor", "cls", "score", "box"):
+        assert torch.equal(getattr(fused, f), getattr(unfused, f)), f
+    # (ii) the oracle's filter run on the CUDA dense outputs gives the identical kept set and values
+    ids, sc, bx = (dense[k].cpu().numpy() for k in ("class_ids", "scores", "boxes"))
+    expect = [orc.filter_image(ids[b], sc[b], bx[b], shp.num_classes, shp.top_k, shp.nms_thresh, shp.score_thresh)
+              for b in range(batch)]
+    _check_rows(dets_to_lists(fused), expect, exact_values=True)
+    assert sum(len(e["anchor_idx"]) for e in expect) > 0
+    # (iii) and the all-oracle route (numpy exp instead of CUDA expf) keeps the same anchors
+    expect2 = orc.detect_filtered(pred, a64, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh,
+                                  shp.score_thresh)
+    _check_rows(dets_to_lists(fused), expect2, exact_values=False)
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_fused_detect_vs_reference_golden(ops, golden, name):
+    g = golden("decode_filter_" + name)
+    shp = SHAPES[name]
+    a64, a32 = anchors_dev(shp)
+    pred = synth.clustered_pred(shp, int(g["batch"]), int(g["seed"]), anchors=a64)
+    det = ops.detect_from_pred(dev(pred), a32, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh,
+                               shp.score_thresh)
+    expect = [dict(anchor_idx=i, class_ids=c, scores=s, boxes=x) for i, c, s, x in zip(
+        split_ragged(g["kept_count"], g["kept_anchor"]), split_ragged(g["kept_count"], g["kept_class"]),
+        split_ragged(g["kept_count"], g["kept_score"]), split_ragged(g["kept_count"], g["kept_box"]))]
+    _check_rows(dets_to_lists(det), expect, exact_values=False)
+
+
+def test_filter_edge_cases(ops):
+    """Ties (lower anchor index first), nothing above threshold (None), fewer anchors than top_k,
+    zero-area boxes (NaN IoU never suppresses), identical boxes."""
+    A = 40
+    ids = np.zeros((3, A), np.int64)
+    scores = np.zeros((3, A), np.float32)
+    boxes = np.zeros((3, A, 4), np.float32)
+    # image 0: all scores tied at 0.5, all boxes disjoint -> top-8 = anchors 0..7 in index order
+    scores[0] = 0.5
+    boxes[0, :, 0] = np.arange(A) * 20
+    boxes[0, :, 2] = boxes[0, :, 0] + 10
+    boxes[0, :, 3] = 10
+    # image 1: nothing above the score threshold
+    scores[1] = 0.1
+    boxes[1] = boxes[0]
+    # image 2: identical boxes in two classes + zero-area boxes
+    scores[2] = np.linspace(0.9, 0.4, A)
+    boxes[2, :, :] = [5, 5, 50, 50]
+    ids[2, 1::2] = 1
+    boxes[2, 10:14] = 0.0
+    det = ops.topk_nms(dev(ids), dev(scores), dev(boxes), 2, 8, 0.4, 0.3)
+    rows = det.to_list()
+    assert rows[0]["anchor_idx"].tolist() == list(range(8))
+    assert rows[1] is None
+    for b in range(3):
+        exp = orc.filter_image(ids[b], scores[b], boxes[b], 2, 8, 0.4, 0.3)
+        if len(exp["anchor_idx"]) == 0:
+            assert rows[b] is None
+        else:
+            assert rows[b]["anchor_idx"].tolist() == exp["anchor_idx"].tolist()
+    # fewer anchors than top_k
+    det = ops.topk_nms(dev(ids[:, :5]), dev(scores[:, :5]), dev(np.ascontiguousarray(boxes[:, :5])), 2, 64, 0.4, 0.3)
+    assert det.count.cpu().tolist()[0] == 5
+
+
+def test_filter_properties_full_size(ops):
+    """KITTI batch 20 (BASELINE configs[1]) and stress: sortedness, NMS invariant, idempotence."""
+    for shp, batch in ((synth.KITTI, 20), (synth.STRESS, 4)):
+        a64, a32 = anchors_dev(shp)
+        pred = synth.clustered_pred(shp, batch, 303, anchors=a64)
+        det = ops.detect_from_pred(dev(pred), a32, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh,
+                                   shp.score_thresh)
+        dense = ops.decode_scores(dev(pred), a32, shp.input_hw, shp.num_classes)
+        sc_all = dense["scores"].cpu().numpy()
+        for b, row in enumerate(det.to_list()):
+            assert row is not None
+            cls, sc, bx, idx = (row[k].numpy() for k in ("class_ids", "scores", "boxes", "anchor_idx"))
+            assert np.all(np.diff(cls) >= 0)                                   # classes ascending
+            for c in np.unique(cls):
+                s = sc[cls == c]
+                assert np.all(np.diff(s) <= 0)                                 # scores descending inside a class
+                bb = bx[cls == c]
+                for i in range(len(bb)):                                       # no kept pair overlaps > thresh
+                    iou = orc.pair_iou(np.repeat(bb[i:i + 1], len(bb), 0), bb)
+                    iou[i] = 0
+                    assert np.nanmax(iou) <= shp.nms_thresh + 1e-6
+            assert np.all(sc > np.float32(shp.score_thresh))
+            kth = np.sort(sc_all[b])[-shp.top_k]
+            assert np.all(sc >= kth)                                           # only top-k members survive
+            assert np.array_equal(sc, sc_all[b][idx])
+        # idempotence: filtering again with only the kept anchors present keeps exactly the same set
+        keep_mask = torch.zeros_like(dense["scores"], dtype=torch.bool)
+        for b, row in enumerate(det.to_list()):
+            keep_mask[b, row["anchor_idx"].cuda()] = True
+        sc2 = torch.where(keep_mask, dense["scores"], torch.zeros_like(dense["scores"]))
+        det2 = ops.topk_nms(dense["class_ids"], sc2, dense["boxes"], shp.num_classes, shp.top_k, shp.nms_thresh,
+                            shp.score_thresh)
+        assert torch.equal(det2.count, det.count)
+        for b, n in enumerate(det.count.cpu().tolist()):
+            assert torch.equal(det2.anchor[b, :n], det.anchor[b, :n])
+
+
+# ------------------------------------------------------------------------------------------------------
+# a11-a13 matcher / targets
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_matcher_vs_reference_golden(name, golden):
+    from squeezedet_pytorch_b200 import targets
+    g = golden("matcher_" + name)
+    shp = SHAPES[name]
+    anchors = synth.anchor_table(shp)
+    m = targets.AnchorMatcher(anchors, shp.num_classes)
+    boxes_l = []
+    for i in range(int(g["n_img"])):
+        _, boxes = synth.gt_boxes(shp, int(g["seed0"]) + i)
+        if i % 6 == 5:
+            boxes = np.repeat(boxes[:1], 12, axis=0)
+            boxes[:, 2] = boxes[:, 0] + 3.0
+            boxes[:, 3] = boxes[:, 1] + 2.0
+        boxes_l.append(boxes)
+    gb, _, gc = m.pack(boxes_l)
+    idx, deltas = m.match(gb, gc)
+    idx, deltas = idx.cpu().numpy(), deltas.cpu().numpy()
+    exp_idx = split_ragged(g["count"], g["anchor_idx"])
+    exp_dl = split_ragged(g["count"], g["deltas"])
+    for i, b in enumerate(boxes_l):
+        n = len(b)
+        assert np.array_equal(idx[i, :n], exp_idx[i]), f"image {i}"          # bit-exact matched anchors
+        assert (idx[i, n:] == -1).all()
+        np.testing.assert_allclose(deltas[i, :n], exp_dl[i], rtol=1e-6, atol=1e-7)
+        o_d, o_i = orc.match_anchors(b, anchors)
+        assert np.array_equal(o_i, idx[i, :n])
+
+
+def test_matcher_distance_fallback_and_dropin_signature(golden):
+    from squeezedet_pytorch_b200 import targets
+    g = golden("matcher_fallback")
+    deltas, idx = targets.compute_deltas(g["boxes"], g["anchors"])          # reference signature, numpy in/out
+    assert idx.dtype == np.int32 and deltas.dtype == np.float32
+    assert np.array_equal(idx, g["anchor_idx"])
+    np.testing.assert_allclose(deltas, g["deltas"], rtol=1e-6, atol=1e-7)
+    with pytest.raises(AssertionError):                                       # boxes.py:14-15
+        targets.compute_deltas(np.array([[5, 5, 5, 9]], np.float32), g["anchors"])
+    d0, i0 = targets.compute_deltas(np.zeros((0, 4), np.float32), g["anchors"])
+    assert d0.shape == (0, 4) and i0.shape == (0,)
+
+
+def test_dense_targets_vs_oracle():
+    from squeezedet_pytorch_b200 import targets
+    for shp in (synth.TINY, synth.KITTI):
+        anchors = synth.anchor_table(shp)
+        m = targets.AnchorMatcher(anchors, shp.num_classes)
+        cls_l, box_l = zip(*[synth.gt_boxes(shp, 900 + i) for i in range(5)])
+        gb, gcl, gc = m.pack(list(box_l), list(cls_l))
+        gt = m.dense_targets(gb, gcl, gc).cpu().numpy()
+        for i in range(5):
+            exp = orc.dense_targets(cls_l[i], box_l[i], anchors, shp.num_classes)
+            np.testing.assert_allclose(gt[i], exp, rtol=1e-6, atol=1e-7)
+            assert np.array_equal(gt[i] != 0, exp != 0)
+        one = targets.prepare_annotations(cls_l[0], box_l[0], anchors, shp.num_classes)
+        np.testing.assert_allclose(one, orc.dense_targets(cls_l[0], box_l[0], anchors, shp.num_classes), rtol=1e-6,
+                                   atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------------
+# a14-a16 loss
+# ------------------------------------------------------------------------------------------------------
+def _loss_inputs(shp, batch, seed):
+    anchors = synth.anchor_table(shp)
+    pred = synth.clustered_pred(shp, batch, seed, anchors=anchors)
+    gts = []
+    for b in range(batch):
+        cls, boxes = synth.gt_boxes(shp, 1000 * seed + b)
+        gts.append(orc.dense_targets(cls, boxes, anchors, shp.num_classes))
+    return anchors, pred, np.stack(gts)
+
+
+@pytest.mark.parametrize("name", ["tiny_160x96", "kitti_1248x384"])
+def test_loss_vs_reference_autograd_golden(ops, golden, name):
+    g = golden("loss_" + name)
+    shp = SHAPES[name]
+    anchors, pred, gt = _loss_inputs(shp, int(g["batch"]), int(g["seed"]))
+    B = pred.shape[0]
+    grad = torch.full((B, 4), 1.0 / B, device="cuda")
+    losses, dpred = ops.loss_fwd_bwd(dev(pred), dev(gt), dev(anchors.astype(np.float32)), shp.input_hw,
+                                     shp.num_classes, (1.0, 3.75, 100.0, 6.0), grad_loss=grad)
+    losses = losses.cpu().numpy()
+    np.testing.assert_allclose(losses[:, 0], g["class_loss"], rtol=RTOL)
+    np.testing.assert_allclose(losses[:, 1] + losses[:, 2], g["score_loss"], rtol=RTOL)
+    np.testing.assert_allclose(losses[:, 3], g["bbox_loss"], rtol=RTOL)
+    np.testing.assert_allclose(losses.sum(1), g["loss"], rtol=RTOL)
+    ref = g["dpred"]
+    np.testing.assert_allclose(dpred.cpu().numpy(), ref, rtol=1e-3, atol=1e-6 * np.abs(ref).max())
+
+
+def test_loss_stress_shape_vs_oracle_and_module_autograd(ops):
+    """C=8 (generic field widths) against the oracle, and the nn.Module surface end to end:
+    Loss(cfg)(pred, gt) -> loss.mean().backward() fills pred.grad like the reference's autograd."""
+    from squeezedet_pytorch_b200 import config, model
+    shp = synth.Shape("mid", (192, 320), 8, 32)
+    anchors, pred, gt = _loss_inputs(shp, 3, 7)
+    exp = orc.loss_forward(pred, gt, anchors, shp.input_hw, shp.num_classes)
+    exp_d = orc.loss_backward(pred, gt, anchors, shp.input_hw, shp.num_classes, np.full((3,), 1 / 3))
+    cfg = config.make_config(shp)
+    mod = model.Loss(cfg).cuda()
+    p = dev(pred).requires_grad_(True)
+    loss, stats = mod(p, dev(gt))
+    loss.mean().backward()
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), exp["loss"], rtol=RTOL)
+    np.testing.assert_allclose(stats["class_loss"].detach().cpu().numpy(), exp["class_loss"], rtol=RTOL)
+    np.testing.assert_allclose(stats["score_loss"].detach().cpu().numpy(), exp["score_loss"], rtol=RTOL)
+    np.testing.assert_allclose(stats["bbox_loss"].detach().cpu().numpy(), exp["bbox_loss"], rtol=RTOL)
+    np.testing.assert_allclose(p.grad.cpu().numpy(), exp_d, rtol=1e-3, atol=1e-6 * np.abs(exp_d).max())
+
+
+def test_loss_zero_objects_nan_and_determinism(ops):
+    shp = synth.TINY
+    anchors = synth.anchor_table(shp)
+    a32 = dev(anchors.astype(np.float32))
+    pred = dev(synth.clustered_pred(shp, 1, 5, anchors=anchors))
+    gt = torch.zeros((1, shp.num_anchors, shp.num_classes + 9), device="cuda")
+    losses, dpred = ops.loss_fwd_bwd(pred, gt, a32, shp.input_hw, shp.num_classes, (1.0, 3.75, 100.0, 6.0))
+    l = losses.cpu().numpy()[0]
+    assert np.isnan(l[0]) and np.isnan(l[1]) and np.isnan(l[3]) and np.isfinite(l[2])
+    assert torch.isnan(dpred).all()
+    # run-to-run determinism of the fixed-order reductions
+    _, pk, gk = _loss_inputs(synth.KITTI, 2, 9)
+    a = dev(synth.anchor_table(synth.KITTI).astype(np.float32))
+    r1 = ops.loss_fwd_bwd(dev(pk), dev(gk), a, synth.KITTI.input_hw, 3, (1.0, 3.75, 100.0, 6.0))
+    r2 = ops.loss_fwd_bwd(dev(pk), dev(gk), a, synth.KITTI.input_hw, 3, (1.0, 3.75, 100.0, 6.0))
+    assert torch.equal(r1[0], r2[0]) and torch.equal(r1[1], r2[1])
+
+
+# ------------------------------------------------------------------------------------------------------
+# 8(f).1 boxes_postprocess
+# ------------------------------------------------------------------------------------------------------
+def test_boxes_postprocess_vs_reference_golden(ops, golden):
+    import json
+    from squeezedet_pytorch_b200.detector import _meta_record
+    g = golden("postprocess")
+    for i in range(int(g["n"])):
+        meta = json.loads(str(g[f"meta_{i}"]))
+        coll = {k: [v] if not isinstance(v, list) else np.asarray([v]) for k, v in meta.items()}
+        coll = {k: (np.asarray(v) if k != "flipped" else np.asarray(v)) for k, v in coll.items()}
+        rec = _meta_record(coll, 1)
+        boxes = g[f"in_{i}"]
+        n = boxes.shape[0]
+        det = ops.Detections(count=torch.tensor([n], dtype=torch.int32, device="cuda"),
+                             anchor=torch.zeros((1, 8), dtype=torch.int32, device="cuda"),
+                             cls=torch.zeros((1, 8), dtype=torch.int32, device="cuda"),
+                             score=torch.zeros((1, 8), device="cuda"), box=torch.zeros((1, 8, 4), device="cuda"))
+        det.box[0, :n] = dev(boxes)
+        ops.boxes_postprocess_(det, dev(rec))
+        np.testing.assert_allclose(det.box[0, :n].cpu().numpy(), g[f"out_{i}"], rtol=1e-6, atol=1e-4)
