@@ -55,6 +55,8 @@ extern "C" {
 /* feature-map memory layouts accepted by the ConvDet head */
 #define SQD_LAYOUT_NCHW 0
 #define SQD_LAYOUT_NHWC 1 /* torch channels_last: logical NCHW, physical NHWC */
+#define SQD_LAYOUT_SPLIT_NHWC 2 /* [hi plane | lo plane], each (B,gh,gw,Cin) tf32-exact fp32: output of
+                                   sqd_convdet_split_features, consumed by the tcgen05 algorithm only */
 
 /* ConvDet algorithms */
 #define SQD_CONV_TCGEN05_3XTF32 0 /* tcgen05.mma kind::tf32, hi/lo split operands, fp32 TMEM accumulators */
@@ -78,6 +80,12 @@ SQD_API const char *sqd_last_error(void);
  * ------------------------------------------------------------------------------------------- */
 SQD_API size_t sqd_convdet_packed_weight_bytes(int cout, int cin);
 SQD_API int sqd_convdet_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, void *stream);
+/* hi/lo tf32 split of a feature map into NHWC planes (the tcgen05 kernel's A operand).  sqd_convdet_forward
+ * does this internally for NCHW / NHWC input; a producer that can emit the planes itself (or reuses them)
+ * passes them with SQD_LAYOUT_SPLIT_NHWC and skips the pass. */
+SQD_API size_t sqd_convdet_split_bytes(int batch, int cin, int gh, int gw);
+SQD_API int sqd_convdet_split_features(const float *d_feat, int layout, int batch, int cin, int gh, int gw,
+                                       void *d_planes, void *stream);
 SQD_API size_t sqd_convdet_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout, int algo);
 SQD_API int sqd_convdet_forward(const float *d_feat, int layout, const void *d_packed, const float *d_weight,
                         const float *d_bias, int batch, int cin, int gh, int gw, int cout, float *d_pred,
@@ -181,7 +189,7 @@ SQD_API int sqd_boxes_postprocess(float *d_boxes, const int32_t *d_count, const 
 /* Debug aid: synchronise `stream`, return 0 if the last tcgen05 ConvDet launch on this workspace
  * drained cleanly, else the role (1 TMA producer, 2 MMA issuer, 3 epilogue) whose bounded mbarrier
  * wait timed out.  The kernels never spin forever. */
-SQD_API int sqd_convdet_status(const void *d_workspace, int batch, int cin, int gh, int gw, void *stream);
+SQD_API int sqd_convdet_status(const void *d_workspace, void *stream);
 
 #ifdef __cplusplus
 }

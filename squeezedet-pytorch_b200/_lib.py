@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsqdet_b200.so")
 
-LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+LAYOUT_NCHW, LAYOUT_NHWC, LAYOUT_SPLIT_NHWC = 0, 1, 2
 CONV_TCGEN05_3XTF32, CONV_SIMT_FP32 = 0, 1
 
 _lib = None
@@ -30,7 +30,9 @@ SIGNATURES = {
     "sqd_convdet_pack_weights": (_i, [_vp, _i, _i, _vp, _vp]),
     "sqd_convdet_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "sqd_convdet_forward": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
-    "sqd_convdet_status": (_i, [_vp, _i, _i, _i, _i, _vp]),
+    "sqd_convdet_status": (_i, [_vp, _vp]),
+    "sqd_convdet_split_bytes": (_sz, [_i, _i, _i, _i]),
+    "sqd_convdet_split_features": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "sqd_decode_scores": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sqd_topk_nms": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sqd_detect_from_pred": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp]),

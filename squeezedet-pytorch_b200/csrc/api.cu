@@ -9,11 +9,13 @@ size_t sqd_simt_workspace_bytes(int cin, int cout);
 int sqd_convdet_simt(const float *d_feat, int layout, const float *d_weight, const float *d_bias, int batch, int cin,
                      int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
 size_t sqd_tc_packed_bytes(int cout, int cin);
-size_t sqd_tc_workspace_bytes(int batch, int cin, int gh, int gw);
+size_t sqd_tc_workspace_bytes(int batch, int cin, int gh, int gw, int layout);
+int sqd_tc_split_features(const float *d_feat, int layout, int batch, int cin, int gh, int gw, float *d_planes,
+                          cudaStream_t st);
 int sqd_tc_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, cudaStream_t st);
 int sqd_convdet_tc(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                    int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
-const int *sqd_tc_status_ptr(const void *d_workspace, int batch, int cin, int gh, int gw);
+const int *sqd_tc_status_ptr(const void *d_workspace);
 
 static thread_local char g_err[512] = "";
 
@@ -44,24 +46,25 @@ extern "C" int sqd_convdet_pack_weights(const float *d_weight, int cout, int cin
 }
 
 extern "C" size_t sqd_convdet_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout, int algo) {
-    (void)layout;
     if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0) return 256;
     if (algo == SQD_CONV_SIMT_FP32) return align_up(sqd_simt_workspace_bytes(cin, cout), 256);
-    return align_up(sqd_tc_workspace_bytes(batch, cin, gh, gw), 256);
+    return align_up(sqd_tc_workspace_bytes(batch, cin, gh, gw, layout), 256);
 }
 
 extern "C" int sqd_convdet_forward(const float *d_feat, int layout, const void *d_packed, const float *d_weight,
                                    const float *d_bias, int batch, int cin, int gh, int gw, int cout, float *d_pred,
                                    void *d_workspace, size_t workspace_bytes, int algo, void *stream) {
+    if (batch == 0) return SQD_OK;  // empty batch: nothing to enqueue, pointers may be NULL
     SQD_REQUIRE(d_feat && d_bias && d_pred && d_workspace, SQD_E_NULL, "sqd_convdet_forward: NULL pointer");
-    SQD_REQUIRE(layout == SQD_LAYOUT_NCHW || layout == SQD_LAYOUT_NHWC, SQD_E_SHAPE, "sqd_convdet_forward: bad layout %d",
-                layout);
+    SQD_REQUIRE(layout == SQD_LAYOUT_NCHW || layout == SQD_LAYOUT_NHWC || layout == SQD_LAYOUT_SPLIT_NHWC, SQD_E_SHAPE,
+                "sqd_convdet_forward: bad layout %d", layout);
+    SQD_REQUIRE(!(layout == SQD_LAYOUT_SPLIT_NHWC && algo != SQD_CONV_TCGEN05_3XTF32), SQD_E_UNSUPPORTED,
+                "sqd_convdet_forward: pre-split planes are only consumed by the tcgen05 algorithm");
     SQD_REQUIRE(batch >= 0 && cin > 0 && gh > 0 && gw > 0 && cout > 0, SQD_E_SHAPE, "sqd_convdet_forward: bad shape");
     SQD_REQUIRE(sqd_aligned16(d_feat) && sqd_aligned16(d_pred) && sqd_aligned16(d_workspace), SQD_E_ALIGN,
                 "sqd_convdet_forward: feat/pred/workspace must be 16-byte aligned");
     SQD_REQUIRE(workspace_bytes >= sqd_convdet_workspace_bytes(batch, cin, gh, gw, cout, layout, algo), SQD_E_WORKSPACE,
                 "sqd_convdet_forward: workspace too small (%zu bytes)", workspace_bytes);
-    if (batch == 0) return SQD_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (algo == SQD_CONV_SIMT_FP32) {
         SQD_REQUIRE(d_weight, SQD_E_NULL, "sqd_convdet_forward: SIMT algorithm needs the raw weight tensor");
@@ -72,12 +75,31 @@ extern "C" int sqd_convdet_forward(const float *d_feat, int layout, const void *
     return sqd_convdet_tc(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
 }
 
+extern "C" size_t sqd_convdet_split_bytes(int batch, int cin, int gh, int gw) {
+    if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0) return 0;
+    return (size_t)2 * batch * gh * gw * cin * sizeof(float);
+}
+
+extern "C" int sqd_convdet_split_features(const float *d_feat, int layout, int batch, int cin, int gh, int gw,
+                                          void *d_planes, void *stream) {
+    if (batch == 0) return SQD_OK;  // empty batch: nothing to enqueue, pointers may be NULL
+    SQD_REQUIRE(d_feat && d_planes, SQD_E_NULL, "sqd_convdet_split_features: NULL pointer");
+    SQD_REQUIRE(layout == SQD_LAYOUT_NCHW || layout == SQD_LAYOUT_NHWC, SQD_E_SHAPE,
+                "sqd_convdet_split_features: bad layout %d", layout);
+    SQD_REQUIRE(batch >= 0 && cin >= 32 && cin % 32 == 0 && gh > 0 && gw > 0, SQD_E_SHAPE,
+                "sqd_convdet_split_features: bad shape");
+    SQD_REQUIRE(sqd_aligned16(d_feat) && sqd_aligned16(d_planes), SQD_E_ALIGN,
+                "sqd_convdet_split_features: pointers must be 16-byte aligned");
+    return sqd_tc_split_features(d_feat, layout, batch, cin, gh, gw, static_cast<float *>(d_planes),
+                                 static_cast<cudaStream_t>(stream));
+}
+
 // Synchronises `stream` and reports whether the last tcgen05 launch that used this workspace drained cleanly
 // (0) or hit a bounded-wait timeout (>0: 1 producer, 2 MMA issuer, 3 epilogue).  Debug / test aid.
-extern "C" int sqd_convdet_status(const void *d_workspace, int batch, int cin, int gh, int gw, void *stream) {
+extern "C" int sqd_convdet_status(const void *d_workspace, void *stream) {
     SQD_REQUIRE(d_workspace, SQD_E_NULL, "sqd_convdet_status: NULL workspace");
     int h = -1;
-    SQD_CUDA(cudaMemcpyAsync(&h, sqd_tc_status_ptr(d_workspace, batch, cin, gh, gw), sizeof(int), cudaMemcpyDeviceToHost,
+    SQD_CUDA(cudaMemcpyAsync(&h, sqd_tc_status_ptr(d_workspace), sizeof(int), cudaMemcpyDeviceToHost,
                              static_cast<cudaStream_t>(stream)));
     SQD_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     if (h != 0) sqd_set_error("tcgen05 ConvDet pipeline timed out (role %d)", h);
@@ -97,6 +119,7 @@ extern "C" int sqd_head_detect_fused(const float *d_feat, int layout, const void
                                      double nms_thresh, double score_thresh, int32_t *d_count, int32_t *d_out_anchor,
                                      int32_t *d_out_class, float *d_out_score, float *d_out_box, void *d_workspace,
                                      size_t workspace_bytes, int algo, void *stream) {
+    if (batch == 0) return SQD_OK;  // empty batch: nothing to enqueue, pointers may be NULL
     SQD_REQUIRE(anchors_per_grid >= 1 && num_classes >= 1, SQD_E_SHAPE, "sqd_head_detect_fused: bad anchor/class count");
     const int cout = anchors_per_grid * (num_classes + 5);
     SQD_REQUIRE(d_workspace, SQD_E_NULL, "sqd_head_detect_fused: NULL workspace");
@@ -141,10 +164,10 @@ __global__ void postprocess_kernel(float4 *boxes, const int *count, const float 
 
 extern "C" int sqd_boxes_postprocess(float *d_boxes, const int32_t *d_count, const float *d_meta, int batch, int top_k,
                                      void *stream) {
+    if (batch == 0) return SQD_OK;  // empty batch: nothing to enqueue, pointers may be NULL
     SQD_REQUIRE(d_boxes && d_count && d_meta, SQD_E_NULL, "sqd_boxes_postprocess: NULL pointer");
     SQD_REQUIRE(batch >= 0 && top_k >= 1, SQD_E_SHAPE, "sqd_boxes_postprocess: bad shape");
     SQD_REQUIRE(sqd_aligned16(d_boxes), SQD_E_ALIGN, "sqd_boxes_postprocess: boxes must be 16-byte aligned");
-    if (batch == 0) return SQD_OK;
     postprocess_kernel<<<batch, 64, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<float4 *>(d_boxes), d_count,
                                                                            d_meta, top_k);
     SQD_LAUNCH_CHECK("postprocess_kernel");

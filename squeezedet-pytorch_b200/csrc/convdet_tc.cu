@@ -10,14 +10,21 @@
 //    The box lands as 128 rows x 128 B, 128B-swizzled = the canonical K-major UMMA layout.
 //  * B operand = packed weights [Npad][9*Cin] K-major (k = tap*Cin + c), a 2-D TMA box {32, Npad}.
 //  * 3xTF32: features and weights are pre-split into tf32-exact hi and lo planes
-//    (hi = rna_tf32(x), lo = rna_tf32(x - hi)); D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with fp32
-//    accumulation in TMEM.  One tf32 pass flips top-k order; three passes recover fp32-level
-//    products.  Algorithmic FLOPs per image: 2*M*Cout*K (the 3 passes and N padding are NOT counted).
+//    (hi = rna_tf32(x), lo = rna_tf32(x - hi)); D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.  One tf32 pass flips
+//    top-k order; three passes recover fp32-level products.
+//    Algorithmic FLOPs per image: 2*M*Cout*K (the 3 passes and N padding are NOT counted).
+//  * Chunked accumulation: the tensor core TRUNCATES when it adds into the fp32 TMEM accumulator (measured on
+//    B200: accumulating all 2592 MMAs in TMEM biases every output towards zero by ~2e-5 relative, 20x the
+//    fp32 rounding noise).  So K is cut into chunks of `chunk_stages` pipeline stages; each chunk accumulates
+//    from zero into one of two TMEM accumulators, and the epilogue warps add finished chunks into fp32
+//    REGISTERS with round-to-nearest while the MMAs of the next chunk run into the other accumulator.
 //  * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
-//    lane), warps 2..5 = epilogue (tcgen05.ld -> +bias -> pred in the reference's (B, A, C+5) layout).
+//    lane), warps 2..5 = accumulate/epilogue (tcgen05.ld -> register sum -> +bias -> pred in the reference's
+//    (B, A, C+5) layout).
 //    smem ring of kStages x {A_hi, A_lo, B_hi, B_lo} with full/empty mbarriers; tcgen05.commit frees slots.
 //  * Every mbarrier wait is bounded: on timeout the CTA sets a status word and drains instead of hanging.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -200,9 +207,10 @@ struct TcParams {
     int cin, gh, gw, cout;
     int tiles_x;
     int num_stages;
+    int chunk_stages;  // pipeline stages accumulated inside TMEM before the sum moves to registers
     const float *bias;
     float *pred;
-    int *status;  // 0 ok; else 1 + role that timed out
+    int *status;  // 0 ok; else the role whose bounded wait timed out (1 TMA, 2 MMA/full, 3 accumulate, 4 MMA/tmem)
 };
 
 template <int NPAD>
@@ -212,7 +220,8 @@ convdet_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                   const TcParams p) {
     constexpr int kBBytes = NPAD * kBlockK * 4;
     constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-    constexpr uint32_t kTmemCols = NPAD <= 32 ? 32 : (NPAD <= 64 ? 64 : 128);
+    constexpr uint32_t kAccStride = NPAD <= 16 ? 16 : (NPAD <= 32 ? 32 : (NPAD <= 64 ? 64 : 128));  // columns per accumulator
+    constexpr uint32_t kTmemCols = 2 * kAccStride;                                                   // two accumulators
     constexpr uint32_t kIdesc = umma_idesc_tf32(128, NPAD);
 
     extern __shared__ uint8_t smem_raw[];
@@ -221,8 +230,9 @@ convdet_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     uint8_t *ctrl = smem + (size_t)S * kStageBytes;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(ctrl);
     uint64_t *empty_bar = full_bar + 8;
-    uint64_t *tmem_full_bar = empty_bar + 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+    uint64_t *tmem_full_bar = empty_bar + 8;   // [2]
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;  // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
     volatile int *abort_flag = reinterpret_cast<volatile int *>(tmem_slot + 1);
     float *s_bias = reinterpret_cast<float *>(tmem_slot + 2);  // NPAD floats
 
@@ -231,6 +241,8 @@ convdet_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     const int x0 = (tile % p.tiles_x) * kTileX, y0 = (tile / p.tiles_x) * kTileY;
     const int cblocks = p.cin / kBlockK;
     const int iters = cblocks * 9;
+    const int chunk = p.chunk_stages;
+    const int chunks = (iters + chunk - 1) / chunk;
 
     if (threadIdx.x == 0) {
         *abort_flag = 0;
@@ -238,7 +250,10 @@ convdet_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             mbar_init(full_bar + s, 1);
             mbar_init(empty_bar + s, 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tmem_full_bar + b, 1);
+            mbar_init(tmem_empty_bar + b, 4);  // one arrival per accumulate warp
+        }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -279,44 +294,76 @@ convdet_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         // ===== MMA issuer (single thread) =====
         if (lane == 0) {
             bool ok = true;
-            for (int it = 0; it < iters && ok; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                if (!mbar_wait(full_bar + s, ph, abort_flag)) {
-                    atomicCAS(p.status, 0, 2);
+            int it = 0;
+            for (int c = 0; c < chunks && ok; ++c) {
+                const int buf = c & 1;
+                const uint32_t acc_ph = (uint32_t)(c >> 1) & 1u;
+                if (!mbar_wait(tmem_empty_bar + buf, acc_ph ^ 1u, abort_flag)) {  // accumulator drained by the warps
+                    atomicCAS(p.status, 0, 4);
                     ok = false;
                     break;
                 }
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes);
-                const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + kABytes);
-                const uint64_t b_hi = umma_desc_sw128(sa + 2 * kABytes), b_lo = umma_desc_sw128(sa + 2 * kABytes + kBBytes);
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * kAccStride;
+                for (int j = 0; j < chunk && it < iters; ++j, ++it) {
+                    const int s = it % S;
+                    const uint32_t ph = (uint32_t)(it / S) & 1u;
+                    if (!mbar_wait(full_bar + s, ph, abort_flag)) {
+                        atomicCAS(p.status, 0, 2);
+                        ok = false;
+                        break;
+                    }
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes);
+                    const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + kABytes);
+                    const uint64_t b_hi = umma_desc_sw128(sa + 2 * kABytes),
+                                   b_lo = umma_desc_sw128(sa + 2 * kABytes + kBBytes);
 #pragma unroll
-                for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
-                    const uint64_t adv = (uint64_t)((ks * kUmmaK * 4) >> 4);  // +32 B per K step, in 16 B units
-                    // small cross terms first, then the dominant hi*hi product
-                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, kIdesc, (it | ks) ? 1u : 0u);
-                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, kIdesc, 1u);
-                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, kIdesc, 1u);
+                    for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
+                        const uint64_t adv = (uint64_t)((ks * kUmmaK * 4) >> 4);  // +32 B per K step, in 16 B units
+                        // small cross terms first, then the dominant hi*hi product; each chunk starts from zero
+                        umma_tf32(d_tmem, a_lo + adv, b_hi + adv, kIdesc, (j | ks) ? 1u : 0u);
+                        umma_tf32(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
+                        umma_tf32(d_tmem, a_hi + adv, b_hi + adv, kIdesc, 1u);
+                    }
+                    umma_commit(empty_bar + s);  // slot reusable once these MMAs have read it
                 }
-                umma_commit(empty_bar + s);  // slot reusable once these MMAs have read it
+                umma_commit(tmem_full_bar + buf);  // chunk complete (also fires after an aborted loop)
             }
-            umma_commit(tmem_full_bar);      // accumulator complete (also fires after an aborted loop)
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> (+bias) -> pred =====
-        const bool ok = mbar_wait(tmem_full_bar, 0, abort_flag);
-        if (!ok && lane == 0) atomicCAS(p.status, 0, 3);
-        tc_fence_after();
-        __syncwarp();
+        // ===== accumulate + epilogue warps: TMEM chunk -> fp32 registers (RN) ... -> (+bias) -> pred =====
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;          // accumulator row == cell inside the 8x16 tile
         const int y = y0 + row / kTileX, x = x0 + row % kTileX;
-        uint32_t v[NPAD];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float acc[NPAD];
 #pragma unroll
-        for (int c = 0; c < NPAD; c += 16) tmem_ld_x16(taddr + c, v + c);
-        tmem_ld_wait();
+        for (int n = 0; n < NPAD; ++n) acc[n] = 0.f;
+        bool ok = true;
+        for (int c = 0; c < chunks; ++c) {
+            const int buf = c & 1;
+            const uint32_t acc_ph = (uint32_t)(c >> 1) & 1u;
+            if (!mbar_wait(tmem_full_bar + buf, acc_ph, abort_flag)) {
+                if (lane == 0) atomicCAS(p.status, 0, 3);
+                ok = false;
+                break;
+            }
+            tc_fence_after();
+            __syncwarp();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * kAccStride;
+#pragma unroll
+            for (int n0 = 0; n0 < NPAD; n0 += 16) {
+                uint32_t v[16];
+                tmem_ld_x16(taddr + n0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[n0 + i] += __uint_as_float(v[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar + buf);  // this warp is done reading the accumulator
+        }
+        __syncwarp();
         if (ok && y < p.gh && x < p.gw) {
             float *out = p.pred + (((size_t)img * p.gh + y) * p.gw + x) * p.cout;
             if ((p.cout & 3) == 0) {
@@ -324,13 +371,12 @@ convdet_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 #pragma unroll
                 for (int n = 0; n < NPAD; n += 4)
                     if (n < p.cout)
-                        o4[n >> 2] = make_float4(__uint_as_float(v[n]) + s_bias[n], __uint_as_float(v[n + 1]) + s_bias[n + 1],
-                                                 __uint_as_float(v[n + 2]) + s_bias[n + 2],
-                                                 __uint_as_float(v[n + 3]) + s_bias[n + 3]);
+                        o4[n >> 2] = make_float4(acc[n] + s_bias[n], acc[n + 1] + s_bias[n + 1], acc[n + 2] + s_bias[n + 2],
+                                                 acc[n + 3] + s_bias[n + 3]);
             } else {
 #pragma unroll
                 for (int n = 0; n < NPAD; ++n)
-                    if (n < p.cout) out[n] = __uint_as_float(v[n]) + s_bias[n];
+                    if (n < p.cout) out[n] = acc[n] + s_bias[n];
             }
         }
     }
@@ -379,8 +425,28 @@ size_t smem_bytes_for(int npad, int stages) {
 
 size_t sqd_tc_packed_bytes(int cout, int cin) { return (size_t)2 * npad_of(cout) * 9 * cin * sizeof(float); }
 
-size_t sqd_tc_workspace_bytes(int batch, int cin, int gh, int gw) {
+// workspace = [status word, padded to 256 B | A_hi plane | A_lo plane]; pre-split input needs only the status word
+size_t sqd_tc_workspace_bytes(int batch, int cin, int gh, int gw, int layout) {
+    if (layout == SQD_LAYOUT_SPLIT_NHWC) return 256;
     return (size_t)2 * batch * gh * gw * cin * sizeof(float) + 256;
+}
+
+// stand-alone hi/lo split (the first half of sqd_convdet_tc), for callers that keep the planes
+int sqd_tc_split_features(const float *d_feat, int layout, int batch, int cin, int gh, int gw, float *d_planes,
+                          cudaStream_t st) {
+    const size_t plane = (size_t)batch * gh * gw * cin;
+    float *a_hi = d_planes, *a_lo = d_planes + plane;
+    if (layout == SQD_LAYOUT_NHWC) {
+        split_nhwc_kernel<<<4 * SQD_SM_COUNT, 256, 0, st>>>(reinterpret_cast<const float4 *>(d_feat),
+                                                            reinterpret_cast<float4 *>(a_hi),
+                                                            reinterpret_cast<float4 *>(a_lo), plane / 4);
+    } else {
+        const int P = gh * gw;
+        dim3 grid((P + 31) / 32, (cin + 31) / 32, batch);
+        split_nchw_kernel<<<grid, dim3(32, 8), 0, st>>>(d_feat, a_hi, a_lo, cin, P);
+    }
+    SQD_LAUNCH_CHECK("split kernel");
+    return SQD_OK;
 }
 
 int sqd_tc_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, cudaStream_t st) {
@@ -401,7 +467,7 @@ static int launch_tc(const CUtensorMap *maps, const TcParams &p, int tiles, int 
     return SQD_OK;
 }
 
-// d_workspace: [A_hi plane | A_lo plane | status word]
+// d_workspace: [status word (256 B) | A_hi plane | A_lo plane]
 int sqd_convdet_tc(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                    int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st) {
     SQD_REQUIRE(cin % kBlockK == 0, SQD_E_SHAPE, "convdet (tcgen05): Cin %d must be a multiple of %d", cin, kBlockK);
@@ -411,22 +477,20 @@ int sqd_convdet_tc(const float *d_feat, int layout, const void *d_packed, const 
     SQD_REQUIRE(encode != nullptr, SQD_E_DRIVER, "cuTensorMapEncodeTiled not available from the CUDA driver");
     const int npad = npad_of(cout);
     const size_t plane = (size_t)batch * gh * gw * cin;
-    float *a_hi = static_cast<float *>(d_workspace);
-    float *a_lo = a_hi + plane;
-    int *status = reinterpret_cast<int *>(a_lo + plane);
+    int *status = static_cast<int *>(d_workspace);
     SQD_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
-
-    // 1. hi/lo split into NHWC planes
-    if (layout == SQD_LAYOUT_NHWC) {
-        split_nhwc_kernel<<<4 * SQD_SM_COUNT, 256, 0, st>>>(reinterpret_cast<const float4 *>(d_feat),
-                                                            reinterpret_cast<float4 *>(a_hi),
-                                                            reinterpret_cast<float4 *>(a_lo), plane / 4);
+    float *a_hi, *a_lo;
+    if (layout == SQD_LAYOUT_SPLIT_NHWC) {
+        // caller already holds the tf32 hi/lo NHWC planes (sqd_convdet_split_features)
+        a_hi = const_cast<float *>(d_feat);
+        a_lo = a_hi + plane;
     } else {
-        const int P = gh * gw;
-        dim3 grid((P + 31) / 32, (cin + 31) / 32, batch);
-        split_nchw_kernel<<<grid, dim3(32, 8), 0, st>>>(d_feat, a_hi, a_lo, cin, P);
+        // 1. hi/lo split into NHWC planes
+        a_hi = reinterpret_cast<float *>(static_cast<char *>(d_workspace) + 256);
+        a_lo = a_hi + plane;
+        int rc = sqd_tc_split_features(d_feat, layout, batch, cin, gh, gw, a_hi, st);
+        if (rc) return rc;
     }
-    SQD_LAUNCH_CHECK("split kernel");
 
     // 2. tensor maps
     alignas(64) CUtensorMap maps[4];
@@ -463,6 +527,11 @@ int sqd_convdet_tc(const float *d_feat, int layout, const void *d_packed, const 
     p.cin = cin; p.gh = gh; p.gw = gw; p.cout = cout;
     p.tiles_x = (gw + kTileX - 1) / kTileX;
     p.num_stages = stages_for(npad);
+    p.chunk_stages = 4;  // 48 MMAs per TMEM accumulation epoch: accuracy at fp32 level, TMEM reads fully overlapped
+    if (const char *e = getenv("SQD_TC_CHUNK")) {  // tuning / experiment knob
+        const int v = atoi(e);
+        if (v >= 1) p.chunk_stages = v;
+    }
     p.bias = d_bias;
     p.pred = d_pred;
     p.status = status;
@@ -480,8 +549,5 @@ int sqd_convdet_tc(const float *d_feat, int layout, const void *d_packed, const 
     SQD_REQUIRE(false, SQD_E_SHAPE, "convdet (tcgen05): unsupported Cout %d", cout);
 }
 
-// status word lives right after the two feature planes (see sqd_convdet_tc)
-const int *sqd_tc_status_ptr(const void *d_workspace, int batch, int cin, int gh, int gw) {
-    const float *base = static_cast<const float *>(d_workspace);
-    return reinterpret_cast<const int *>(base + (size_t)2 * batch * gh * gw * cin);
-}
+// status word is the first word of the workspace (see sqd_convdet_tc)
+const int *sqd_tc_status_ptr(const void *d_workspace) { return static_cast<const int *>(d_workspace); }

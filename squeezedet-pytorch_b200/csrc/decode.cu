@@ -107,13 +107,13 @@ extern "C" int sqd_decode_scores(const float *d_pred, const float *d_anchors, in
                                  int num_classes, int input_h, int input_w, int64_t *d_class_ids, float *d_scores,
                                  float *d_boxes, float *d_probs, float *d_logp, float *d_conf, float *d_deltas,
                                  void *stream) {
+    if (batch == 0) return SQD_OK;  // empty batch: nothing to enqueue, pointers may be NULL
     SQD_REQUIRE(d_pred && d_anchors, SQD_E_NULL, "sqd_decode_scores: pred/anchors is NULL");
     SQD_REQUIRE(batch >= 0 && num_anchors > 0, SQD_E_SHAPE, "sqd_decode_scores: bad batch/num_anchors");
     SQD_REQUIRE(num_classes >= 1 && num_classes <= SQD_MAX_CLASSES, SQD_E_SHAPE,
                 "sqd_decode_scores: num_classes %d outside [1,%d]", num_classes, SQD_MAX_CLASSES);
     SQD_REQUIRE(sqd_aligned16(d_pred) && sqd_aligned16(d_anchors) && sqd_aligned16(d_boxes) && sqd_aligned16(d_deltas),
                 SQD_E_ALIGN, "sqd_decode_scores: pred/anchors/boxes/deltas must be 16-byte aligned");
-    if (batch == 0) return SQD_OK;
     DecodeArgs a;
     a.pred = d_pred;
     a.anchors = reinterpret_cast<const float4 *>(d_anchors);

@@ -250,6 +250,7 @@ extern "C" int sqd_loss_fwd_bwd(const float *d_pred, const float *d_gt, const fl
                                 int num_anchors, int num_classes, int input_h, int input_w, const float *weights,
                                 const float *d_grad_loss, float *d_losses, float *d_dpred, void *d_workspace,
                                 size_t workspace_bytes, void *stream) {
+    if (batch == 0) return SQD_OK;  // empty batch: nothing to enqueue, pointers may be NULL
     SQD_REQUIRE(d_pred && d_gt && d_anchors && weights && d_losses && d_workspace, SQD_E_NULL,
                 "sqd_loss_fwd_bwd: NULL pointer");
     SQD_REQUIRE(batch >= 0 && num_anchors > 0, SQD_E_SHAPE, "sqd_loss_fwd_bwd: bad shape");
@@ -259,7 +260,6 @@ extern "C" int sqd_loss_fwd_bwd(const float *d_pred, const float *d_gt, const fl
     SQD_REQUIRE(sqd_aligned16(d_pred) && sqd_aligned16(d_gt) && sqd_aligned16(d_anchors) && sqd_aligned16(d_dpred) &&
                     sqd_aligned16(d_workspace),
                 SQD_E_ALIGN, "sqd_loss_fwd_bwd: pointers must be 16-byte aligned");
-    if (batch == 0) return SQD_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int S = pick_slices(batch);
     int per_slice = (num_anchors + S - 1) / S;

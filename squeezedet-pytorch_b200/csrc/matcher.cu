@@ -173,6 +173,7 @@ __global__ void scatter_targets_kernel(const float4 *gt_boxes, const int *gt_cla
 extern "C" int sqd_match_anchors(const float *d_gt_boxes, const int32_t *d_gt_count, int batch, int gmax,
                                  const double *d_anchors64, int num_anchors, int32_t *d_anchor_idx,
                                  float *d_deltas, void *stream) {
+    if (batch == 0) return SQD_OK;  // empty batch: nothing to enqueue, pointers may be NULL
     SQD_REQUIRE(d_gt_boxes && d_gt_count && d_anchors64 && d_anchor_idx && d_deltas, SQD_E_NULL,
                 "sqd_match_anchors: NULL pointer");
     SQD_REQUIRE(batch >= 0 && gmax >= 1 && gmax <= SQD_MAX_GT, SQD_E_SHAPE, "sqd_match_anchors: gmax %d outside [1,%d]",
@@ -181,7 +182,6 @@ extern "C" int sqd_match_anchors(const float *d_gt_boxes, const int32_t *d_gt_co
                 num_anchors);
     SQD_REQUIRE(sqd_aligned16(d_gt_boxes) && sqd_aligned16(d_anchors64) && sqd_aligned16(d_deltas), SQD_E_ALIGN,
                 "sqd_match_anchors: gt_boxes/anchors/deltas must be 16-byte aligned");
-    if (batch == 0) return SQD_OK;
     const size_t smem = (size_t)((num_anchors + 31) / 32) * sizeof(unsigned);
     if (smem > 48 * 1024)
         SQD_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -195,6 +195,7 @@ extern "C" int sqd_match_anchors(const float *d_gt_boxes, const int32_t *d_gt_co
 extern "C" int sqd_build_targets(const float *d_gt_boxes, const int32_t *d_gt_classes, const int32_t *d_gt_count,
                                  const int32_t *d_anchor_idx, const float *d_deltas, int batch, int gmax,
                                  int num_anchors, int num_classes, float *d_gt_dense, void *stream) {
+    if (batch == 0) return SQD_OK;  // empty batch: nothing to enqueue, pointers may be NULL
     SQD_REQUIRE(d_gt_boxes && d_gt_classes && d_gt_count && d_anchor_idx && d_deltas && d_gt_dense, SQD_E_NULL,
                 "sqd_build_targets: NULL pointer");
     SQD_REQUIRE(batch >= 0 && gmax >= 1 && gmax <= SQD_MAX_GT && num_anchors > 0, SQD_E_SHAPE,
@@ -202,7 +203,6 @@ extern "C" int sqd_build_targets(const float *d_gt_boxes, const int32_t *d_gt_cl
     SQD_REQUIRE(num_classes >= 1 && num_classes <= SQD_MAX_CLASSES, SQD_E_SHAPE, "sqd_build_targets: bad num_classes");
     SQD_REQUIRE(sqd_aligned16(d_gt_boxes) && sqd_aligned16(d_deltas), SQD_E_ALIGN,
                 "sqd_build_targets: gt_boxes/deltas must be 16-byte aligned");
-    if (batch == 0) return SQD_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SQD_CUDA(cudaMemsetAsync(d_gt_dense, 0, (size_t)batch * num_anchors * (num_classes + 9) * sizeof(float), st));
     scatter_targets_kernel<<<batch, 64, 0, st>>>(reinterpret_cast<const float4 *>(d_gt_boxes), d_gt_classes,

@@ -336,12 +336,12 @@ extern "C" int sqd_topk_nms(const int64_t *d_class_ids, const float *d_scores, c
                             int num_anchors, int num_classes, int top_k, double nms_thresh, double score_thresh,
                             int32_t *d_count, int32_t *d_out_anchor, int32_t *d_out_class, float *d_out_score,
                             float *d_out_box, void *stream) {
+    if (batch == 0) return SQD_OK;  // empty batch: nothing to enqueue, pointers may be NULL
     SQD_REQUIRE(d_class_ids && d_scores && d_boxes, SQD_E_NULL, "sqd_topk_nms: an input pointer is NULL");
     int rc = check_common("sqd_topk_nms", batch, num_anchors, num_classes, top_k, d_count, d_out_anchor, d_out_class,
                           d_out_score, d_out_box);
     if (rc) return rc;
     SQD_REQUIRE(sqd_aligned16(d_boxes), SQD_E_ALIGN, "sqd_topk_nms: boxes must be 16-byte aligned");
-    if (batch == 0) return SQD_OK;
     FilterOut o{d_count, d_out_anchor, d_out_class, d_out_score, reinterpret_cast<float4 *>(d_out_box)};
     const size_t smem = dyn_smem_bytes(top_k);
     rc = opt_in_smem(filter_dense_kernel, smem);
@@ -357,13 +357,13 @@ extern "C" int sqd_detect_from_pred(const float *d_pred, const float *d_anchors,
                                     int num_classes, int input_h, int input_w, int top_k, double nms_thresh,
                                     double score_thresh, int32_t *d_count, int32_t *d_out_anchor,
                                     int32_t *d_out_class, float *d_out_score, float *d_out_box, void *stream) {
+    if (batch == 0) return SQD_OK;  // empty batch: nothing to enqueue, pointers may be NULL
     SQD_REQUIRE(d_pred && d_anchors, SQD_E_NULL, "sqd_detect_from_pred: pred/anchors is NULL");
     int rc = check_common("sqd_detect_from_pred", batch, num_anchors, num_classes, top_k, d_count, d_out_anchor,
                           d_out_class, d_out_score, d_out_box);
     if (rc) return rc;
     SQD_REQUIRE(sqd_aligned16(d_pred) && sqd_aligned16(d_anchors), SQD_E_ALIGN,
                 "sqd_detect_from_pred: pred/anchors must be 16-byte aligned");
-    if (batch == 0) return SQD_OK;
     FilterOut o{d_count, d_out_anchor, d_out_class, d_out_score, reinterpret_cast<float4 *>(d_out_box)};
     const size_t smem = dyn_smem_bytes(top_k);
     const float4 *anc = reinterpret_cast<const float4 *>(d_anchors);

@@ -88,7 +88,7 @@ def convdet_forward(feat, weight, bias, packed=None, algo=CONV_TCGEN05_3XTF32, n
     check(lib.sqd_convdet_forward(xp, layout, ptr(packed), ptr(w), ptr(b), B, cin, gh, gw, cout, ptr(pred), ptr(ws),
                                   ws.numel(), algo, stream_ptr(x.device)), "sqd_convdet_forward")
     if check_status and algo == CONV_TCGEN05_3XTF32:
-        check(lib.sqd_convdet_status(ptr(ws), B, cin, gh, gw, stream_ptr(x.device)), "sqd_convdet_status")
+        check(lib.sqd_convdet_status(ptr(ws), stream_ptr(x.device)), "sqd_convdet_status")
     if num_fields is not None:
         pred = pred.view(B, gh * gw * (cout // num_fields), num_fields)
     return pred
