@@ -61,6 +61,9 @@ extern "C" {
 /* ConvDet algorithms */
 #define SQD_CONV_TCGEN05_3XTF32 0 /* tcgen05.mma kind::tf32, hi/lo split operands, fp32 TMEM accumulators */
 #define SQD_CONV_SIMT_FP32 1      /* CUDA-core fp32 FMA implicit GEMM (validation yardstick)            */
+#define SQD_CONV_TCGEN05_V1 2     /* first tcgen05 kernel (one TMA box per tap, pre-split planes); kept as an
+                                     on-device cross-check of the production kernel                     */
+#define SQD_CONV_TCGEN05_V2 3     /* second kernel (patch reuse, hi/lo split into shared memory, SS-mode MMAs) */
 
 SQD_API int sqd_abi_version(void);
 SQD_API const char *sqd_last_error(void);

@@ -16,6 +16,12 @@ int sqd_tc_pack_weights(const float *d_weight, int cout, int cin, void *d_packed
 int sqd_convdet_tc(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                    int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
 const int *sqd_tc_status_ptr(const void *d_workspace);
+size_t sqd_tc3_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout);
+int sqd_convdet_tc3(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
+                    int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
+size_t sqd_tc2_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout);
+int sqd_convdet_tc2(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
+                    int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
 
@@ -48,7 +54,9 @@ extern "C" int sqd_convdet_pack_weights(const float *d_weight, int cout, int cin
 extern "C" size_t sqd_convdet_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout, int algo) {
     if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0) return 256;
     if (algo == SQD_CONV_SIMT_FP32) return align_up(sqd_simt_workspace_bytes(cin, cout), 256);
-    return align_up(sqd_tc_workspace_bytes(batch, cin, gh, gw, layout), 256);
+    if (algo == SQD_CONV_TCGEN05_V1) return align_up(sqd_tc_workspace_bytes(batch, cin, gh, gw, layout), 256);
+    if (algo == SQD_CONV_TCGEN05_V2) return align_up(sqd_tc2_workspace_bytes(batch, cin, gh, gw, cout, layout), 256);
+    return align_up(sqd_tc3_workspace_bytes(batch, cin, gh, gw, cout, layout), 256);
 }
 
 extern "C" int sqd_convdet_forward(const float *d_feat, int layout, const void *d_packed, const float *d_weight,
@@ -58,8 +66,8 @@ extern "C" int sqd_convdet_forward(const float *d_feat, int layout, const void *
     SQD_REQUIRE(d_feat && d_bias && d_pred && d_workspace, SQD_E_NULL, "sqd_convdet_forward: NULL pointer");
     SQD_REQUIRE(layout == SQD_LAYOUT_NCHW || layout == SQD_LAYOUT_NHWC || layout == SQD_LAYOUT_SPLIT_NHWC, SQD_E_SHAPE,
                 "sqd_convdet_forward: bad layout %d", layout);
-    SQD_REQUIRE(!(layout == SQD_LAYOUT_SPLIT_NHWC && algo != SQD_CONV_TCGEN05_3XTF32), SQD_E_UNSUPPORTED,
-                "sqd_convdet_forward: pre-split planes are only consumed by the tcgen05 algorithm");
+    SQD_REQUIRE(!(layout == SQD_LAYOUT_SPLIT_NHWC && algo != SQD_CONV_TCGEN05_V1), SQD_E_UNSUPPORTED,
+                "sqd_convdet_forward: pre-split planes are only consumed by the v1 tcgen05 kernel");
     SQD_REQUIRE(batch >= 0 && cin > 0 && gh > 0 && gw > 0 && cout > 0, SQD_E_SHAPE, "sqd_convdet_forward: bad shape");
     SQD_REQUIRE(sqd_aligned16(d_feat) && sqd_aligned16(d_pred) && sqd_aligned16(d_workspace), SQD_E_ALIGN,
                 "sqd_convdet_forward: feat/pred/workspace must be 16-byte aligned");
@@ -70,9 +78,14 @@ extern "C" int sqd_convdet_forward(const float *d_feat, int layout, const void *
         SQD_REQUIRE(d_weight, SQD_E_NULL, "sqd_convdet_forward: SIMT algorithm needs the raw weight tensor");
         return sqd_convdet_simt(d_feat, layout, d_weight, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
     }
-    SQD_REQUIRE(algo == SQD_CONV_TCGEN05_3XTF32, SQD_E_UNSUPPORTED, "sqd_convdet_forward: unknown algo %d", algo);
+    SQD_REQUIRE(algo == SQD_CONV_TCGEN05_3XTF32 || algo == SQD_CONV_TCGEN05_V1 || algo == SQD_CONV_TCGEN05_V2,
+                SQD_E_UNSUPPORTED, "sqd_convdet_forward: unknown algo %d", algo);
     SQD_REQUIRE(d_packed, SQD_E_NULL, "sqd_convdet_forward: tcgen05 algorithm needs packed weights");
-    return sqd_convdet_tc(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
+    if (algo == SQD_CONV_TCGEN05_V1)
+        return sqd_convdet_tc(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
+    if (algo == SQD_CONV_TCGEN05_V2)
+        return sqd_convdet_tc2(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
+    return sqd_convdet_tc3(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
 }
 
 extern "C" size_t sqd_convdet_split_bytes(int batch, int cin, int gh, int gw) {

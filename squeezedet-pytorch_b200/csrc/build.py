@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libsqdet_b200.so")
-SOURCES = ["api.cu", "decode.cu", "topk_nms.cu", "matcher.cu", "loss.cu", "convdet_simt.cu", "convdet_tc.cu"]
+SOURCES = ["api.cu", "decode.cu", "topk_nms.cu", "matcher.cu", "loss.cu", "convdet_simt.cu", "convdet_tc.cu", "convdet_tc2.cu", "convdet_tc3.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
          "-I", os.path.join(ROOT, "include"), "-I", HERE]
@@ -35,7 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    headers = [os.path.join(HERE, "common.cuh"), os.path.join(ROOT, "include", "sqdet_b200.h"), __file__]
+    headers = [os.path.join(HERE, "common.cuh"), os.path.join(HERE, "tc_ptx.cuh"), os.path.join(ROOT, "include", "sqdet_b200.h"), __file__]
     objs, procs = [], []
     for src in SOURCES:
         s = os.path.join(HERE, src)

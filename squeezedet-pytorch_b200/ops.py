@@ -79,7 +79,7 @@ def convdet_forward(feat, weight, bias, packed=None, algo=CONV_TCGEN05_3XTF32, n
     w = weight.detach().contiguous()
     b = bias.detach().contiguous()
     cout = w.shape[0]
-    if algo == CONV_TCGEN05_3XTF32 and packed is None:
+    if algo != CONV_SIMT_FP32 and packed is None:
         packed = pack_convdet_weights(w)
     nbytes = lib.sqd_convdet_workspace_bytes(B, cin, gh, gw, cout, layout, algo)
     ws = workspace().get("convdet", nbytes, x.device)
@@ -87,7 +87,7 @@ def convdet_forward(feat, weight, bias, packed=None, algo=CONV_TCGEN05_3XTF32, n
     xp = C.c_void_p(x.data_ptr())  # channels_last tensors are not .is_contiguous(); pointer is still the base
     check(lib.sqd_convdet_forward(xp, layout, ptr(packed), ptr(w), ptr(b), B, cin, gh, gw, cout, ptr(pred), ptr(ws),
                                   ws.numel(), algo, stream_ptr(x.device)), "sqd_convdet_forward")
-    if check_status and algo == CONV_TCGEN05_3XTF32:
+    if check_status and algo != CONV_SIMT_FP32:
         check(lib.sqd_convdet_status(ptr(ws), stream_ptr(x.device)), "sqd_convdet_status")
     if num_fields is not None:
         pred = pred.view(B, gh * gw * (cout // num_fields), num_fields)
@@ -149,7 +149,7 @@ def head_detect(feat, weight, bias, anchors_f32, anchors_per_grid, num_classes, 
     w = weight.detach().contiguous()
     b = bias.detach().contiguous()
     cout = w.shape[0]
-    if algo == CONV_TCGEN05_3XTF32 and packed is None:
+    if algo != CONV_SIMT_FP32 and packed is None:
         packed = pack_convdet_weights(w)
     nbytes = lib.sqd_head_detect_workspace_bytes(B, cin, gh, gw, cout, layout, algo)
     ws = workspace().get("head_detect", nbytes, x.device)
