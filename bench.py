@@ -261,7 +261,7 @@ def main_ours(args):
             _lib.check(lib.sqd_convdet_forward(_lib.ptr(planes), _lib.LAYOUT_SPLIT_NHWC, _lib.ptr(packed), None,
                                                _lib.ptr(bias), B, shp.in_channels, shp.grid_hw[0], shp.grid_hw[1],
                                                shp.out_channels, _lib.ptr(pred), _lib.ptr(ws), ws.numel(),
-                                               _lib.CONV_TCGEN05_3XTF32, st), "convdet")
+                                               _lib.CONV_TCGEN05_F16X3, st), "convdet")
             ev[2].record()
             _lib.check(lib.sqd_detect_from_pred(_lib.ptr(pred), _lib.ptr(anchors), B, shp.num_anchors, shp.num_classes,
                                                 shp.input_hw[0], shp.input_hw[1], shp.top_k, shp.nms_thresh,

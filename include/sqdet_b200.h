@@ -55,15 +55,13 @@ extern "C" {
 /* feature-map memory layouts accepted by the ConvDet head */
 #define SQD_LAYOUT_NCHW 0
 #define SQD_LAYOUT_NHWC 1 /* torch channels_last: logical NCHW, physical NHWC */
-#define SQD_LAYOUT_SPLIT_NHWC 2 /* [hi plane | lo plane], each (B,gh,gw,Cin) tf32-exact fp32: output of
+#define SQD_LAYOUT_SPLIT_NHWC 2 /* [max|x| per image: B x u32][x1 plane][x2 plane], planes (B,gh,gw,Cin) fp16: output of
                                    sqd_convdet_split_features, consumed by the tcgen05 algorithm only */
 
 /* ConvDet algorithms */
-#define SQD_CONV_TCGEN05_3XTF32 0 /* tcgen05.mma kind::tf32, hi/lo split operands, fp32 TMEM accumulators */
-#define SQD_CONV_SIMT_FP32 1      /* CUDA-core fp32 FMA implicit GEMM (validation yardstick)            */
-#define SQD_CONV_TCGEN05_V1 2     /* first tcgen05 kernel (one TMA box per tap, pre-split planes); kept as an
-                                     on-device cross-check of the production kernel                     */
-#define SQD_CONV_TCGEN05_V2 3     /* second kernel (patch reuse, hi/lo split into shared memory, SS-mode MMAs) */
+#define SQD_CONV_TCGEN05_F16X3 0 /* tcgen05.mma kind::f16, two-term fp16 split of power-of-two scaled operands
+                                    (3 products = fp32-level accuracy), fp32 TMEM accumulators, chunked */
+#define SQD_CONV_SIMT_FP32 1     /* CUDA-core fp32 FMA implicit GEMM (validation yardstick)            */
 
 SQD_API int sqd_abi_version(void);
 SQD_API const char *sqd_last_error(void);
@@ -78,12 +76,13 @@ SQD_API const char *sqd_last_error(void);
  *   d_bias   (Cout) fp32
  *   d_pred   (B, gh*gw*K, C+5) fp32 == (B, gh, gw, Cout) ; Cout = K*(C+5)
  *
- * sqd_convdet_pack_weights() derives the kernel-side weight planes (tap-major, hi/lo tf32 split,
- * N padded to a multiple of 16) ONCE per weight update; they are derived data and never saved.
+ * sqd_convdet_pack_weights() derives the kernel-side weight matrix (tap-major K, two-term fp16 split of
+ * the power-of-two scaled weights, N padded to a multiple of 16) ONCE per weight update; derived data,
+ * never saved.  Cin must be a multiple of 64, Cout <= 128.
  * ------------------------------------------------------------------------------------------- */
 SQD_API size_t sqd_convdet_packed_weight_bytes(int cout, int cin);
 SQD_API int sqd_convdet_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, void *stream);
-/* hi/lo tf32 split of a feature map into NHWC planes (the tcgen05 kernel's A operand).  sqd_convdet_forward
+/* per-image max|x| + two-term fp16 split of a feature map into NHWC planes (the tcgen05 kernel's A operand).  sqd_convdet_forward
  * does this internally for NCHW / NHWC input; a producer that can emit the planes itself (or reuses them)
  * passes them with SQD_LAYOUT_SPLIT_NHWC and skips the pass. */
 SQD_API size_t sqd_convdet_split_bytes(int batch, int cin, int gh, int gw);

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsqdet_b200.so")
 
 LAYOUT_NCHW, LAYOUT_NHWC, LAYOUT_SPLIT_NHWC = 0, 1, 2
-CONV_TCGEN05_3XTF32, CONV_SIMT_FP32, CONV_TCGEN05_V1, CONV_TCGEN05_V2 = 0, 1, 2, 3
+CONV_TCGEN05_F16X3, CONV_SIMT_FP32 = 0, 1
 
 _lib = None
 _lock = threading.Lock()

@@ -4,23 +4,17 @@
 
 #include "common.cuh"
 
-// implemented in convdet_simt.cu / convdet_tc.cu
+// implemented in convdet_simt.cu / convdet_f16.cu
 size_t sqd_simt_workspace_bytes(int cin, int cout);
 int sqd_convdet_simt(const float *d_feat, int layout, const float *d_weight, const float *d_bias, int batch, int cin,
                      int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
-size_t sqd_tc_packed_bytes(int cout, int cin);
-size_t sqd_tc_workspace_bytes(int batch, int cin, int gh, int gw, int layout);
-int sqd_tc_split_features(const float *d_feat, int layout, int batch, int cin, int gh, int gw, float *d_planes,
-                          cudaStream_t st);
-int sqd_tc_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, cudaStream_t st);
-int sqd_convdet_tc(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
-                   int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
-const int *sqd_tc_status_ptr(const void *d_workspace);
-size_t sqd_tc3_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout);
-int sqd_convdet_tc3(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
-                    int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
-size_t sqd_tc2_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout);
-int sqd_convdet_tc2(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
+size_t sqd_f16_packed_bytes(int cout, int cin);
+int sqd_f16_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, cudaStream_t st);
+size_t sqd_f16_split_bytes(int batch, int cin, int gh, int gw);
+int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, int gh, int gw, void *d_planes,
+                           cudaStream_t st);
+size_t sqd_f16_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout);
+int sqd_convdet_f16(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                     int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
@@ -40,23 +34,21 @@ extern "C" const char *sqd_last_error(void) { return g_err; }
 // ---- a1 -------------------------------------------------------------------------------------------
 extern "C" size_t sqd_convdet_packed_weight_bytes(int cout, int cin) {
     if (cout <= 0 || cin <= 0) return 0;
-    return sqd_tc_packed_bytes(cout, cin);
+    return sqd_f16_packed_bytes(cout, cin);
 }
 
 extern "C" int sqd_convdet_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, void *stream) {
     SQD_REQUIRE(d_weight && d_packed, SQD_E_NULL, "sqd_convdet_pack_weights: NULL pointer");
-    SQD_REQUIRE(cout >= 1 && cout <= 128 && cin >= 32 && cin % 32 == 0, SQD_E_SHAPE,
-                "sqd_convdet_pack_weights: need 1<=Cout<=128 and Cin a multiple of 32 (got %d, %d)", cout, cin);
+    SQD_REQUIRE(cout >= 1 && cout <= 128 && cin >= 64 && cin % 64 == 0, SQD_E_SHAPE,
+                "sqd_convdet_pack_weights: need 1<=Cout<=128 and Cin a multiple of 64 (got %d, %d)", cout, cin);
     SQD_REQUIRE(sqd_aligned16(d_packed), SQD_E_ALIGN, "sqd_convdet_pack_weights: packed buffer must be 16-byte aligned");
-    return sqd_tc_pack_weights(d_weight, cout, cin, d_packed, static_cast<cudaStream_t>(stream));
+    return sqd_f16_pack_weights(d_weight, cout, cin, d_packed, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t sqd_convdet_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout, int algo) {
     if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0) return 256;
     if (algo == SQD_CONV_SIMT_FP32) return align_up(sqd_simt_workspace_bytes(cin, cout), 256);
-    if (algo == SQD_CONV_TCGEN05_V1) return align_up(sqd_tc_workspace_bytes(batch, cin, gh, gw, layout), 256);
-    if (algo == SQD_CONV_TCGEN05_V2) return align_up(sqd_tc2_workspace_bytes(batch, cin, gh, gw, cout, layout), 256);
-    return align_up(sqd_tc3_workspace_bytes(batch, cin, gh, gw, cout, layout), 256);
+    return align_up(sqd_f16_workspace_bytes(batch, cin, gh, gw, cout, layout), 256);
 }
 
 extern "C" int sqd_convdet_forward(const float *d_feat, int layout, const void *d_packed, const float *d_weight,
@@ -66,8 +58,8 @@ extern "C" int sqd_convdet_forward(const float *d_feat, int layout, const void *
     SQD_REQUIRE(d_feat && d_bias && d_pred && d_workspace, SQD_E_NULL, "sqd_convdet_forward: NULL pointer");
     SQD_REQUIRE(layout == SQD_LAYOUT_NCHW || layout == SQD_LAYOUT_NHWC || layout == SQD_LAYOUT_SPLIT_NHWC, SQD_E_SHAPE,
                 "sqd_convdet_forward: bad layout %d", layout);
-    SQD_REQUIRE(!(layout == SQD_LAYOUT_SPLIT_NHWC && algo != SQD_CONV_TCGEN05_V1), SQD_E_UNSUPPORTED,
-                "sqd_convdet_forward: pre-split planes are only consumed by the v1 tcgen05 kernel");
+    SQD_REQUIRE(!(layout == SQD_LAYOUT_SPLIT_NHWC && algo != SQD_CONV_TCGEN05_F16X3), SQD_E_UNSUPPORTED,
+                "sqd_convdet_forward: pre-split planes are only consumed by the tcgen05 algorithm");
     SQD_REQUIRE(batch >= 0 && cin > 0 && gh > 0 && gw > 0 && cout > 0, SQD_E_SHAPE, "sqd_convdet_forward: bad shape");
     SQD_REQUIRE(sqd_aligned16(d_feat) && sqd_aligned16(d_pred) && sqd_aligned16(d_workspace), SQD_E_ALIGN,
                 "sqd_convdet_forward: feat/pred/workspace must be 16-byte aligned");
@@ -78,19 +70,14 @@ extern "C" int sqd_convdet_forward(const float *d_feat, int layout, const void *
         SQD_REQUIRE(d_weight, SQD_E_NULL, "sqd_convdet_forward: SIMT algorithm needs the raw weight tensor");
         return sqd_convdet_simt(d_feat, layout, d_weight, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
     }
-    SQD_REQUIRE(algo == SQD_CONV_TCGEN05_3XTF32 || algo == SQD_CONV_TCGEN05_V1 || algo == SQD_CONV_TCGEN05_V2,
-                SQD_E_UNSUPPORTED, "sqd_convdet_forward: unknown algo %d", algo);
+    SQD_REQUIRE(algo == SQD_CONV_TCGEN05_F16X3, SQD_E_UNSUPPORTED, "sqd_convdet_forward: unknown algo %d", algo);
     SQD_REQUIRE(d_packed, SQD_E_NULL, "sqd_convdet_forward: tcgen05 algorithm needs packed weights");
-    if (algo == SQD_CONV_TCGEN05_V1)
-        return sqd_convdet_tc(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
-    if (algo == SQD_CONV_TCGEN05_V2)
-        return sqd_convdet_tc2(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
-    return sqd_convdet_tc3(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
+    return sqd_convdet_f16(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
 }
 
 extern "C" size_t sqd_convdet_split_bytes(int batch, int cin, int gh, int gw) {
     if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0) return 0;
-    return (size_t)2 * batch * gh * gw * cin * sizeof(float);
+    return sqd_f16_split_bytes(batch, cin, gh, gw);
 }
 
 extern "C" int sqd_convdet_split_features(const float *d_feat, int layout, int batch, int cin, int gh, int gw,
@@ -99,12 +86,11 @@ extern "C" int sqd_convdet_split_features(const float *d_feat, int layout, int b
     SQD_REQUIRE(d_feat && d_planes, SQD_E_NULL, "sqd_convdet_split_features: NULL pointer");
     SQD_REQUIRE(layout == SQD_LAYOUT_NCHW || layout == SQD_LAYOUT_NHWC, SQD_E_SHAPE,
                 "sqd_convdet_split_features: bad layout %d", layout);
-    SQD_REQUIRE(batch >= 0 && cin >= 32 && cin % 32 == 0 && gh > 0 && gw > 0, SQD_E_SHAPE,
+    SQD_REQUIRE(batch >= 0 && cin >= 64 && cin % 64 == 0 && gh > 0 && gw > 0, SQD_E_SHAPE,
                 "sqd_convdet_split_features: bad shape");
     SQD_REQUIRE(sqd_aligned16(d_feat) && sqd_aligned16(d_planes), SQD_E_ALIGN,
                 "sqd_convdet_split_features: pointers must be 16-byte aligned");
-    return sqd_tc_split_features(d_feat, layout, batch, cin, gh, gw, static_cast<float *>(d_planes),
-                                 static_cast<cudaStream_t>(stream));
+    return sqd_f16_split_features(d_feat, layout, batch, cin, gh, gw, d_planes, static_cast<cudaStream_t>(stream));
 }
 
 // Synchronises `stream` and reports whether the last tcgen05 launch that used this workspace drained cleanly
@@ -112,7 +98,7 @@ extern "C" int sqd_convdet_split_features(const float *d_feat, int layout, int b
 extern "C" int sqd_convdet_status(const void *d_workspace, void *stream) {
     SQD_REQUIRE(d_workspace, SQD_E_NULL, "sqd_convdet_status: NULL workspace");
     int h = -1;
-    SQD_CUDA(cudaMemcpyAsync(&h, sqd_tc_status_ptr(d_workspace), sizeof(int), cudaMemcpyDeviceToHost,
+    SQD_CUDA(cudaMemcpyAsync(&h, static_cast<const int *>(d_workspace), sizeof(int), cudaMemcpyDeviceToHost,
                              static_cast<cudaStream_t>(stream)));
     SQD_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     if (h != 0) sqd_set_error("tcgen05 ConvDet pipeline timed out (role %d)", h);

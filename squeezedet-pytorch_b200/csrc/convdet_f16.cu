@@ -1,0 +1,747 @@
+// a1: ConvDet 3x3 head as a persistent tcgen05 / TMEM implicit GEMM fed by TMA (sm_100a), "f16x3":
+// fp32-level products from THREE half-precision tensor-core passes.
+// Reference: SqueezeDetBase.convdet + permute(0,2,3,1) + view, src/model/squeezedet.py:73-75,83-87
+// (cuDNN conv with N=72 plus an NCHW->NHWC copy kernel there).
+//
+// GEMM view per image: M = gh*gw cells, N = Cout = K_anchors*(C+5) (72 KITTI, padded to 80), K = 9*Cin = 6912.
+//
+// Why fp16 and not tf32: both carry an 11-bit significand, but kind::f16 runs at twice the kind::tf32 rate and
+// its operands are half as wide, which matters because this small-N GEMM is SHARED-MEMORY bound (an SS-mode
+// tcgen05.mma streams A (128 rows) and B (N rows) through the 128 B/clk port; tools/micro/umma_rate.cu).  What
+// fp16 lacks is exponent range, so both operands are scaled by exact powers of two first:
+//     x*s = x1 + x2/2^11 (+ <= 2^-22 relative),  x1 = fp16(x*s),  x2 = fp16((x*s - x1) * 2^11)
+// with s = 2^e chosen per IMAGE for the features (from a max|x| pre-pass) and per tensor for the weights so that
+// max|x*s| lies in [2^13, 2^14): no overflow, and elements down to 2^-27 of the maximum keep full precision
+// (smaller ones degrade gracefully to an absolute error of 2^-49 of the maximum).  Then
+//     a*w*(s_a*s_w) = a1*w1 + (a1*w2 + a2*w1)/2^11   (the dropped a2*w2 term is 2^-22 relative, like 3xTF32)
+//
+//  * pre-pass (the only extra HBM traffic): features fp32 NCHW or NHWC -> two fp16 NHWC planes (x1, x2); reads
+//    4 B and writes 4 B per element, fused with the NCHW->NHWC transpose the K-major A operand needs anyway.
+//  * M tile = 8 x 16 cells = 128 rows = one UMMA_M.  A "unit" of work is (tile, 64-channel block, dx): ONE 4-D TMA
+//    box {64 ch, 16 x, 10 y, 1 img} per plane at (c0, x0+dx-1, y0-1, b); conv padding = TMA out-of-bounds zero fill.
+//    The box lands as 160 rows x 128 B, 128B-swizzled; the three dy taps are the SAME patch read through UMMA
+//    descriptors offset by 16 rows (2048 B, swizzle-atom aligned) -> A is fetched 3x per channel block, not 9x.
+//  * B = packed weights, one fp16 matrix [2*Npad][9*Cin] K-major (k = tap*Cin + c): rows [0,Npad) hold w2, rows
+//    [Npad,2Npad) hold w1, so per K step (16 channels) only TWO MMAs are issued:
+//        D[:, 0:2N]  (+)= A1 * [w2 | w1]^T     (N = 2*Npad: cross term a1*w2 | main term a1*w1)
+//        D[:, 0:N]    +=  A2 * w1^T            (cross term a2*w1, same 2^11 scale as a1*w2)
+//  * Chunked accumulation: the tensor core truncates when adding into the fp32 TMEM accumulator (measured:
+//    profiles/r01_tc_accuracy_vs_chunk.txt), so every unit (24 MMAs) accumulates from zero into one of two TMEM
+//    accumulators and four accumulate warps fold finished units into fp32 registers (main + cross/2^11, round to
+//    nearest) while the next unit's MMAs run into the other accumulator.
+//  * Persistent, balanced schedule: grid = min(#SMs, #tiles); the unit range is cut evenly, so a CTA owns
+//    [tail of a tile][whole tiles][head of a tile].  A split tile is finished deterministically: the head
+//    holder publishes its partial sums, the tail holder (higher CTA index, its tail segment is processed
+//    LAST) adds them in a fixed order.  Waiters only ever wait for lower-indexed CTAs.
+//  * Warp roles (224 threads): 0 A-TMA, 1 TMEM alloc + MMA issue (converged warp, one elected lane), 2 B-TMA,
+//    3..6 accumulate + epilogue (x 1/(s_a*s_w), + bias -> pred in the reference's (B, A, C+5) layout).
+//  * Every wait is bounded: on timeout the CTA raises a status word and drains instead of hanging.
+// Algorithmic FLOPs per image: 2*M*Cout*K (the three passes and the N padding are NOT counted).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+using namespace sqd_tc;
+
+constexpr int kTileX = 16, kTileY = 8, kPatchY = kTileY + 2;
+constexpr int kBlockK = 64;   // channels per unit (128 B of fp16 = one swizzle row)
+constexpr int kUmmaK = 16;    // f16 MMA K
+constexpr int kPlaneBytes = kPatchY * kTileX * kBlockK * 2;  // 20480: one plane of one A stage
+constexpr int kAStageBytes = 2 * kPlaneBytes;                // x1 patch then x2 patch
+constexpr int kDyBytes = kTileX * kBlockK * 2;               // 2048: one y row of the patch = descriptor step per dy
+constexpr int kThreads = 224;
+constexpr int kWarpATma = 0, kWarpMma = 1, kWarpBTma = 2, kWarpAcc0 = 3;
+constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;    // 2^11: the second term is stored scaled up
+constexpr int kHeaderBytes = 256;                            // packed weights: [header][fp16 matrix]
+
+struct PackedHeader {
+    unsigned amax_bits;  // max |w| as fp32 bits
+    float scale;         // s_w = 2^e
+    float inv_scale;     // 1 / s_w
+    int npad, cin;
+};
+
+// power-of-two scale s with amax*s in [2^13, 2^14); exponent clamped so that s and 1/s are normal floats
+__device__ __forceinline__ float pow2_scale_for(float amax) {
+    if (!(amax > 0.f) || amax > 3.0e38f) return 1.f;
+    int ex;
+    frexpf(amax, &ex);  // amax = m * 2^ex, m in [0.5, 1)
+    int e = 14 - ex;
+    e = e < -126 ? -126 : (e > 126 ? 126 : e);
+    return ldexpf(1.f, e);
+}
+
+__device__ __forceinline__ void split_f16(float xs, __half &h1, __half &h2) {
+    h1 = __float2half_rn(xs);
+    h2 = __float2half_rn((xs - __half2float(h1)) * kLoScale);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pre-passes
+// ---------------------------------------------------------------------------------------------------
+// max |x| per image (any layout: an image is one contiguous run of n4 float4).  Non-negative floats order like
+// their bit patterns, so the reduction is an integer atomicMax.  NaN inputs are ignored by fmaxf.
+__global__ void absmax_kernel(const float4 *__restrict__ in, size_t n4, unsigned *__restrict__ amax_bits) {
+    const float4 *src = in + (size_t)blockIdx.y * n4;
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(src + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float s[32];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) atomicMax(amax_bits + blockIdx.y, __float_as_uint(m));
+    }
+}
+
+// NHWC fp32 -> x1 / x2 fp16 planes (same layout); grid.y = image
+__global__ void split_nhwc_f16_kernel(const float4 *__restrict__ in, uint2 *__restrict__ p1, uint2 *__restrict__ p2,
+                                      size_t n4, const unsigned *__restrict__ amax_bits) {
+    const float s = pow2_scale_for(__uint_as_float(amax_bits[blockIdx.y]));
+    const size_t base = (size_t)blockIdx.y * n4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = ld_stream_f4(in + base + i);
+        __half a1[4], a2[4];
+        split_f16(v.x * s, a1[0], a2[0]);
+        split_f16(v.y * s, a1[1], a2[1]);
+        split_f16(v.z * s, a1[2], a2[2]);
+        split_f16(v.w * s, a1[3], a2[3]);
+        p1[base + i] = *reinterpret_cast<const uint2 *>(a1);
+        p2[base + i] = *reinterpret_cast<const uint2 *>(a2);
+    }
+}
+
+// NCHW (B,Cin,P) fp32 -> NHWC (B,P,Cin) fp16 planes through a 64 ch x 64 cell shared tile; P = gh*gw.
+// Reads are 256 B rows along P, writes are 128 B rows along C (one half2 per lane).  256 threads.
+__global__ void split_nchw_f16_kernel(const float *__restrict__ in, __half2 *__restrict__ p1, __half2 *__restrict__ p2,
+                                      int cin, int P, const unsigned *__restrict__ amax_bits) {
+    __shared__ float tile[64][65];
+    const int b = blockIdx.z, c0 = blockIdx.y * 64, q0 = blockIdx.x * 64;
+    const float s = pow2_scale_for(__uint_as_float(amax_bits[b]));
+    const float *src = in + (size_t)b * cin * P;
+    const int col = threadIdx.x & 63, r0 = threadIdx.x >> 6;
+#pragma unroll 4
+    for (int j = r0; j < 64; j += 4) {
+        const int q = q0 + col;
+        tile[j][col] = q < P ? __ldg(src + (size_t)(c0 + j) * P + q) : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int j = w; j < 64; j += 8) {
+        const int q = q0 + j;
+        if (q >= P) break;
+        __half a1[2], a2[2];
+        split_f16(tile[2 * lane][j] * s, a1[0], a2[0]);
+        split_f16(tile[2 * lane + 1][j] * s, a1[1], a2[1]);
+        const size_t o = (((size_t)b * P + q) * cin + c0) / 2 + lane;
+        p1[o] = __halves2half2(a1[0], a1[1]);
+        p2[o] = __halves2half2(a2[0], a2[1]);
+    }
+}
+
+__global__ void weight_absmax_kernel(const float *__restrict__ w, size_t n, PackedHeader *hdr) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(&hdr->amax_bits, __float_as_uint(m));
+}
+
+// (Cout,Cin,3,3) fp32 -> fp16 [2*npad][9*cin]: rows [0,npad) = w2 (scaled residual), rows [npad,2npad) = w1
+__global__ void pack_weights_f16_kernel(const float *__restrict__ w, int cout, int cin, int npad, PackedHeader *hdr,
+                                        __half *__restrict__ mat) {
+    const float s = pow2_scale_for(__uint_as_float(hdr->amax_bits));
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        hdr->scale = s;
+        hdr->inv_scale = 1.f / s;
+        hdr->npad = npad;
+        hdr->cin = cin;
+    }
+    const size_t ktot = (size_t)9 * cin, total = (size_t)npad * ktot;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / ktot);
+        const size_t k = i % ktot;
+        const int tap = (int)(k / cin), c = (int)(k % cin);
+        float v = 0.f;
+        if (n < cout) v = w[((size_t)n * cin + c) * 9 + tap];
+        __half h1, h2;
+        split_f16(v * s, h1, h2);
+        mat[i] = h2;
+        mat[total + i] = h1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------------
+// cute::UMMA::InstrDescriptor: c=F32 (1 @bit 4), a=b=F16 (0 @bits 7,10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, M=128, kind::f16
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 accumulate warps
+
+struct F16Params {
+    int cin, gh, gw, cout;
+    int tiles_x, tiles_per_img, total_tiles;
+    int upt;            // units per tile = (cin/64) * 3
+    int units_per_cta;  // even cut of total_tiles*upt over the grid (>= upt)
+    int a_stages, b_stages;
+    const float *bias;
+    const unsigned *amax_bits;   // (B) max|x| per image, fp32 bits
+    const PackedHeader *whdr;
+    float *pred;
+    float *partial;  // (grid, 128, NPAD) partial sums of split tiles
+    int *flags;      // (grid) 1 = partial[cta] published
+    int *status;     // 0 ok; else the role whose bounded wait timed out
+};
+
+struct Sched {  // the permuted unit sequence of one CTA: [whole tiles + head segment][deferred tail segment]
+    long long u0;
+    int n, main_len, upt;
+    __device__ __forceinline__ long long unit(int i) const {
+        const int len_tail = n - main_len;
+        return i < main_len ? u0 + len_tail + i : u0 + (i - main_len);
+    }
+};
+
+template <int NPAD>
+__global__ void __launch_bounds__(kThreads, 1)
+convdet_f16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
+                   const __grid_constant__ CUtensorMap map_b, const F16Params p) {
+    constexpr int kBStageBytes = 2 * NPAD * kBlockK * 2;  // [w2 rows | w1 rows] of one tap: one K-major tile of 2*NPAD rows
+    constexpr int kW1Offset = NPAD * kBlockK * 2;         // byte offset of the w1 rows inside a B stage (multiple of 2048)
+    constexpr int kAccCols = 2 * NPAD;                    // [cross | main]
+    constexpr uint32_t kTmemCols = 512;
+    constexpr uint32_t kIdescCat = umma_idesc_f16(128, 2 * NPAD);
+    constexpr uint32_t kIdescOne = umma_idesc_f16(128, NPAD);
+    static_assert(2 * kAccCols <= 512, "TMEM budget");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int AS = p.a_stages, BS = p.b_stages;
+    uint8_t *a_ring = smem;
+    uint8_t *b_ring = smem + (size_t)AS * kAStageBytes;
+    uint8_t *ctrl = b_ring + (size_t)BS * kBStageBytes;
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(ctrl);    // [4]
+    uint64_t *a_empty = a_full + 4;                           // [4]
+    uint64_t *b_full = a_empty + 4;                           // [8]
+    uint64_t *b_empty = b_full + 8;                           // [8]
+    uint64_t *tmem_full = b_empty + 8;                        // [2]
+    uint64_t *tmem_empty = tmem_full + 2;                     // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    volatile int *abort_flag = reinterpret_cast<volatile int *>(tmem_slot + 1);
+    float *s_bias = reinterpret_cast<float *>(tmem_slot + 2);  // NPAD floats
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cta = blockIdx.x;
+
+    // ---- this CTA's slice of the unit space --------------------------------------------------------------
+    const long long total_units = (long long)p.total_tiles * p.upt;
+    Sched sc;
+    sc.upt = p.upt;
+    sc.u0 = (long long)cta * p.units_per_cta;
+    {
+        long long u1 = sc.u0 + p.units_per_cta;
+        if (u1 > total_units) u1 = total_units;
+        sc.n = u1 > sc.u0 ? (int)(u1 - sc.u0) : 0;
+        const int r0 = (int)(sc.u0 % p.upt);
+        int len_tail = r0 ? p.upt - r0 : 0;   // the range starts inside a tile: that tail segment is done last
+        if (len_tail > sc.n) len_tail = sc.n;
+        sc.main_len = sc.n - len_tail;
+    }
+    const int n_units = sc.n;
+
+    if (threadIdx.x == 0) {
+        *abort_flag = 0;
+        for (int s = 0; s < AS; ++s) {
+            mbar_init(a_full + s, 1);
+            mbar_init(a_empty + s, 1);
+        }
+        for (int s = 0; s < BS; ++s) {
+            mbar_init(b_full + s, 1);
+            mbar_init(b_empty + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tmem_full + b, 1);
+            mbar_init(tmem_empty + b, 4);  // one arrival per accumulate warp
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if ((warp == kWarpATma || warp == kWarpBTma) && lane == 0) {
+        tma_prefetch_desc(&map_a1);
+        tma_prefetch_desc(&map_a2);
+        tma_prefetch_desc(&map_b);
+    }
+    for (int i = threadIdx.x; i < NPAD; i += kThreads) s_bias[i] = i < p.cout ? __ldg(p.bias + i) : 0.f;
+    if (warp == kWarpMma) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == kWarpATma) {
+        // ===== A producer: the x1 and x2 patches of one unit (warp stays converged, one elected lane issues) =====
+        for (int i = 0; i < n_units; ++i) {
+            const int s = i % AS;
+            const uint32_t ph = (uint32_t)(i / AS) & 1u;
+            if (!mbar_wait_warp(a_empty + s, ph ^ 1u, abort_flag)) {
+                if (lane == 0) atomicCAS(p.status, 0, 1);
+                break;
+            }
+            const long long u = sc.unit(i);
+            const int tile = (int)(u / p.upt), r = (int)(u % p.upt);
+            const int cb = r / 3, dxi = r - cb * 3;
+            const int img = tile / p.tiles_per_img, t = tile - img * p.tiles_per_img;
+            const int x0 = (t % p.tiles_x) * kTileX, y0 = (t / p.tiles_x) * kTileY;
+            if (elect_one_sync()) {
+                uint8_t *st = a_ring + (size_t)s * kAStageBytes;
+                mbar_arrive_expect_tx(a_full + s, kAStageBytes);
+                tma_load_4d(&map_a1, a_full + s, st, cb * kBlockK, x0 + dxi - 1, y0 - 1, img);
+                tma_load_4d(&map_a2, a_full + s, st + kPlaneBytes, cb * kBlockK, x0 + dxi - 1, y0 - 1, img);
+            }
+            __syncwarp();
+        }
+    } else if (warp == kWarpBTma) {
+        // ===== B producer: the [w2 | w1] tile of one tap per step =====
+        bool ok = true;
+        for (int i = 0; i < n_units && ok; ++i) {
+            const long long u = sc.unit(i);
+            const int r = (int)(u % p.upt);
+            const int cb = r / 3, dxi = r - cb * 3;
+            for (int dyi = 0; dyi < 3; ++dyi) {
+                const int j = i * 3 + dyi;
+                const int s = j % BS;
+                const uint32_t ph = (uint32_t)(j / BS) & 1u;
+                if (!mbar_wait_warp(b_empty + s, ph ^ 1u, abort_flag)) {
+                    if (lane == 0) atomicCAS(p.status, 0, 5);
+                    ok = false;
+                    break;
+                }
+                const int tap = dyi * 3 + dxi;
+                if (elect_one_sync()) {
+                    mbar_arrive_expect_tx(b_full + s, kBStageBytes);
+                    tma_load_2d(&map_b, b_full + s, b_ring + (size_t)s * kBStageBytes, tap * p.cin + cb * kBlockK, 0);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == kWarpMma) {
+        // ===== MMA issuer: 24 SS-mode MMAs per unit into a fresh TMEM accumulator.  The warp stays converged and
+        // one elected lane issues, so descriptors live in uniform registers. =====
+        bool ok = true;
+        for (int i = 0; i < n_units && ok; ++i) {
+            const int buf = i & 1;
+            const uint32_t acc_ph = (uint32_t)(i >> 1) & 1u;
+            const int as = i % AS;
+            const uint32_t a_ph = (uint32_t)(i / AS) & 1u;
+            if (!mbar_wait_warp(tmem_empty + buf, acc_ph ^ 1u, abort_flag)) {
+                if (lane == 0) atomicCAS(p.status, 0, 4);
+                break;
+            }
+            if (!mbar_wait_warp(a_full + as, a_ph, abort_flag)) {
+                if (lane == 0) atomicCAS(p.status, 0, 2);
+                break;
+            }
+            const uint32_t d_tmem = tmem_base + (uint32_t)buf * kAccCols;
+            const uint32_t a_addr = smem_u32(a_ring + (size_t)as * kAStageBytes);
+            for (int dyi = 0; dyi < 3; ++dyi) {
+                const int j = i * 3 + dyi;
+                const int bs = j % BS;
+                const uint32_t b_ph = (uint32_t)(j / BS) & 1u;
+                if (!mbar_wait_warp(b_full + bs, b_ph, abort_flag)) {
+                    if (lane == 0) atomicCAS(p.status, 0, 6);
+                    ok = false;
+                    break;
+                }
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(b_ring + (size_t)bs * kBStageBytes);
+                const uint64_t b_cat = umma_desc_sw128(b_addr);              // 2*NPAD rows: w2 then w1
+                const uint64_t b_w1 = umma_desc_sw128(b_addr + kW1Offset);   // NPAD rows of w1
+                const uint64_t a1 = umma_desc_sw128(a_addr + dyi * kDyBytes);
+                const uint64_t a2 = umma_desc_sw128(a_addr + kPlaneBytes + dyi * kDyBytes);
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
+                        const uint64_t adv = (uint64_t)((ks * kUmmaK * 2) >> 4);  // +32 B per K step, in 16 B units
+                        umma_f16_ss(d_tmem, a1 + adv, b_cat + adv, kIdescCat, (dyi | ks) ? 1u : 0u);
+                        umma_f16_ss(d_tmem, a2 + adv, b_w1 + adv, kIdescOne, 1u);
+                    }
+                    umma_commit(b_empty + bs);  // weight slot reusable once these MMAs have read it
+                }
+                __syncwarp();
+            }
+            if (elect_one_sync()) {
+                umma_commit(a_empty + as);      // patch slot reusable
+                umma_commit(tmem_full + buf);   // unit complete (also fires after an aborted tap loop)
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== accumulate + epilogue warps: TMEM unit -> fp32 registers (RN) ... -> scale, +bias -> pred =====
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;          // accumulator row == cell inside the 8x16 tile
+        const int et = threadIdx.x - kWarpAcc0 * 32;  // 0..127
+        const float inv_sw = p.whdr->inv_scale;
+        float acc[NPAD];
+        int seg_r0 = 0;
+        for (int i = 0; i < n_units; ++i) {
+            const long long u = sc.unit(i);
+            const int tile = (int)(u / p.upt), r = (int)(u % p.upt);
+            if (i == 0 || r == 0 || i == sc.main_len) {
+                seg_r0 = r;
+#pragma unroll
+                for (int n = 0; n < NPAD; ++n) acc[n] = 0.f;
+            }
+            const int buf = i & 1;
+            const uint32_t acc_ph = (uint32_t)(i >> 1) & 1u;
+            if (!mbar_wait(tmem_full + buf, acc_ph, abort_flag)) {
+                if (lane == 0) atomicCAS(p.status, 0, 3);
+                break;
+            }
+            tc_fence_after();
+            __syncwarp();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * kAccCols;
+#pragma unroll
+            for (int n0 = 0; n0 < NPAD; n0 += 16) {
+                uint32_t v[16], w[16];
+                tmem_ld_x16(taddr + n0, v);          // a1*w2 + a2*w1   (x 2^11)
+                tmem_ld_x16(taddr + NPAD + n0, w);   // a1*w1
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    acc[n0 + k] = fadd(acc[n0 + k], fmaf(__uint_as_float(v[k]), kLoInv, __uint_as_float(w[k])));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + buf);  // this warp is done reading the accumulator
+
+            const bool seg_end = (i == n_units - 1) || (r == p.upt - 1) || (i == sc.main_len - 1);
+            if (!seg_end) continue;
+            const bool from_start = seg_r0 == 0, to_end = r == p.upt - 1;
+            if (from_start && !to_end) {
+                // head of a split tile: publish the partial sums for the next CTA (which holds the tail)
+                float4 *dst = reinterpret_cast<float4 *>(p.partial + ((size_t)cta * 128 + row) * NPAD);
+#pragma unroll
+                for (int n = 0; n < NPAD; n += 4) dst[n >> 2] = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+                __threadfence();
+                epi_bar();
+                if (et == 0) st_release(p.flags + cta, 1);
+                continue;
+            }
+            if (!from_start && to_end) {
+                // tail of a split tile (processed last): add the head published by the previous CTA, fixed order
+                if (et == 0) {
+                    unsigned spin = 0;
+                    while (ld_acquire(p.flags + cta - 1) == 0) {
+                        if (++spin > kSpinLimit || *abort_flag) {
+                            *abort_flag = 1;
+                            atomicCAS(p.status, 0, 8);
+                            break;
+                        }
+                    }
+                }
+                epi_bar();  // (on abort keep going: every later wait fails for all four warps at the same unit)
+                const float4 *src = reinterpret_cast<const float4 *>(p.partial + ((size_t)(cta - 1) * 128 + row) * NPAD);
+#pragma unroll
+                for (int n = 0; n < NPAD; n += 4) {
+                    const float4 h = __ldcg(src + (n >> 2));
+                    acc[n] = fadd(h.x, acc[n]); acc[n + 1] = fadd(h.y, acc[n + 1]);
+                    acc[n + 2] = fadd(h.z, acc[n + 2]); acc[n + 3] = fadd(h.w, acc[n + 3]);
+                }
+            } else if (!(from_start && to_end)) {
+                if (lane == 0) atomicCAS(p.status, 0, 9);  // a segment strictly inside a tile: scheduler invariant broken
+                continue;
+            }
+            // whole tile in registers: x 1/(s_a*s_w), + bias -> pred
+            const int img = tile / p.tiles_per_img, t = tile - img * p.tiles_per_img;
+            const int x = (t % p.tiles_x) * kTileX + row % kTileX, y = (t / p.tiles_x) * kTileY + row / kTileX;
+            const float inv = fmul(1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_bits + img))), inv_sw);
+            if (y < p.gh && x < p.gw) {
+                float *out = p.pred + (((size_t)img * p.gh + y) * p.gw + x) * p.cout;
+                if ((p.cout & 3) == 0) {
+                    float4 *o4 = reinterpret_cast<float4 *>(out);
+#pragma unroll
+                    for (int n = 0; n < NPAD; n += 4)
+                        if (n < p.cout)
+                            o4[n >> 2] = make_float4(fadd(fmul(acc[n], inv), s_bias[n]), fadd(fmul(acc[n + 1], inv), s_bias[n + 1]),
+                                                     fadd(fmul(acc[n + 2], inv), s_bias[n + 2]),
+                                                     fadd(fmul(acc[n + 3], inv), s_bias[n + 3]));
+                } else {
+#pragma unroll
+                    for (int n = 0; n < NPAD; ++n)
+                        if (n < p.cout) out[n] = fadd(fmul(acc[n], inv), s_bias[n]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == kWarpMma) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;  // benign race: every thread resolves the same pointer
+    if (fn) return fn;
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+    return fn;
+}
+
+int npad_of(int cout) { return (cout + 15) / 16 * 16; }
+
+constexpr size_t kSmemLimit = 227 * 1024;
+constexpr size_t kCtrlBytes = 1024;
+
+int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+int a_stages_for(int npad) {
+    int s = env_int("SQD_F16_A_STAGES", 2);
+    (void)npad;
+    return s < 1 ? 1 : (s > 4 ? 4 : s);
+}
+
+int b_stages_for(int npad) {
+    const size_t stage = (size_t)2 * npad * kBlockK * 2;
+    size_t s = (kSmemLimit - 1024 /*align*/ - kCtrlBytes - (size_t)a_stages_for(npad) * kAStageBytes) / stage;
+    if (s > 8) s = 8;
+    const int cap = env_int("SQD_F16_B_STAGES", 8);
+    if ((int)s > cap && cap >= 1) s = cap;
+    return (int)s;
+}
+
+size_t smem_bytes_for(int npad, int a_stages, int b_stages) {
+    return 1024 + (size_t)a_stages * kAStageBytes + (size_t)b_stages * 2 * npad * kBlockK * 2 + kCtrlBytes;
+}
+
+int grid_for(int total_tiles) { return total_tiles < SQD_SM_COUNT ? total_tiles : SQD_SM_COUNT; }
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// planes buffer (also the SQD_LAYOUT_SPLIT_NHWC input): [amax bits: B x u32, padded to 256 B][x1 plane][x2 plane]
+struct PlaneLayout {
+    size_t p1_off, p2_off, total;
+};
+PlaneLayout plane_layout(int batch, int cin, int gh, int gw) {
+    PlaneLayout l;
+    const size_t plane = align256((size_t)batch * gh * gw * cin * sizeof(__half));
+    l.p1_off = align256((size_t)batch * sizeof(unsigned));
+    l.p2_off = l.p1_off + plane;
+    l.total = l.p2_off + plane;
+    return l;
+}
+
+// workspace layout: [status (256 B)][flags: 256 ints][partials: #SM*128*npad floats][planes unless pre-split input]
+struct WsLayout {
+    size_t flags_off, partial_off, planes_off, total;
+};
+WsLayout ws_layout(int batch, int cin, int gh, int gw, int cout, int layout) {
+    WsLayout w;
+    w.flags_off = 256;
+    w.partial_off = w.flags_off + 256 * sizeof(int);
+    w.planes_off = align256(w.partial_off + (size_t)SQD_SM_COUNT * 128 * npad_of(cout) * sizeof(float));
+    w.total = w.planes_off + (layout == SQD_LAYOUT_SPLIT_NHWC ? 0 : plane_layout(batch, cin, gh, gw).total);
+    return w;
+}
+
+template <int NPAD>
+int launch_f16(const CUtensorMap *maps, const F16Params &p, int grid, cudaStream_t st) {
+    const size_t smem = smem_bytes_for(NPAD, p.a_stages, p.b_stages);
+    SQD_CUDA(cudaFuncSetAttribute(convdet_f16_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    convdet_f16_kernel<NPAD><<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], p);
+    SQD_LAUNCH_CHECK("convdet_f16_kernel");
+    return SQD_OK;
+}
+
+}  // namespace
+
+size_t sqd_f16_packed_bytes(int cout, int cin) {
+    return kHeaderBytes + (size_t)2 * npad_of(cout) * 9 * cin * sizeof(__half);
+}
+
+int sqd_f16_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, cudaStream_t st) {
+    SQD_REQUIRE(cin % kBlockK == 0, SQD_E_SHAPE, "convdet (tcgen05): Cin %d must be a multiple of %d", cin, kBlockK);
+    SQD_REQUIRE(cout >= 1 && cout <= 128, SQD_E_SHAPE, "convdet (tcgen05): Cout %d outside [1,128]", cout);
+    PackedHeader *hdr = static_cast<PackedHeader *>(d_packed);
+    __half *mat = reinterpret_cast<__half *>(static_cast<char *>(d_packed) + kHeaderBytes);
+    SQD_CUDA(cudaMemsetAsync(d_packed, 0, kHeaderBytes, st));
+    const size_t n = (size_t)cout * cin * 9;
+    weight_absmax_kernel<<<SQD_SM_COUNT, 256, 0, st>>>(d_weight, n, hdr);
+    SQD_LAUNCH_CHECK("weight_absmax_kernel");
+    pack_weights_f16_kernel<<<SQD_SM_COUNT * 4, 256, 0, st>>>(d_weight, cout, cin, npad_of(cout), hdr, mat);
+    SQD_LAUNCH_CHECK("pack_weights_f16_kernel");
+    return SQD_OK;
+}
+
+size_t sqd_f16_split_bytes(int batch, int cin, int gh, int gw) { return plane_layout(batch, cin, gh, gw).total; }
+
+int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, int gh, int gw, void *d_planes,
+                           cudaStream_t st) {
+    SQD_REQUIRE(cin % kBlockK == 0, SQD_E_SHAPE, "convdet (tcgen05): Cin %d must be a multiple of %d", cin, kBlockK);
+    const PlaneLayout pl = plane_layout(batch, cin, gh, gw);
+    char *base = static_cast<char *>(d_planes);
+    unsigned *amax = reinterpret_cast<unsigned *>(base);
+    const int P = gh * gw;
+    const size_t n4 = (size_t)P * cin / 4;
+    SQD_CUDA(cudaMemsetAsync(amax, 0, pl.p1_off, st));
+    {
+        int bx = (int)((n4 + 256 * 8 - 1) / (256 * 8));
+        if (bx > 64) bx = 64;
+        if (bx < 1) bx = 1;
+        absmax_kernel<<<dim3(bx, batch), 256, 0, st>>>(reinterpret_cast<const float4 *>(d_feat), n4, amax);
+        SQD_LAUNCH_CHECK("absmax_kernel");
+    }
+    if (layout == SQD_LAYOUT_NHWC) {
+        int bx = (int)((n4 + 256 * 4 - 1) / (256 * 4));
+        if (bx < 1) bx = 1;
+        split_nhwc_f16_kernel<<<dim3(bx, batch), 256, 0, st>>>(reinterpret_cast<const float4 *>(d_feat),
+                                                              reinterpret_cast<uint2 *>(base + pl.p1_off),
+                                                              reinterpret_cast<uint2 *>(base + pl.p2_off), n4, amax);
+        SQD_LAUNCH_CHECK("split_nhwc_f16_kernel");
+    } else {
+        dim3 grid((P + 63) / 64, cin / 64, batch);
+        split_nchw_f16_kernel<<<grid, 256, 0, st>>>(d_feat, reinterpret_cast<__half2 *>(base + pl.p1_off),
+                                                   reinterpret_cast<__half2 *>(base + pl.p2_off), cin, P, amax);
+        SQD_LAUNCH_CHECK("split_nchw_f16_kernel");
+    }
+    return SQD_OK;
+}
+
+size_t sqd_f16_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout) {
+    return ws_layout(batch, cin, gh, gw, cout, layout).total;
+}
+
+int sqd_convdet_f16(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
+                    int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st) {
+    SQD_REQUIRE(cin % kBlockK == 0, SQD_E_SHAPE, "convdet (tcgen05): Cin %d must be a multiple of %d", cin, kBlockK);
+    SQD_REQUIRE(cout >= 1 && cout <= 128, SQD_E_SHAPE, "convdet (tcgen05): Cout %d outside [1,128]", cout);
+    EncodeTiledFn encode = get_encode_fn();
+    SQD_REQUIRE(encode != nullptr, SQD_E_DRIVER, "cuTensorMapEncodeTiled not available from the CUDA driver");
+    const int npad = npad_of(cout);
+    const WsLayout w = ws_layout(batch, cin, gh, gw, cout, layout);
+    char *ws = static_cast<char *>(d_workspace);
+    int *status = reinterpret_cast<int *>(ws);
+    int *flags = reinterpret_cast<int *>(ws + w.flags_off);
+    float *partial = reinterpret_cast<float *>(ws + w.partial_off);
+    SQD_CUDA(cudaMemsetAsync(ws, 0, w.partial_off, st));  // status + flags
+
+    // 1. fp16 planes (x1, x2) + per-image max: from the workspace, or handed in pre-split
+    const char *planes = reinterpret_cast<const char *>(d_feat);
+    if (layout != SQD_LAYOUT_SPLIT_NHWC) {
+        int rc = sqd_f16_split_features(d_feat, layout, batch, cin, gh, gw, ws + w.planes_off, st);
+        if (rc) return rc;
+        planes = ws + w.planes_off;
+    }
+    const PlaneLayout pl = plane_layout(batch, cin, gh, gw);
+
+    // 2. tensor maps
+    alignas(64) CUtensorMap maps[3];
+    for (int i = 0; i < 2; ++i) {
+        const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)gw, (cuuint64_t)gh, (cuuint64_t)batch};
+        const cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)gw * cin * 2, (cuuint64_t)gh * gw * cin * 2};
+        const cuuint32_t box[4] = {kBlockK, kTileX, kPatchY, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        void *base = const_cast<char *>(planes + (i == 0 ? pl.p1_off : pl.p2_off));
+        CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SQD_REQUIRE(r == CUDA_SUCCESS, SQD_E_DRIVER, "cuTensorMapEncodeTiled(features) failed: CUresult %d", (int)r);
+    }
+    {
+        const size_t ktot = (size_t)9 * cin;
+        void *mat = const_cast<char *>(static_cast<const char *>(d_packed) + kHeaderBytes);
+        const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)(2 * npad)};
+        const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+        const cuuint32_t box[2] = {kBlockK, (cuuint32_t)(2 * npad)};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&maps[2], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, mat, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SQD_REQUIRE(r == CUDA_SUCCESS, SQD_E_DRIVER, "cuTensorMapEncodeTiled(weights) failed: CUresult %d", (int)r);
+    }
+
+    // 3. the persistent GEMM
+    F16Params p;
+    p.cin = cin; p.gh = gh; p.gw = gw; p.cout = cout;
+    p.tiles_x = (gw + kTileX - 1) / kTileX;
+    p.tiles_per_img = p.tiles_x * ((gh + kTileY - 1) / kTileY);
+    const long long total_tiles = (long long)p.tiles_per_img * batch;
+    SQD_REQUIRE(total_tiles < (1ll << 30), SQD_E_SHAPE, "convdet (tcgen05): too many tiles");
+    p.total_tiles = (int)total_tiles;
+    p.upt = cin / kBlockK * 3;
+    const int grid = grid_for(p.total_tiles);
+    const long long total_units = total_tiles * p.upt;
+    long long upc = (total_units + grid - 1) / grid;
+    if (upc < p.upt) upc = p.upt;  // grid == #tiles: whole tiles only
+    p.units_per_cta = (int)upc;
+    p.a_stages = a_stages_for(npad);
+    p.b_stages = b_stages_for(npad);
+    p.bias = d_bias;
+    p.amax_bits = reinterpret_cast<const unsigned *>(planes);
+    p.whdr = static_cast<const PackedHeader *>(d_packed);
+    p.pred = d_pred;
+    p.partial = partial;
+    p.flags = flags;
+    p.status = status;
+    switch (npad / 16) {
+        case 1: return launch_f16<16>(maps, p, grid, st);
+        case 2: return launch_f16<32>(maps, p, grid, st);
+        case 3: return launch_f16<48>(maps, p, grid, st);
+        case 4: return launch_f16<64>(maps, p, grid, st);
+        case 5: return launch_f16<80>(maps, p, grid, st);
+        case 6: return launch_f16<96>(maps, p, grid, st);
+        case 7: return launch_f16<112>(maps, p, grid, st);
+        case 8: return launch_f16<128>(maps, p, grid, st);
+    }
+    SQD_REQUIRE(false, SQD_E_SHAPE, "convdet (tcgen05): unsupported Cout %d", cout);
+}

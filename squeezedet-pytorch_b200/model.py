@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import CONV_TCGEN05_3XTF32
+from ._lib import CONV_TCGEN05_F16X3
 
 
 class Fire(nn.Module):
@@ -84,7 +84,7 @@ class SqueezeDetBase(nn.Module):
         self.features = nn.Sequential(*layers)
         self.dropout = nn.Dropout(cfg.dropout_prob, inplace=True) if cfg.dropout_prob > 0 else None
         self.convdet = nn.Conv2d(head_in, cfg.anchors_per_grid * (cfg.num_classes + 5), kernel_size=3, padding=1)
-        self.conv_algo = getattr(cfg, "conv_algo", CONV_TCGEN05_3XTF32)
+        self.conv_algo = getattr(cfg, "conv_algo", CONV_TCGEN05_F16X3)
         self._packed = None
         self._packed_version = None
         self.init_weights()

@@ -11,7 +11,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import CONV_SIMT_FP32, CONV_TCGEN05_3XTF32, LAYOUT_NCHW, LAYOUT_NHWC, check, load, ptr, stream_ptr, workspace
+from ._lib import CONV_SIMT_FP32, CONV_TCGEN05_F16X3, LAYOUT_NCHW, LAYOUT_NHWC, check, load, ptr, stream_ptr, workspace
 
 
 @dataclass
@@ -71,7 +71,7 @@ def pack_convdet_weights(weight: torch.Tensor) -> torch.Tensor:
     return packed
 
 
-def convdet_forward(feat, weight, bias, packed=None, algo=CONV_TCGEN05_3XTF32, num_fields=None, check_status=False):
+def convdet_forward(feat, weight, bias, packed=None, algo=CONV_TCGEN05_F16X3, num_fields=None, check_status=False):
     """feat (B,Cin,gh,gw) -> pred (B, gh*gw*K, C+5) [or (B,gh,gw,Cout) when num_fields is None]."""
     lib = load()
     layout, x = feature_layout(feat)
@@ -141,7 +141,7 @@ def detect_from_pred(pred, anchors_f32, input_hw, num_classes, top_k, nms_thresh
 
 
 def head_detect(feat, weight, bias, anchors_f32, anchors_per_grid, num_classes, input_hw, top_k, nms_thresh,
-                score_thresh, packed=None, algo=CONV_TCGEN05_3XTF32, out: Detections = None) -> Detections:
+                score_thresh, packed=None, algo=CONV_TCGEN05_F16X3, out: Detections = None) -> Detections:
     """Fire11 features -> final detections (ConvDet + decode + top-k + NMS) through one ABI call."""
     lib = load()
     layout, x = feature_layout(feat)

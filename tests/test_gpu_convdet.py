@@ -38,14 +38,14 @@ def _err(a, b):
 @pytest.mark.parametrize("algo_name", ["simt", "tcgen05"])
 @pytest.mark.parametrize("layout", ["nchw", "channels_last"])
 def test_convdet_vs_reference_golden(ops, golden, name, algo_name, layout):
-    from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32, CONV_TCGEN05_3XTF32
+    from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32, CONV_TCGEN05_F16X3
     g = golden("head_e2e_" + name)
     shp = SHAPES[name]
     feat, w, b = _case(g, shp)
     x = dev(feat)
     if layout == "channels_last":
         x = x.contiguous(memory_format=torch.channels_last)
-    algo = CONV_SIMT_FP32 if algo_name == "simt" else CONV_TCGEN05_3XTF32
+    algo = CONV_SIMT_FP32 if algo_name == "simt" else CONV_TCGEN05_F16X3
     pred = ops.convdet_forward(x, dev(w), dev(b), algo=algo, num_fields=shp.num_fields, check_status=True)
     assert pred.shape == (feat.shape[0], shp.num_anchors, shp.num_fields)
     got = pred.cpu().numpy()
@@ -58,14 +58,14 @@ def test_convdet_vs_reference_golden(ops, golden, name, algo_name, layout):
 def test_convdet_accuracy_vs_float64(ops):
     """Error of each fp32 implementation against a float64 evaluation (tiny shape): the 3xTF32
     tensor-core kernel must be as accurate as fp32 CUDA-core FMA / the reference's CPU conv."""
-    from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32, CONV_TCGEN05_3XTF32
+    from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32, CONV_TCGEN05_F16X3
     shp = synth.TINY
     feat = synth.features(shp, 2, 77)
     w, b = synth.convdet_params(shp, 78)
     p64 = orc.convdet_forward_f64(feat, w, b, shp.num_anchors, shp.num_fields)
     ref32 = orc.convdet_forward(feat, w, b, shp.num_anchors, shp.num_fields)
     simt = ops.convdet_forward(dev(feat), dev(w), dev(b), algo=CONV_SIMT_FP32, num_fields=shp.num_fields).cpu().numpy()
-    tc = ops.convdet_forward(dev(feat), dev(w), dev(b), algo=CONV_TCGEN05_3XTF32, num_fields=shp.num_fields,
+    tc = ops.convdet_forward(dev(feat), dev(w), dev(b), algo=CONV_TCGEN05_F16X3, num_fields=shp.num_fields,
                              check_status=True).cpu().numpy()
     e_ref, e_simt, e_tc = _err(ref32, p64), _err(simt, p64), _err(tc, p64)
     print(f"vs float64: torch-cpu max/rms {e_ref}, simt {e_simt}, tcgen05-3xtf32 {e_tc}")
@@ -104,13 +104,13 @@ def test_head_to_detections_kept_indices(ops, golden, name):
 def test_head_properties_full_batch(ops):
     """BASELINE configs[1] size (B=20, KITTI): tcgen05 vs SIMT on the GPU, linearity of the conv in its
     input, and equality of the fused ABI call with the staged one."""
-    from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32, CONV_TCGEN05_3XTF32
+    from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32, CONV_TCGEN05_F16X3
     shp = synth.KITTI
     g = torch.Generator(device="cuda").manual_seed(5)
     feat = torch.relu(torch.randn((20, shp.in_channels, *shp.grid_hw), generator=g, device="cuda"))
     w, b = synth.convdet_params(shp, 9)
     w, b = dev(w), dev(b)
-    tc = ops.convdet_forward(feat, w, b, algo=CONV_TCGEN05_3XTF32, num_fields=8, check_status=True)
+    tc = ops.convdet_forward(feat, w, b, algo=CONV_TCGEN05_F16X3, num_fields=8, check_status=True)
     simt = ops.convdet_forward(feat, w, b, algo=CONV_SIMT_FP32, num_fields=8)
     assert torch.allclose(tc, simt, rtol=1e-4, atol=2e-5), float((tc - simt).abs().max())
     zero_b = torch.zeros_like(b)

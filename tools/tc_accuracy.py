@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import oracle as orc  # noqa: E402
 from squeezedet_pytorch_b200 import ops, synth  # noqa: E402
-from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32, CONV_TCGEN05_3XTF32  # noqa: E402
+from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32, CONV_TCGEN05_F16X3  # noqa: E402
 
 shp = synth.KITTI
 feat = synth.features(shp, 2, 32)
@@ -34,7 +34,7 @@ simt = ops.convdet_forward(x, wd, bd, algo=CONV_SIMT_FP32, num_fields=8).cpu().n
 print("SIMT fp32 FMA             %.3e  %.3e  %+.3e" % err(simt))
 for chunk in (1, 2, 3, 4, 6, 8, 12, 24, 72, 216):
     os.environ["SQD_TC_CHUNK"] = str(chunk)
-    out = ops.convdet_forward(x, wd, bd, algo=CONV_TCGEN05_3XTF32, num_fields=8, check_status=True).cpu().numpy()
+    out = ops.convdet_forward(x, wd, bd, algo=CONV_TCGEN05_F16X3, num_fields=8, check_status=True).cpu().numpy()
     packed = ops.pack_convdet_weights(wd)
     for _ in range(3):
         ops.convdet_forward(big, wd, bd, packed=packed)
