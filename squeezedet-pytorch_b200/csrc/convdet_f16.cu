@@ -218,6 +218,7 @@ struct F16Params {
     int upt;            // units per tile = (cin/64) * 3
     int units_per_cta;  // even cut of total_tiles*upt over the grid (>= upt)
     int a_stages, b_stages;
+    int dbg;            // debug (SQD_F16_DBG): 1 = skip MMA issue, 2 = skip A loads, 4 = skip B loads
     const float *bias;
     const unsigned *amax_bits;   // (B) max|x| per image, fp32 bits
     const PackedHeader *whdr;
@@ -225,6 +226,8 @@ struct F16Params {
     float *partial;  // (grid, 128, NPAD) partial sums of split tiles
     int *flags;      // (grid) 1 = partial[cta] published
     int *status;     // 0 ok; else the role whose bounded wait timed out
+    long long *trace;  // debug (SQD_F16_TRACE = device address): per-unit clock64 stamps of CTA trace_cta, 32 slots per unit
+    int trace_cta;
 };
 
 struct Sched {  // the permuted unit sequence of one CTA: [whole tiles + head segment][deferred tail segment]
@@ -235,6 +238,60 @@ struct Sched {  // the permuted unit sequence of one CTA: [whole tiles + head se
         return i < main_len ? u0 + len_tail + i : u0 + (i - main_len);
     }
 };
+
+// Walks the unit sequence of a CTA without per-unit divisions: (tile, r) are decoded from the linear unit index only
+// at the two points where the sequence jumps (i == 0 and i == main_len) and stepped incrementally otherwise.
+struct UnitIter {
+    int tile, r;          // tile index, unit index inside the tile (r = cb*3 + dxi)
+    int cb, dxi;          // 64-channel block, dx tap
+    int img, tx, ty;      // image, tile column / row inside the image
+    __device__ __forceinline__ void seek(long long u, const F16Params &p);
+    __device__ __forceinline__ void next(const F16Params &p);
+};
+
+#define SQD_TRACE(slot, i) \
+    do { if (p.trace && cta == p.trace_cta && lane == 0 && (i) < 512) p.trace[(i) * 32 + (slot)] = clock64(); } while (0)
+
+struct Ring {  // stage index + phase bit of a circular buffer of n stages
+    int s;
+    uint32_t ph;
+    __device__ __forceinline__ void advance(int n) {
+        if (++s == n) {
+            s = 0;
+            ph ^= 1u;
+        }
+    }
+};
+
+__device__ __forceinline__ void UnitIter::seek(long long u, const F16Params &p) {
+    tile = (int)(u / p.upt);
+    r = (int)(u - (long long)tile * p.upt);
+    cb = r / 3;
+    dxi = r - cb * 3;
+    img = tile / p.tiles_per_img;
+    const int t = tile - img * p.tiles_per_img;
+    ty = t / p.tiles_x;
+    tx = t - ty * p.tiles_x;
+}
+__device__ __forceinline__ void UnitIter::next(const F16Params &p) {
+    ++r;
+    if (++dxi == 3) {
+        dxi = 0;
+        ++cb;
+    }
+    if (r == p.upt) {
+        r = 0;
+        cb = 0;
+        ++tile;
+        if (++tx == p.tiles_x) {
+            tx = 0;
+            if (++ty * p.tiles_x == p.tiles_per_img) {
+                ty = 0;
+                ++img;
+            }
+        }
+    }
+}
 
 template <int NPAD>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -314,100 +371,111 @@ convdet_f16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
 
     if (warp == kWarpATma) {
         // ===== A producer: the x1 and x2 patches of one unit (warp stays converged, one elected lane issues) =====
+        UnitIter it;
+        Ring ra{0, 0};
         for (int i = 0; i < n_units; ++i) {
-            const int s = i % AS;
-            const uint32_t ph = (uint32_t)(i / AS) & 1u;
-            if (!mbar_wait_warp(a_empty + s, ph ^ 1u, abort_flag)) {
+            if (i == 0 || i == sc.main_len) it.seek(sc.unit(i), p); else it.next(p);
+            if (!mbar_wait_warp(a_empty + ra.s, ra.ph ^ 1u, abort_flag)) {
                 if (lane == 0) atomicCAS(p.status, 0, 1);
                 break;
             }
-            const long long u = sc.unit(i);
-            const int tile = (int)(u / p.upt), r = (int)(u % p.upt);
-            const int cb = r / 3, dxi = r - cb * 3;
-            const int img = tile / p.tiles_per_img, t = tile - img * p.tiles_per_img;
-            const int x0 = (t % p.tiles_x) * kTileX, y0 = (t / p.tiles_x) * kTileY;
+            SQD_TRACE(0, i);
             if (elect_one_sync()) {
-                uint8_t *st = a_ring + (size_t)s * kAStageBytes;
-                mbar_arrive_expect_tx(a_full + s, kAStageBytes);
-                tma_load_4d(&map_a1, a_full + s, st, cb * kBlockK, x0 + dxi - 1, y0 - 1, img);
-                tma_load_4d(&map_a2, a_full + s, st + kPlaneBytes, cb * kBlockK, x0 + dxi - 1, y0 - 1, img);
+                uint8_t *st = a_ring + (size_t)ra.s * kAStageBytes;
+                const int x = it.tx * kTileX + it.dxi - 1, y = it.ty * kTileY - 1;
+                if (p.dbg & 2) {
+                    mbar_arrive(a_full + ra.s);
+                } else {
+                    mbar_arrive_expect_tx(a_full + ra.s, kAStageBytes);
+                    tma_load_4d(&map_a1, a_full + ra.s, st, it.cb * kBlockK, x, y, it.img);
+                    tma_load_4d(&map_a2, a_full + ra.s, st + kPlaneBytes, it.cb * kBlockK, x, y, it.img);
+                }
             }
             __syncwarp();
+            ra.advance(AS);
         }
     } else if (warp == kWarpBTma) {
         // ===== B producer: the [w2 | w1] tile of one tap per step =====
+        UnitIter it;
+        Ring rb{0, 0};
         bool ok = true;
         for (int i = 0; i < n_units && ok; ++i) {
-            const long long u = sc.unit(i);
-            const int r = (int)(u % p.upt);
-            const int cb = r / 3, dxi = r - cb * 3;
+            if (i == 0 || i == sc.main_len) it.seek(sc.unit(i), p); else it.next(p);
             for (int dyi = 0; dyi < 3; ++dyi) {
-                const int j = i * 3 + dyi;
-                const int s = j % BS;
-                const uint32_t ph = (uint32_t)(j / BS) & 1u;
-                if (!mbar_wait_warp(b_empty + s, ph ^ 1u, abort_flag)) {
+                if (!mbar_wait_warp(b_empty + rb.s, rb.ph ^ 1u, abort_flag)) {
                     if (lane == 0) atomicCAS(p.status, 0, 5);
                     ok = false;
                     break;
                 }
-                const int tap = dyi * 3 + dxi;
+                if (dyi == 0) SQD_TRACE(1, i);
+                const int tap = dyi * 3 + it.dxi;
                 if (elect_one_sync()) {
-                    mbar_arrive_expect_tx(b_full + s, kBStageBytes);
-                    tma_load_2d(&map_b, b_full + s, b_ring + (size_t)s * kBStageBytes, tap * p.cin + cb * kBlockK, 0);
+                    if (p.dbg & 4) {
+                        mbar_arrive(b_full + rb.s);
+                    } else {
+                        mbar_arrive_expect_tx(b_full + rb.s, kBStageBytes);
+                        tma_load_2d(&map_b, b_full + rb.s, b_ring + (size_t)rb.s * kBStageBytes, tap * p.cin + it.cb * kBlockK, 0);
+                    }
                 }
                 __syncwarp();
+                rb.advance(BS);
             }
         }
     } else if (warp == kWarpMma) {
         // ===== MMA issuer: 24 SS-mode MMAs per unit into a fresh TMEM accumulator.  The warp stays converged and
         // one elected lane issues, so descriptors live in uniform registers. =====
+        Ring ra{0, 0}, rb{0, 0};
         bool ok = true;
         for (int i = 0; i < n_units && ok; ++i) {
             const int buf = i & 1;
             const uint32_t acc_ph = (uint32_t)(i >> 1) & 1u;
-            const int as = i % AS;
-            const uint32_t a_ph = (uint32_t)(i / AS) & 1u;
             if (!mbar_wait_warp(tmem_empty + buf, acc_ph ^ 1u, abort_flag)) {
                 if (lane == 0) atomicCAS(p.status, 0, 4);
                 break;
             }
-            if (!mbar_wait_warp(a_full + as, a_ph, abort_flag)) {
+            SQD_TRACE(2, i);
+            if (!mbar_wait_warp(a_full + ra.s, ra.ph, abort_flag)) {
                 if (lane == 0) atomicCAS(p.status, 0, 2);
                 break;
             }
+            SQD_TRACE(3, i);
             const uint32_t d_tmem = tmem_base + (uint32_t)buf * kAccCols;
-            const uint32_t a_addr = smem_u32(a_ring + (size_t)as * kAStageBytes);
+            const uint32_t a_addr = smem_u32(a_ring + (size_t)ra.s * kAStageBytes);
             for (int dyi = 0; dyi < 3; ++dyi) {
-                const int j = i * 3 + dyi;
-                const int bs = j % BS;
-                const uint32_t b_ph = (uint32_t)(j / BS) & 1u;
-                if (!mbar_wait_warp(b_full + bs, b_ph, abort_flag)) {
+                if (!mbar_wait_warp(b_full + rb.s, rb.ph, abort_flag)) {
                     if (lane == 0) atomicCAS(p.status, 0, 6);
                     ok = false;
                     break;
                 }
+                SQD_TRACE(4 + 2 * dyi, i);
                 tc_fence_after();
-                const uint32_t b_addr = smem_u32(b_ring + (size_t)bs * kBStageBytes);
+                const uint32_t b_addr = smem_u32(b_ring + (size_t)rb.s * kBStageBytes);
                 const uint64_t b_cat = umma_desc_sw128(b_addr);              // 2*NPAD rows: w2 then w1
                 const uint64_t b_w1 = umma_desc_sw128(b_addr + kW1Offset);   // NPAD rows of w1
                 const uint64_t a1 = umma_desc_sw128(a_addr + dyi * kDyBytes);
                 const uint64_t a2 = umma_desc_sw128(a_addr + kPlaneBytes + dyi * kDyBytes);
                 if (elect_one_sync()) {
+                    if (!(p.dbg & 1)) {
 #pragma unroll
-                    for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
-                        const uint64_t adv = (uint64_t)((ks * kUmmaK * 2) >> 4);  // +32 B per K step, in 16 B units
-                        umma_f16_ss(d_tmem, a1 + adv, b_cat + adv, kIdescCat, (dyi | ks) ? 1u : 0u);
-                        umma_f16_ss(d_tmem, a2 + adv, b_w1 + adv, kIdescOne, 1u);
+                        for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
+                            const uint64_t adv = (uint64_t)((ks * kUmmaK * 2) >> 4);  // +32 B per K step, in 16 B units
+                            umma_f16_ss(d_tmem, a1 + adv, b_cat + adv, kIdescCat, (dyi | ks) ? 1u : 0u);
+                            umma_f16_ss(d_tmem, a2 + adv, b_w1 + adv, kIdescOne, 1u);
+                        }
                     }
-                    umma_commit(b_empty + bs);  // weight slot reusable once these MMAs have read it
+                    umma_commit(b_empty + rb.s);  // weight slot reusable once these MMAs have read it
                 }
                 __syncwarp();
+                SQD_TRACE(5 + 2 * dyi, i);
+                rb.advance(BS);
             }
             if (elect_one_sync()) {
-                umma_commit(a_empty + as);      // patch slot reusable
+                umma_commit(a_empty + ra.s);    // patch slot reusable
                 umma_commit(tmem_full + buf);   // unit complete (also fires after an aborted tap loop)
             }
             __syncwarp();
+            SQD_TRACE(10, i);
+            ra.advance(AS);
         }
     } else {
         // ===== accumulate + epilogue warps: TMEM unit -> fp32 registers (RN) ... -> scale, +bias -> pred =====
@@ -417,9 +485,10 @@ convdet_f16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
         const float inv_sw = p.whdr->inv_scale;
         float acc[NPAD];
         int seg_r0 = 0;
+        UnitIter it;
         for (int i = 0; i < n_units; ++i) {
-            const long long u = sc.unit(i);
-            const int tile = (int)(u / p.upt), r = (int)(u % p.upt);
+            if (i == 0 || i == sc.main_len) it.seek(sc.unit(i), p); else it.next(p);
+            const int r = it.r;
             if (i == 0 || r == 0 || i == sc.main_len) {
                 seg_r0 = r;
 #pragma unroll
@@ -433,6 +502,7 @@ convdet_f16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
             }
             tc_fence_after();
             __syncwarp();
+            if (warp == kWarpAcc0) SQD_TRACE(11, i);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * kAccCols;
 #pragma unroll
             for (int n0 = 0; n0 < NPAD; n0 += 16) {
@@ -447,6 +517,7 @@ convdet_f16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + buf);  // this warp is done reading the accumulator
+            if (warp == kWarpAcc0) SQD_TRACE(12, i);
 
             const bool seg_end = (i == n_units - 1) || (r == p.upt - 1) || (i == sc.main_len - 1);
             if (!seg_end) continue;
@@ -486,11 +557,10 @@ convdet_f16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
                 continue;
             }
             // whole tile in registers: x 1/(s_a*s_w), + bias -> pred
-            const int img = tile / p.tiles_per_img, t = tile - img * p.tiles_per_img;
-            const int x = (t % p.tiles_x) * kTileX + row % kTileX, y = (t / p.tiles_x) * kTileY + row / kTileX;
-            const float inv = fmul(1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_bits + img))), inv_sw);
+            const int x = it.tx * kTileX + row % kTileX, y = it.ty * kTileY + row / kTileX;
+            const float inv = fmul(1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_bits + it.img))), inv_sw);
             if (y < p.gh && x < p.gw) {
-                float *out = p.pred + (((size_t)img * p.gh + y) * p.gw + x) * p.cout;
+                float *out = p.pred + (((size_t)it.img * p.gh + y) * p.gw + x) * p.cout;
                 if ((p.cout & 3) == 0) {
                     float4 *o4 = reinterpret_cast<float4 *>(out);
 #pragma unroll
@@ -726,6 +796,7 @@ int sqd_convdet_f16(const float *d_feat, int layout, const void *d_packed, const
     p.units_per_cta = (int)upc;
     p.a_stages = a_stages_for(npad);
     p.b_stages = b_stages_for(npad);
+    p.dbg = env_int("SQD_F16_DBG", 0);
     p.bias = d_bias;
     p.amax_bits = reinterpret_cast<const unsigned *>(planes);
     p.whdr = static_cast<const PackedHeader *>(d_packed);
@@ -733,6 +804,9 @@ int sqd_convdet_f16(const float *d_feat, int layout, const void *d_packed, const
     p.partial = partial;
     p.flags = flags;
     p.status = status;
+    p.trace = nullptr;
+    p.trace_cta = env_int("SQD_F16_TRACE_CTA", 0);
+    if (const char *e = getenv("SQD_F16_TRACE")) p.trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
     switch (npad / 16) {
         case 1: return launch_f16<16>(maps, p, grid, st);
         case 2: return launch_f16<32>(maps, p, grid, st);

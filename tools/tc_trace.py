@@ -1,40 +1,67 @@
-"""Debug: per-unit pipeline timeline of CTA 0 of the tcgen05 ConvDet kernel (clock64 stamps)."""
-import os, sys
+"""Debug: per-unit pipeline timeline of one CTA of the tcgen05 ConvDet kernel (clock64 stamps).
+usage: python tools/tc_trace.py [SQD_F16_DBG=7 ...]   (each argument = one env setting to trace under)"""
+import ctypes as C
+import os
+import sys
+
 import numpy as np
 import torch
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from squeezedet_pytorch_b200 import ops, synth
+from squeezedet_pytorch_b200 import _lib, ops, synth  # noqa: E402
 
-shp = synth.KITTI
-feat = torch.relu(torch.randn((20, 768, 24, 78), device="cuda")).contiguous(memory_format=torch.channels_last)
+shp, B = synth.KITTI, 20
+lib = _lib.load()
+dev = torch.device("cuda")
+feat = torch.relu(torch.randn((B, 768, 24, 78), device=dev))
 w, b = synth.convdet_params(shp, 9)
-w, b = torch.from_numpy(w).cuda(), torch.from_numpy(b).cuda()
+w, b = torch.from_numpy(w).to(dev), torch.from_numpy(b).to(dev)
 packed = ops.pack_convdet_weights(w)
-for _ in range(3):
-    ops.convdet_forward(feat, w, b, packed=packed)
-trace = torch.zeros((512, 32), dtype=torch.int64, device="cuda")
-os.environ["SQD_TC_TRACE"] = hex(trace.data_ptr())
-ops.convdet_forward(feat, w, b, packed=packed, check_status=True)
-del os.environ["SQD_TC_TRACE"]
-t = trace.cpu().numpy()
-n = int((t[:, 3] > 0).sum())
-t0 = t[0, 0]
-names = ["A_tma_issue", "cvt_start", "cvt_done", "mma_start", "mma_issued", "acc_start", "acc_done", "B_tma_issue",
-         "c0_computed", "c0_slotfree", "c0_stored", "c1_computed", "c1_slotfree", "c1_stored", "c2_computed", "-"]
-print("unit " + " ".join(f"{x:>12s}" for x in names) + "   (cycles since first A issue)")
-for i in list(range(0, 6)) + list(range(70, 74)) + list(range(n - 3, n)):
-    print(f"{i:4d} " + " ".join(f"{int(v - t0):9d}" for v in t[i][:25]))
-d = np.diff(t[:n, 3])
-print("units", n, "mean period (mma_start to mma_start)", d.mean(), "median", np.median(d))
-print("mean cvt_start - A_issue (TMA latency)", (t[:n, 1] - t[:n, 0]).mean(), " cvt duration", (t[:n, 2] - t[:n, 1]).mean())
-print("mean mma_start - cvt_done", (t[:n, 3] - t[:n, 2]).mean(), " mma issue duration", (t[:n, 4] - t[:n, 3]).mean())
-print("mean acc_start - mma_issued (MMA drain)", (t[:n, 5] - t[:n, 4]).mean(), " acc duration", (t[:n, 6] - t[:n, 5]).mean())
-print("converter dy0: compute", (t[:n, 8] - t[:n, 1]).mean(), "wait slot", (t[:n, 9] - t[:n, 8]).mean(), "store", (t[:n, 10] - t[:n, 9]).mean())
-print("converter dy1: compute", (t[:n, 11] - t[:n, 10]).mean(), "wait slot", (t[:n, 12] - t[:n, 11]).mean(), "store", (t[:n, 13] - t[:n, 12]).mean())
-print("converter dy2: compute", (t[:n, 14] - t[:n, 13]).mean())
-for d in range(3):
-    print(f"mma dy{d}: wait A slot", (t[1:n, 16 + 3 * d] - (t[1:n, 3] if d == 0 else t[1:n, 16 + 3 * d - 1])).mean(),
-          "wait B", (t[1:n, 17 + 3 * d] - t[1:n, 16 + 3 * d]).mean(), "issue", (t[1:n, 18 + 3 * d] - t[1:n, 17 + 3 * d]).mean())
-print("A ready(i,0) - c0_stored(i)", (t[1:n, 16] - t[1:n, 10]).mean(), " slot0 free seen by converter(i+1) - step(i,0) issued", (t[2:n, 9] - t[1:n - 1, 18]).mean())
-print("B issue(i, dy0) lead over mma need:", (t[1:n, 17] - t[1:n, 7]).mean())
+gh, gw = shp.grid_hw
+planes = torch.empty(lib.sqd_convdet_split_bytes(B, 768, gh, gw), dtype=torch.uint8, device=dev)
+st = _lib.stream_ptr(dev)
+_lib.check(lib.sqd_convdet_split_features(C.c_void_p(feat.data_ptr()), 0, B, 768, gh, gw, _lib.ptr(planes), st), "split")
+ws = torch.empty(lib.sqd_convdet_workspace_bytes(B, 768, gh, gw, 72, 2, 0), dtype=torch.uint8, device=dev)
+pred = torch.empty((B, gh, gw, 72), device=dev)
+
+
+def gemm():
+    _lib.check(lib.sqd_convdet_forward(_lib.ptr(planes), 2, _lib.ptr(packed), None, _lib.ptr(b), B, 768, gh, gw, 72,
+                                       _lib.ptr(pred), _lib.ptr(ws), ws.numel(), 0, st), "gemm")
+
+
+NAMES = ["A_issue", "B_issue0", "m_tmem_ok", "m_a_ok", "m_b0_ok", "m_b0_iss", "m_b1_ok", "m_b1_iss", "m_b2_ok", "m_b2_iss",
+         "m_end", "acc_start", "acc_done"]
+for setting in (sys.argv[1:] or [""]):
+    keys = []
+    for kv in filter(None, setting.split(",")):
+        k, v = kv.split("=")
+        os.environ[k] = v
+        keys.append(k)
+    for _ in range(3):
+        gemm()
+    trace = torch.zeros((512, 32), dtype=torch.int64, device=dev)
+    os.environ["SQD_F16_TRACE"] = hex(trace.data_ptr())
+    gemm()
+    torch.cuda.synchronize()
+    del os.environ["SQD_F16_TRACE"]
+    t = trace.cpu().numpy()
+    n = int((t[:, 10] > 0).sum())
+    t0 = t[0, 0]
+    print(f"==== {setting or 'default'}: {n} units traced")
+    print("unit " + " ".join(f"{x:>9s}" for x in NAMES))
+    for i in list(range(0, 5)) + list(range(36, 40)) + list(range(n - 3, n)):
+        print(f"{i:4d} " + " ".join(f"{int(v - t0):9d}" for v in t[i][:13]))
+    m = slice(2, n - 2)
+    print("period (m_end to m_end): mean %.0f median %.0f" % (np.diff(t[:n, 10]).mean(), np.median(np.diff(t[:n, 10]))))
+    print("mma: wait tmem_empty %.0f | wait a_full %.0f | per dy: wait b_full %.0f %.0f %.0f, issue %.0f %.0f %.0f | tail commits %.0f | loop back %.0f" % (
+        (t[m, 2] - t[1:n - 3, 10]).mean(), (t[m, 3] - t[m, 2]).mean(),
+        (t[m, 4] - t[m, 3]).mean(), (t[m, 6] - t[m, 5]).mean(), (t[m, 8] - t[m, 7]).mean(),
+        (t[m, 5] - t[m, 4]).mean(), (t[m, 7] - t[m, 6]).mean(), (t[m, 9] - t[m, 8]).mean(),
+        (t[m, 10] - t[m, 9]).mean(), 0.0))
+    print("acc: start after m_end %.0f | drain duration %.0f | idle between drains %.0f" % (
+        (t[m, 11] - t[m, 10]).mean(), (t[m, 12] - t[m, 11]).mean(), (t[3:n - 1, 11] - t[m, 12]).mean()))
+    print("A issue lead over m_a_ok %.0f | B issue(dy0) lead over m_b0_ok %.0f" % ((t[m, 3] - t[m, 0]).mean(), (t[m, 4] - t[m, 1]).mean()))
+    for k in keys:
+        del os.environ[k]
