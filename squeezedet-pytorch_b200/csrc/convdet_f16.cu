@@ -86,13 +86,24 @@ __device__ __forceinline__ void split_f16(float xs, __half &h1, __half &h2) {
 // ---------------------------------------------------------------------------------------------------
 // max |x| per image (any layout: an image is one contiguous run of n4 float4).  Non-negative floats order like
 // their bit patterns, so the reduction is an integer atomicMax.  NaN inputs are ignored by fmaxf.
-__global__ void absmax_kernel(const float4 *__restrict__ in, size_t n4, unsigned *__restrict__ amax_bits) {
+__global__ void __launch_bounds__(256) absmax_kernel(const float4 *__restrict__ in, size_t n4, unsigned *__restrict__ amax_bits) {
     const float4 *src = in + (size_t)blockIdx.y * n4;
-    float m = 0.f;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        const float4 v = __ldg(src + i);
-        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {  // four independent 16-byte loads in flight per thread
+        const float4 a = ld_stream_f4(src + i), b = ld_stream_f4(src + i + stride);
+        const float4 c = ld_stream_f4(src + i + 2 * stride), d = ld_stream_f4(src + i + 3 * stride);
+        m0 = fmaxf(fmaxf(m0, fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
+        m1 = fmaxf(fmaxf(m1, fmaxf(fabsf(b.x), fabsf(b.y))), fmaxf(fabsf(b.z), fabsf(b.w)));
+        m2 = fmaxf(fmaxf(m2, fmaxf(fabsf(c.x), fabsf(c.y))), fmaxf(fabsf(c.z), fabsf(c.w)));
+        m3 = fmaxf(fmaxf(m3, fmaxf(fabsf(d.x), fabsf(d.y))), fmaxf(fabsf(d.z), fabsf(d.w)));
     }
+    for (; i < n4; i += stride) {
+        const float4 a = ld_stream_f4(src + i);
+        m0 = fmaxf(fmaxf(m0, fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
+    }
+    float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 #pragma unroll
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     __shared__ float s[32];
@@ -124,30 +135,36 @@ __global__ void split_nhwc_f16_kernel(const float4 *__restrict__ in, uint2 *__re
 }
 
 // NCHW (B,Cin,P) fp32 -> NHWC (B,P,Cin) fp16 planes through a 64 ch x 64 cell shared tile; P = gh*gw.
-// Reads are 256 B rows along P, writes are 128 B rows along C (one half2 per lane).  256 threads.
-__global__ void split_nchw_f16_kernel(const float *__restrict__ in, __half2 *__restrict__ p1, __half2 *__restrict__ p2,
-                                      int cin, int P, const unsigned *__restrict__ amax_bits) {
+// Reads: every thread issues its 16 loads (256 B rows along P) before the first use.  Writes: 8 B per lane
+// (4 channels), half a warp per 128-byte channel row of a cell.  256 threads.
+__global__ void __launch_bounds__(256) split_nchw_f16_kernel(const float *__restrict__ in, uint2 *__restrict__ p1,
+                                                             uint2 *__restrict__ p2, int cin, int P,
+                                                             const unsigned *__restrict__ amax_bits) {
     __shared__ float tile[64][65];
     const int b = blockIdx.z, c0 = blockIdx.y * 64, q0 = blockIdx.x * 64;
     const float s = pow2_scale_for(__uint_as_float(amax_bits[b]));
     const float *src = in + (size_t)b * cin * P;
     const int col = threadIdx.x & 63, r0 = threadIdx.x >> 6;
-#pragma unroll 4
-    for (int j = r0; j < 64; j += 4) {
-        const int q = q0 + col;
-        tile[j][col] = q < P ? __ldg(src + (size_t)(c0 + j) * P + q) : 0.f;
-    }
+    const int q = q0 + col;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = q < P ? __ldg(src + (size_t)(c0 + r0 + 4 * j) * P + q) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) tile[r0 + 4 * j][col] = v[j];
     __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int j = w; j < 64; j += 8) {
-        const int q = q0 + j;
-        if (q >= P) break;
-        __half a1[2], a2[2];
-        split_f16(tile[2 * lane][j] * s, a1[0], a2[0]);
-        split_f16(tile[2 * lane + 1][j] * s, a1[1], a2[1]);
-        const size_t o = (((size_t)b * P + q) * cin + c0) / 2 + lane;
-        p1[o] = __halves2half2(a1[0], a1[1]);
-        p2[o] = __halves2half2(a2[0], a2[1]);
+    const int l16 = threadIdx.x & 15, g = threadIdx.x >> 4;  // 16 lanes x 4 channels per cell, 16 cells per pass
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const int j = g + 16 * jj;
+        const int qq = q0 + j;
+        if (qq < P) {
+            __half a1[4], a2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_f16(tile[4 * l16 + e][j] * s, a1[e], a2[e]);
+            const size_t o = (((size_t)b * P + qq) * cin + c0) / 4 + l16;
+            p1[o] = *reinterpret_cast<const uint2 *>(a1);
+            p2[o] = *reinterpret_cast<const uint2 *>(a2);
+        }
     }
 }
 
@@ -706,7 +723,7 @@ int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, 
     SQD_CUDA(cudaMemsetAsync(amax, 0, pl.p1_off, st));
     {
         int bx = (int)((n4 + 256 * 8 - 1) / (256 * 8));
-        if (bx > 64) bx = 64;
+        if (bx > 32) bx = 32;
         if (bx < 1) bx = 1;
         absmax_kernel<<<dim3(bx, batch), 256, 0, st>>>(reinterpret_cast<const float4 *>(d_feat), n4, amax);
         SQD_LAUNCH_CHECK("absmax_kernel");
@@ -720,8 +737,8 @@ int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, 
         SQD_LAUNCH_CHECK("split_nhwc_f16_kernel");
     } else {
         dim3 grid((P + 63) / 64, cin / 64, batch);
-        split_nchw_f16_kernel<<<grid, 256, 0, st>>>(d_feat, reinterpret_cast<__half2 *>(base + pl.p1_off),
-                                                   reinterpret_cast<__half2 *>(base + pl.p2_off), cin, P, amax);
+        split_nchw_f16_kernel<<<grid, 256, 0, st>>>(d_feat, reinterpret_cast<uint2 *>(base + pl.p1_off),
+                                                   reinterpret_cast<uint2 *>(base + pl.p2_off), cin, P, amax);
         SQD_LAUNCH_CHECK("split_nchw_f16_kernel");
     }
     return SQD_OK;

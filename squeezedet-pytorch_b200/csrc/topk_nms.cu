@@ -3,18 +3,29 @@
 // Reference: src/engine/detector.py:87-122 (full torch.argsort of A scores, 3 torchvision.ops.nms
 // calls and >= 3C+3 host syncs PER IMAGE) and torchvision's CPU nms kernel for the IoU arithmetic.
 //
-// One CTA per image.
+// One thread-block CLUSTER of 1/2/4/8 CTAs per image (small batches would otherwise leave most SMs idle: one CTA
+// per image is latency bound at batch 20).  Each CTA scans its slice of the anchors and keeps its local top-k;
+// rank 0 then pulls the other ranks' survivors through distributed shared memory, selects the top-k of the <= 2048
+// candidates, sorts them and runs phases 2-3.  The union of local top-k lists contains the global top-k, and the 64-bit keys
+// are totally ordered, so the result does not depend on the cluster size.
 //  1. Scan: every thread scores its anchors; a candidate is a 64-bit key
 //        [ order-preserving score bits : 32 | 0xFFFFFF - anchor : 24 | class : 8 ]
 //     so "larger key" == (score desc, anchor index asc) -- the declared tie policy.
 //     Candidates above the running k-th-best threshold are appended to a 2048-entry shared buffer;
-//     when a round could overflow it, the buffer is bitonic-sorted, cut to k and the threshold
-//     raised.  After the first cut almost nothing passes (expected k*ln(A/2048) more candidates).
+//     when a round could overflow it, the exact top-k of the buffer is SELECTED (MSB-first radix select on the
+//     keys, no sort) and the threshold raised.  After the first cut almost nothing passes (expected
+//     k*ln(A/2048) more candidates).  Only the final k survivors are sorted (by ranking).
 //  2. The k survivors (sorted) get their boxes; a k x k same-class IoU bitmask is built with one
 //     ballot per 32 pairs; one warp runs the sequential greedy sweep over the mask rows.
 //  3. Kept rows with score > thresh are emitted class-ascending / score-descending.
+// The running threshold starts at the score threshold (exact, see score_floor_key), so on real inputs only a few
+// hundred anchors per image ever enter the candidate buffer and mid-scan compactions do not happen.
 // Algorithmic HBM bytes per image: A*(C+5)*4 (fused) or A*4 (+ a few KB of gathers) for the dense form.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -23,6 +34,7 @@ constexpr int kUnroll = 2;
 constexpr int kRound = kThreads * kUnroll;  // anchors consumed per round
 constexpr int kCap = 2048;                  // candidate buffer entries (>= SQD_MAX_TOPK + kRound)
 static_assert(kCap >= SQD_MAX_TOPK + kRound, "candidate buffer too small");
+static_assert(kCap / 2 >= SQD_MAX_TOPK, "rank_sort uses the upper half of the buffer as its destination");
 
 typedef unsigned long long u64;
 
@@ -39,6 +51,15 @@ __device__ __forceinline__ u64 make_key(float score, int anchor, int cls) {
 __device__ __forceinline__ int key_anchor(u64 k) { return (int)(0xFFFFFFu - (unsigned)((k >> 8) & 0xFFFFFFu)); }
 __device__ __forceinline__ int key_class(u64 k) { return (int)(k & 0xFFu); }
 __device__ __forceinline__ float key_score(u64 k) { return unorder_bits((unsigned)(k >> 32)); }
+
+// Exact pre-filter: an anchor with score <= score_thresh can never be emitted (final strict filter) and can never
+// suppress an emitted box (greedy NMS only lets HIGHER scores suppress), so it only ever occupies a top-k slot that
+// no surviving anchor needs.  Starting the running threshold at "largest key with score == score_thresh" keeps
+// such anchors out of the candidate buffer altogether; the result is identical to the reference's
+// top-k -> NMS -> score filter order (detector.py:88-114).
+__device__ __forceinline__ u64 score_floor_key(float score_thr) {
+    return ((u64)order_bits(score_thr) << 32) | 0xFFFFFFFFull;
+}
 
 // ---- candidate sources ---------------------------------------------------------------------------
 template <int CS>
@@ -82,49 +103,136 @@ struct FromDense {  // Detector.filter's own contract: dense ids / scores / boxe
     __device__ __forceinline__ float4 box(int a) const { return __ldg(boxes + a); }
 };
 
-// ---- block-wide bitonic sort (descending) of buf[0..n2), n2 a power of two ------------------------
-__device__ void bitonic_desc(u64 *buf, int n2) {
-    for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (n2 >> 1); t += kThreads) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
-                const int l = i | j;
-                const bool desc = ((i & k) == 0);
-                const u64 x = buf[i], y = buf[l];
-                if ((x < y) == desc) {
-                    buf[i] = y;
-                    buf[l] = x;
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
 struct Shared {
     u64 buf[kCap];
+    int hist[256];
     int count;
     int n_valid;
+    int sel_bin, sel_need, sel_done;
     u64 thresh;
 };
 
-// Sort the candidates, keep the best k, raise the threshold.  All threads must call.
-__device__ void compact(Shared &sh, int k) {
-    const int cnt = min(sh.count, kCap);
-    int n2 = 2;
-    while (n2 < cnt) n2 <<= 1;
-    for (int i = cnt + threadIdx.x; i < n2; i += kThreads) sh.buf[i] = 0ull;
+// ---- exact top-k SELECTION (no sort) ---------------------------------------------------------------
+// MSB-first radix select over the 64-bit keys with 8-bit digits: every pass histograms the digit of the keys that
+// still share the prefix of the k-th largest key and narrows the prefix by one digit; it stops as soon as the
+// selected bin is needed in full.  Keys are unique (the anchor index is part of the key), so exactly k keys
+// satisfy key >= sel_lo.  Keys live in registers during the passes (kCap / kThreads per thread); the survivors
+// are written back unsorted, and the running threshold becomes sel_lo - 1.  All threads must call.
+__device__ void select_topk(Shared &sh, int k) {
+    constexpr int kPer = kCap / kThreads;
     __syncthreads();
-    bitonic_desc(sh.buf, n2);
-    if (threadIdx.x == 0) {
-        if (cnt >= k) {
-            sh.count = k;
-            sh.thresh = sh.buf[k - 1];
-        } else {
-            sh.count = cnt;
+    const int cnt = min(sh.count, kCap);
+    if (cnt <= k) {           // nothing to cut (uniform)
+        if (threadIdx.x == 0) sh.count = cnt;
+        __syncthreads();
+        return;
+    }
+    u64 my[kPer];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+        const int idx = threadIdx.x + i * kThreads;
+        my[i] = idx < cnt ? sh.buf[idx] : 0ull;  // 0 is below every real key (score bits of a finite float are never 0)
+    }
+    const int lane = threadIdx.x & 31;
+    u64 prefix = 0ull;
+    int need = k, shift = 56;
+    for (; shift >= 0; shift -= 8) {
+        if (threadIdx.x < 256) sh.hist[threadIdx.x] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            const bool in = my[i] != 0ull && (shift == 56 || (my[i] >> (shift + 8)) == (prefix >> (shift + 8)));
+            const unsigned digit = (unsigned)(my[i] >> shift) & 255u;
+            // warp-aggregated histogram update: one atomic per distinct digit per warp
+            const unsigned act = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const unsigned peers = __match_any_sync(act, digit);
+                if (lane == __ffs(peers) - 1) atomicAdd(&sh.hist[digit], __popc(peers));
+            }
         }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // lane l owns bins [8l, 8l+8); find the bin b with  #(digit > b) < need <= #(digit >= b)
+            int c[8], own = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                c[j] = sh.hist[lane * 8 + j];
+                own += c[j];
+            }
+            int above = own;  // inclusive suffix sum over lanes >= this one
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_down_sync(0xffffffffu, above, o);
+                if (lane + o < 32) above += v;
+            }
+            const int higher = above - own;  // keys in bins of higher lanes
+            if (higher < need && need <= above) {
+                int acc = higher;
+                for (int j = 7; j >= 0; --j) {
+                    if (acc + c[j] >= need) {
+                        sh.sel_bin = lane * 8 + j;
+                        sh.sel_need = need - acc;
+                        sh.sel_done = (c[j] == need - acc) ? 1 : 0;
+                        break;
+                    }
+                    acc += c[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (u64)(unsigned)sh.sel_bin << shift;
+        need = sh.sel_need;
+        if (sh.sel_done) break;  // the whole bin is needed: no further digits to resolve (uniform)
+    }
+    if (shift < 0) shift = 0;
+    const u64 sel_lo = prefix;  // lower (unresolved) digits are zero: selected <=> key >= sel_lo
+    __syncthreads();            // everyone has read sel_*; buf may be overwritten now
+    if (threadIdx.x == 0) {
+        sh.count = 0;
+        sh.thresh = sel_lo - 1ull;
     }
     __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kPer; ++i)
+        if (my[i] >= sel_lo && my[i] != 0ull) sh.buf[atomicAdd(&sh.count, 1)] = my[i];
+    __syncthreads();
+}
+
+// Sort the (<= k <= kCap/2) survivors in descending order by ranking: rank(i) = #{j : key_j > key_i}.
+// k*k/kThreads comparisons per thread (8 for k = 64); keys are unique so ranks are a permutation.
+__device__ void rank_sort(Shared &sh) {
+    const int m = sh.count;
+    u64 *out = sh.buf + kCap / 2;
+    for (int i = threadIdx.x; i < m; i += kThreads) {
+        const u64 key = sh.buf[i];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) rank += sh.buf[j] > key ? 1 : 0;
+        out[rank] = key;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += kThreads) sh.buf[i] = out[i];
+    __syncthreads();
+}
+
+// Cluster merge: every rank holds its (unsorted) local top-k in sh.buf[0..sh.count).  Rank 0 appends the other
+// ranks' lists (read through DSMEM) to its own and cuts the union to k again.  All threads of all CTAs must call.
+__device__ void cluster_merge(Shared &sh, int k, int cs) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();  // local lists complete and visible cluster-wide
+    if (cluster.block_rank() == 0) {
+        int total = sh.count;
+        __syncthreads();
+        for (int r = 1; r < cs; ++r) {
+            const Shared *rs = cluster.map_shared_rank(&sh, r);
+            const int cnt = min(rs->count, k);
+            for (int i = threadIdx.x; i < cnt; i += kThreads) sh.buf[total + i] = rs->buf[i];
+            total += cnt;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) sh.count = total;
+        select_topk(sh, k);
+    }
+    cluster.sync();  // remote lists no longer needed: the other ranks may exit
 }
 
 struct FilterOut {
@@ -223,10 +331,13 @@ __device__ void nms_and_emit(const Src &src, Shared &sh, unsigned char *dyn, int
 template <int CS>
 __global__ void __launch_bounds__(kThreads) detect_from_pred_kernel(const float *pred, const float4 *anchors, int A,
                                                                     int C, float wmax, float hmax, int k,
-                                                                    float nms_thr_f, float score_thr_f, FilterOut o) {
+                                                                    float nms_thr_f, float score_thr_f, FilterOut o,
+                                                                    int cs) {
     __shared__ Shared sh;
     extern __shared__ __align__(16) unsigned char dyn[];
-    const int img = blockIdx.x;
+    const int img = blockIdx.x / cs, rank = blockIdx.x - img * cs;
+    const int chunk = (A + cs - 1) / cs;
+    const int a_begin = rank * chunk, a_end = min(A, a_begin + chunk);
     FromPred<CS> src;
     src.pred = pred + (size_t)img * A * ((CS > 0 ? CS : C) + 5);
     src.anchors = anchors;
@@ -235,16 +346,16 @@ __global__ void __launch_bounds__(kThreads) detect_from_pred_kernel(const float 
     src.hmax = hmax;
     if (threadIdx.x == 0) {
         sh.count = 0;
-        sh.thresh = 0ull;
+        sh.thresh = score_floor_key(score_thr_f);
     }
     __syncthreads();
-    for (int base = 0; base < A; base += kRound) {
+    for (int base = a_begin; base < a_end; base += kRound) {
         const u64 thr = sh.thresh;
         u64 keys[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const int a = base + u * kThreads + threadIdx.x;
-            keys[u] = a < A ? src.key(a) : 0ull;
+            keys[u] = a < a_end ? src.key(a) : 0ull;
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
@@ -254,40 +365,46 @@ __global__ void __launch_bounds__(kThreads) detect_from_pred_kernel(const float 
             }
         // Barrier + vote in one: the thread that performs the round's last append observes the final
         // count, so the OR is true for everyone iff the buffer could overflow next round (uniform branch).
-        if (__syncthreads_or(*(volatile int *)&sh.count > kCap - kRound)) compact(sh, k);
+        if (__syncthreads_or(*(volatile int *)&sh.count > kCap - kRound)) select_topk(sh, k);
     }
-    __syncthreads();
-    compact(sh, k);
+    select_topk(sh, k);
+    if (cs > 1) {
+        cluster_merge(sh, k, cs);
+        if (rank != 0) return;
+    }
+    rank_sort(sh);
     nms_and_emit(src, sh, dyn, k, C, nms_thr_f, score_thr_f, o, img);
 }
 
 __global__ void __launch_bounds__(kThreads) filter_dense_kernel(const long long *class_ids, const float *scores,
                                                                const float4 *boxes, int A, int C, int k,
-                                                               float nms_thr_f, float score_thr_f, FilterOut o) {
+                                                               float nms_thr_f, float score_thr_f, FilterOut o, int cs) {
     __shared__ Shared sh;
     extern __shared__ __align__(16) unsigned char dyn[];
-    const int img = blockIdx.x;
+    const int img = blockIdx.x / cs, rank = blockIdx.x - img * cs;
+    const int chunk = (A + cs - 1) / cs;
+    const int a_begin = rank * chunk, a_end = min(A, a_begin + chunk);
     FromDense src;
     src.class_ids = class_ids + (size_t)img * A;
     src.scores = scores + (size_t)img * A;
     src.boxes = boxes + (size_t)img * A;
     if (threadIdx.x == 0) {
         sh.count = 0;
-        sh.thresh = 0ull;
+        sh.thresh = score_floor_key(score_thr_f);
     }
     __syncthreads();
-    for (int base = 0; base < A; base += kRound) {
+    for (int base = a_begin; base < a_end; base += kRound) {
         const unsigned thr_hi = (unsigned)(sh.thresh >> 32);
         float s[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const int a = base + u * kThreads + threadIdx.x;
-            s[u] = a < A ? src.score(a) : 0.f;
+            s[u] = a < a_end ? src.score(a) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const int a = base + u * kThreads + threadIdx.x;
-            if (a < A && order_bits(s[u]) >= thr_hi) {  // cheap pre-test on the score word only
+            if (a < a_end && order_bits(s[u]) >= thr_hi) {  // cheap pre-test on the score word only
                 const u64 key = src.key_of(s[u], a);
                 if (key > sh.thresh) {
                     const int pos = atomicAdd(&sh.count, 1);
@@ -295,10 +412,14 @@ __global__ void __launch_bounds__(kThreads) filter_dense_kernel(const long long 
                 }
             }
         }
-        if (__syncthreads_or(*(volatile int *)&sh.count > kCap - kRound)) compact(sh, k);
+        if (__syncthreads_or(*(volatile int *)&sh.count > kCap - kRound)) select_topk(sh, k);
     }
-    __syncthreads();
-    compact(sh, k);
+    select_topk(sh, k);
+    if (cs > 1) {
+        cluster_merge(sh, k, cs);
+        if (rank != 0) return;
+    }
+    rank_sort(sh);
     nms_and_emit(src, sh, dyn, k, C, nms_thr_f, score_thr_f, o, img);
 }
 
@@ -330,6 +451,36 @@ int opt_in_smem(K kernel, size_t bytes) {
     return SQD_OK;
 }
 
+// CTAs per image: as many as keep the merged candidate list inside the shared buffer (k*cs <= kCap) and are
+// useful for filling the GPU at this batch size (at most ~4 CTAs per SM in flight); at least 2 rounds per CTA.
+int cluster_size_for(int batch, int A, int k) {
+    int cs = 8;
+    while (cs > 1 && ((long long)k * cs > kCap || (long long)batch * cs > 4ll * SQD_SM_COUNT || A / cs < 2 * kRound)) cs >>= 1;
+    return cs;
+}
+
+template <class K, class... Args>
+int launch_clustered(const char *name, K kernel, int batch, int cs, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(batch * cs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    if (e != cudaSuccess) {
+        sqd_set_error("launch of %s failed: %s", name, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return SQD_OK;
+}
+
 }  // namespace
 
 extern "C" int sqd_topk_nms(const int64_t *d_class_ids, const float *d_scores, const float *d_boxes, int batch,
@@ -346,11 +497,10 @@ extern "C" int sqd_topk_nms(const int64_t *d_class_ids, const float *d_scores, c
     const size_t smem = dyn_smem_bytes(top_k);
     rc = opt_in_smem(filter_dense_kernel, smem);
     if (rc) return rc;
-    filter_dense_kernel<<<batch, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const long long *>(d_class_ids), d_scores, reinterpret_cast<const float4 *>(d_boxes),
-        num_anchors, num_classes, top_k, float_at_or_below(nms_thresh), (float)score_thresh, o);
-    SQD_LAUNCH_CHECK("filter_dense_kernel");
-    return SQD_OK;
+    return launch_clustered("filter_dense_kernel", filter_dense_kernel, batch, cluster_size_for(batch, num_anchors, top_k),
+                            smem, static_cast<cudaStream_t>(stream), reinterpret_cast<const long long *>(d_class_ids),
+                            d_scores, reinterpret_cast<const float4 *>(d_boxes), num_anchors, num_classes, top_k,
+                            float_at_or_below(nms_thresh), (float)score_thresh, o, cluster_size_for(batch, num_anchors, top_k));
 }
 
 extern "C" int sqd_detect_from_pred(const float *d_pred, const float *d_anchors, int batch, int num_anchors,
@@ -370,22 +520,20 @@ extern "C" int sqd_detect_from_pred(const float *d_pred, const float *d_anchors,
     const float wmax = (float)(input_w - 1), hmax = (float)(input_h - 1);
     const float nthr = float_at_or_below(nms_thresh), sthr = (float)score_thresh;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int cs = cluster_size_for(batch, num_anchors, top_k);
     if (num_classes == 3) {
         rc = opt_in_smem(detect_from_pred_kernel<3>, smem);
         if (rc) return rc;
-        detect_from_pred_kernel<3><<<batch, kThreads, smem, st>>>(d_pred, anc, num_anchors, num_classes, wmax, hmax,
-                                                                  top_k, nthr, sthr, o);
+        return launch_clustered("detect_from_pred_kernel", detect_from_pred_kernel<3>, batch, cs, smem, st, d_pred, anc,
+                                num_anchors, num_classes, wmax, hmax, top_k, nthr, sthr, o, cs);
     } else if (num_classes == 8) {
         rc = opt_in_smem(detect_from_pred_kernel<8>, smem);
         if (rc) return rc;
-        detect_from_pred_kernel<8><<<batch, kThreads, smem, st>>>(d_pred, anc, num_anchors, num_classes, wmax, hmax,
-                                                                  top_k, nthr, sthr, o);
-    } else {
-        rc = opt_in_smem(detect_from_pred_kernel<0>, smem);
-        if (rc) return rc;
-        detect_from_pred_kernel<0><<<batch, kThreads, smem, st>>>(d_pred, anc, num_anchors, num_classes, wmax, hmax,
-                                                                  top_k, nthr, sthr, o);
+        return launch_clustered("detect_from_pred_kernel", detect_from_pred_kernel<8>, batch, cs, smem, st, d_pred, anc,
+                                num_anchors, num_classes, wmax, hmax, top_k, nthr, sthr, o, cs);
     }
-    SQD_LAUNCH_CHECK("detect_from_pred_kernel");
-    return SQD_OK;
+    rc = opt_in_smem(detect_from_pred_kernel<0>, smem);
+    if (rc) return rc;
+    return launch_clustered("detect_from_pred_kernel", detect_from_pred_kernel<0>, batch, cs, smem, st, d_pred, anc,
+                            num_anchors, num_classes, wmax, hmax, top_k, nthr, sthr, o, cs);
 }
