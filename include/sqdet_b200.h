@@ -143,6 +143,21 @@ SQD_API int sqd_head_detect_fused(const float *d_feat, int layout, const void *d
                           int32_t *d_out_class, float *d_out_score, float *d_out_box, void *d_workspace,
                           size_t workspace_bytes, int algo, void *stream);
 
+/* Host-buffer form of sqd_head_detect_fused (what Detector.detect does around the model call: batch to device,
+ * results back to numpy, src/engine/detector.py:22,37).  h_* are HOST pointers (page-locked for the copies to be
+ * asynchronous); the call enqueues, per group of `chunk_images` images, the H2D copy on `copy_stream` and the kernels
+ * on `stream`, so the copy of group g+1 overlaps the compute of group g, then the D2H copies of the five output
+ * arrays on `stream`.  The caller synchronises `stream` before reading the outputs.  copy_stream NULL = no overlap;
+ * chunk_images <= 0 = one group.  The workspace holds the device staging of features and outputs. */
+SQD_API size_t sqd_head_detect_host_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int top_k, int layout,
+                                                    int algo, int chunk_images);
+SQD_API int sqd_head_detect_host(const float *h_feat, int layout, const void *d_packed, const float *d_weight,
+                                 const float *d_bias, const float *d_anchors, int batch, int cin, int gh, int gw,
+                                 int anchors_per_grid, int num_classes, int input_h, int input_w, int top_k,
+                                 double nms_thresh, double score_thresh, int32_t *h_count, int32_t *h_out_anchor,
+                                 int32_t *h_out_class, float *h_out_score, float *h_out_box, void *d_workspace,
+                                 size_t workspace_bytes, int algo, int chunk_images, void *stream, void *copy_stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a11-a12  compute_deltas: greedy sequential anchor<->ground-truth matching in float64.
  *     Replaces numpy compute_overlaps + compute_deltas, src/utils/boxes.py:70-135.

@@ -39,6 +39,9 @@ SIGNATURES = {
     "sqd_head_detect_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "sqd_head_detect_fused": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _d,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "sqd_head_detect_host_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "sqd_head_detect_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _d,
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp, _vp]),
     "sqd_match_anchors": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "sqd_build_targets": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "sqd_loss_workspace_bytes": (_sz, [_i, _i]),

@@ -135,6 +135,97 @@ extern "C" int sqd_head_detect_fused(const float *d_feat, int layout, const void
                                 stream);
 }
 
+// ---- fused a1-a9 with HOST buffers: chunked copy/compute pipeline ---------------------------------------------
+namespace {
+struct HostWs {
+    size_t feat_off, count_off, anchor_off, cls_off, score_off, box_off, fused_off, total;
+};
+HostWs host_ws_layout(int batch, int cin, int gh, int gw, int cout, int top_k, int layout, int algo, int chunk) {
+    HostWs w;
+    size_t off = 0;
+    w.feat_off = off;   off += align_up((size_t)batch * cin * gh * gw * sizeof(float), 256);
+    w.count_off = off;  off += align_up((size_t)batch * sizeof(int32_t), 256);
+    w.anchor_off = off; off += align_up((size_t)batch * top_k * sizeof(int32_t), 256);
+    w.cls_off = off;    off += align_up((size_t)batch * top_k * sizeof(int32_t), 256);
+    w.score_off = off;  off += align_up((size_t)batch * top_k * sizeof(float), 256);
+    w.box_off = off;    off += align_up((size_t)batch * top_k * 4 * sizeof(float), 256);
+    w.fused_off = off;  off += sqd_head_detect_workspace_bytes(chunk, cin, gh, gw, cout, layout, algo);
+    w.total = off;
+    return w;
+}
+int clamp_chunk(int batch, int chunk) { return chunk <= 0 || chunk > batch ? batch : chunk; }
+}  // namespace
+
+extern "C" size_t sqd_head_detect_host_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int top_k, int layout,
+                                                       int algo, int chunk_images) {
+    if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0 || top_k <= 0) return 256;
+    return host_ws_layout(batch, cin, gh, gw, cout, top_k, layout, algo, clamp_chunk(batch, chunk_images)).total;
+}
+
+extern "C" int sqd_head_detect_host(const float *h_feat, int layout, const void *d_packed, const float *d_weight,
+                                    const float *d_bias, const float *d_anchors, int batch, int cin, int gh, int gw,
+                                    int anchors_per_grid, int num_classes, int input_h, int input_w, int top_k,
+                                    double nms_thresh, double score_thresh, int32_t *h_count, int32_t *h_out_anchor,
+                                    int32_t *h_out_class, float *h_out_score, float *h_out_box, void *d_workspace,
+                                    size_t workspace_bytes, int algo, int chunk_images, void *stream, void *copy_stream) {
+    if (batch == 0) return SQD_OK;
+    SQD_REQUIRE(h_feat && h_count && h_out_anchor && h_out_class && h_out_score && h_out_box && d_workspace, SQD_E_NULL,
+                "sqd_head_detect_host: NULL pointer");
+    SQD_REQUIRE(layout == SQD_LAYOUT_NCHW || layout == SQD_LAYOUT_NHWC, SQD_E_SHAPE, "sqd_head_detect_host: bad layout %d",
+                layout);
+    SQD_REQUIRE(anchors_per_grid >= 1 && num_classes >= 1 && batch > 0 && top_k >= 1, SQD_E_SHAPE,
+                "sqd_head_detect_host: bad shape");
+    const int cout = anchors_per_grid * (num_classes + 5);
+    const int chunk = clamp_chunk(batch, chunk_images);
+    const HostWs w = host_ws_layout(batch, cin, gh, gw, cout, top_k, layout, algo, chunk);
+    SQD_REQUIRE(workspace_bytes >= w.total, SQD_E_WORKSPACE, "sqd_head_detect_host: workspace too small (%zu < %zu bytes)",
+                workspace_bytes, w.total);
+    SQD_REQUIRE(sqd_aligned16(d_workspace), SQD_E_ALIGN, "sqd_head_detect_host: workspace must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t cst = copy_stream ? static_cast<cudaStream_t>(copy_stream) : st;
+    char *ws = static_cast<char *>(d_workspace);
+    float *d_feat = reinterpret_cast<float *>(ws + w.feat_off);
+    int32_t *d_count = reinterpret_cast<int32_t *>(ws + w.count_off);
+    int32_t *d_anchor = reinterpret_cast<int32_t *>(ws + w.anchor_off);
+    int32_t *d_cls = reinterpret_cast<int32_t *>(ws + w.cls_off);
+    float *d_score = reinterpret_cast<float *>(ws + w.score_off);
+    float *d_box = reinterpret_cast<float *>(ws + w.box_off);
+    const size_t img_elems = (size_t)cin * gh * gw;
+    const int nchunks = (batch + chunk - 1) / chunk;
+    cudaEvent_t ev = nullptr;
+    if (cst != st) {
+        // the staging buffer may still be read by kernels of the previous call on `stream`
+        SQD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        SQD_CUDA(cudaEventRecord(ev, st));
+        SQD_CUDA(cudaStreamWaitEvent(cst, ev, 0));
+        SQD_CUDA(cudaEventDestroy(ev));
+    }
+    int rc = SQD_OK;
+    for (int c = 0; c < nchunks && rc == SQD_OK; ++c) {
+        const int b0 = c * chunk, nb = (b0 + chunk <= batch) ? chunk : batch - b0;
+        SQD_CUDA(cudaMemcpyAsync(d_feat + b0 * img_elems, h_feat + b0 * img_elems, nb * img_elems * sizeof(float),
+                                 cudaMemcpyHostToDevice, cst));
+        if (cst != st) {
+            SQD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            SQD_CUDA(cudaEventRecord(ev, cst));
+            SQD_CUDA(cudaStreamWaitEvent(st, ev, 0));
+            SQD_CUDA(cudaEventDestroy(ev));  // released by the driver once the recorded work has completed
+        }
+        rc = sqd_head_detect_fused(d_feat + b0 * img_elems, layout, d_packed, d_weight, d_bias, d_anchors, nb, cin, gh, gw,
+                                   anchors_per_grid, num_classes, input_h, input_w, top_k, nms_thresh, score_thresh,
+                                   d_count + b0, d_anchor + (size_t)b0 * top_k, d_cls + (size_t)b0 * top_k,
+                                   d_score + (size_t)b0 * top_k, d_box + (size_t)b0 * top_k * 4, ws + w.fused_off,
+                                   workspace_bytes - w.fused_off, algo, stream);
+    }
+    if (rc) return rc;
+    SQD_CUDA(cudaMemcpyAsync(h_count, d_count, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SQD_CUDA(cudaMemcpyAsync(h_out_anchor, d_anchor, (size_t)batch * top_k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SQD_CUDA(cudaMemcpyAsync(h_out_class, d_cls, (size_t)batch * top_k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SQD_CUDA(cudaMemcpyAsync(h_out_score, d_score, (size_t)batch * top_k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SQD_CUDA(cudaMemcpyAsync(h_out_box, d_box, (size_t)batch * top_k * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return SQD_OK;
+}
+
 // ---- 8(f) rank 1: boxes_postprocess -----------------------------------------------------------------
 // Reference order (src/utils/boxes.py:145-166): /scale, -padding, +crops, flip, +drifts.  One 10-float record
 // per image: [scale_y, scale_x, pad_top, pad_left, crop_top, crop_left, flip_width (<=0: not flipped),

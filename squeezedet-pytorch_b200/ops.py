@@ -162,6 +162,58 @@ def head_detect(feat, weight, bias, anchors_f32, anchors_per_grid, num_classes, 
     return det
 
 
+class HostDetections:
+    """Pinned host buffers for head_detect_host (same fields as Detections)."""
+
+    def __init__(self, batch, top_k):
+        self.count = torch.empty((batch,), dtype=torch.int32).pin_memory()
+        self.anchor = torch.empty((batch, top_k), dtype=torch.int32).pin_memory()
+        self.cls = torch.empty((batch, top_k), dtype=torch.int32).pin_memory()
+        self.score = torch.empty((batch, top_k), dtype=torch.float32).pin_memory()
+        self.box = torch.empty((batch, top_k, 4), dtype=torch.float32).pin_memory()
+
+    def to_list(self):
+        return Detections(self.count, self.anchor, self.cls, self.score, self.box).to_list()
+
+
+_copy_streams = {}
+
+
+def head_detect_host(host_feat, weight, bias, anchors_f32, anchors_per_grid, num_classes, input_hw, top_k, nms_thresh,
+                     score_thresh, packed=None, algo=CONV_TCGEN05_F16X3, out: HostDetections = None, chunk_images=5,
+                     overlap=True, sync=True) -> HostDetections:
+    """HOST feature maps (B,Cin,gh,gw) fp32 (pinned, NCHW-contiguous) -> HOST detections through ONE ABI call that
+    pipelines H2D copies with the kernels (sqd_head_detect_host).  `weight`/`bias`/`anchors` live on the device."""
+    lib = load()
+    if host_feat.is_cuda or not host_feat.is_contiguous() or host_feat.dtype != torch.float32:
+        raise _lib.SqdError("head_detect_host needs a contiguous fp32 HOST tensor (B,Cin,gh,gw)")
+    dev = weight.device
+    B, cin, gh, gw = host_feat.shape
+    w = weight.detach().contiguous()
+    b = bias.detach().contiguous()
+    cout = w.shape[0]
+    if packed is None:
+        packed = pack_convdet_weights(w)
+    nbytes = lib.sqd_head_detect_host_workspace_bytes(B, cin, gh, gw, cout, top_k, LAYOUT_NCHW, algo, chunk_images)
+    ws = workspace().get("head_detect_host", nbytes, dev)
+    det = out if out is not None else HostDetections(B, top_k)
+    cst = None
+    if overlap:
+        key = torch.device(dev).index
+        if key not in _copy_streams:
+            _copy_streams[key] = torch.cuda.Stream(device=dev)
+        cst = C.c_void_p(_copy_streams[key].cuda_stream)
+    hp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    check(lib.sqd_head_detect_host(hp(host_feat), LAYOUT_NCHW, ptr(packed), ptr(w), ptr(b), ptr(anchors_f32), B, cin, gh,
+                                   gw, anchors_per_grid, num_classes, int(input_hw[0]), int(input_hw[1]), top_k,
+                                   float(nms_thresh), float(score_thresh), hp(det.count), hp(det.anchor), hp(det.cls),
+                                   hp(det.score), hp(det.box), ptr(ws), ws.numel(), algo, int(chunk_images),
+                                   stream_ptr(dev), cst), "sqd_head_detect_host")
+    if sync:
+        torch.cuda.current_stream(dev).synchronize()
+    return det
+
+
 # ---- a11-a13 ---------------------------------------------------------------------------------------
 def match_anchors(gt_boxes, gt_count, anchors_f64):
     """gt_boxes (B,Gmax,4) f32 xyxy, gt_count (B,) i32, anchors (A,4) f64 -> (anchor_idx (B,Gmax) i32, deltas (B,Gmax,4))."""

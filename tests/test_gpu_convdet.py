@@ -161,3 +161,18 @@ def test_module_surface(ops):
     loss.mean().backward()
     assert loss.shape == (3,) and set(stats) == {"loss", "class_loss", "score_loss", "bbox_loss"}
     assert tnet.base.convdet.weight.grad is not None and torch.isfinite(tnet.base.convdet.weight.grad).all()
+
+
+@pytest.mark.parametrize("chunk", [0, 1, 3])
+def test_head_detect_host_equals_device_call(ops, chunk):
+    """sqd_head_detect_host (pinned host buffers, chunked copy/compute pipeline) returns exactly what the
+    device-resident fused call returns, for any image-group size (ragged last group included)."""
+    shp = synth.KITTI
+    feat = synth.features(shp, 5, 21)
+    w, b = synth.convdet_params(shp, 22)
+    a32 = dev(synth.anchor_table(shp).astype(np.float32))
+    ref = ops.head_detect(dev(feat), dev(w), dev(b), a32, 9, 3, shp.input_hw, shp.top_k, shp.nms_thresh, shp.score_thresh)
+    host = ops.head_detect_host(torch.from_numpy(feat).pin_memory(), dev(w), dev(b), a32, 9, 3, shp.input_hw, shp.top_k,
+                                shp.nms_thresh, shp.score_thresh, chunk_images=chunk)
+    for f in ("count", "anchor", "cls", "score", "box"):
+        assert torch.equal(getattr(ref, f).cpu(), getattr(host, f)), f
