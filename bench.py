@@ -332,10 +332,10 @@ def main_ours(args):
                     "steps": Ke, "note": "sqd_head_detect_host: pinned host features -> H2D in groups of %d images overlapped with the kernels "
                             "-> D2H of the detections, stream sync every step" % args.e2e_chunk},
             "gpu_launches": 4 * K,
-            "kernels_per_step": ["absmax_kernel", "split_nchw_f16_kernel|split_nhwc_f16_kernel", "convdet_f16_kernel<80>", "detect_from_pred_kernel<3>"],
+            "kernels_per_step": ["absmax_kernel", "split_nchw_f16_kernel|split_nhwc_f16_kernel", "convdet_f16_pair_kernel<80>", "detect_from_pred_kernel<3>"],
             "kernel_ms": kern,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops"], "traffic": None, "kernel": "convdet_f16_kernel<80>",
+                         "frac": achieved / peaks["tflops"], "traffic": None, "kernel": "convdet_f16_pair_kernel<80>",
                          "peak_source": peaks["source"] + ", dense bf16 burst",
                          "note": "algorithmic FLOPs 2*1872*72*6912 per image; the kernel issues 3 fp16 passes on N padded "
                                  "to 80 for fp32-level accuracy, so frac <= 1/3 * 72/80 = 0.30 by construction"},

@@ -59,9 +59,12 @@ extern "C" {
                                    sqd_convdet_split_features, consumed by the tcgen05 algorithm only */
 
 /* ConvDet algorithms */
-#define SQD_CONV_TCGEN05_F16X3 0 /* tcgen05.mma kind::f16, two-term fp16 split of power-of-two scaled operands
-                                    (3 products = fp32-level accuracy), fp32 TMEM accumulators, chunked */
+#define SQD_CONV_TCGEN05_F16X3 0 /* production: tcgen05.mma cta_group::2 kind::f16 on CTA pairs (M = 256), two-term fp16
+                                    split of power-of-two scaled operands (3 products = fp32-level accuracy),
+                                    fp32 TMEM accumulators drained in chunks, each CTA holds half of the weight tile */
 #define SQD_CONV_SIMT_FP32 1     /* CUDA-core fp32 FMA implicit GEMM (validation yardstick)            */
+#define SQD_CONV_TCGEN05_F16X3_1CTA 2 /* same arithmetic, one CTA per tile (cta_group::1); kept as an on-device
+                                    cross-check of the pair kernel                                          */
 
 SQD_API int sqd_abi_version(void);
 SQD_API const char *sqd_last_error(void);

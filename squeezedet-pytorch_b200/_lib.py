@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsqdet_b200.so")
 
 LAYOUT_NCHW, LAYOUT_NHWC, LAYOUT_SPLIT_NHWC = 0, 1, 2
-CONV_TCGEN05_F16X3, CONV_SIMT_FP32 = 0, 1
+CONV_TCGEN05_F16X3, CONV_SIMT_FP32, CONV_TCGEN05_F16X3_1CTA = 0, 1, 2
 
 _lib = None
 _lock = threading.Lock()

@@ -14,6 +14,8 @@ size_t sqd_f16_split_bytes(int batch, int cin, int gh, int gw);
 int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, int gh, int gw, void *d_planes,
                            cudaStream_t st);
 size_t sqd_f16_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout);
+int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
+                         int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
 int sqd_convdet_f16(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                     int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
 
@@ -58,7 +60,7 @@ extern "C" int sqd_convdet_forward(const float *d_feat, int layout, const void *
     SQD_REQUIRE(d_feat && d_bias && d_pred && d_workspace, SQD_E_NULL, "sqd_convdet_forward: NULL pointer");
     SQD_REQUIRE(layout == SQD_LAYOUT_NCHW || layout == SQD_LAYOUT_NHWC || layout == SQD_LAYOUT_SPLIT_NHWC, SQD_E_SHAPE,
                 "sqd_convdet_forward: bad layout %d", layout);
-    SQD_REQUIRE(!(layout == SQD_LAYOUT_SPLIT_NHWC && algo != SQD_CONV_TCGEN05_F16X3), SQD_E_UNSUPPORTED,
+    SQD_REQUIRE(!(layout == SQD_LAYOUT_SPLIT_NHWC && algo == SQD_CONV_SIMT_FP32), SQD_E_UNSUPPORTED,
                 "sqd_convdet_forward: pre-split planes are only consumed by the tcgen05 algorithm");
     SQD_REQUIRE(batch >= 0 && cin > 0 && gh > 0 && gw > 0 && cout > 0, SQD_E_SHAPE, "sqd_convdet_forward: bad shape");
     SQD_REQUIRE(sqd_aligned16(d_feat) && sqd_aligned16(d_pred) && sqd_aligned16(d_workspace), SQD_E_ALIGN,
@@ -70,8 +72,11 @@ extern "C" int sqd_convdet_forward(const float *d_feat, int layout, const void *
         SQD_REQUIRE(d_weight, SQD_E_NULL, "sqd_convdet_forward: SIMT algorithm needs the raw weight tensor");
         return sqd_convdet_simt(d_feat, layout, d_weight, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
     }
-    SQD_REQUIRE(algo == SQD_CONV_TCGEN05_F16X3, SQD_E_UNSUPPORTED, "sqd_convdet_forward: unknown algo %d", algo);
+    SQD_REQUIRE(algo == SQD_CONV_TCGEN05_F16X3 || algo == SQD_CONV_TCGEN05_F16X3_1CTA, SQD_E_UNSUPPORTED,
+                "sqd_convdet_forward: unknown algo %d", algo);
     SQD_REQUIRE(d_packed, SQD_E_NULL, "sqd_convdet_forward: tcgen05 algorithm needs packed weights");
+    if (algo == SQD_CONV_TCGEN05_F16X3)
+        return sqd_convdet_f16_pair(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
     return sqd_convdet_f16(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
 }
 

@@ -177,9 +177,12 @@ __global__ void weight_absmax_kernel(const float *__restrict__ w, size_t n, Pack
     if ((threadIdx.x & 31) == 0) atomicMax(&hdr->amax_bits, __float_as_uint(m));
 }
 
-// (Cout,Cin,3,3) fp32 -> fp16 [2*npad][9*cin]: rows [0,npad) = w2 (scaled residual), rows [npad,2npad) = w1
+// (Cout,Cin,3,3) fp32 -> two fp16 matrices [2*npad][9*cin]:
+//   mat  (1-CTA kernel): rows [0,npad) = w2 (scaled residual), rows [npad,2npad) = w1
+//   mat2 (CTA-pair kernel), H = npad/2: rows [r*npad, r*npad+H) = w2 of channels [r*H,(r+1)*H), the next H rows = w1 of
+//        the same channels, for pair rank r = 0,1 -- each CTA of a pair loads its own contiguous npad rows
 __global__ void pack_weights_f16_kernel(const float *__restrict__ w, int cout, int cin, int npad, PackedHeader *hdr,
-                                        __half *__restrict__ mat) {
+                                        __half *__restrict__ mat, __half *__restrict__ mat2) {
     const float s = pow2_scale_for(__uint_as_float(hdr->amax_bits));
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         hdr->scale = s;
@@ -198,6 +201,9 @@ __global__ void pack_weights_f16_kernel(const float *__restrict__ w, int cout, i
         split_f16(v * s, h1, h2);
         mat[i] = h2;
         mat[total + i] = h1;
+        const int H = npad >> 1, r = n / H, j = n - r * H;
+        mat2[((size_t)(r * npad + j)) * ktot + k] = h2;
+        mat2[((size_t)(r * npad + H + j)) * ktot + k] = h1;
     }
 }
 
@@ -253,6 +259,11 @@ struct Sched {  // the permuted unit sequence of one CTA: [whole tiles + head se
     __device__ __forceinline__ long long unit(int i) const {
         const int len_tail = n - main_len;
         return i < main_len ? u0 + len_tail + i : u0 + (i - main_len);
+    }
+    // unit i closes its accumulation chunk: the chunk is full, or the unit ends a segment of the sequence
+    // (end of a tile, end of the main part, end of the CTA's range).  in_chunk = units already in the chunk.
+    __device__ __forceinline__ bool chunk_ends(int i, int r, int in_chunk, int chunk_units) const {
+        return in_chunk + 1 >= chunk_units || i == n - 1 || i == main_len - 1 || r == upt - 1;
     }
 };
 
@@ -604,6 +615,388 @@ convdet_f16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2): two SMs of a TPC work on two M tiles with ONE issuing thread and ONE copy of B.
+// ---------------------------------------------------------------------------------------------------
+// Why: the 1-CTA kernel is bound by (1) L2->SM traffic -- every CTA streams the whole 2.2 MB weight matrix per tile --
+// and (2) the single MMA-issuing thread (barrier round trips + ~46 cycles per tcgen05.mma).  With cta_group::2 an MMA has
+// M = 256 (128 rows per CTA), each CTA holds only HALF of the B rows (the tensor core reads the other half from the
+// peer's shared memory), and one thread issues for both SMs: B traffic per tile and issue cost per FLOP both halve.
+//
+//  * pair-tile j = tiles {j, j + PT} (PT = ceil(tiles/2)); rank r of the pair owns tile j + r*PT.  A ghost tile
+//    (odd tile count) loads zeros (TMA out-of-bounds image index) and is never stored.
+//  * B tile of one tap in CTA r: rows [0,H) = w2 of channels [rH,(r+1)H), rows [H,2H) = w1 of the same channels.
+//        MMA1: D[:, 0:2N)   (+)= A1 * B^T        -> columns [cross(0:H) | main(0:H) | cross(H:2H) | main(H:2H)]
+//        MMA2: D[:, 2N:3N)  (+)= A2 * B[H:2H)^T  -> columns [cross2(0:H) | cross2(H:2H)]   (own columns: the N halves
+//              of the pair do not line up with MMA1's cross columns)
+//  * unit-granular stages: one stage = the unit's two A patches + its three B tiles (70 KB at Npad = 80, 3 stages).
+//    Per unit the issuing thread does two barrier waits, 24 MMAs and two multicast commits:
+//        full[s]   leader only: both CTAs' TMA bytes of stage s landed (cta_group::2 TMA credits the leader's barrier)
+//        sfree[s]  both CTAs  : the MMAs reading stage s completed            (tcgen05.commit multicast)
+//        tfull[b]  both CTAs  : TMEM accumulator b holds a finished unit      (tcgen05.commit multicast)
+//        tempty[b] leader only: all 8 accumulate warps of the pair drained accumulator b (remote mbarrier arrives)
+//  * 192 threads: warp 0 TMA producer, warp 1 TMEM alloc (+ MMA issue in the leader), warps 2..5 accumulate/epilogue.
+constexpr int kThreads2 = 192;
+constexpr int kWarpTma2 = 0, kWarpMma2 = 1, kWarpAcc2 = 2;
+
+__device__ __forceinline__ void umma_f16_ss_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+struct PairParams {
+    int cin, gh, gw, cout, batch;
+    int tiles_x, tiles_per_img, total_tiles, pair_tiles;
+    int upt;             // units per tile = (cin/64) * 3
+    int units_per_pair;  // even cut of pair_tiles*upt over the pairs (>= upt)
+    int stages;
+    int chunk_units;     // units accumulated inside TMEM before the sum moves to registers (1 or 2)
+    int dbg;
+    const float *bias;
+    const unsigned *amax_bits;
+    const PackedHeader *whdr;
+    float *pred;
+    float *partial;  // (grid, 128, NPAD)
+    int *flags;      // (grid)
+    int *status;
+    long long *trace;
+    int trace_cta;
+};
+
+struct PairIter {  // like UnitIter, for the tile of one rank; img may run past the batch for a ghost tile
+    int r, cb, dxi, img, tx, ty;
+    __device__ __forceinline__ void seek(long long u, int tile_offset, const PairParams &p) {
+        const int pt = (int)(u / p.upt);
+        r = (int)(u - (long long)pt * p.upt);
+        cb = r / 3;
+        dxi = r - cb * 3;
+        const int tile = pt + tile_offset;
+        img = tile / p.tiles_per_img;
+        const int t = tile - img * p.tiles_per_img;
+        ty = t / p.tiles_x;
+        tx = t - ty * p.tiles_x;
+    }
+    __device__ __forceinline__ void next(const PairParams &p) {
+        ++r;
+        if (++dxi == 3) {
+            dxi = 0;
+            ++cb;
+        }
+        if (r == p.upt) {
+            r = 0;
+            cb = 0;
+            if (++tx == p.tiles_x) {
+                tx = 0;
+                if (++ty * p.tiles_x == p.tiles_per_img) {
+                    ty = 0;
+                    ++img;
+                }
+            }
+        }
+    }
+};
+
+#define SQD_TRACE2(slot, i) \
+    do { if (p.trace && cta == p.trace_cta && lane == 0 && (i) < 512) p.trace[(i) * 32 + (slot)] = clock64(); } while (0)
+
+__device__ __forceinline__ bool pair_wait_warp(uint64_t *bar, uint32_t parity, volatile int *abort_flag, bool spin) {
+    return spin ? mbar_spin_warp(bar, parity, abort_flag) : mbar_wait_warp(bar, parity, abort_flag);
+}
+
+template <int NPAD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
+                        const __grid_constant__ CUtensorMap map_b, const PairParams p) {
+    constexpr int H = NPAD / 2;
+    constexpr int kBTapBytes = NPAD * kBlockK * 2;          // this CTA's half of one tap: [w2 H rows | w1 H rows]
+    constexpr int kW1Offset = H * kBlockK * 2;              // multiple of 1024 (H is a multiple of 8)
+    constexpr int kStageBytes = kAStageBytes + 3 * kBTapBytes;
+    constexpr int kAccCols = 3 * NPAD;                      // [MMA1: 2*NPAD | MMA2: NPAD]
+    constexpr int kAccBufs = (2 * kAccCols <= 512) ? 2 : 1;
+    constexpr uint32_t kTmemCols = 512;
+    constexpr uint32_t kIdesc1 = umma_idesc_f16(256, 2 * NPAD);
+    constexpr uint32_t kIdesc2 = umma_idesc_f16(256, NPAD);
+    static_assert(kAccCols <= 512, "TMEM budget");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int S = p.stages;
+    uint8_t *ctrl = smem + (size_t)S * kStageBytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ctrl);   // [4]
+    uint64_t *sfree = full + 4;                            // [4]
+    uint64_t *tfull = sfree + 4;                           // [2]
+    uint64_t *tempty = tfull + 2;                          // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    volatile int *abort_flag = reinterpret_cast<volatile int *>(tmem_slot + 1);
+    float *s_bias = reinterpret_cast<float *>(tmem_slot + 2);  // NPAD floats
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cta = blockIdx.x;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = cta >> 1, npairs = gridDim.x >> 1;
+    const int tile_offset = rank ? p.pair_tiles : 0;
+    const bool spin = (p.dbg & 8) != 0;   // debug: 8 = poll mbarrier.test_wait instead of parking in try_wait (slower)
+
+    // ---- this pair's slice of the (pair-tile, unit) space ----------------------------------------------------
+    const long long total_units = (long long)p.pair_tiles * p.upt;
+    Sched sc;
+    sc.upt = p.upt;
+    sc.u0 = (long long)pair * p.units_per_pair;
+    {
+        long long u1 = sc.u0 + p.units_per_pair;
+        if (u1 > total_units) u1 = total_units;
+        sc.n = u1 > sc.u0 ? (int)(u1 - sc.u0) : 0;
+        const int r0 = (int)(sc.u0 % p.upt);
+        int len_tail = r0 ? p.upt - r0 : 0;
+        if (len_tail > sc.n) len_tail = sc.n;
+        sc.main_len = sc.n - len_tail;
+    }
+    const int n_units = sc.n;
+    (void)npairs;
+
+    if (threadIdx.x == 0) {
+        *abort_flag = 0;
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(sfree + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull + b, 1);
+            mbar_init(tempty + b, 8);  // 4 accumulate warps x 2 CTAs
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == kWarpTma2 && lane == 0) {
+        tma_prefetch_desc(&map_a1);
+        tma_prefetch_desc(&map_a2);
+        tma_prefetch_desc(&map_b);
+    }
+    for (int i = threadIdx.x; i < NPAD; i += kThreads2) s_bias[i] = i < p.cout ? __ldg(p.bias + i) : 0.f;
+    if (warp == kWarpMma2) tmem_alloc_2cta(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // both CTAs: barriers initialised, TMEM allocated, before any remote arrive / multicast
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == kWarpTma2) {
+        // ===== producer: this CTA's A patches (own tile) and its half of the three B tiles of one unit =====
+        PairIter it;
+        Ring rs{0, 0};
+        for (int i = 0; i < n_units; ++i) {
+            if (i == 0 || i == sc.main_len) it.seek(sc.unit(i), tile_offset, p); else it.next(p);
+            if (!pair_wait_warp(sfree + rs.s, rs.ph ^ 1u, abort_flag, spin)) {
+                if (lane == 0) atomicCAS(p.status, 0, 1);
+                break;
+            }
+            SQD_TRACE2(0, i);
+            if (elect_one_sync()) {
+                uint8_t *st = smem + (size_t)rs.s * kStageBytes;
+                const int x = it.tx * kTileX + it.dxi - 1, y = it.ty * kTileY - 1;
+                const int bytes = ((p.dbg & 2) ? 0 : kAStageBytes) + ((p.dbg & 4) ? 0 : 3 * kBTapBytes);
+                if (rank == 0) mbar_arrive_expect_tx(full + rs.s, 2 * bytes);  // both CTAs' bytes
+                if (!(p.dbg & 2)) {
+                    tma_load_4d_2cta(&map_a1, full + rs.s, st, it.cb * kBlockK, x, y, it.img);
+                    tma_load_4d_2cta(&map_a2, full + rs.s, st + kPlaneBytes, it.cb * kBlockK, x, y, it.img);
+                }
+                if (!(p.dbg & 4)) {
+#pragma unroll
+                    for (int dyi = 0; dyi < 3; ++dyi)
+                        tma_load_2d_2cta(&map_b, full + rs.s, st + kAStageBytes + dyi * kBTapBytes,
+                                         (dyi * 3 + it.dxi) * p.cin + it.cb * kBlockK, (int)rank * NPAD);
+                }
+            }
+            __syncwarp();
+            rs.advance(S);
+        }
+    } else if (warp == kWarpMma2) {
+        if (rank == 0) {
+            // ===== MMA issuer (leader CTA): 24 M=256 MMAs per unit; converged warp, one elected lane issues =====
+            Ring rs{0, 0};
+            int chunk = 0, in_chunk = 0;  // a chunk = up to p.chunk_units consecutive units of one segment in one accumulator
+            PairIter it;
+            for (int i = 0; i < n_units; ++i) {
+                if (i == 0 || i == sc.main_len) it.seek(sc.unit(i), tile_offset, p); else it.next(p);
+                const int buf = kAccBufs == 2 ? (chunk & 1) : 0;
+                const uint32_t acc_ph = kAccBufs == 2 ? ((uint32_t)(chunk >> 1) & 1u) : ((uint32_t)chunk & 1u);
+                if (in_chunk == 0) {
+                    if (!pair_wait_warp(tempty + buf, acc_ph ^ 1u, abort_flag, spin)) {
+                        if (lane == 0) atomicCAS(p.status, 0, 4);
+                        break;
+                    }
+                }
+                SQD_TRACE2(2, i);
+                if (!pair_wait_warp(full + rs.s, rs.ph, abort_flag, spin)) {
+                    if (lane == 0) atomicCAS(p.status, 0, 2);
+                    break;
+                }
+                SQD_TRACE2(3, i);
+                tc_fence_after();
+                const uint32_t d1 = tmem_base + (uint32_t)buf * kAccCols, d2 = d1 + 2 * NPAD;
+                const uint32_t st = smem_u32(smem + (size_t)rs.s * kStageBytes);
+                const bool chunk_end = sc.chunk_ends(i, it.r, in_chunk, p.chunk_units);
+                if (elect_one_sync()) {
+                    if (!(p.dbg & 1)) {
+#pragma unroll
+                        for (int dyi = 0; dyi < 3; ++dyi) {
+                            const uint64_t a1 = umma_desc_sw128(st + dyi * kDyBytes);
+                            const uint64_t a2 = umma_desc_sw128(st + kPlaneBytes + dyi * kDyBytes);
+                            const uint64_t b = umma_desc_sw128(st + kAStageBytes + dyi * kBTapBytes);
+                            const uint64_t bw1 = umma_desc_sw128(st + kAStageBytes + dyi * kBTapBytes + kW1Offset);
+#pragma unroll
+                            for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
+                                const uint64_t adv = (uint64_t)((ks * kUmmaK * 2) >> 4);
+                                const uint32_t accum = (in_chunk | dyi | ks) ? 1u : 0u;
+                                umma_f16_ss_2cta(d1, a1 + adv, b + adv, kIdesc1, accum);
+                                umma_f16_ss_2cta(d2, a2 + adv, bw1 + adv, kIdesc2, accum);
+                            }
+                        }
+                    }
+                    umma_commit_2cta(sfree + rs.s, 3);                  // stage reusable in both CTAs
+                    if (chunk_end) umma_commit_2cta(tfull + buf, 3);    // chunk complete (both CTAs' accumulate warps)
+                }
+                __syncwarp();
+                SQD_TRACE2(10, i);
+                rs.advance(S);
+                if (chunk_end) {
+                    ++chunk;
+                    in_chunk = 0;
+                } else {
+                    ++in_chunk;
+                }
+            }
+        }
+    } else {
+        // ===== accumulate + epilogue warps (both CTAs, each on its own 128 TMEM lanes) =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int et = threadIdx.x - kWarpAcc2 * 32;  // 0..127
+        const float inv_sw = p.whdr->inv_scale;
+        float acc[NPAD];
+        int seg_r0 = 0, chunk = 0, in_chunk = 0;
+        PairIter it;
+        for (int i = 0; i < n_units; ++i) {
+            if (i == 0 || i == sc.main_len) it.seek(sc.unit(i), tile_offset, p); else it.next(p);
+            const int r = it.r;
+            if (i == 0 || r == 0 || i == sc.main_len) {
+                seg_r0 = r;
+#pragma unroll
+                for (int n = 0; n < NPAD; ++n) acc[n] = 0.f;
+            }
+            const bool chunk_end = sc.chunk_ends(i, r, in_chunk, p.chunk_units);
+            if (!chunk_end) {   // the tensor core keeps accumulating this chunk in TMEM
+                ++in_chunk;
+                continue;
+            }
+            in_chunk = 0;
+            const int buf = kAccBufs == 2 ? (chunk & 1) : 0;
+            const uint32_t acc_ph = kAccBufs == 2 ? ((uint32_t)(chunk >> 1) & 1u) : ((uint32_t)chunk & 1u);
+            ++chunk;
+            if (!pair_wait_warp(tfull + buf, acc_ph, abort_flag, spin)) {
+                if (lane == 0) atomicCAS(p.status, 0, 3);
+                break;
+            }
+            tc_fence_after();
+            __syncwarp();
+            if (warp == kWarpAcc2) SQD_TRACE2(11, i);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * kAccCols;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int j0 = 0; j0 < H; j0 += 8) {
+                    uint32_t c1[8], mn[8], c2[8];
+                    tmem_ld_x8(taddr + h * NPAD + j0, c1);             // a1*w2
+                    tmem_ld_x8(taddr + h * NPAD + H + j0, mn);         // a1*w1
+                    tmem_ld_x8(taddr + 2 * NPAD + h * H + j0, c2);     // a2*w1
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float cross = fadd(__uint_as_float(c1[k]), __uint_as_float(c2[k]));
+                        acc[h * H + j0 + k] = fadd(acc[h * H + j0 + k], fmaf(cross, kLoInv, __uint_as_float(mn[k])));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(tempty + buf);
+                else mbar_arrive_cluster(tempty + buf, 0);
+            }
+            if (warp == kWarpAcc2) SQD_TRACE2(12, i);
+
+            const bool seg_end = (i == n_units - 1) || (r == p.upt - 1) || (i == sc.main_len - 1);
+            if (!seg_end) continue;
+            const bool from_start = seg_r0 == 0, to_end = r == p.upt - 1;
+            if (from_start && !to_end) {
+                // head of a split pair-tile: publish for the same rank of the next pair
+                float4 *dst = reinterpret_cast<float4 *>(p.partial + ((size_t)cta * 128 + row) * NPAD);
+#pragma unroll
+                for (int n = 0; n < NPAD; n += 4) dst[n >> 2] = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+                __threadfence();
+                epi_bar();
+                if (et == 0) st_release(p.flags + cta, 1);
+                continue;
+            }
+            if (!from_start && to_end) {
+                if (et == 0) {
+                    unsigned spin = 0;
+                    while (ld_acquire(p.flags + cta - 2) == 0) {
+                        if (++spin > kSpinLimit || *abort_flag) {
+                            *abort_flag = 1;
+                            atomicCAS(p.status, 0, 8);
+                            break;
+                        }
+                    }
+                }
+                epi_bar();
+                const float4 *src = reinterpret_cast<const float4 *>(p.partial + ((size_t)(cta - 2) * 128 + row) * NPAD);
+#pragma unroll
+                for (int n = 0; n < NPAD; n += 4) {
+                    const float4 hd = __ldcg(src + (n >> 2));
+                    acc[n] = fadd(hd.x, acc[n]); acc[n + 1] = fadd(hd.y, acc[n + 1]);
+                    acc[n + 2] = fadd(hd.z, acc[n + 2]); acc[n + 3] = fadd(hd.w, acc[n + 3]);
+                }
+            } else if (!(from_start && to_end)) {
+                if (lane == 0) atomicCAS(p.status, 0, 9);
+                continue;
+            }
+            // whole tile in registers: x 1/(s_a*s_w), + bias -> pred   (ghost tile: img == batch, nothing stored)
+            const int x = it.tx * kTileX + row % kTileX, y = it.ty * kTileY + row / kTileX;
+            if (it.img < p.batch && y < p.gh && x < p.gw) {
+                const float inv = fmul(1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_bits + it.img))), inv_sw);
+                float *out = p.pred + (((size_t)it.img * p.gh + y) * p.gw + x) * p.cout;
+                if ((p.cout & 3) == 0) {
+                    float4 *o4 = reinterpret_cast<float4 *>(out);
+#pragma unroll
+                    for (int n = 0; n < NPAD; n += 4)
+                        if (n < p.cout)
+                            o4[n >> 2] = make_float4(fadd(fmul(acc[n], inv), s_bias[n]), fadd(fmul(acc[n + 1], inv), s_bias[n + 1]),
+                                                     fadd(fmul(acc[n + 2], inv), s_bias[n + 2]),
+                                                     fadd(fmul(acc[n + 3], inv), s_bias[n + 3]));
+                } else {
+#pragma unroll
+                    for (int n = 0; n < NPAD; ++n)
+                        if (n < p.cout) out[n] = fadd(fmul(acc[n], inv), s_bias[n]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still touch its shared memory / barriers
+    tc_fence_after();
+    if (warp == kWarpMma2) {
+        __syncwarp();
+        tmem_dealloc_2cta(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -693,7 +1086,7 @@ int launch_f16(const CUtensorMap *maps, const F16Params &p, int grid, cudaStream
 }  // namespace
 
 size_t sqd_f16_packed_bytes(int cout, int cin) {
-    return kHeaderBytes + (size_t)2 * npad_of(cout) * 9 * cin * sizeof(__half);
+    return kHeaderBytes + (size_t)2 * 2 * npad_of(cout) * 9 * cin * sizeof(__half);  // 1-CTA and CTA-pair layouts
 }
 
 int sqd_f16_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, cudaStream_t st) {
@@ -705,9 +1098,121 @@ int sqd_f16_pack_weights(const float *d_weight, int cout, int cin, void *d_packe
     const size_t n = (size_t)cout * cin * 9;
     weight_absmax_kernel<<<SQD_SM_COUNT, 256, 0, st>>>(d_weight, n, hdr);
     SQD_LAUNCH_CHECK("weight_absmax_kernel");
-    pack_weights_f16_kernel<<<SQD_SM_COUNT * 4, 256, 0, st>>>(d_weight, cout, cin, npad_of(cout), hdr, mat);
+    pack_weights_f16_kernel<<<SQD_SM_COUNT * 4, 256, 0, st>>>(d_weight, cout, cin, npad_of(cout), hdr, mat,
+                                                              mat + (size_t)2 * npad_of(cout) * 9 * cin);
     SQD_LAUNCH_CHECK("pack_weights_f16_kernel");
     return SQD_OK;
+}
+
+namespace {
+int pair_stages_for(int npad) {
+    const size_t stage = (size_t)kAStageBytes + (size_t)3 * npad * kBlockK * 2;
+    size_t s = (kSmemLimit - 1024 - kCtrlBytes) / stage;
+    if (s > 4) s = 4;
+    const int cap = env_int("SQD_F16_PAIR_STAGES", 4);
+    if ((int)s > cap && cap >= 1) s = cap;
+    return (int)s;
+}
+
+template <int NPAD>
+int launch_pair(const CUtensorMap *maps, const PairParams &p, int grid, cudaStream_t st) {
+    const size_t smem = 1024 + (size_t)p.stages * (kAStageBytes + 3 * NPAD * kBlockK * 2) + kCtrlBytes;
+    SQD_CUDA(cudaFuncSetAttribute(convdet_f16_pair_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    convdet_f16_pair_kernel<NPAD><<<grid, kThreads2, smem, st>>>(maps[0], maps[1], maps[2], p);
+    SQD_LAUNCH_CHECK("convdet_f16_pair_kernel");
+    return SQD_OK;
+}
+}  // namespace
+
+int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, int gh, int gw, void *d_planes,
+                           cudaStream_t st);
+
+int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
+                         int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st) {
+    SQD_REQUIRE(cin % kBlockK == 0, SQD_E_SHAPE, "convdet (tcgen05): Cin %d must be a multiple of %d", cin, kBlockK);
+    SQD_REQUIRE(cout >= 1 && cout <= 128, SQD_E_SHAPE, "convdet (tcgen05): Cout %d outside [1,128]", cout);
+    EncodeTiledFn encode = get_encode_fn();
+    SQD_REQUIRE(encode != nullptr, SQD_E_DRIVER, "cuTensorMapEncodeTiled not available from the CUDA driver");
+    const int npad = npad_of(cout);
+    const WsLayout w = ws_layout(batch, cin, gh, gw, cout, layout);
+    char *ws = static_cast<char *>(d_workspace);
+    SQD_CUDA(cudaMemsetAsync(ws, 0, w.partial_off, st));  // status + flags
+
+    const char *planes = reinterpret_cast<const char *>(d_feat);
+    if (layout != SQD_LAYOUT_SPLIT_NHWC) {
+        int rc = sqd_f16_split_features(d_feat, layout, batch, cin, gh, gw, ws + w.planes_off, st);
+        if (rc) return rc;
+        planes = ws + w.planes_off;
+    }
+    const PlaneLayout pl = plane_layout(batch, cin, gh, gw);
+
+    alignas(64) CUtensorMap maps[3];
+    for (int i = 0; i < 2; ++i) {
+        const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)gw, (cuuint64_t)gh, (cuuint64_t)batch};
+        const cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)gw * cin * 2, (cuuint64_t)gh * gw * cin * 2};
+        const cuuint32_t box[4] = {kBlockK, kTileX, kPatchY, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        void *base = const_cast<char *>(planes + (i == 0 ? pl.p1_off : pl.p2_off));
+        CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SQD_REQUIRE(r == CUDA_SUCCESS, SQD_E_DRIVER, "cuTensorMapEncodeTiled(features) failed: CUresult %d", (int)r);
+    }
+    {
+        const size_t ktot = (size_t)9 * cin;
+        void *mat2 = const_cast<char *>(static_cast<const char *>(d_packed) + kHeaderBytes) + (size_t)2 * npad * ktot * sizeof(__half);
+        const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)(2 * npad)};
+        const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+        const cuuint32_t box[2] = {kBlockK, (cuuint32_t)npad};   // one CTA's half: npad rows
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&maps[2], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, mat2, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SQD_REQUIRE(r == CUDA_SUCCESS, SQD_E_DRIVER, "cuTensorMapEncodeTiled(weights) failed: CUresult %d", (int)r);
+    }
+
+    PairParams p;
+    p.cin = cin; p.gh = gh; p.gw = gw; p.cout = cout; p.batch = batch;
+    p.tiles_x = (gw + kTileX - 1) / kTileX;
+    p.tiles_per_img = p.tiles_x * ((gh + kTileY - 1) / kTileY);
+    const long long total_tiles = (long long)p.tiles_per_img * batch;
+    SQD_REQUIRE(total_tiles < (1ll << 30), SQD_E_SHAPE, "convdet (tcgen05): too many tiles");
+    p.total_tiles = (int)total_tiles;
+    p.pair_tiles = (int)((total_tiles + 1) / 2);
+    p.upt = cin / kBlockK * 3;
+    const int max_pairs = SQD_SM_COUNT / 2;
+    const int npairs = p.pair_tiles < max_pairs ? p.pair_tiles : max_pairs;
+    const long long total_units = (long long)p.pair_tiles * p.upt;
+    long long upp = (total_units + npairs - 1) / npairs;
+    if (upp < p.upt) upp = p.upt;
+    p.units_per_pair = (int)upp;
+    p.stages = pair_stages_for(npad);
+    SQD_REQUIRE(p.stages >= 2, SQD_E_SHAPE, "convdet (tcgen05): shared memory too small for two stages");
+    p.chunk_units = env_int("SQD_F16_CHUNK", 2);
+    if (p.chunk_units < 1) p.chunk_units = 1;
+    p.dbg = env_int("SQD_F16_DBG", 0);
+    p.bias = d_bias;
+    p.amax_bits = reinterpret_cast<const unsigned *>(planes);
+    p.whdr = static_cast<const PackedHeader *>(d_packed);
+    p.pred = d_pred;
+    p.partial = reinterpret_cast<float *>(ws + w.partial_off);
+    p.flags = reinterpret_cast<int *>(ws + w.flags_off);
+    p.status = reinterpret_cast<int *>(ws);
+    p.trace = nullptr;
+    p.trace_cta = env_int("SQD_F16_TRACE_CTA", 0);
+    if (const char *e = getenv("SQD_F16_TRACE")) p.trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
+    const int grid = 2 * npairs;
+    switch (npad / 16) {
+        case 1: return launch_pair<16>(maps, p, grid, st);
+        case 2: return launch_pair<32>(maps, p, grid, st);
+        case 3: return launch_pair<48>(maps, p, grid, st);
+        case 4: return launch_pair<64>(maps, p, grid, st);
+        case 5: return launch_pair<80>(maps, p, grid, st);
+        case 6: return launch_pair<96>(maps, p, grid, st);
+        case 7: return launch_pair<112>(maps, p, grid, st);
+        case 8: return launch_pair<128>(maps, p, grid, st);
+    }
+    SQD_REQUIRE(false, SQD_E_SHAPE, "convdet (tcgen05): unsupported Cout %d", cout);
 }
 
 size_t sqd_f16_split_bytes(int batch, int cin, int gh, int gw) { return plane_layout(batch, cin, gh, gw).total; }

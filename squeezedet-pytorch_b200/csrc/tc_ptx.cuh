@@ -56,6 +56,31 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
 __device__ __forceinline__ bool mbar_wait_warp(uint64_t *bar, uint32_t parity, volatile int *abort_flag) {
     return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag));
 }
+// Non-suspending variant: mbarrier.test_wait in a tight loop (try_wait may park the thread for a system-dependent
+// time; a polling loop reacts to remote / multicast arrivals sooner).  Same bounded-spin contract as mbar_wait.
+__device__ __forceinline__ bool mbar_spin(uint64_t *bar, uint32_t parity, volatile int *abort_flag) {
+    const uint32_t addr = smem_u32(bar);
+    for (unsigned spin = 0; spin < kSpinLimit; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return true;
+        if ((spin & 1023u) == 1023u && *abort_flag) return false;
+    }
+    *abort_flag = 1;
+    return false;
+}
+// one polling lane, verdict broadcast to the (converged) warp
+__device__ __forceinline__ bool mbar_spin_warp(uint64_t *bar, uint32_t parity, volatile int *abort_flag) {
+    int ok = 1;
+    if ((threadIdx.x & 31) == 0) ok = mbar_spin(bar, parity, abort_flag) ? 1 : 0;
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -134,5 +159,63 @@ __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
+
+// ---- CTA-pair (cta_group::2) variants; PTX strings as in cute/arch/{tmem_allocator_sm100,copy_sm100_tma,mma_sm100_umma}.hpp
+// and cutlass/arch/barrier.h -------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> the pair's leader
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// TMA loads issued by either CTA of a pair: data lands in the issuing CTA's shared memory, the transaction bytes are
+// credited to the mbarrier at the same offset in the LEADER CTA.
+__device__ __forceinline__ void tma_load_4d_2cta(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2,
+                                                 int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// mbarrier (same offset in every CTA of `cta_mask`) arrives when all previously issued MMAs of this thread completed
+__device__ __forceinline__ void umma_commit_2cta(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 
 }  // namespace sqd_tc

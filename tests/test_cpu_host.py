@@ -34,8 +34,8 @@ def test_library_exports_every_declared_symbol():
 def test_size_queries_need_no_gpu():
     from squeezedet_pytorch_b200 import _lib
     lib = _lib.load()
-    # KITTI: Cout 72 -> padded 80 rows, two fp16 terms, 256-byte header
-    assert lib.sqd_convdet_packed_weight_bytes(72, 768) == 256 + 2 * 80 * 9 * 768 * 2
+    # KITTI: Cout 72 -> padded 80 rows, two fp16 terms, two layouts (CTA-pair and 1-CTA kernels), 256-byte header
+    assert lib.sqd_convdet_packed_weight_bytes(72, 768) == 256 + 2 * 2 * 80 * 9 * 768 * 2
     # workspace holds the two fp16 NHWC planes of the batch
     assert lib.sqd_convdet_workspace_bytes(20, 768, 24, 78, 72, 0, 0) >= 2 * 20 * 768 * 24 * 78 * 2
     assert lib.sqd_convdet_split_bytes(20, 768, 24, 78) >= 2 * 20 * 768 * 24 * 78 * 2

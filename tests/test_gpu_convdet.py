@@ -176,3 +176,16 @@ def test_head_detect_host_equals_device_call(ops, chunk):
                                 shp.nms_thresh, shp.score_thresh, chunk_images=chunk)
     for f in ("count", "anchor", "cls", "score", "box"):
         assert torch.equal(getattr(ref, f).cpu(), getattr(host, f)), f
+
+
+@pytest.mark.parametrize("name,batch", [("tiny_160x96", 3), ("kitti_1248x384", 7)])
+def test_pair_kernel_matches_single_cta_kernel(ops, name, batch):
+    """The production CTA-pair kernel (cta_group::2, odd tile counts -> ghost tile, split tiles across pairs) against
+    the one-CTA-per-tile kernel: same products, only the accumulation chunking differs."""
+    from squeezedet_pytorch_b200._lib import CONV_TCGEN05_F16X3, CONV_TCGEN05_F16X3_1CTA
+    shp = SHAPES[name]
+    feat = synth.features(shp, batch, 31)
+    w, b = synth.convdet_params(shp, 32)
+    pair = ops.convdet_forward(dev(feat), dev(w), dev(b), algo=CONV_TCGEN05_F16X3, check_status=True)
+    one = ops.convdet_forward(dev(feat), dev(w), dev(b), algo=CONV_TCGEN05_F16X3_1CTA, check_status=True)
+    assert torch.allclose(pair, one, rtol=2e-5, atol=5e-6), float((pair - one).abs().max())

@@ -8,7 +8,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from squeezedet_pytorch_b200 import ops, synth  # noqa: E402
-from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32, CONV_TCGEN05_F16X3  # noqa: E402
+from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32, CONV_TCGEN05_F16X3, CONV_TCGEN05_F16X3_1CTA  # noqa: E402
+
+TC = CONV_TCGEN05_F16X3_1CTA if "--1cta" in sys.argv else CONV_TCGEN05_F16X3
 
 
 def run(shape, batch, layout, feat_scale=1.0, w_scale=1.0, ragged=False):
@@ -23,7 +25,7 @@ def run(shape, batch, layout, feat_scale=1.0, w_scale=1.0, ragged=False):
     w, b = torch.from_numpy(w).cuda() * w_scale, torch.from_numpy(b).cuda()
     ref = torch.nn.functional.conv2d(feat.double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1).contiguous()
     simt = ops.convdet_forward(feat, w, b, algo=CONV_SIMT_FP32).double()
-    tc = ops.convdet_forward(feat, w, b, algo=CONV_TCGEN05_F16X3, check_status=True).double()
+    tc = ops.convdet_forward(feat, w, b, algo=TC, check_status=True).double()
     den = ref.abs().flatten(1).mean(1).view(-1, 1, 1, 1)  # per-image typical magnitude
     e_tc, e_simt = ((tc - ref) / den).abs(), ((simt - ref) / den).abs()
     print(f"{shape.name:18s} B={batch:<4d} {layout:13s} fs={feat_scale:g} ws={w_scale:g} ragged={int(ragged)} | "
@@ -48,12 +50,12 @@ if __name__ == "__main__":
         feat, w, b = run(synth.KITTI, 20, layout)
         packed = ops.pack_convdet_weights(w)
         for _ in range(3):
-            ops.convdet_forward(feat, w, b, packed=packed, algo=CONV_TCGEN05_F16X3)
+            ops.convdet_forward(feat, w, b, packed=packed, algo=TC)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(20):
-            ops.convdet_forward(feat, w, b, packed=packed, algo=CONV_TCGEN05_F16X3)
+            ops.convdet_forward(feat, w, b, packed=packed, algo=TC)
         e1.record()
         torch.cuda.synchronize()
         print(f"KITTI B=20 {layout:13s} f16x3: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per convdet_forward "

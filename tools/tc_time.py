@@ -10,6 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from squeezedet_pytorch_b200 import _lib, ops, synth  # noqa: E402
 
+ALGO = int(os.environ.get("TC_ALGO", "0"))
 shp, B = synth.KITTI, int(os.environ.get("TC_BATCH", "20"))
 lib = _lib.load()
 dev = torch.device("cuda")
@@ -29,7 +30,7 @@ pred = torch.empty((B, gh, gw, shp.out_channels), device=dev)
 
 def gemm(i):
     _lib.check(lib.sqd_convdet_forward(_lib.ptr(planes[i % 3]), 2, _lib.ptr(packed), None, _lib.ptr(b), B, shp.in_channels, gh, gw,
-                                       shp.out_channels, _lib.ptr(pred), _lib.ptr(ws), ws.numel(), 0, st), "gemm")
+                                       shp.out_channels, _lib.ptr(pred), _lib.ptr(ws), ws.numel(), ALGO, st), "gemm")
 
 
 for setting in (sys.argv[1:] or [""]):

@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from squeezedet_pytorch_b200 import _lib, ops, synth  # noqa: E402
 
+ALGO = int(os.environ.get("TC_ALGO", "0"))
 shp, B = synth.KITTI, 20
 lib = _lib.load()
 dev = torch.device("cuda")
@@ -28,7 +29,7 @@ pred = torch.empty((B, gh, gw, 72), device=dev)
 
 def gemm():
     _lib.check(lib.sqd_convdet_forward(_lib.ptr(planes), 2, _lib.ptr(packed), None, _lib.ptr(b), B, 768, gh, gw, 72,
-                                       _lib.ptr(pred), _lib.ptr(ws), ws.numel(), 0, st), "gemm")
+                                       _lib.ptr(pred), _lib.ptr(ws), ws.numel(), ALGO, st), "gemm")
 
 
 NAMES = ["A_issue", "B_issue0", "m_tmem_ok", "m_a_ok", "m_b0_ok", "m_b0_iss", "m_b1_ok", "m_b1_iss", "m_b2_ok", "m_b2_iss",
@@ -54,6 +55,15 @@ for setting in (sys.argv[1:] or [""]):
     for i in list(range(0, 5)) + list(range(36, 40)) + list(range(n - 3, n)):
         print(f"{i:4d} " + " ".join(f"{int(v - t0):9d}" for v in t[i][:13]))
     m = slice(2, n - 2)
+    if ALGO == 0:
+        d = lambda a, b: float((t[m, a] - t[m, b]).mean())  # noqa: E731
+        print("pair: period %.0f | mma: wait tempty %.0f, wait full %.0f, issue+commit %.0f | producer issue -> full seen %.0f | "
+              "acc: tfull seen after m_end %.0f, drain %.0f | tempty seen by mma(i+2) after acc_done(i) %.0f" % (
+                  np.diff(t[:n, 10]).mean(), float((t[m, 2] - t[1:n - 3, 10]).mean()), d(3, 2), d(10, 3), d(3, 0), d(11, 10), d(12, 11),
+                  float((t[4:n, 2] - t[2:n - 2, 12]).mean())))
+        for k in keys:
+            del os.environ[k]
+        continue
     print("period (m_end to m_end): mean %.0f median %.0f" % (np.diff(t[:n, 10]).mean(), np.median(np.diff(t[:n, 10]))))
     print("mma: wait tmem_empty %.0f | wait a_full %.0f | per dy: wait b_full %.0f %.0f %.0f, issue %.0f %.0f %.0f | tail commits %.0f | loop back %.0f" % (
         (t[m, 2] - t[1:n - 3, 10]).mean(), (t[m, 3] - t[m, 2]).mean(),
