@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SQD_ABI_VERSION 1
+#define SQD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SQD_API __attribute__((visibility("default")))
@@ -129,15 +129,23 @@ SQD_API int sqd_topk_nms(const int64_t *d_class_ids, const float *d_scores, cons
                  int32_t *d_count, int32_t *d_out_anchor, int32_t *d_out_class, float *d_out_score,
                  float *d_out_box, void *stream);
 
-/* Fused a2-a9: pred -> final detections in ONE launch; the dense (B,A) ids/scores/boxes of the
- * SqueezeDet.forward contract are never materialised (reads A*(C+5)*4 bytes per image once). */
+/* Fused a2-a9: pred -> final detections; the dense (B,A) ids/scores/boxes of the SqueezeDet.forward contract
+ * are never materialised (reads A*(C+5)*4 bytes per image once).
+ *   d_workspace != NULL (sqd_detect_workspace_bytes): two launches -- a streaming scan of pred that appends the
+ *     anchors above the score threshold to per-image candidate lists (HBM bound, the whole grid on the whole batch),
+ *     then one CTA per image selects / sorts / suppresses / emits.  The form to use for large batches.
+ *   d_workspace == NULL: one launch, a thread-block cluster per image does both (no scratch memory).
+ * Both forms return identical results. */
+SQD_API size_t sqd_detect_workspace_bytes(int batch, int num_anchors);
 SQD_API int sqd_detect_from_pred(const float *d_pred, const float *d_anchors, int batch, int num_anchors, int num_classes,
                          int input_h, int input_w, int top_k, double nms_thresh, double score_thresh,
                          int32_t *d_count, int32_t *d_out_anchor, int32_t *d_out_class, float *d_out_score,
-                         float *d_out_box, void *stream);
+                         float *d_out_box, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* Fused a1-a9: Fire11 features -> final detections (Detector.detect's device work,
- * src/engine/detector.py:20-31).  Workspace from sqd_head_detect_workspace_bytes(). */
+ * src/engine/detector.py:20-31).  Workspace from sqd_head_detect_workspace_bytes().  With the tcgen05 algorithm the
+ * GEMM epilogue itself scores the anchors (softmax x sigmoid, argmax) and fills the candidate lists, so the filter
+ * that follows reads a few hundred keys per image instead of scanning pred. */
 SQD_API size_t sqd_head_detect_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout, int algo);
 SQD_API int sqd_head_detect_fused(const float *d_feat, int layout, const void *d_packed, const float *d_weight,
                           const float *d_bias, const float *d_anchors, int batch, int cin, int gh, int gw,
@@ -145,6 +153,18 @@ SQD_API int sqd_head_detect_fused(const float *d_feat, int layout, const void *d
                           double nms_thresh, double score_thresh, int32_t *d_count, int32_t *d_out_anchor,
                           int32_t *d_out_class, float *d_out_score, float *d_out_box, void *d_workspace,
                           size_t workspace_bytes, int algo, void *stream);
+
+/* Diagnostic twin of sqd_head_detect_fused (tcgen05 algorithm, NCHW / NHWC input): the same kernel sequence with CUDA
+ * events recorded on `stream` between the stages.  Synchronises the stream and returns the stage durations in
+ * milliseconds in the HOST array h_stage_ms[3]: [0] split pre-pass, [1] ConvDet GEMM (+ score epilogue), [2] filter.
+ * Used by bench.py for the per-kernel roofline figures. */
+SQD_API size_t sqd_head_detect_profile_workspace_bytes(int batch, int cin, int gh, int gw, int cout);
+SQD_API int sqd_head_detect_profile(const float *d_feat, int layout, const void *d_packed, const float *d_bias,
+                                    const float *d_anchors, int batch, int cin, int gh, int gw, int anchors_per_grid,
+                                    int num_classes, int input_h, int input_w, int top_k, double nms_thresh,
+                                    double score_thresh, int32_t *d_count, int32_t *d_out_anchor, int32_t *d_out_class,
+                                    float *d_out_score, float *d_out_box, void *d_workspace, size_t workspace_bytes,
+                                    void *stream, float *h_stage_ms);
 
 /* Host-buffer form of sqd_head_detect_fused (what Detector.detect does around the model call: batch to device,
  * results back to numpy, src/engine/detector.py:22,37).  h_* are HOST pointers (page-locked for the copies to be

@@ -35,10 +35,14 @@ SIGNATURES = {
     "sqd_convdet_split_features": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "sqd_decode_scores": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sqd_topk_nms": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "sqd_detect_from_pred": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sqd_detect_workspace_bytes": (_sz, [_i, _i]),
+    "sqd_detect_from_pred": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sqd_head_detect_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "sqd_head_detect_fused": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _d,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "sqd_head_detect_profile_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "sqd_head_detect_profile": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _d,
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, C.POINTER(C.c_float)]),
     "sqd_head_detect_host_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i, _i]),
     "sqd_head_detect_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _d,
                                   _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp, _vp]),

@@ -15,7 +15,20 @@ int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, 
                            cudaStream_t st);
 size_t sqd_f16_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout);
 int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
-                         int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
+                         int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st,
+                         const SqdCandEmit *emit);
+// implemented in topk_nms.cu
+size_t sqd_cand_bytes(int batch, int num_anchors);
+SqdCand sqd_cand_layout(void *ws, int batch, int num_anchors);
+int sqd_score_candidates(const float *d_pred, int batch, int num_anchors, int num_classes, double score_thresh,
+                         SqdCand cand, cudaStream_t st);
+int sqd_detect_from_candidates(SqdCand cand, const float *d_pred, const float *d_anchors, int batch, int num_anchors,
+                               int num_classes, int input_h, int input_w, int top_k, double nms_thresh,
+                               double score_thresh, int32_t *d_count, int32_t *d_out_anchor, int32_t *d_out_class,
+                               float *d_out_score, float *d_out_box, cudaStream_t st);
+int sqd_detect_check_args(const char *fn, const void *d_pred, const void *d_anchors, int batch, int num_anchors,
+                          int num_classes, int top_k, const void *count, const void *anchor, const void *cls,
+                          const void *score, const void *box);
 int sqd_convdet_f16(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                     int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
 
@@ -53,9 +66,10 @@ extern "C" size_t sqd_convdet_workspace_bytes(int batch, int cin, int gh, int gw
     return align_up(sqd_f16_workspace_bytes(batch, cin, gh, gw, cout, layout), 256);
 }
 
-extern "C" int sqd_convdet_forward(const float *d_feat, int layout, const void *d_packed, const float *d_weight,
-                                   const float *d_bias, int batch, int cin, int gh, int gw, int cout, float *d_pred,
-                                   void *d_workspace, size_t workspace_bytes, int algo, void *stream) {
+static int convdet_forward_impl(const float *d_feat, int layout, const void *d_packed, const float *d_weight,
+                                const float *d_bias, int batch, int cin, int gh, int gw, int cout, float *d_pred,
+                                void *d_workspace, size_t workspace_bytes, int algo, void *stream, const SqdCandEmit *emit) {
+    if (emit) *emit->done = 0;
     if (batch == 0) return SQD_OK;  // empty batch: nothing to enqueue, pointers may be NULL
     SQD_REQUIRE(d_feat && d_bias && d_pred && d_workspace, SQD_E_NULL, "sqd_convdet_forward: NULL pointer");
     SQD_REQUIRE(layout == SQD_LAYOUT_NCHW || layout == SQD_LAYOUT_NHWC || layout == SQD_LAYOUT_SPLIT_NHWC, SQD_E_SHAPE,
@@ -76,8 +90,15 @@ extern "C" int sqd_convdet_forward(const float *d_feat, int layout, const void *
                 "sqd_convdet_forward: unknown algo %d", algo);
     SQD_REQUIRE(d_packed, SQD_E_NULL, "sqd_convdet_forward: tcgen05 algorithm needs packed weights");
     if (algo == SQD_CONV_TCGEN05_F16X3)
-        return sqd_convdet_f16_pair(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
+        return sqd_convdet_f16_pair(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st, emit);
     return sqd_convdet_f16(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
+}
+
+extern "C" int sqd_convdet_forward(const float *d_feat, int layout, const void *d_packed, const float *d_weight,
+                                   const float *d_bias, int batch, int cin, int gh, int gw, int cout, float *d_pred,
+                                   void *d_workspace, size_t workspace_bytes, int algo, void *stream) {
+    return convdet_forward_impl(d_feat, layout, d_packed, d_weight, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace,
+                                workspace_bytes, algo, stream, nullptr);
 }
 
 extern "C" size_t sqd_convdet_split_bytes(int batch, int cin, int gh, int gw) {
@@ -111,11 +132,55 @@ extern "C" int sqd_convdet_status(const void *d_workspace, void *stream) {
 }
 
 // ---- fused a1-a9 -----------------------------------------------------------------------------------
+// workspace: [pred (B,A,C+5)][candidate lists: counts + (B,A) keys][ConvDet workspace]
 extern "C" size_t sqd_head_detect_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout, int algo) {
     if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0) return 256;
     const size_t pred = align_up((size_t)batch * gh * gw * cout * sizeof(float), 256);
-    return pred + sqd_convdet_workspace_bytes(batch, cin, gh, gw, cout, layout, algo);
+    // anchors per image = gh*gw*K <= gh*gw*cout/6 (an anchor has at least 6 fields)
+    const size_t cand = sqd_cand_bytes(batch, gh * gw * (cout / 6 + 1));
+    return pred + cand + sqd_convdet_workspace_bytes(batch, cin, gh, gw, cout, layout, algo);
 }
+
+namespace {
+// Shared body of sqd_head_detect_fused / sqd_head_detect_profile.  ev (optional, 3 events) are recorded after the
+// split pre-pass (profile form only, where the caller ran it), after the GEMM and after the filter.
+int head_detect_impl(const float *d_feat, int layout, const void *d_packed, const float *d_weight, const float *d_bias,
+                     const float *d_anchors, int batch, int cin, int gh, int gw, int anchors_per_grid, int num_classes,
+                     int input_h, int input_w, int top_k, double nms_thresh, double score_thresh, int32_t *d_count,
+                     int32_t *d_out_anchor, int32_t *d_out_class, float *d_out_score, float *d_out_box,
+                     void *d_workspace, size_t workspace_bytes, int algo, void *stream, cudaEvent_t *ev) {
+    const int cout = anchors_per_grid * (num_classes + 5);
+    const int A = gh * gw * anchors_per_grid;
+    const size_t pred_bytes = align_up((size_t)batch * gh * gw * cout * sizeof(float), 256);
+    const size_t cand_bytes = sqd_cand_bytes(batch, gh * gw * (cout / 6 + 1));
+    float *pred = static_cast<float *>(d_workspace);
+    void *cand_ws = static_cast<char *>(d_workspace) + pred_bytes;
+    void *conv_ws = static_cast<char *>(d_workspace) + pred_bytes + cand_bytes;
+    int rc = sqd_detect_check_args("sqd_head_detect_fused", pred, d_anchors, batch, A, num_classes, top_k, d_count,
+                                   d_out_anchor, d_out_class, d_out_score, d_out_box);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const SqdCand cand = sqd_cand_layout(cand_ws, batch, A);
+    SQD_CUDA(cudaMemsetAsync(cand.count, 0, (size_t)batch * sizeof(int), st));
+    int emitted = 0;
+    SqdCandEmit emit{cand, num_classes, (float)score_thresh, &emitted};
+    // a1 (+ a2-a7 scoring in the GEMM epilogue where the shape has a fused instantiation)
+    rc = convdet_forward_impl(d_feat, layout, d_packed, d_weight, d_bias, batch, cin, gh, gw, cout, pred, conv_ws,
+                              workspace_bytes - pred_bytes - cand_bytes, algo, stream, &emit);
+    if (rc) return rc;
+    if (ev) SQD_CUDA(cudaEventRecord(ev[0], st));
+    if (!emitted) {
+        rc = sqd_score_candidates(pred, batch, A, num_classes, score_thresh, cand, st);
+        if (rc) return rc;
+    }
+    // a8-a9 on the candidates
+    rc = sqd_detect_from_candidates(cand, pred, d_anchors, batch, A, num_classes, input_h, input_w, top_k, nms_thresh,
+                                    score_thresh, d_count, d_out_anchor, d_out_class, d_out_score, d_out_box, st);
+    if (rc) return rc;
+    if (ev) SQD_CUDA(cudaEventRecord(ev[1], st));
+    return SQD_OK;
+}
+}  // namespace
 
 extern "C" int sqd_head_detect_fused(const float *d_feat, int layout, const void *d_packed, const float *d_weight,
                                      const float *d_bias, const float *d_anchors, int batch, int cin, int gh, int gw,
@@ -129,15 +194,55 @@ extern "C" int sqd_head_detect_fused(const float *d_feat, int layout, const void
     SQD_REQUIRE(d_workspace, SQD_E_NULL, "sqd_head_detect_fused: NULL workspace");
     SQD_REQUIRE(workspace_bytes >= sqd_head_detect_workspace_bytes(batch, cin, gh, gw, cout, layout, algo),
                 SQD_E_WORKSPACE, "sqd_head_detect_fused: workspace too small (%zu bytes)", workspace_bytes);
-    const size_t pred_bytes = align_up((size_t)(batch > 0 ? batch : 0) * gh * gw * cout * sizeof(float), 256);
-    float *pred = static_cast<float *>(d_workspace);
-    void *conv_ws = static_cast<char *>(d_workspace) + pred_bytes;
-    int rc = sqd_convdet_forward(d_feat, layout, d_packed, d_weight, d_bias, batch, cin, gh, gw, cout, pred, conv_ws,
-                                 workspace_bytes - pred_bytes, algo, stream);
-    if (rc) return rc;
-    return sqd_detect_from_pred(pred, d_anchors, batch, gh * gw * anchors_per_grid, num_classes, input_h, input_w, top_k,
-                                nms_thresh, score_thresh, d_count, d_out_anchor, d_out_class, d_out_score, d_out_box,
-                                stream);
+    return head_detect_impl(d_feat, layout, d_packed, d_weight, d_bias, d_anchors, batch, cin, gh, gw, anchors_per_grid,
+                            num_classes, input_h, input_w, top_k, nms_thresh, score_thresh, d_count, d_out_anchor,
+                            d_out_class, d_out_score, d_out_box, d_workspace, workspace_bytes, algo, stream, nullptr);
+}
+
+// Diagnostic twin of sqd_head_detect_fused: the same kernel sequence with CUDA events recorded on `stream` between
+// the stages; synchronises the stream and returns the stage durations in milliseconds:
+// h_stage_ms[0] split pre-pass (max|x| + fp16 planes), [1] ConvDet GEMM (+ score epilogue), [2] filter (select/NMS/emit,
+// preceded by the pred scan when the epilogue did not score).  tcgen05 algorithm, NCHW / NHWC input only.
+extern "C" size_t sqd_head_detect_profile_workspace_bytes(int batch, int cin, int gh, int gw, int cout) {
+    if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0) return 256;
+    return sqd_head_detect_workspace_bytes(batch, cin, gh, gw, cout, SQD_LAYOUT_SPLIT_NHWC, SQD_CONV_TCGEN05_F16X3) +
+           align_up(sqd_f16_split_bytes(batch, cin, gh, gw), 256);
+}
+
+extern "C" int sqd_head_detect_profile(const float *d_feat, int layout, const void *d_packed, const float *d_bias,
+                                       const float *d_anchors, int batch, int cin, int gh, int gw, int anchors_per_grid,
+                                       int num_classes, int input_h, int input_w, int top_k, double nms_thresh,
+                                       double score_thresh, int32_t *d_count, int32_t *d_out_anchor,
+                                       int32_t *d_out_class, float *d_out_score, float *d_out_box, void *d_workspace,
+                                       size_t workspace_bytes, void *stream, float *h_stage_ms) {
+    SQD_REQUIRE(batch > 0 && anchors_per_grid >= 1 && num_classes >= 1, SQD_E_SHAPE, "sqd_head_detect_profile: bad shape");
+    SQD_REQUIRE(layout == SQD_LAYOUT_NCHW || layout == SQD_LAYOUT_NHWC, SQD_E_SHAPE, "sqd_head_detect_profile: bad layout");
+    SQD_REQUIRE(d_feat && d_workspace && h_stage_ms, SQD_E_NULL, "sqd_head_detect_profile: NULL pointer");
+    const int cout = anchors_per_grid * (num_classes + 5);
+    const size_t fused_bytes =
+        sqd_head_detect_workspace_bytes(batch, cin, gh, gw, cout, SQD_LAYOUT_SPLIT_NHWC, SQD_CONV_TCGEN05_F16X3);
+    SQD_REQUIRE(workspace_bytes >= sqd_head_detect_profile_workspace_bytes(batch, cin, gh, gw, cout), SQD_E_WORKSPACE,
+                "sqd_head_detect_profile: workspace too small (%zu bytes)", workspace_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    void *planes = static_cast<char *>(d_workspace) + fused_bytes;
+    cudaEvent_t ev[4];
+    for (int i = 0; i < 4; ++i) SQD_CUDA(cudaEventCreate(&ev[i]));
+    int rc = SQD_OK;
+    SQD_CUDA(cudaEventRecord(ev[0], st));
+    rc = sqd_convdet_split_features(d_feat, layout, batch, cin, gh, gw, planes, stream);
+    if (rc == SQD_OK) {
+        SQD_CUDA(cudaEventRecord(ev[1], st));
+        rc = head_detect_impl(static_cast<const float *>(planes), SQD_LAYOUT_SPLIT_NHWC, d_packed, nullptr, d_bias, d_anchors,
+                              batch, cin, gh, gw, anchors_per_grid, num_classes, input_h, input_w, top_k, nms_thresh,
+                              score_thresh, d_count, d_out_anchor, d_out_class, d_out_score, d_out_box, d_workspace,
+                              fused_bytes, SQD_CONV_TCGEN05_F16X3, stream, ev + 2);
+    }
+    if (rc == SQD_OK) {
+        SQD_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < 3; ++i) SQD_CUDA(cudaEventElapsedTime(h_stage_ms + i, ev[i], ev[i + 1]));
+    }
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+    return rc;
 }
 
 // ---- fused a1-a9 with HOST buffers: chunked copy/compute pipeline ---------------------------------------------

@@ -130,3 +130,81 @@ __device__ __forceinline__ float4 sqd_decode_box(float4 anc, float dx, float dy,
     b.w = sqd_clamp(fadd(cy, hh), hmax);
     return b;
 }
+
+// ---- ranking keys and per-image candidate lists (shared by the ConvDet epilogue and the filter kernels) ----
+// A candidate is a 64-bit key  [ order-preserving score bits : 32 | 0xFFFFFF - anchor : 24 | class : 8 ]
+// so "larger key" == (score desc, anchor index asc) -- the declared tie policy.
+typedef unsigned long long sqd_u64;
+
+__device__ __forceinline__ unsigned sqd_order_bits(float s) {
+    const unsigned b = __float_as_uint(s);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float sqd_unorder_bits(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ sqd_u64 sqd_make_key(float score, int anchor, int cls) {
+    return ((sqd_u64)sqd_order_bits(score) << 32) | ((sqd_u64)(0xFFFFFFu - (unsigned)anchor) << 8) | (sqd_u64)(cls & 0xFF);
+}
+// Exact pre-filter: an anchor with score <= score_thresh can never be emitted (final strict filter) and can never
+// suppress an emitted box (greedy NMS only lets HIGHER scores suppress), so it only ever occupies a top-k slot that
+// no surviving anchor needs.  Keys above "largest key with score == score_thresh" are the only ones that matter;
+// the result is identical to the reference's top-k -> NMS -> score filter order (detector.py:88-114).
+__device__ __forceinline__ sqd_u64 sqd_score_floor_key(float score_thr) {
+    return ((sqd_u64)sqd_order_bits(score_thr) << 32) | 0xFFFFFFFFull;
+}
+
+// Per-image candidate lists in global memory: keys[img*stride + i], i < count[img] (unordered; the keys are unique
+// and totally ordered, so every consumer is order independent).  stride >= num_anchors, so a list never overflows.
+struct SqdCand {
+    int *count;       // (B), zeroed by the host wrapper before the producer kernel
+    sqd_u64 *keys;    // (B, stride)
+    int stride;
+};
+
+// Warp-aggregated append (one atomic per image present in the warp).  Must be called by all 32 lanes, converged.
+__device__ __forceinline__ void sqd_cand_append(const SqdCand &c, bool pass, int img, sqd_u64 key) {
+    const unsigned act = __ballot_sync(0xffffffffu, pass);
+    if (!pass) return;
+    const unsigned peers = __match_any_sync(act, img);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(c.count + img, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const int pos = base + __popc(peers & ((1u << lane) - 1u));
+    if (pos < c.stride) c.keys[(size_t)img * c.stride + pos] = key;
+}
+
+// N candidates per lane, ALL rows of the warp in the same image (img warp-uniform): one atomic per call.
+// Must be called by all 32 lanes, converged.
+template <int N>
+__device__ __forceinline__ void sqd_cand_append_warp(const SqdCand &c, int img, const bool (&pass)[N],
+                                                     const sqd_u64 (&key)[N]) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int off[N];
+    int total = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const unsigned b = __ballot_sync(0xffffffffu, pass[i]);
+        off[i] = total + __popc(b & lt);
+        total += __popc(b);
+    }
+    if (total == 0) return;  // warp-uniform
+    int base = 0;
+    if (lane == 0) base = atomicAdd(c.count + img, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    sqd_u64 *dst = c.keys + (size_t)img * c.stride + base;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (pass[i] && base + off[i] < c.stride) dst[off[i]] = key[i];
+}
+
+// request to the tcgen05 ConvDet launcher: fill `cand` from the epilogue if the shape allows it
+struct SqdCandEmit {
+    SqdCand cand;
+    int num_classes;
+    float score_thr;
+    int *done;   // host: set to 1 if the epilogue will emit, 0 if the caller must scan pred itself
+};

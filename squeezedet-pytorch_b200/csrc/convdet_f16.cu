@@ -665,6 +665,10 @@ struct PairParams {
     int *status;
     long long *trace;
     int trace_cta;
+    // fused score epilogue (template CS > 0 only): candidates above the score threshold go to per-image lists
+    SqdCand cand;        // cand.count == nullptr: no emission
+    float score_thr;
+    int anchors_per_cell;
 };
 
 struct PairIter {  // like UnitIter, for the tile of one rank; img may run past the batch for a ghost tile
@@ -707,7 +711,11 @@ __device__ __forceinline__ bool pair_wait_warp(uint64_t *bar, uint32_t parity, v
     return spin ? mbar_spin_warp(bar, parity, abort_flag) : mbar_wait_warp(bar, parity, abort_flag);
 }
 
-template <int NPAD>
+// CS > 0: the epilogue also scores the cell's anchors (CS classes, NF = CS+5 fields per anchor) from the finished
+// fp32 logits -- class softmax x confidence sigmoid, first-max argmax, the same sqd_score_anchor every filter kernel
+// uses -- and appends the anchors above the score threshold to per-image candidate lists (SqdCand), so the filter
+// that follows never scans pred.
+template <int NPAD, int CS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                         const __grid_constant__ CUtensorMap map_b, const PairParams p) {
@@ -880,6 +888,96 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
         float acc[NPAD];
         int seg_r0 = 0, chunk = 0, in_chunk = 0;
         PairIter it;
+        // ---- fused score epilogue, software pipelined (CS > 0 and a candidate sink only) ---------------------------
+        // Scoring the 9 anchors of a cell costs ~0.5 us per anchor of dependent exp/div latency; done in one go
+        // after a tile it keeps these warps away from the TMEM accumulators for longer than the two buffers cover
+        // and stalls the tensor pipe (measured +13 %).  Instead the finished tile becomes "pending" and ONE anchor per
+        // thread is scored after each chunk drain, in the time the warp would otherwise wait for the next chunk:
+        // the four scoring logits are read back from the pred row this thread just stored (L2 hit), the warp
+        // appends its candidates with one atomic whose result is only consumed at the next step.
+        constexpr int kNF = (CS > 0 ? CS : 1) + 5;
+        const bool emit = CS > 0 && p.cand.count != nullptr;
+        const sqd_u64 floor_key = sqd_score_floor_key(p.score_thr);
+        const float *pend_row = nullptr;   // this thread's cell of the pending tile (nullptr: outside the image)
+        int pend_k = 1 << 30, pend_img = 0, pend_a0 = 0;      // pend_k >= anchors_per_cell: nothing pending (warp-uniform)
+        sqd_u64 prev_key = 0ull;
+        int prev_off = -1, prev_base = 0, prev_img = 0;
+        bool prev_any = false;                                  // warp-uniform: a step's append is waiting to be retired
+        auto score_step = [&]() {
+            if (prev_any) {   // retire the previous step: its atomic has had a whole chunk period to return
+                const int base = __shfl_sync(0xffffffffu, prev_base, 0);
+                if (prev_off >= 0 && base + prev_off < p.cand.stride)
+                    p.cand.keys[(size_t)prev_img * p.cand.stride + base + prev_off] = prev_key;
+                prev_any = false;
+            }
+            if (pend_k >= p.anchors_per_cell) return;
+            float f[(CS > 0 ? CS : 1) + 1];
+            if (pend_row != nullptr) {
+                const float *src = pend_row + pend_k * kNF;
+                if (CS == 3) {
+                    const float4 v = __ldcg(reinterpret_cast<const float4 *>(src));
+                    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j <= CS; ++j) f[j] = __ldcg(src + j);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j <= CS; ++j) f[j] = 0.f;
+            }
+            float scv;
+            int cl;
+            sqd_score_anchor<(CS > 0 ? CS : 1)>(f, CS, scv, cl);
+            const sqd_u64 key = sqd_make_key(scv, pend_a0 + pend_k, cl);
+            const bool pass = pend_row != nullptr && key > floor_key;
+            const unsigned b = __ballot_sync(0xffffffffu, pass);
+            if (b) {
+                if (lane == 0) prev_base = atomicAdd(p.cand.count + pend_img, __popc(b));
+                prev_off = pass ? __popc(b & ((1u << lane) - 1u)) : -1;
+                prev_key = key;
+                prev_img = pend_img;
+                prev_any = true;
+            }
+            ++pend_k;
+        };
+        // Everything still pending at once (the CTA's last tile, or a segment too short to hide the previous tile):
+        // independent anchors give the scheduler ILP and the warp appends with ONE atomic.
+        auto flush_pending = [&]() {
+            constexpr int KMAX = NPAD / kNF;
+            if (prev_any) {
+                const int base = __shfl_sync(0xffffffffu, prev_base, 0);
+                if (prev_off >= 0 && base + prev_off < p.cand.stride)
+                    p.cand.keys[(size_t)prev_img * p.cand.stride + base + prev_off] = prev_key;
+                prev_any = false;
+            }
+            if (pend_k >= p.anchors_per_cell) return;
+            bool pass[KMAX];
+            sqd_u64 key[KMAX];
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                const bool want = k >= pend_k && k < p.anchors_per_cell && pend_row != nullptr;
+                float f[(CS > 0 ? CS : 1) + 1];
+#pragma unroll
+                for (int j = 0; j <= CS; ++j) f[j] = 0.f;
+                if (want) {
+                    const float *src = pend_row + k * kNF;
+                    if (CS == 3) {
+                        const float4 v = __ldcg(reinterpret_cast<const float4 *>(src));
+                        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j <= CS; ++j) f[j] = __ldcg(src + j);
+                    }
+                }
+                float scv;
+                int cl;
+                sqd_score_anchor<(CS > 0 ? CS : 1)>(f, CS, scv, cl);
+                key[k] = sqd_make_key(scv, pend_a0 + k, cl);
+                pass[k] = want && key[k] > floor_key;
+            }
+            sqd_cand_append_warp<KMAX>(p.cand, pend_img, pass, key);
+            pend_k = 1 << 30;
+        };
         for (int i = 0; i < n_units; ++i) {
             if (i == 0 || i == sc.main_len) it.seek(sc.unit(i), tile_offset, p); else it.next(p);
             const int r = it.r;
@@ -928,6 +1026,10 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                 else mbar_arrive_cluster(tempty + buf, 0);
             }
             if (warp == kWarpAcc2) SQD_TRACE2(12, i);
+            if (emit) {
+                __syncwarp();
+                score_step();   // one anchor of the pending tile per chunk period
+            }
 
             const bool seg_end = (i == n_units - 1) || (r == p.upt - 1) || (i == sc.main_len - 1);
             if (!seg_end) continue;
@@ -967,23 +1069,37 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
             }
             // whole tile in registers: x 1/(s_a*s_w), + bias -> pred   (ghost tile: img == batch, nothing stored)
             const int x = it.tx * kTileX + row % kTileX, y = it.ty * kTileY + row / kTileX;
-            if (it.img < p.batch && y < p.gh && x < p.gw) {
-                const float inv = fmul(1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_bits + it.img))), inv_sw);
+            const bool inb = it.img < p.batch && y < p.gh && x < p.gw;
+            const float inv = inb ? fmul(1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_bits + it.img))), inv_sw) : 0.f;
+#pragma unroll
+            for (int n = 0; n < NPAD; ++n) acc[n] = fadd(fmul(acc[n], inv), s_bias[n]);
+            if (inb) {
                 float *out = p.pred + (((size_t)it.img * p.gh + y) * p.gw + x) * p.cout;
                 if ((p.cout & 3) == 0) {
                     float4 *o4 = reinterpret_cast<float4 *>(out);
 #pragma unroll
                     for (int n = 0; n < NPAD; n += 4)
-                        if (n < p.cout)
-                            o4[n >> 2] = make_float4(fadd(fmul(acc[n], inv), s_bias[n]), fadd(fmul(acc[n + 1], inv), s_bias[n + 1]),
-                                                     fadd(fmul(acc[n + 2], inv), s_bias[n + 2]),
-                                                     fadd(fmul(acc[n + 3], inv), s_bias[n + 3]));
+                        if (n < p.cout) o4[n >> 2] = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
                 } else {
 #pragma unroll
                     for (int n = 0; n < NPAD; ++n)
-                        if (n < p.cout) out[n] = fadd(fmul(acc[n], inv), s_bias[n]);
+                        if (n < p.cout) out[n] = acc[n];
                 }
             }
+            if (emit) {
+                __syncwarp();
+                flush_pending();   // a previous tile not fully scored yet (short segments)
+                if (it.img < p.batch) {   // ghost tiles have nothing to score (warp-uniform)
+                    pend_row = inb ? p.pred + (((size_t)it.img * p.gh + y) * p.gw + x) * p.cout : nullptr;
+                    pend_img = it.img;
+                    pend_a0 = (y * p.gw + x) * p.anchors_per_cell;
+                    pend_k = 0;
+                }
+            }
+        }
+        if (emit) {   // the CTA's last tile: nothing left to hide behind
+            __syncwarp();
+            flush_pending();
         }
     }
     tc_fence_before();
@@ -1114,11 +1230,11 @@ int pair_stages_for(int npad) {
     return (int)s;
 }
 
-template <int NPAD>
+template <int NPAD, int CS = 0>
 int launch_pair(const CUtensorMap *maps, const PairParams &p, int grid, cudaStream_t st) {
     const size_t smem = 1024 + (size_t)p.stages * (kAStageBytes + 3 * NPAD * kBlockK * 2) + kCtrlBytes;
-    SQD_CUDA(cudaFuncSetAttribute(convdet_f16_pair_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    convdet_f16_pair_kernel<NPAD><<<grid, kThreads2, smem, st>>>(maps[0], maps[1], maps[2], p);
+    SQD_CUDA(cudaFuncSetAttribute(convdet_f16_pair_kernel<NPAD, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    convdet_f16_pair_kernel<NPAD, CS><<<grid, kThreads2, smem, st>>>(maps[0], maps[1], maps[2], p);
     SQD_LAUNCH_CHECK("convdet_f16_pair_kernel");
     return SQD_OK;
 }
@@ -1127,8 +1243,14 @@ int launch_pair(const CUtensorMap *maps, const PairParams &p, int grid, cudaStre
 int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, int gh, int gw, void *d_planes,
                            cudaStream_t st);
 
+// emit (optional): ask the epilogue to score the anchors and fill per-image candidate lists (emit->cand, counts already
+// zeroed on `st`).  *emit->done is set to 1 when the epilogue will do it; the caller otherwise runs the stand-alone
+// scan over pred.  MEASURED (profiles/r01_fused_score_epilogue.txt): scoring inside the GEMM kernel costs more than the
+// separate 8 us scan kernel it replaces (+23 us at B = 20, +15 % at B = 256, immediate or software-pipelined), so it is
+// an opt-in experiment (SQD_FUSED_SCORE=1), not the default.
 int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
-                         int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st) {
+                         int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st,
+                         const SqdCandEmit *emit) {
     SQD_REQUIRE(cin % kBlockK == 0, SQD_E_SHAPE, "convdet (tcgen05): Cin %d must be a multiple of %d", cin, kBlockK);
     SQD_REQUIRE(cout >= 1 && cout <= 128, SQD_E_SHAPE, "convdet (tcgen05): Cout %d outside [1,128]", cout);
     EncodeTiledFn encode = get_encode_fn();
@@ -1202,6 +1324,24 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
     p.trace_cta = env_int("SQD_F16_TRACE_CTA", 0);
     if (const char *e = getenv("SQD_F16_TRACE")) p.trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
     const int grid = 2 * npairs;
+    p.cand.count = nullptr;
+    p.cand.keys = nullptr;
+    p.cand.stride = 0;
+    p.score_thr = 0.f;
+    p.anchors_per_cell = 0;
+    if (emit) {
+        *emit->done = 0;
+        const int nf = emit->num_classes + 5;
+        const bool shape_ok = cout % nf == 0 && ((emit->num_classes == 3 && npad == 80) || (emit->num_classes == 8 && npad == 128));
+        if (shape_ok && env_int("SQD_FUSED_SCORE", 0)) {
+            p.cand = emit->cand;
+            p.score_thr = emit->score_thr;
+            p.anchors_per_cell = cout / nf;
+            *emit->done = 1;
+            if (npad == 80) return launch_pair<80, 3>(maps, p, grid, st);
+            return launch_pair<128, 8>(maps, p, grid, st);
+        }
+    }
     switch (npad / 16) {
         case 1: return launch_pair<16>(maps, p, grid, st);
         case 2: return launch_pair<32>(maps, p, grid, st);

@@ -34,32 +34,18 @@ constexpr int kUnroll = 2;
 constexpr int kRound = kThreads * kUnroll;  // anchors consumed per round
 constexpr int kCap = 2048;                  // candidate buffer entries (>= SQD_MAX_TOPK + kRound)
 static_assert(kCap >= SQD_MAX_TOPK + kRound, "candidate buffer too small");
+static_assert(2 * kThreads >= SQD_MAX_TOPK, "the emit phase handles two candidates per thread");
 static_assert(kCap / 2 >= SQD_MAX_TOPK, "rank_sort uses the upper half of the buffer as its destination");
 
-typedef unsigned long long u64;
+typedef sqd_u64 u64;
 
-__device__ __forceinline__ unsigned order_bits(float s) {
-    const unsigned b = __float_as_uint(s);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float unorder_bits(unsigned k) {
-    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-__device__ __forceinline__ u64 make_key(float score, int anchor, int cls) {
-    return ((u64)order_bits(score) << 32) | ((u64)(0xFFFFFFu - (unsigned)anchor) << 8) | (u64)(cls & 0xFF);
-}
+__device__ __forceinline__ unsigned order_bits(float s) { return sqd_order_bits(s); }
+__device__ __forceinline__ u64 make_key(float score, int anchor, int cls) { return sqd_make_key(score, anchor, cls); }
 __device__ __forceinline__ int key_anchor(u64 k) { return (int)(0xFFFFFFu - (unsigned)((k >> 8) & 0xFFFFFFu)); }
 __device__ __forceinline__ int key_class(u64 k) { return (int)(k & 0xFFu); }
-__device__ __forceinline__ float key_score(u64 k) { return unorder_bits((unsigned)(k >> 32)); }
-
-// Exact pre-filter: an anchor with score <= score_thresh can never be emitted (final strict filter) and can never
-// suppress an emitted box (greedy NMS only lets HIGHER scores suppress), so it only ever occupies a top-k slot that
-// no surviving anchor needs.  Starting the running threshold at "largest key with score == score_thresh" keeps
-// such anchors out of the candidate buffer altogether; the result is identical to the reference's
-// top-k -> NMS -> score filter order (detector.py:88-114).
-__device__ __forceinline__ u64 score_floor_key(float score_thr) {
-    return ((u64)order_bits(score_thr) << 32) | 0xFFFFFFFFull;
-}
+__device__ __forceinline__ float key_score(u64 k) { return sqd_unorder_bits((unsigned)(k >> 32)); }
+// The running threshold starts at the score threshold: exact, see sqd_score_floor_key (common.cuh).
+__device__ __forceinline__ u64 score_floor_key(float score_thr) { return sqd_score_floor_key(score_thr); }
 
 // ---- candidate sources ---------------------------------------------------------------------------
 template <int CS>
@@ -243,32 +229,41 @@ struct FilterOut {
     float4 *box;
 };
 
-// Phase 2+3, shared by both sources.  sh.buf[0..m) holds the sorted survivors.
+// Phase 2+3, shared by all sources.  sh.buf[0..m) holds the sorted survivors (m <= k <= 2*kThreads).
+//  * suppressor bitsets: word w of candidate i has bit b set iff j = 32w+b < i, same class and IoU(i,j) > thresh
+//  * greedy sweep without a 64-step serial chain: keep(i) = !exists j<i: keep(j) & sup(j,i) is solved block by block
+//    (32 candidates per block, final keep words of earlier blocks applied first); inside a block the warp iterates
+//    word' = ballot(pre & (own & word) == 0) to its fixed point -- after r rounds the first r lanes are final, and a
+//    fixed point satisfies the defining recurrence, whose solution is unique.  Typically 2-4 rounds per block.
+//  * output position = rank of (class, index) among the kept rows: class ascending / score descending.
 template <class Src>
 __device__ void nms_and_emit(const Src &src, Shared &sh, unsigned char *dyn, int k, int num_classes, float nms_thr_f,
                              float score_thr_f, const FilterOut &o, int img) {
     const int m = sh.count;
-    const int wpr = (k + 31) >> 5;  // mask words per row
+    const int wpr = (k + 31) >> 5;  // mask words per candidate
     float4 *sbox = reinterpret_cast<float4 *>(dyn);
     float *sarea = reinterpret_cast<float *>(sbox + k);
-    unsigned *mask = reinterpret_cast<unsigned *>(sarea + k);
-    unsigned char *valid = reinterpret_cast<unsigned char *>(mask + (size_t)k * wpr);
+    unsigned *col = reinterpret_cast<unsigned *>(sarea + k);
+    unsigned *okey = col + (size_t)k * wpr;
+    unsigned *keepw = okey + k;
 
     for (int i = threadIdx.x; i < m; i += kThreads) {
         const float4 b = src.box(key_anchor(sh.buf[i]));
         sbox[i] = b;
         sarea[i] = fmul(fsub(b.z, b.x), fsub(b.w, b.y));  // torchvision: (x2-x1)*(y2-y1), no +1
-        valid[i] = 0;
     }
     __syncthreads();
 
-    // same-class suppression mask: bit j of row i set iff j>i, class equal and IoU(i,j) > thresh
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = kThreads >> 5;
     for (int item = warp; item < m * wpr; item += nwarp) {
         const int i = item / wpr, w = item - i * wpr;
+        if ((w << 5) >= i) {  // no j < i in this word (warp-uniform)
+            if (lane == 0) col[item] = 0u;
+            continue;
+        }
         const int j = (w << 5) + lane;
         bool sup = false;
-        if (j > i && j < m && key_class(sh.buf[j]) == key_class(sh.buf[i])) {
+        if (j < i && key_class(sh.buf[j]) == key_class(sh.buf[i])) {
             const float4 a = sbox[i], b = sbox[j];
             const float iw = fmaxf(0.f, fsub(fminf(a.z, b.z), fmaxf(a.x, b.x)));
             const float ih = fmaxf(0.f, fsub(fminf(a.w, b.w), fmaxf(a.y, b.y)));
@@ -277,48 +272,54 @@ __device__ void nms_and_emit(const Src &src, Shared &sh, unsigned char *dyn, int
             sup = iou > nms_thr_f;  // false for NaN (0/0 of zero-area boxes), like the reference
         }
         const unsigned bits = __ballot_sync(0xffffffffu, sup);
-        if (lane == 0) mask[item] = bits;
+        if (lane == 0) col[item] = bits;
     }
     __syncthreads();
 
-    // greedy sweep in descending-score order (one warp; lane l owns word l of the removed set)
     if (warp == 0) {
-        unsigned removed = 0u;  // word `lane`
-        for (int i = 0; i < m; ++i) {
-            const unsigned word = __shfl_sync(0xffffffffu, removed, i >> 5);
-            if (!((word >> (i & 31)) & 1u)) {
-                if (lane < wpr) removed |= mask[i * wpr + lane];
-                if (lane == 0) valid[i] = key_score(sh.buf[i]) > score_thr_f ? 1 : 0;
+        for (int t = 0; (t << 5) < m; ++t) {
+            const int i = (t << 5) + lane;
+            bool pre = i < m;
+            for (int w = 0; w < t; ++w) pre = pre && (col[i * wpr + w] & keepw[w]) == 0u;
+            const unsigned own = i < m ? col[i * wpr + t] : 0u;
+            unsigned word = __ballot_sync(0xffffffffu, pre);
+            for (;;) {
+                const unsigned nw = __ballot_sync(0xffffffffu, pre && (own & word) == 0u);
+                if (nw == word) break;
+                word = nw;
             }
+            if (lane == 0) keepw[t] = word;
+            __syncwarp();
         }
     }
     __syncthreads();
 
     // emit: class ascending, then descending score (== position) inside a class
-    int n_valid_local = 0;
-    for (int t = threadIdx.x; t < m; t += kThreads) {
-        if (!valid[t]) continue;
-        const int ct = key_class(sh.buf[t]);
+    unsigned mine[2];
+    int n_valid = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int t = threadIdx.x + h * kThreads;
+        bool v = false;
+        if (t < m) v = ((keepw[t >> 5] >> (t & 31)) & 1u) && key_score(sh.buf[t]) > score_thr_f;
+        mine[h] = v ? ((unsigned)key_class(sh.buf[t]) << 16) | (unsigned)t : 0xFFFFFFFFu;
+        if (t < m) okey[t] = mine[h];
+        n_valid += __syncthreads_count(v);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int t = threadIdx.x + h * kThreads;
+        if (mine[h] == 0xFFFFFFFFu) continue;
         int pos = 0;
-        for (int u = 0; u < m; ++u) {
-            if (!valid[u]) continue;
-            const int cu = key_class(sh.buf[u]);
-            pos += (cu < ct || (cu == ct && u < t)) ? 1 : 0;
-        }
+        for (int u = 0; u < m; ++u) pos += okey[u] < mine[h] ? 1 : 0;
         const size_t r = (size_t)img * k + pos;
         o.anchor[r] = key_anchor(sh.buf[t]);
-        o.cls[r] = ct;
+        o.cls[r] = key_class(sh.buf[t]);
         o.score[r] = key_score(sh.buf[t]);
         o.box[r] = sbox[t];
-        ++n_valid_local;
     }
-    if (threadIdx.x == 0) sh.n_valid = 0;
-    __syncthreads();
-    if (n_valid_local) atomicAdd(&sh.n_valid, n_valid_local);
-    __syncthreads();
-    const int nv = sh.n_valid;
-    if (threadIdx.x == 0) o.count[img] = nv;
-    for (int t = nv + threadIdx.x; t < k; t += kThreads) {  // deterministic padding rows
+    if (threadIdx.x == 0) o.count[img] = n_valid;
+    for (int t = n_valid + threadIdx.x; t < k; t += kThreads) {  // deterministic padding rows
         const size_t r = (size_t)img * k + t;
         o.anchor[r] = -1;
         o.cls[r] = -1;
@@ -423,9 +424,229 @@ __global__ void __launch_bounds__(kThreads) filter_dense_kernel(const long long 
     nms_and_emit(src, sh, dyn, k, C, nms_thr_f, score_thr_f, o, img);
 }
 
+// ---- two-phase form: (1) streaming scan -> per-image candidate lists, (2) per-image select / NMS / emit --------------
+// Phase 1 is a pure HBM stream over pred (the whole grid works on the whole batch, no per-image serial phases);
+// only anchors above the score threshold (exact pre-filter) are appended, typically 1-3 % of them.  Phase 2 reads
+// those few keys and runs the same select -> sort -> NMS -> emit tail as the one-kernel form.  The tcgen05 ConvDet
+// epilogue can produce the candidate lists itself (convdet_f16.cu), in which case phase 1 never runs and pred is
+// only touched for the <= k surviving boxes of an image.
+constexpr int kScanThreads = 256;
+constexpr int kScanUnroll = 4;
+
+template <int CS>
+__global__ void __launch_bounds__(kScanThreads) score_candidates_kernel(const float *__restrict__ pred, unsigned total,
+                                                                        unsigned A, int C, float score_thr_f, SqdCand cand) {
+    const u64 floor_key = score_floor_key(score_thr_f);
+    if (CS == 3) {
+        // 32-byte rows: the four scoring fields are the first 16 bytes of a row
+        const float4 *p4 = reinterpret_cast<const float4 *>(pred);
+        const unsigned step = gridDim.x * kScanThreads * kScanUnroll;
+        for (unsigned base = blockIdx.x * kScanThreads * kScanUnroll; base < total; base += step) {  // warp-uniform trip count
+            float4 v[kScanUnroll];
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; ++u) {
+                const unsigned g = base + u * kScanThreads + threadIdx.x;
+                v[u] = g < total ? ld_stream_f4(p4 + 2 * (size_t)g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            bool pass[kScanUnroll];
+            u64 key[kScanUnroll];
+            unsigned img[kScanUnroll];
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; ++u) {
+                const unsigned g = base + u * kScanThreads + threadIdx.x;
+                const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                float s;
+                int c;
+                sqd_score_anchor<3>(f, 3, s, c);
+                img[u] = g / A;
+                key[u] = make_key(s, (int)(g - img[u] * A), c);
+                pass[u] = g < total && key[u] > floor_key;
+            }
+            // rows of this warp in this round: [first, last]; one image -> one atomic for all of them
+            const unsigned first = base + (threadIdx.x & ~31u), last = first + (kScanUnroll - 1) * kScanThreads + 31u;
+            if (first / A == min(last, total - 1u) / A) {
+                sqd_cand_append_warp<kScanUnroll>(cand, (int)(first / A), pass, key);
+            } else {
+#pragma unroll
+                for (int u = 0; u < kScanUnroll; ++u) sqd_cand_append(cand, pass[u], (int)img[u], key[u]);
+            }
+        }
+    } else {
+        // any field count: stage 256 contiguous rows through shared memory with 16-byte streaming loads
+        extern __shared__ __align__(16) float slab[];
+        const int Cn = CS > 0 ? CS : C;
+        const int NF = Cn + 5;
+        for (unsigned row0 = blockIdx.x * kScanThreads; row0 < total; row0 += gridDim.x * kScanThreads) {
+            const int n = (int)min((unsigned)kScanThreads, total - row0);
+            const float *src = pred + (size_t)row0 * NF;
+            const int count = n * NF, nvec = count >> 2;  // slab start is 16-byte aligned: 256*NF*4 is a multiple of 16
+            const float4 *src4 = reinterpret_cast<const float4 *>(src);
+            float4 *dst4 = reinterpret_cast<float4 *>(slab);
+            for (int i = threadIdx.x; i < nvec; i += kScanThreads) dst4[i] = ld_stream_f4(src4 + i);
+            for (int i = (nvec << 2) + threadIdx.x; i < count; i += kScanThreads) slab[i] = src[i];
+            __syncthreads();
+            const bool in = (int)threadIdx.x < n;
+            float f[SQD_CMAX(CS) + 1];
+#pragma unroll
+            for (int j = 0; j < SQD_CMAX(CS) + 1; ++j)
+                if (j <= Cn) f[j] = in ? slab[threadIdx.x * NF + j] : 0.f;
+            float s;
+            int c;
+            sqd_score_anchor<CS>(f, Cn, s, c);
+            const unsigned g = row0 + threadIdx.x;
+            const unsigned img = g / A;
+            const u64 key = make_key(s, (int)(g - img * A), c);
+            sqd_cand_append(cand, in && key > floor_key, (int)img, key);
+            __syncthreads();
+        }
+    }
+}
+
+// Exact top-k of a long candidate list without sorting or compaction rounds: MSB-first radix select on the 32 score
+// bits with 11-bit digits (a 2048-bin shared histogram per level, keys re-read from L2), stopping as soon as the keys
+// at or above the threshold bin fit the sort buffer; those are then collected (unordered) into sh.buf.  Typical lists
+// (thousands of distinct scores) need ONE level: histogram pass + collect pass.  Returns false (nothing collected) if
+// even single-score bins overflow the buffer (massive exact ties): the caller then uses the running-threshold loop.
+__device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, int n, int k, float score_thr_f) {
+    constexpr int kBins = 2048, kPerThread = kBins / kThreads;
+    constexpr int kCollectCap = kCap / 2;
+    int *hist = reinterpret_cast<int *>(sh.buf + kCap / 2);  // upper half of the key buffer: free until the sort
+    __shared__ int s_wtot[kThreads / 32];
+    __shared__ int s_tb, s_above_add, s_tb_cnt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned lo = order_bits(score_thr_f) + 1u, hi = 0xFFFFFFFFu;  // undecided score-bit range (inclusive)
+    int above = 0;                                                 // keys with score bits > hi: selected for sure
+    const unsigned top = order_bits(1.0f);                         // scores are probabilities: <= 1
+    const unsigned span = (top > lo ? top : lo) - lo;
+    int shift = 0;
+    while ((span >> shift) >= (unsigned)kBins) ++shift;
+    for (int level = 0; level < 4; ++level) {
+        for (int i = threadIdx.x; i < kBins; i += kThreads) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+            const unsigned sb = (unsigned)(__ldcg(keys + i) >> 32);
+            if (sb >= lo && sb <= hi) atomicAdd(&hist[min((sb - lo) >> shift, (unsigned)(kBins - 1))], 1);
+        }
+        __syncthreads();
+        int c[kPerThread], own = 0;
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) {
+            c[j] = hist[threadIdx.x * kPerThread + j];
+            own += c[j];
+        }
+        int suf = own;  // inclusive suffix sum over the lanes >= this one
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_down_sync(0xffffffffu, suf, o);
+            if (lane + o < 32) suf += v;
+        }
+        if (lane == 0) s_wtot[warp] = suf;
+        __syncthreads();
+        int higher = 0;
+        for (int w = warp + 1; w < kThreads / 32; ++w) higher += s_wtot[w];
+        const int incl = suf + higher, excl = incl - own;  // keys in bins of threads >= / > this one
+        const int need = k - above;
+        if (excl < need && need <= incl) {  // exactly one thread: the range holds at least `need` keys
+            int acc = excl;
+#pragma unroll
+            for (int j = kPerThread - 1; j >= 0; --j) {
+                if (acc + c[j] >= need) {
+                    s_tb = threadIdx.x * kPerThread + j;
+                    s_above_add = acc;
+                    s_tb_cnt = c[j];
+                    break;
+                }
+                acc += c[j];
+            }
+        }
+        __syncthreads();
+        const int tb = s_tb;
+        const unsigned lo_new = lo + ((unsigned)tb << shift);
+        const int above_new = above + s_above_add;
+        if (above_new + s_tb_cnt <= kCollectCap) {
+            // collect every key at or above the threshold bin (>= k of them, <= kCollectCap)
+            __syncthreads();  // all reads of hist / s_* done before buf and the counter are written
+            for (int i = threadIdx.x; i < n; i += kThreads) {
+                const u64 key = __ldcg(keys + i);
+                if ((unsigned)(key >> 32) >= lo_new) sh.buf[atomicAdd(&sh.count, 1)] = key;
+            }
+            __syncthreads();
+            return true;
+        }
+        if (shift == 0) break;  // one exact score value with too many anchors: give up (uniform)
+        if (tb != kBins - 1) hi = lo_new + ((1u << shift) - 1u);
+        lo = lo_new;
+        above = above_new;
+        shift = shift > 11 ? shift - 11 : 0;
+        __syncthreads();
+    }
+    return false;
+}
+
+// Phase 2: one CTA per image over its candidate list (a few hundred keys on real inputs; at most A).
+__global__ void __launch_bounds__(kThreads) detect_from_candidates_kernel(SqdCand cand, const float *pred,
+                                                                          const float4 *anchors, int A, int C, float wmax,
+                                                                          float hmax, int k, float nms_thr_f,
+                                                                          float score_thr_f, FilterOut o) {
+    __shared__ Shared sh;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const int img = blockIdx.x;
+    const int n = min(cand.count[img], cand.stride);
+    const u64 *keys = cand.keys + (size_t)img * cand.stride;
+    FromPred<0> src;
+    src.pred = pred + (size_t)img * A * (C + 5);
+    src.anchors = anchors;
+    src.C = C;
+    src.wmax = wmax;
+    src.hmax = hmax;
+    if (threadIdx.x == 0) {
+        sh.count = 0;
+        sh.thresh = score_floor_key(score_thr_f);
+    }
+    __syncthreads();
+    bool have = false;
+    if (n <= max(k + 192, 256) && n <= kCap / 2) {
+        // short list: sort it directly
+        for (int i = threadIdx.x; i < n; i += kThreads) sh.buf[i] = __ldcg(keys + i);
+        if (threadIdx.x == 0) sh.count = n;
+        __syncthreads();
+        have = true;
+    } else {
+        have = hist_select_collect(sh, keys, n, k, score_thr_f);
+    }
+    if (have) {
+        rank_sort(sh);  // descending: the first k entries are the top-k
+        if (threadIdx.x == 0 && sh.count > k) sh.count = k;
+        __syncthreads();
+    } else {
+        // fallback (massive exact score ties): running-threshold scan with exact radix selects
+        if (threadIdx.x == 0) sh.count = 0;
+        __syncthreads();
+        for (int base = 0; base < n; base += kRound) {
+            const u64 thr = sh.thresh;
+            u64 kk[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int i = base + u * kThreads + threadIdx.x;
+                kk[u] = i < n ? __ldcg(keys + i) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                if (kk[u] > thr) {
+                    const int pos = atomicAdd(&sh.count, 1);
+                    if (pos < kCap) sh.buf[pos] = kk[u];
+                }
+            if (__syncthreads_or(*(volatile int *)&sh.count > kCap - kRound)) select_topk(sh, k);
+        }
+        select_topk(sh, k);
+        rank_sort(sh);
+    }
+    nms_and_emit(src, sh, dyn, k, C, nms_thr_f, score_thr_f, o, img);
+}
+
 size_t dyn_smem_bytes(int k) {
     const size_t wpr = (k + 31) / 32;
-    return (size_t)k * 16 + (size_t)k * 4 + (size_t)k * wpr * 4 + (size_t)k + 16;
+    return (size_t)k * 16 + (size_t)k * 4 + (size_t)k * wpr * 4 + (size_t)k * 4 + wpr * 4 + 16;
 }
 
 float float_at_or_below(double t) {  // largest float <= t: (double)iou > t  <=>  iou > this
@@ -503,23 +724,106 @@ extern "C" int sqd_topk_nms(const int64_t *d_class_ids, const float *d_scores, c
                             float_at_or_below(nms_thresh), (float)score_thresh, o, cluster_size_for(batch, num_anchors, top_k));
 }
 
+// ---- two-phase host side (also used by api.cu for the fused head) -------------------------------------------
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t sqd_cand_bytes(int batch, int num_anchors) {
+    return align256((size_t)batch * sizeof(int)) + align256((size_t)batch * num_anchors * sizeof(u64));
+}
+
+SqdCand sqd_cand_layout(void *ws, int batch, int num_anchors) {
+    SqdCand c;
+    c.count = static_cast<int *>(ws);
+    c.keys = reinterpret_cast<u64 *>(static_cast<char *>(ws) + align256((size_t)batch * sizeof(int)));
+    c.stride = num_anchors;
+    return c;
+}
+
+// phase 1: pred -> candidate lists (cand.count must have been zeroed on the stream)
+int sqd_score_candidates(const float *d_pred, int batch, int num_anchors, int num_classes, double score_thresh,
+                         SqdCand cand, cudaStream_t st) {
+    const long long total = (long long)batch * num_anchors;
+    SQD_REQUIRE(total < (1ll << 31), SQD_E_SHAPE, "detect: batch*num_anchors %lld does not fit 31 bits", total);
+    const float sthr = (float)score_thresh;
+    const int max_grid = SQD_SM_COUNT * 8;
+    if (num_classes == 3) {
+        long long g = (total + kScanThreads * kScanUnroll - 1) / (kScanThreads * kScanUnroll);
+        const int grid = (int)(g < max_grid ? g : max_grid);
+        score_candidates_kernel<3><<<grid, kScanThreads, 0, st>>>(d_pred, (unsigned)total, (unsigned)num_anchors, 3, sthr, cand);
+    } else {
+        long long g = (total + kScanThreads - 1) / kScanThreads;
+        const int grid = (int)(g < max_grid ? g : max_grid);
+        const size_t smem = (size_t)kScanThreads * (num_classes + 5) * sizeof(float);
+        if (num_classes == 8)
+            score_candidates_kernel<8><<<grid, kScanThreads, smem, st>>>(d_pred, (unsigned)total, (unsigned)num_anchors, 8, sthr, cand);
+        else
+            score_candidates_kernel<0><<<grid, kScanThreads, smem, st>>>(d_pred, (unsigned)total, (unsigned)num_anchors, num_classes, sthr, cand);
+    }
+    SQD_LAUNCH_CHECK("score_candidates_kernel");
+    return SQD_OK;
+}
+
+// phase 2: candidate lists -> final detections
+int sqd_detect_from_candidates(SqdCand cand, const float *d_pred, const float *d_anchors, int batch, int num_anchors,
+                               int num_classes, int input_h, int input_w, int top_k, double nms_thresh,
+                               double score_thresh, int32_t *d_count, int32_t *d_out_anchor, int32_t *d_out_class,
+                               float *d_out_score, float *d_out_box, cudaStream_t st) {
+    FilterOut o{d_count, d_out_anchor, d_out_class, d_out_score, reinterpret_cast<float4 *>(d_out_box)};
+    const size_t smem = dyn_smem_bytes(top_k);
+    int rc = opt_in_smem(detect_from_candidates_kernel, smem);
+    if (rc) return rc;
+    detect_from_candidates_kernel<<<batch, kThreads, smem, st>>>(cand, d_pred, reinterpret_cast<const float4 *>(d_anchors),
+                                                                 num_anchors, num_classes, (float)(input_w - 1),
+                                                                 (float)(input_h - 1), top_k, float_at_or_below(nms_thresh),
+                                                                 (float)score_thresh, o);
+    SQD_LAUNCH_CHECK("detect_from_candidates_kernel");
+    return SQD_OK;
+}
+
+int sqd_detect_check_args(const char *fn, const void *d_pred, const void *d_anchors, int batch, int num_anchors,
+                          int num_classes, int top_k, const void *count, const void *anchor, const void *cls,
+                          const void *score, const void *box) {
+    SQD_REQUIRE(d_pred && d_anchors, SQD_E_NULL, "%s: pred/anchors is NULL", fn);
+    int rc = check_common(fn, batch, num_anchors, num_classes, top_k, count, anchor, cls, score, box);
+    if (rc) return rc;
+    SQD_REQUIRE(sqd_aligned16(d_pred) && sqd_aligned16(d_anchors), SQD_E_ALIGN, "%s: pred/anchors must be 16-byte aligned", fn);
+    return SQD_OK;
+}
+
+extern "C" size_t sqd_detect_workspace_bytes(int batch, int num_anchors) {
+    if (batch <= 0 || num_anchors <= 0) return 256;
+    return sqd_cand_bytes(batch, num_anchors);
+}
+
 extern "C" int sqd_detect_from_pred(const float *d_pred, const float *d_anchors, int batch, int num_anchors,
                                     int num_classes, int input_h, int input_w, int top_k, double nms_thresh,
                                     double score_thresh, int32_t *d_count, int32_t *d_out_anchor,
-                                    int32_t *d_out_class, float *d_out_score, float *d_out_box, void *stream) {
+                                    int32_t *d_out_class, float *d_out_score, float *d_out_box, void *d_workspace,
+                                    size_t workspace_bytes, void *stream) {
     if (batch == 0) return SQD_OK;  // empty batch: nothing to enqueue, pointers may be NULL
-    SQD_REQUIRE(d_pred && d_anchors, SQD_E_NULL, "sqd_detect_from_pred: pred/anchors is NULL");
-    int rc = check_common("sqd_detect_from_pred", batch, num_anchors, num_classes, top_k, d_count, d_out_anchor,
-                          d_out_class, d_out_score, d_out_box);
+    int rc = sqd_detect_check_args("sqd_detect_from_pred", d_pred, d_anchors, batch, num_anchors, num_classes, top_k,
+                                   d_count, d_out_anchor, d_out_class, d_out_score, d_out_box);
     if (rc) return rc;
-    SQD_REQUIRE(sqd_aligned16(d_pred) && sqd_aligned16(d_anchors), SQD_E_ALIGN,
-                "sqd_detect_from_pred: pred/anchors must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d_workspace) {
+        // two-phase form: streaming scan -> candidate lists -> per-image tail
+        SQD_REQUIRE(workspace_bytes >= sqd_cand_bytes(batch, num_anchors), SQD_E_WORKSPACE,
+                    "sqd_detect_from_pred: workspace too small (%zu bytes)", workspace_bytes);
+        SQD_REQUIRE(sqd_aligned16(d_workspace), SQD_E_ALIGN, "sqd_detect_from_pred: workspace must be 16-byte aligned");
+        const SqdCand cand = sqd_cand_layout(d_workspace, batch, num_anchors);
+        SQD_CUDA(cudaMemsetAsync(cand.count, 0, (size_t)batch * sizeof(int), st));
+        rc = sqd_score_candidates(d_pred, batch, num_anchors, num_classes, score_thresh, cand, st);
+        if (rc) return rc;
+        return sqd_detect_from_candidates(cand, d_pred, d_anchors, batch, num_anchors, num_classes, input_h, input_w, top_k,
+                                          nms_thresh, score_thresh, d_count, d_out_anchor, d_out_class, d_out_score,
+                                          d_out_box, st);
+    }
+    // workspace-free form: one launch, a cluster of CTAs per image scans, selects and filters
     FilterOut o{d_count, d_out_anchor, d_out_class, d_out_score, reinterpret_cast<float4 *>(d_out_box)};
     const size_t smem = dyn_smem_bytes(top_k);
     const float4 *anc = reinterpret_cast<const float4 *>(d_anchors);
     const float wmax = (float)(input_w - 1), hmax = (float)(input_h - 1);
     const float nthr = float_at_or_below(nms_thresh), sthr = (float)score_thresh;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int cs = cluster_size_for(batch, num_anchors, top_k);
     if (num_classes == 3) {
         rc = opt_in_smem(detect_from_pred_kernel<3>, smem);

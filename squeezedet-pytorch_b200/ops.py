@@ -127,15 +127,21 @@ def topk_nms(class_ids, scores, boxes, num_classes, top_k, nms_thresh, score_thr
     return det
 
 
-def detect_from_pred(pred, anchors_f32, input_hw, num_classes, top_k, nms_thresh, score_thresh) -> Detections:
-    """Fused decode + score + top-k + NMS from the ConvDet output, one launch."""
+def detect_from_pred(pred, anchors_f32, input_hw, num_classes, top_k, nms_thresh, score_thresh, two_phase=True,
+                     out: Detections = None) -> Detections:
+    """Fused decode + score + top-k + NMS from the ConvDet output.  two_phase: streaming scan into candidate lists
+    + per-image tail (needs scratch); otherwise one clustered launch without scratch.  Same results."""
     lib = load()
     pred = pred.contiguous()
     B, A, _ = pred.shape
-    det = _alloc_detections(B, top_k, pred.device)
+    det = out if out is not None else _alloc_detections(B, top_k, pred.device)
+    ws, nbytes = None, 0
+    if two_phase:
+        nbytes = lib.sqd_detect_workspace_bytes(B, A)
+        ws = workspace().get("detect", nbytes, pred.device)
     check(lib.sqd_detect_from_pred(ptr(pred), ptr(anchors_f32), B, A, num_classes, int(input_hw[0]), int(input_hw[1]),
                                    top_k, float(nms_thresh), float(score_thresh), ptr(det.count), ptr(det.anchor),
-                                   ptr(det.cls), ptr(det.score), ptr(det.box), stream_ptr(pred.device)),
+                                   ptr(det.cls), ptr(det.score), ptr(det.box), ptr(ws), nbytes, stream_ptr(pred.device)),
           "sqd_detect_from_pred")
     return det
 
@@ -160,6 +166,26 @@ def head_detect(feat, weight, bias, anchors_f32, anchors_per_grid, num_classes, 
                                     ptr(det.cls), ptr(det.score), ptr(det.box), ptr(ws), ws.numel(), algo,
                                     stream_ptr(x.device)), "sqd_head_detect_fused")
     return det
+
+
+def head_detect_profile(feat, bias, anchors_f32, anchors_per_grid, num_classes, input_hw, top_k, nms_thresh,
+                        score_thresh, packed, out: Detections = None):
+    """Diagnostic twin of head_detect: same kernels, returns (Detections, [split_ms, convdet_ms, filter_ms]) measured
+    with CUDA events on the launching stream (sqd_head_detect_profile; synchronises)."""
+    lib = load()
+    layout, x = feature_layout(feat)
+    B, cin, gh, gw = x.shape
+    cout = anchors_per_grid * (num_classes + 5)
+    nbytes = lib.sqd_head_detect_profile_workspace_bytes(B, cin, gh, gw, cout)
+    ws = workspace().get("head_detect_profile", nbytes, x.device)
+    det = out if out is not None else _alloc_detections(B, top_k, x.device)
+    ms = (C.c_float * 3)()
+    check(lib.sqd_head_detect_profile(C.c_void_p(x.data_ptr()), layout, ptr(packed), ptr(bias.detach().contiguous()),
+                                      ptr(anchors_f32), B, cin, gh, gw, anchors_per_grid, num_classes, int(input_hw[0]),
+                                      int(input_hw[1]), top_k, float(nms_thresh), float(score_thresh), ptr(det.count),
+                                      ptr(det.anchor), ptr(det.cls), ptr(det.score), ptr(det.box), ptr(ws), ws.numel(),
+                                      stream_ptr(x.device), ms), "sqd_head_detect_profile")
+    return det, [float(v) for v in ms]
 
 
 class HostDetections:

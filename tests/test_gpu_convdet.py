@@ -189,3 +189,27 @@ def test_pair_kernel_matches_single_cta_kernel(ops, name, batch):
     pair = ops.convdet_forward(dev(feat), dev(w), dev(b), algo=CONV_TCGEN05_F16X3, check_status=True)
     one = ops.convdet_forward(dev(feat), dev(w), dev(b), algo=CONV_TCGEN05_F16X3_1CTA, check_status=True)
     assert torch.allclose(pair, one, rtol=2e-5, atol=5e-6), float((pair - one).abs().max())
+
+
+@pytest.mark.parametrize("name,batch", [("tiny_160x96", 5), ("kitti_1248x384", 7), ("stress_2496x768", 2)])
+@pytest.mark.parametrize("score_thresh", [None, -1.0])
+def test_epilogue_candidates_equal_scan_of_pred(ops, monkeypatch, name, batch, score_thresh):
+    """sqd_head_detect_fused: the GEMM epilogue scoring the anchors itself (candidate lists filled from the fp32
+    accumulators; opt-in, SQD_FUSED_SCORE=1) gives exactly what the default stand-alone scan of the stored pred gives, and what
+    the staged ConvDet -> sqd_detect_from_pred route gives.  score_thresh -1: every anchor becomes a candidate."""
+    shp = {x.name: x for x in (synth.TINY, synth.KITTI, synth.STRESS)}[name]
+    thr = shp.score_thresh if score_thresh is None else score_thresh
+    feat, (w, b) = dev(synth.features(shp, batch, 41)), synth.convdet_params(shp, 42)
+    w, b = dev(w), dev(b)
+    a32 = dev(synth.anchor_table(shp).astype(np.float32))
+    args = (a32, shp.anchors_per_grid, shp.num_classes, shp.input_hw, shp.top_k, shp.nms_thresh, thr)
+    monkeypatch.setenv("SQD_FUSED_SCORE", "1")
+    fused = ops.head_detect(feat, w, b, *args)
+    monkeypatch.delenv("SQD_FUSED_SCORE", raising=False)
+    scanned = ops.head_detect(feat, w, b, *args)
+    pred = ops.convdet_forward(feat, w, b, num_fields=shp.num_fields, check_status=True)
+    staged = ops.detect_from_pred(pred, a32, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh, thr, two_phase=False)
+    for f in ("count", "anchor", "cls", "score", "box"):
+        assert torch.equal(getattr(fused, f), getattr(scanned, f)), f
+        assert torch.equal(getattr(fused, f), getattr(staged, f)), f
+    assert int(fused.count.sum()) > 0

@@ -158,6 +158,38 @@ def test_fused_detect_equals_unfused_and_oracle(ops, name, batch):
     _check_rows(dets_to_lists(fused), expect2, exact_values=False)
 
 
+@pytest.mark.parametrize("name,batch", [("tiny_160x96", 5), ("kitti_1248x384", 9), ("stress_2496x768", 3)])
+@pytest.mark.parametrize("score_thresh", [None, -1.0])
+def test_detect_two_phase_equals_clustered(ops, name, batch, score_thresh):
+    """sqd_detect_from_pred with scratch (streaming scan -> candidate lists -> per-image tail) and without (one
+    clustered launch) are the same function; score_thresh -1 sends EVERY anchor through the candidate lists
+    (list length == A, mid-scan compactions in the tail)."""
+    shp = SHAPES[name]
+    thr = shp.score_thresh if score_thresh is None else score_thresh
+    a64, a32 = anchors_dev(shp)
+    dp = dev(synth.clustered_pred(shp, batch, 404, anchors=a64))
+    two = ops.detect_from_pred(dp, a32, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh, thr, two_phase=True)
+    one = ops.detect_from_pred(dp, a32, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh, thr, two_phase=False)
+    for f in ("count", "anchor", "cls", "score", "box"):
+        assert torch.equal(getattr(two, f), getattr(one, f)), f
+    assert int(two.count.sum()) > 0
+
+
+def test_detect_two_phase_generic_class_count(ops):
+    """A class count without a specialised kernel (C = 5) goes through the generic staged scan."""
+    shp = synth.Shape("c5", (96, 160), 5, 16)
+    a64, a32 = anchors_dev(shp)
+    rs = np.random.RandomState(7)
+    pred = rs.standard_normal((3, shp.num_anchors, shp.num_fields)).astype(np.float32)
+    dp = dev(pred)
+    two = ops.detect_from_pred(dp, a32, shp.input_hw, 5, shp.top_k, shp.nms_thresh, 0.05, two_phase=True)
+    one = ops.detect_from_pred(dp, a32, shp.input_hw, 5, shp.top_k, shp.nms_thresh, 0.05, two_phase=False)
+    for f in ("count", "anchor", "cls", "score", "box"):
+        assert torch.equal(getattr(two, f), getattr(one, f)), f
+    expect = orc.detect_filtered(pred, a64, shp.input_hw, 5, shp.top_k, shp.nms_thresh, 0.05)
+    _check_rows(dets_to_lists(two), expect, exact_values=False)
+
+
 @pytest.mark.parametrize("name", list(SHAPES))
 def test_fused_detect_vs_reference_golden(ops, golden, name):
     g = golden("decode_filter_" + name)
