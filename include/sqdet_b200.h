@@ -55,8 +55,9 @@ extern "C" {
 /* feature-map memory layouts accepted by the ConvDet head */
 #define SQD_LAYOUT_NCHW 0
 #define SQD_LAYOUT_NHWC 1 /* torch channels_last: logical NCHW, physical NHWC */
-#define SQD_LAYOUT_SPLIT_NHWC 2 /* [max|x| per image: B x u32][x1 plane][x2 plane], planes (B,gh,gw,Cin) fp16: output of
-                                   sqd_convdet_split_features, consumed by the tcgen05 algorithm only */
+#define SQD_LAYOUT_SPLIT_NHWC 2 /* [max|x| per (image, 64-channel block): B*(Cin/64) x u32, padded to 256 B][x1 plane][x2 plane],
+                                   planes (B,gh,gw,Cin) fp16: output of sqd_convdet_split_features, consumed by the
+                                   tcgen05 algorithm only */
 
 /* ConvDet algorithms */
 #define SQD_CONV_TCGEN05_F16X3 0 /* production: tcgen05.mma cta_group::2 kind::f16 on CTA pairs (M = 256), two-term fp16
@@ -85,7 +86,8 @@ SQD_API const char *sqd_last_error(void);
  * ------------------------------------------------------------------------------------------- */
 SQD_API size_t sqd_convdet_packed_weight_bytes(int cout, int cin);
 SQD_API int sqd_convdet_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, void *stream);
-/* per-image max|x| + two-term fp16 split of a feature map into NHWC planes (the tcgen05 kernel's A operand).  sqd_convdet_forward
+/* max|x| per (image, 64-channel block) + two-term fp16 split of a feature map into NHWC planes (the tcgen05 kernel's
+ * A operand); one pass over HBM for NCHW input (a thread-block cluster per slab).  sqd_convdet_forward
  * does this internally for NCHW / NHWC input; a producer that can emit the planes itself (or reuses them)
  * passes them with SQD_LAYOUT_SPLIT_NHWC and skips the pass. */
 SQD_API size_t sqd_convdet_split_bytes(int batch, int cin, int gh, int gw);

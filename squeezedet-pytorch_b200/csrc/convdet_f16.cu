@@ -10,13 +10,17 @@
 // tcgen05.mma streams A (128 rows) and B (N rows) through the 128 B/clk port; tools/micro/umma_rate.cu).  What
 // fp16 lacks is exponent range, so both operands are scaled by exact powers of two first:
 //     x*s = x1 + x2/2^11 (+ <= 2^-22 relative),  x1 = fp16(x*s),  x2 = fp16((x*s - x1) * 2^11)
-// with s = 2^e chosen per IMAGE for the features (from a max|x| pre-pass) and per tensor for the weights so that
-// max|x*s| lies in [2^13, 2^14): no overflow, and elements down to 2^-27 of the maximum keep full precision
+// with s = 2^e chosen per (IMAGE, 64-CHANNEL BLOCK) for the features and per tensor for the weights so that
+// max|x*s| lies in [2^13, 2^14): no overflow, and elements down to 2^-27 of the block maximum keep full precision
 // (smaller ones degrade gracefully to an absolute error of 2^-49 of the maximum).  Then
 //     a*w*(s_a*s_w) = a1*w1 + (a1*w2 + a2*w1)/2^11   (the dropped a2*w2 term is 2^-22 relative, like 3xTF32)
+// A TMEM accumulation chunk never crosses a channel block, and the accumulate warps multiply it by the block's 1/s_a
+// (exact) while folding it into their fp32 registers.
 //
-//  * pre-pass (the only extra HBM traffic): features fp32 NCHW or NHWC -> two fp16 NHWC planes (x1, x2); reads
-//    4 B and writes 4 B per element, fused with the NCHW->NHWC transpose the K-major A operand needs anyway.
+//  * pre-pass (the only extra HBM traffic): features fp32 NCHW -> two fp16 NHWC planes (x1, x2) in ONE pass: a
+//    thread-block cluster holds an (image, channel block) slab in shared memory, finds its max and writes the split,
+//    transposed planes (4 B read + 4 B written per element; the K-major A operand needs the transpose anyway).
+//    channels_last input and oversized grids take a max pass + a split pass.
 //  * M tile = 8 x 16 cells = 128 rows = one UMMA_M.  A "unit" of work is (tile, 64-channel block, dx): ONE 4-D TMA
 //    box {64 ch, 16 x, 10 y, 1 img} per plane at (c0, x0+dx-1, y0-1, b); conv padding = TMA out-of-bounds zero fill.
 //    The box lands as 160 rows x 128 B, 128B-swizzled; the three dy taps are the SAME patch read through UMMA
@@ -40,6 +44,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+
+#include <cooperative_groups.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -82,10 +88,17 @@ __device__ __forceinline__ void split_f16(float xs, __half &h1, __half &h2) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// pre-passes
+// pre-passes: fp32 features -> two fp16 NHWC planes, scaled per (image, 64-channel block)
 // ---------------------------------------------------------------------------------------------------
-// max |x| per image (any layout: an image is one contiguous run of n4 float4).  Non-negative floats order like
-// their bit patterns, so the reduction is an integer atomicMax.  NaN inputs are ignored by fmaxf.
+// Scale granularity.  One tcgen05.mma needs a single scale for all rows of its A slab, and a slab is (pixels of one
+// tile, 16 channels of ONE 64-channel block), so the finest granularity that keeps the GEMM exact is (image, channel
+// block): the accumulate warps multiply each drained chunk (which never crosses a channel block) by the block's
+// 2^-e while folding it into fp32 registers (a power of two: exact).  An (image, block) slab of an NCHW tensor is one
+// contiguous run of 64*P floats, small enough for a thread-block CLUSTER to hold in shared memory -- so max|x| and
+// the split need ONE pass over HBM (4 B read + 4 B written per element) instead of a max pass plus a split pass.
+
+// max |x| of contiguous runs of n4 float4 (one run per blockIdx.y).  Non-negative floats order like their bit
+// patterns, so the reduction is an integer atomicMax.  NaN inputs are ignored by fmaxf.
 __global__ void __launch_bounds__(256) absmax_kernel(const float4 *__restrict__ in, size_t n4, unsigned *__restrict__ amax_bits) {
     const float4 *src = in + (size_t)blockIdx.y * n4;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -117,32 +130,52 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float4 *__restrict__ 
     }
 }
 
-// NHWC fp32 -> x1 / x2 fp16 planes (same layout); grid.y = image
+// NHWC (channels_last): per (image, channel block) max.  blockDim.x = cin/4: thread t owns channel quad t (so its
+// channel block is fixed), the block walks cells blockIdx.x, +gridDim.x, ...; 16 consecutive lanes share a block.
+__global__ void absmax_nhwc_kernel(const float4 *__restrict__ in, int P, int cin4, unsigned *__restrict__ amax_bits) {
+    const float4 *src = in + (size_t)blockIdx.y * P * cin4 + threadIdx.x;
+    float m0 = 0.f, m1 = 0.f;
+    int q = blockIdx.x;
+    for (; q + (int)gridDim.x < P; q += 2 * gridDim.x) {
+        const float4 a = ld_stream_f4(src + (size_t)q * cin4), b = ld_stream_f4(src + (size_t)(q + gridDim.x) * cin4);
+        m0 = fmaxf(fmaxf(m0, fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
+        m1 = fmaxf(fmaxf(m1, fmaxf(fabsf(b.x), fabsf(b.y))), fmaxf(fabsf(b.z), fabsf(b.w)));
+    }
+    if (q < P) {
+        const float4 a = ld_stream_f4(src + (size_t)q * cin4);
+        m0 = fmaxf(fmaxf(m0, fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
+    }
+    float m = fmaxf(m0, m1);
+#pragma unroll
+    for (int o = 8; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));  // within the 16 lanes of a block
+    if ((threadIdx.x & 15) == 0) atomicMax(amax_bits + (size_t)blockIdx.y * (cin4 >> 4) + (threadIdx.x >> 4), __float_as_uint(m));
+}
+
+// NHWC fp32 -> x1 / x2 fp16 planes (same layout); blockDim.x = cin/4 like absmax_nhwc_kernel; grid.y = image
 __global__ void split_nhwc_f16_kernel(const float4 *__restrict__ in, uint2 *__restrict__ p1, uint2 *__restrict__ p2,
-                                      size_t n4, const unsigned *__restrict__ amax_bits) {
-    const float s = pow2_scale_for(__uint_as_float(amax_bits[blockIdx.y]));
-    const size_t base = (size_t)blockIdx.y * n4;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        const float4 v = ld_stream_f4(in + base + i);
+                                      int P, int cin4, const unsigned *__restrict__ amax_bits) {
+    const float s = pow2_scale_for(__uint_as_float(amax_bits[(size_t)blockIdx.y * (cin4 >> 4) + (threadIdx.x >> 4)]));
+    const size_t base = (size_t)blockIdx.y * P * cin4 + threadIdx.x;
+    for (int q = blockIdx.x; q < P; q += gridDim.x) {
+        const float4 v = ld_stream_f4(in + base + (size_t)q * cin4);
         __half a1[4], a2[4];
         split_f16(v.x * s, a1[0], a2[0]);
         split_f16(v.y * s, a1[1], a2[1]);
         split_f16(v.z * s, a1[2], a2[2]);
         split_f16(v.w * s, a1[3], a2[3]);
-        p1[base + i] = *reinterpret_cast<const uint2 *>(a1);
-        p2[base + i] = *reinterpret_cast<const uint2 *>(a2);
+        p1[base + (size_t)q * cin4] = *reinterpret_cast<const uint2 *>(a1);
+        p2[base + (size_t)q * cin4] = *reinterpret_cast<const uint2 *>(a2);
     }
 }
 
-// NCHW (B,Cin,P) fp32 -> NHWC (B,P,Cin) fp16 planes through a 64 ch x 64 cell shared tile; P = gh*gw.
-// Reads: every thread issues its 16 loads (256 B rows along P) before the first use.  Writes: 8 B per lane
-// (4 channels), half a warp per 128-byte channel row of a cell.  256 threads.
+// NCHW (B,Cin,P) fp32 -> NHWC (B,P,Cin) fp16 planes through a 64 ch x 64 cell shared tile, scales already known
+// (two-pass fallback for shapes the one-pass kernel does not take).  P = gh*gw.  256 threads.
 __global__ void __launch_bounds__(256) split_nchw_f16_kernel(const float *__restrict__ in, uint2 *__restrict__ p1,
                                                              uint2 *__restrict__ p2, int cin, int P,
                                                              const unsigned *__restrict__ amax_bits) {
     __shared__ float tile[64][65];
     const int b = blockIdx.z, c0 = blockIdx.y * 64, q0 = blockIdx.x * 64;
-    const float s = pow2_scale_for(__uint_as_float(amax_bits[b]));
+    const float s = pow2_scale_for(__uint_as_float(amax_bits[(size_t)b * (cin >> 6) + blockIdx.y]));
     const float *src = in + (size_t)b * cin * P;
     const int col = threadIdx.x & 63, r0 = threadIdx.x >> 6;
     const int q = q0 + col;
@@ -165,6 +198,117 @@ __global__ void __launch_bounds__(256) split_nchw_f16_kernel(const float *__rest
             p1[o] = *reinterpret_cast<const uint2 *>(a1);
             p2[o] = *reinterpret_cast<const uint2 *>(a2);
         }
+    }
+}
+
+// ONE-PASS NCHW split.  A cluster of `cs` CTAs owns one (image, 64-channel block) slab = 64 rows of P floats; CTA r
+// takes the float4 columns [r*n4/cs, (r+1)*n4/cs) of every row (n4 = P/4).
+//   1. stream the sub-slab into shared memory (16-byte loads; 16-byte chunks XOR-swizzled by the channel so that the
+//      transposed reads of step 3 are at most 2-way bank conflicted), tracking max|x|;
+//   2. block max -> pushed into every CTA of the cluster through distributed shared memory -> cluster.sync();
+//   3. scale by 2^e, split into (x1, x2) and write the NHWC planes: 16 lanes x 4 channels = one 128-byte row of a cell.
+constexpr int kSplitMaxCluster = 16;
+template <int kSplitThreads, bool kRowLoads>
+__global__ void __launch_bounds__(kSplitThreads) split_nchw_cluster_kernel(const float *__restrict__ in, uint2 *__restrict__ p1,
+                                                                           uint2 *__restrict__ p2, int cin, int P,
+                                                                           unsigned *__restrict__ amax_bits, int cs, int nq4p) {
+    extern __shared__ __align__(16) float4 tile4[];  // [64][nq4p]
+    __shared__ float s_red[kSplitThreads / 32];
+    __shared__ unsigned s_cmax[kSplitMaxCluster];
+    namespace cgx = cooperative_groups;
+    cgx::cluster_group cluster = cgx::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int slab = blockIdx.x / cs, ncb = cin >> 6;
+    const int b = slab / ncb, cb = slab - b * ncb, c0 = cb << 6;
+    const int n4 = P >> 2;
+    const int q4b = (int)((long long)rank * n4 / cs), q4e = (int)((long long)(rank + 1) * n4 / cs), nq4 = q4e - q4b;
+    const float4 *src = reinterpret_cast<const float4 *>(in + ((size_t)b * cin + c0) * P) + q4b;
+
+    // 1. stream the sub-slab in: 4 independent 16-byte loads in flight per thread
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kWarps = kSplitThreads / 32;
+    float m = 0.f;
+    if (kRowLoads) {
+        // a warp covers a row segment; rows warp, warp + kWarps, ... (no index division)
+        for (int c0r = warp; c0r < 64; c0r += 4 * kWarps) {
+#pragma unroll 2
+            for (int jb = 0; jb < nq4; jb += 32) {
+                const int j = jb + lane;
+                float4 v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    v[i] = (j < nq4 && c0r + kWarps * i < 64) ? ld_stream_f4(src + (size_t)(c0r + kWarps * i) * n4 + j)
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = c0r + kWarps * i;
+                    if (j < nq4 && c < 64) {
+                        m = fmaxf(fmaxf(m, fmaxf(fabsf(v[i].x), fabsf(v[i].y))), fmaxf(fabsf(v[i].z), fabsf(v[i].w)));
+                        tile4[c * nq4p + (j ^ ((c >> 2) & 7))] = v[i];
+                    }
+                }
+            }
+        }
+    } else {
+        const int total = 64 * nq4;
+        for (int base = 0; base < total; base += 4 * kSplitThreads) {
+            float4 v[4];
+            int cc[4], jj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * kSplitThreads + threadIdx.x;
+                cc[u] = idx / nq4;
+                jj[u] = idx - cc[u] * nq4;
+                v[u] = idx < total ? ld_stream_f4(src + (size_t)cc[u] * n4 + jj[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (base + u * kSplitThreads + (int)threadIdx.x < total) {
+                    m = fmaxf(fmaxf(m, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+                    tile4[cc[u] * nq4p + (jj[u] ^ ((cc[u] >> 2) & 7))] = v[u];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < kSplitThreads / 32 ? s_red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((int)threadIdx.x < cs) cluster.map_shared_rank(s_cmax, threadIdx.x)[rank] = __float_as_uint(m);
+    }
+    cluster.sync();  // every CTA's maximum has landed in every CTA's s_cmax; also the block barrier for tile4
+    unsigned mb = 0u;
+    for (int r = 0; r < cs; ++r) mb = max(mb, s_cmax[r]);
+    if (rank == 0 && threadIdx.x == 0) amax_bits[slab] = mb;
+    const float s = pow2_scale_for(__uint_as_float(mb));
+
+    // 3. 16 lanes x 4 channels = the 128-byte row of one cell and plane; 32 cells per pass
+    const int l16 = threadIdx.x & 15, slot = threadIdx.x >> 4;
+    const float *tile = reinterpret_cast<const float *>(tile4);
+    const int sw = l16 & 7;  // == ((4*l16 + k) >> 2) & 7 for k = 0..3
+    const float *trow = tile + (size_t)(4 * l16) * nq4p * 4;
+    const int kstride = nq4p * 4;
+    const size_t cin4 = (size_t)(cin >> 2);
+    size_t o = ((size_t)b * P + 4 * q4b + slot) * cin4 + (c0 >> 2) + l16;
+    for (int q = slot; q < 4 * nq4; q += kSplitThreads / 16, o += (kSplitThreads / 16) * cin4) {
+        const float *src_q = trow + ((q >> 2) ^ sw) * 4 + (q & 3);
+        const float x0 = src_q[0] * s, x1 = src_q[kstride] * s, x2 = src_q[2 * kstride] * s, x3 = src_q[3 * kstride] * s;
+        // two-term split, two elements per instruction where the ISA has a packed form
+        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn((x0 - f01.x) * kLoScale, (x1 - f01.y) * kLoScale);
+        const __half2 l23 = __floats2half2_rn((x2 - f23.x) * kLoScale, (x3 - f23.y) * kLoScale);
+        uint2 w1, w2;
+        w1.x = *reinterpret_cast<const unsigned *>(&h01);
+        w1.y = *reinterpret_cast<const unsigned *>(&h23);
+        w2.x = *reinterpret_cast<const unsigned *>(&l01);
+        w2.y = *reinterpret_cast<const unsigned *>(&l23);
+        p1[o] = w1;
+        p2[o] = w2;
     }
 }
 
@@ -243,7 +387,7 @@ struct F16Params {
     int a_stages, b_stages;
     int dbg;            // debug (SQD_F16_DBG): 1 = skip MMA issue, 2 = skip A loads, 4 = skip B loads
     const float *bias;
-    const unsigned *amax_bits;   // (B) max|x| per image, fp32 bits
+    const unsigned *amax_bits;   // (B, Cin/64) max|x| per image and channel block, fp32 bits
     const PackedHeader *whdr;
     float *pred;
     float *partial;  // (grid, 128, NPAD) partial sums of split tiles
@@ -262,8 +406,9 @@ struct Sched {  // the permuted unit sequence of one CTA: [whole tiles + head se
     }
     // unit i closes its accumulation chunk: the chunk is full, or the unit ends a segment of the sequence
     // (end of a tile, end of the main part, end of the CTA's range).  in_chunk = units already in the chunk.
+    // A chunk never crosses a 64-channel block (r = cb*3 + dx): the block's feature scale is applied per chunk.
     __device__ __forceinline__ bool chunk_ends(int i, int r, int in_chunk, int chunk_units) const {
-        return in_chunk + 1 >= chunk_units || i == n - 1 || i == main_len - 1 || r == upt - 1;
+        return in_chunk + 1 >= chunk_units || r % 3 == 2 || i == n - 1 || i == main_len - 1 || r == upt - 1;
     }
 };
 
@@ -532,6 +677,9 @@ convdet_f16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
             __syncwarp();
             if (warp == kWarpAcc0) SQD_TRACE(11, i);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * kAccCols;
+            // 1 / (feature scale of this image and channel block): a power of two, so the fma below rounds once,
+            // exactly like an fp32 add of the unscaled unit
+            const float inv_a = 1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_bits + (size_t)it.img * (p.cin / kBlockK) + it.cb)));
 #pragma unroll
             for (int n0 = 0; n0 < NPAD; n0 += 16) {
                 uint32_t v[16], w[16];
@@ -540,7 +688,7 @@ convdet_f16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
                 tmem_ld_wait();
 #pragma unroll
                 for (int k = 0; k < 16; ++k)
-                    acc[n0 + k] = fadd(acc[n0 + k], fmaf(__uint_as_float(v[k]), kLoInv, __uint_as_float(w[k])));
+                    acc[n0 + k] = fmaf(fmaf(__uint_as_float(v[k]), kLoInv, __uint_as_float(w[k])), inv_a, acc[n0 + k]);
             }
             tc_fence_before();
             __syncwarp();
@@ -586,7 +734,7 @@ convdet_f16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
             }
             // whole tile in registers: x 1/(s_a*s_w), + bias -> pred
             const int x = it.tx * kTileX + row % kTileX, y = it.ty * kTileY + row / kTileX;
-            const float inv = fmul(1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_bits + it.img))), inv_sw);
+            const float inv = inv_sw;   // the feature scales were divided out chunk by chunk
             if (y < p.gh && x < p.gw) {
                 float *out = p.pred + (((size_t)it.img * p.gh + y) * p.gw + x) * p.cout;
                 if ((p.cout & 3) == 0) {
@@ -1003,6 +1151,11 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
             __syncwarp();
             if (warp == kWarpAcc2) SQD_TRACE2(11, i);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * kAccCols;
+            // 1 / (feature scale of this image and channel block); all units of a chunk share the block.  A power of
+            // two, so the fma below rounds once, exactly like an fp32 add of the unscaled chunk.  Ghost tile: any value.
+            const float inv_a = it.img < p.batch
+                ? 1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_bits + (size_t)it.img * (p.cin / kBlockK) + it.cb)))
+                : 1.f;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -1015,7 +1168,7 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const float cross = fadd(__uint_as_float(c1[k]), __uint_as_float(c2[k]));
-                        acc[h * H + j0 + k] = fadd(acc[h * H + j0 + k], fmaf(cross, kLoInv, __uint_as_float(mn[k])));
+                        acc[h * H + j0 + k] = fmaf(fmaf(cross, kLoInv, __uint_as_float(mn[k])), inv_a, acc[h * H + j0 + k]);
                     }
                 }
             }
@@ -1070,7 +1223,7 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
             // whole tile in registers: x 1/(s_a*s_w), + bias -> pred   (ghost tile: img == batch, nothing stored)
             const int x = it.tx * kTileX + row % kTileX, y = it.ty * kTileY + row / kTileX;
             const bool inb = it.img < p.batch && y < p.gh && x < p.gw;
-            const float inv = inb ? fmul(1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_bits + it.img))), inv_sw) : 0.f;
+            const float inv = inv_sw;   // the feature scales were divided out chunk by chunk
 #pragma unroll
             for (int n = 0; n < NPAD; ++n) acc[n] = fadd(fmul(acc[n], inv), s_bias[n]);
             if (inb) {
@@ -1164,14 +1317,15 @@ int grid_for(int total_tiles) { return total_tiles < SQD_SM_COUNT ? total_tiles 
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// planes buffer (also the SQD_LAYOUT_SPLIT_NHWC input): [amax bits: B x u32, padded to 256 B][x1 plane][x2 plane]
+// planes buffer (also the SQD_LAYOUT_SPLIT_NHWC input):
+//   [max|x| bits per (image, 64-channel block): B*(Cin/64) x u32, padded to 256 B][x1 plane][x2 plane]
 struct PlaneLayout {
     size_t p1_off, p2_off, total;
 };
 PlaneLayout plane_layout(int batch, int cin, int gh, int gw) {
     PlaneLayout l;
     const size_t plane = align256((size_t)batch * gh * gw * cin * sizeof(__half));
-    l.p1_off = align256((size_t)batch * sizeof(unsigned));
+    l.p1_off = align256((size_t)batch * (cin / kBlockK) * sizeof(unsigned));
     l.p2_off = l.p1_off + plane;
     l.total = l.p2_off + plane;
     return l;
@@ -1310,7 +1464,7 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
     p.units_per_pair = (int)upp;
     p.stages = pair_stages_for(npad);
     SQD_REQUIRE(p.stages >= 2, SQD_E_SHAPE, "convdet (tcgen05): shared memory too small for two stages");
-    p.chunk_units = env_int("SQD_F16_CHUNK", 2);
+    p.chunk_units = env_int("SQD_F16_CHUNK", 3);   // one 64-channel block (3 dx units) per TMEM chunk
     if (p.chunk_units < 1) p.chunk_units = 1;
     p.dbg = env_int("SQD_F16_DBG", 0);
     p.bias = d_bias;
@@ -1357,35 +1511,107 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
 
 size_t sqd_f16_split_bytes(int batch, int cin, int gh, int gw) { return plane_layout(batch, cin, gh, gw).total; }
 
+namespace {
+// cluster size for the one-pass NCHW split: the smallest that lets >= 3 CTAs share an SM (<= 72 KB each), else the
+// smallest that fits at all; 0 = shape not eligible (two-pass fallback)
+int split_cluster_size(int P, size_t *smem_out, int *nq4p_out) {
+    if (P % 4 != 0 || env_int("SQD_SPLIT_TWO_PASS", 0)) return 0;
+    const int n4 = P / 4;
+    int pick = 0;
+    const int force = env_int("SQD_SPLIT_CS", 0);
+    for (int pass = 0; pass < 2 && !pick; ++pass)
+        for (int cs = 1; cs <= kSplitMaxCluster; cs <<= 1) {
+            if (cs > n4) break;
+            if (force && cs != force) continue;
+            const int nq4 = (n4 + cs - 1) / cs;              // largest share of any rank
+            const int nq4p = (nq4 + 7) & ~7;
+            const size_t smem = (size_t)64 * nq4p * sizeof(float4);
+            if (smem <= (pass == 0 ? (size_t)72 * 1024 : (size_t)200 * 1024)) {
+                pick = cs;
+                *smem_out = smem;
+                *nq4p_out = nq4p;
+                break;
+            }
+        }
+    return pick;
+}
+}  // namespace
+
 int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, int gh, int gw, void *d_planes,
                            cudaStream_t st) {
     SQD_REQUIRE(cin % kBlockK == 0, SQD_E_SHAPE, "convdet (tcgen05): Cin %d must be a multiple of %d", cin, kBlockK);
+    SQD_REQUIRE(cin <= 4096, SQD_E_SHAPE, "convdet (tcgen05): Cin %d > 4096", cin);
     const PlaneLayout pl = plane_layout(batch, cin, gh, gw);
     char *base = static_cast<char *>(d_planes);
     unsigned *amax = reinterpret_cast<unsigned *>(base);
-    const int P = gh * gw;
-    const size_t n4 = (size_t)P * cin / 4;
+    uint2 *p1 = reinterpret_cast<uint2 *>(base + pl.p1_off), *p2 = reinterpret_cast<uint2 *>(base + pl.p2_off);
+    const int P = gh * gw, ncb = cin / kBlockK;
+    if (layout == SQD_LAYOUT_NHWC) {
+        // channels_last: a (image, block) slab is strided, so max and split stay two passes over the image
+        SQD_CUDA(cudaMemsetAsync(amax, 0, pl.p1_off, st));
+        int bx = P < 64 ? P : 64;
+        if ((long long)bx * batch < 2 * SQD_SM_COUNT) bx = P < 256 ? P : 256;
+        absmax_nhwc_kernel<<<dim3(bx, batch), cin / 4, 0, st>>>(reinterpret_cast<const float4 *>(d_feat), P, cin / 4, amax);
+        SQD_LAUNCH_CHECK("absmax_nhwc_kernel");
+        int sx = P < 128 ? P : 128;
+        if ((long long)sx * batch < 4 * SQD_SM_COUNT) sx = P < 512 ? P : 512;
+        split_nhwc_f16_kernel<<<dim3(sx, batch), cin / 4, 0, st>>>(reinterpret_cast<const float4 *>(d_feat), p1, p2, P,
+                                                                  cin / 4, amax);
+        SQD_LAUNCH_CHECK("split_nhwc_f16_kernel");
+        return SQD_OK;
+    }
+    size_t smem = 0;
+    int nq4p = 0;
+    const int cs = split_cluster_size(P, &smem, &nq4p);
+    if (cs > 0) {
+        // one pass: a cluster per (image, channel block) slab
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((size_t)batch * ncb * cs));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const int threads = env_int("SQD_SPLIT_THREADS", 512), rows = env_int("SQD_SPLIT_ROWS", 0);
+        cudaError_t e = cudaErrorInvalidValue;
+#define SQD_SPLIT_LAUNCH(T, R)                                                                                              \
+    do {                                                                                                                    \
+        SQD_CUDA(cudaFuncSetAttribute(split_nchw_cluster_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        if (cs > 8)                                                                                                         \
+            SQD_CUDA(cudaFuncSetAttribute(split_nchw_cluster_kernel<T, R>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); \
+        cfg.blockDim = dim3(T);                                                                                             \
+        e = cudaLaunchKernelEx(&cfg, split_nchw_cluster_kernel<T, R>, d_feat, p1, p2, cin, P, amax, cs, nq4p);              \
+    } while (0)
+        if (threads == 256 && rows) SQD_SPLIT_LAUNCH(256, true);
+        else if (threads == 256) SQD_SPLIT_LAUNCH(256, false);
+        else if (threads == 1024 && rows) SQD_SPLIT_LAUNCH(1024, true);
+        else if (threads == 1024) SQD_SPLIT_LAUNCH(1024, false);
+        else if (rows) SQD_SPLIT_LAUNCH(512, true);
+        else SQD_SPLIT_LAUNCH(512, false);
+#undef SQD_SPLIT_LAUNCH
+        if (e != cudaSuccess) {
+            sqd_set_error("launch of split_nchw_cluster_kernel failed: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        return SQD_OK;
+    }
+    // two passes: per-slab max (a slab is one contiguous run of 64*P floats), then the tiled transpose/split
     SQD_CUDA(cudaMemsetAsync(amax, 0, pl.p1_off, st));
     {
+        const size_t n4 = (size_t)kBlockK * P / 4;
         int bx = (int)((n4 + 256 * 8 - 1) / (256 * 8));
-        if (bx > 32) bx = 32;
+        if (bx > 8) bx = 8;
         if (bx < 1) bx = 1;
-        absmax_kernel<<<dim3(bx, batch), 256, 0, st>>>(reinterpret_cast<const float4 *>(d_feat), n4, amax);
+        absmax_kernel<<<dim3(bx, batch * ncb), 256, 0, st>>>(reinterpret_cast<const float4 *>(d_feat), n4, amax);
         SQD_LAUNCH_CHECK("absmax_kernel");
     }
-    if (layout == SQD_LAYOUT_NHWC) {
-        int bx = (int)((n4 + 256 * 4 - 1) / (256 * 4));
-        if (bx < 1) bx = 1;
-        split_nhwc_f16_kernel<<<dim3(bx, batch), 256, 0, st>>>(reinterpret_cast<const float4 *>(d_feat),
-                                                              reinterpret_cast<uint2 *>(base + pl.p1_off),
-                                                              reinterpret_cast<uint2 *>(base + pl.p2_off), n4, amax);
-        SQD_LAUNCH_CHECK("split_nhwc_f16_kernel");
-    } else {
-        dim3 grid((P + 63) / 64, cin / 64, batch);
-        split_nchw_f16_kernel<<<grid, 256, 0, st>>>(d_feat, reinterpret_cast<uint2 *>(base + pl.p1_off),
-                                                   reinterpret_cast<uint2 *>(base + pl.p2_off), cin, P, amax);
-        SQD_LAUNCH_CHECK("split_nchw_f16_kernel");
-    }
+    dim3 grid((P + 63) / 64, ncb, batch);
+    split_nchw_f16_kernel<<<grid, 256, 0, st>>>(d_feat, p1, p2, cin, P, amax);
+    SQD_LAUNCH_CHECK("split_nchw_f16_kernel");
     return SQD_OK;
 }
 

@@ -213,3 +213,34 @@ def test_epilogue_candidates_equal_scan_of_pred(ops, monkeypatch, name, batch, s
         assert torch.equal(getattr(fused, f), getattr(scanned, f)), f
         assert torch.equal(getattr(fused, f), getattr(staged, f)), f
     assert int(fused.count.sum()) > 0
+
+
+@pytest.mark.parametrize("name,batch", [("tiny_160x96", 3), ("kitti_1248x384", 5), ("stress_2496x768", 2)])
+def test_one_pass_split_equals_two_pass(ops, monkeypatch, name, batch):
+    """The cluster-per-slab pre-pass (max|x| + fp16 split in one pass over HBM) and the two-pass fallback produce the
+    same scales and planes, hence bit-identical pred (KITTI: clusters of 8, stress: clusters of 16)."""
+    shp = {x.name: x for x in (synth.TINY, synth.KITTI, synth.STRESS)}[name]
+    feat, (w, b) = dev(synth.features(shp, batch, 51)), synth.convdet_params(shp, 52)
+    w, b = dev(w), dev(b)
+    monkeypatch.delenv("SQD_SPLIT_TWO_PASS", raising=False)
+    one = ops.convdet_forward(feat, w, b, check_status=True)
+    monkeypatch.setenv("SQD_SPLIT_TWO_PASS", "1")
+    two = ops.convdet_forward(feat, w, b, check_status=True)
+    monkeypatch.delenv("SQD_SPLIT_TWO_PASS", raising=False)
+    assert torch.equal(one, two)
+    cl = ops.convdet_forward(feat.contiguous(memory_format=torch.channels_last), w, b, check_status=True)
+    assert torch.equal(one, cl)   # channels_last input: same per-(image, block) scales, same planes
+
+
+def test_split_grid_not_multiple_of_four(ops):
+    """6 x 11 grid (P = 66, not a multiple of 4): the one-pass kernel is not eligible; scales differ wildly between
+    channel blocks and images (1e-6 ... 1e4) and the result still matches the fp32 SIMT kernel."""
+    from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32
+    shp = synth.Shape("odd", (96, 176), 3, 16)
+    feat = synth.features(shp, 3, 61)
+    scale = np.logspace(-6, 4, 3 * 12).reshape(3, 12, 1, 1, 1).astype(np.float32)
+    feat = (feat.reshape(3, 12, 64, *shp.grid_hw) * scale).reshape(feat.shape)
+    w, b = synth.convdet_params(shp, 62)
+    tc = ops.convdet_forward(dev(feat), dev(w), dev(b), check_status=True)
+    simt = ops.convdet_forward(dev(feat), dev(w), dev(b), algo=CONV_SIMT_FP32)
+    assert torch.allclose(tc, simt, rtol=1e-4, atol=2e-5 * float(simt.abs().max())), float((tc - simt).abs().max())
