@@ -110,6 +110,46 @@ __device__ __forceinline__ void sqd_score_anchor(const float *f, int C_rt, float
     cls = best;
 }
 
+// Candidate test + score with the work the RESULT needs, bit-identical to sqd_score_anchor wherever it returns true:
+//  * score = max_c p_c*conf <= conf (p_c <= 1), so conf <= thr decides "not a candidate" after one exp and one division;
+//  * the first-maximum logit has e = exp(0) = 1 exactly and the largest p; unless another class comes within 1e-5 of
+//    it (then rounding could tie the products and the reference's first-index rule matters: full path), the score is
+//    (1/sum)*conf and the other C-1 divisions and products are never needed.  The sum keeps the reference's order.
+template <int CS>
+__device__ __forceinline__ bool sqd_score_candidate(const float *f, int C_rt, float score_thr, float &score, int &cls) {
+    const int C = CS > 0 ? CS : C_rt;
+    const float conf = fdiv(1.0f, fadd(1.0f, expf(-f[C])));
+    if (!(conf > score_thr)) {
+        if (conf == conf) return false;
+        sqd_score_anchor<CS>(f, C_rt, score, cls);   // NaN confidence: rank it exactly like the full path does
+        return true;
+    }
+    float zmax = f[0];
+    int imax = 0;
+#pragma unroll
+    for (int c = 1; c < SQD_CMAX(CS); ++c)
+        if (c < C && f[c] > zmax) {
+            zmax = f[c];
+            imax = c;
+        }
+    float sum = 0.f;
+    bool near = conf < 1e-30f;  // products could underflow into ties
+#pragma unroll
+    for (int c = 0; c < SQD_CMAX(CS); ++c)
+        if (c < C) {
+            const float e = c == imax ? 1.0f : expf(fsub(f[c], zmax));
+            near = near || (c != imax && !(e <= 0.99999f));   // also catches NaN
+            sum = (c == 0) ? e : fadd(sum, e);
+        }
+    if (near || !(zmax == zmax)) {
+        sqd_score_anchor<CS>(f, C_rt, score, cls);
+        return true;
+    }
+    score = fmul(fdiv(1.0f, sum), conf);
+    cls = imax;
+    return true;
+}
+
 __device__ __forceinline__ float sqd_clamp(float v, float hi) {  // torch.clamp: NaN passes through
     return v < 0.f ? 0.f : (v > hi ? hi : v);
 }

@@ -1073,11 +1073,11 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
 #pragma unroll
                 for (int j = 0; j <= CS; ++j) f[j] = 0.f;
             }
-            float scv;
-            int cl;
-            sqd_score_anchor<(CS > 0 ? CS : 1)>(f, CS, scv, cl);
+            float scv = 0.f;
+            int cl = 0;
+            const bool cand_ok = sqd_score_candidate<(CS > 0 ? CS : 1)>(f, CS, p.score_thr, scv, cl);
             const sqd_u64 key = sqd_make_key(scv, pend_a0 + pend_k, cl);
-            const bool pass = pend_row != nullptr && key > floor_key;
+            const bool pass = pend_row != nullptr && cand_ok && key > floor_key;
             const unsigned b = __ballot_sync(0xffffffffu, pass);
             if (b) {
                 if (lane == 0) prev_base = atomicAdd(p.cand.count + pend_img, __popc(b));
@@ -1117,11 +1117,11 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                         for (int j = 0; j <= CS; ++j) f[j] = __ldcg(src + j);
                     }
                 }
-                float scv;
-                int cl;
-                sqd_score_anchor<(CS > 0 ? CS : 1)>(f, CS, scv, cl);
+                float scv = 0.f;
+                int cl = 0;
+                const bool cand_ok = sqd_score_candidate<(CS > 0 ? CS : 1)>(f, CS, p.score_thr, scv, cl);
                 key[k] = sqd_make_key(scv, pend_a0 + k, cl);
-                pass[k] = want && key[k] > floor_key;
+                pass[k] = want && cand_ok && key[k] > floor_key;
             }
             sqd_cand_append_warp<KMAX>(p.cand, pend_img, pass, key);
             pend_k = 1 << 30;

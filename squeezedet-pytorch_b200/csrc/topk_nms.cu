@@ -433,52 +433,46 @@ __global__ void __launch_bounds__(kThreads) filter_dense_kernel(const long long 
 constexpr int kScanThreads = 256;
 constexpr int kScanUnroll = 4;
 
+// grid = (chunks of an image, images): every row of a block belongs to image blockIdx.y, so there is no index
+// division and a warp appends all its candidates with ONE atomic.
 template <int CS>
-__global__ void __launch_bounds__(kScanThreads) score_candidates_kernel(const float *__restrict__ pred, unsigned total,
-                                                                        unsigned A, int C, float score_thr_f, SqdCand cand) {
+__global__ void __launch_bounds__(kScanThreads) score_candidates_kernel(const float *__restrict__ pred, int A, int C,
+                                                                        float score_thr_f, SqdCand cand) {
     const u64 floor_key = score_floor_key(score_thr_f);
+    const int img = blockIdx.y;
     if (CS == 3) {
         // 32-byte rows: the four scoring fields are the first 16 bytes of a row
-        const float4 *p4 = reinterpret_cast<const float4 *>(pred);
-        const unsigned step = gridDim.x * kScanThreads * kScanUnroll;
-        for (unsigned base = blockIdx.x * kScanThreads * kScanUnroll; base < total; base += step) {  // warp-uniform trip count
+        const float4 *p4 = reinterpret_cast<const float4 *>(pred) + 2 * (size_t)img * A;
+        for (int base = blockIdx.x * kScanThreads * kScanUnroll; base < A; base += gridDim.x * kScanThreads * kScanUnroll) {
             float4 v[kScanUnroll];
 #pragma unroll
             for (int u = 0; u < kScanUnroll; ++u) {
-                const unsigned g = base + u * kScanThreads + threadIdx.x;
-                v[u] = g < total ? ld_stream_f4(p4 + 2 * (size_t)g) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int a = base + u * kScanThreads + threadIdx.x;
+                v[u] = a < A ? ld_stream_f4(p4 + 2 * (size_t)a) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             bool pass[kScanUnroll];
             u64 key[kScanUnroll];
-            unsigned img[kScanUnroll];
 #pragma unroll
             for (int u = 0; u < kScanUnroll; ++u) {
-                const unsigned g = base + u * kScanThreads + threadIdx.x;
+                const int a = base + u * kScanThreads + threadIdx.x;
                 const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-                float s;
-                int c;
-                sqd_score_anchor<3>(f, 3, s, c);
-                img[u] = g / A;
-                key[u] = make_key(s, (int)(g - img[u] * A), c);
-                pass[u] = g < total && key[u] > floor_key;
+                float s = 0.f;
+                int c = 0;
+                const bool cand_ok = sqd_score_candidate<3>(f, 3, score_thr_f, s, c);
+                key[u] = make_key(s, a, c);
+                pass[u] = a < A && cand_ok && key[u] > floor_key;
             }
-            // rows of this warp in this round: [first, last]; one image -> one atomic for all of them
-            const unsigned first = base + (threadIdx.x & ~31u), last = first + (kScanUnroll - 1) * kScanThreads + 31u;
-            if (first / A == min(last, total - 1u) / A) {
-                sqd_cand_append_warp<kScanUnroll>(cand, (int)(first / A), pass, key);
-            } else {
-#pragma unroll
-                for (int u = 0; u < kScanUnroll; ++u) sqd_cand_append(cand, pass[u], (int)img[u], key[u]);
-            }
+            sqd_cand_append_warp<kScanUnroll>(cand, img, pass, key);
         }
     } else {
         // any field count: stage 256 contiguous rows through shared memory with 16-byte streaming loads
         extern __shared__ __align__(16) float slab[];
         const int Cn = CS > 0 ? CS : C;
         const int NF = Cn + 5;
-        for (unsigned row0 = blockIdx.x * kScanThreads; row0 < total; row0 += gridDim.x * kScanThreads) {
-            const int n = (int)min((unsigned)kScanThreads, total - row0);
-            const float *src = pred + (size_t)row0 * NF;
+        const float *ipred = pred + (size_t)img * A * NF;   // 16-byte aligned (checked by the host wrapper)
+        for (int row0 = blockIdx.x * kScanThreads; row0 < A; row0 += gridDim.x * kScanThreads) {
+            const int n = min(kScanThreads, A - row0);
+            const float *src = ipred + (size_t)row0 * NF;
             const int count = n * NF, nvec = count >> 2;  // slab start is 16-byte aligned: 256*NF*4 is a multiple of 16
             const float4 *src4 = reinterpret_cast<const float4 *>(src);
             float4 *dst4 = reinterpret_cast<float4 *>(slab);
@@ -490,13 +484,14 @@ __global__ void __launch_bounds__(kScanThreads) score_candidates_kernel(const fl
 #pragma unroll
             for (int j = 0; j < SQD_CMAX(CS) + 1; ++j)
                 if (j <= Cn) f[j] = in ? slab[threadIdx.x * NF + j] : 0.f;
-            float s;
-            int c;
-            sqd_score_anchor<CS>(f, Cn, s, c);
-            const unsigned g = row0 + threadIdx.x;
-            const unsigned img = g / A;
-            const u64 key = make_key(s, (int)(g - img * A), c);
-            sqd_cand_append(cand, in && key > floor_key, (int)img, key);
+            float s = 0.f;
+            int c = 0;
+            const bool cand_ok = sqd_score_candidate<CS>(f, Cn, score_thr_f, s, c);
+            bool pass[1];
+            u64 key[1];
+            key[0] = make_key(s, row0 + (int)threadIdx.x, c);
+            pass[0] = in && cand_ok && key[0] > floor_key;
+            sqd_cand_append_warp<1>(cand, img, pass, key);
             __syncthreads();
         }
     }
@@ -507,13 +502,43 @@ __global__ void __launch_bounds__(kScanThreads) score_candidates_kernel(const fl
 // at or above the threshold bin fit the sort buffer; those are then collected (unordered) into sh.buf.  Typical lists
 // (thousands of distinct scores) need ONE level: histogram pass + collect pass.  Returns false (nothing collected) if
 // even single-score bins overflow the buffer (massive exact ties): the caller then uses the running-threshold loop.
+template <bool kInRegs>
 __device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, int n, int k, float score_thr_f) {
     constexpr int kBins = 2048, kPerThread = kBins / kThreads;
     constexpr int kCollectCap = kCap / 2;
+    constexpr int kHold = 16;  // keys per thread kept in registers when the list has <= kHold*kThreads entries
     int *hist = reinterpret_cast<int *>(sh.buf + kCap / 2);  // upper half of the key buffer: free until the sort
     __shared__ int s_wtot[kThreads / 32];
     __shared__ int s_tb, s_above_add, s_tb_cnt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 my[kInRegs ? kHold : 1];
+    if (kInRegs) {  // ONE pass over the list, all loads in flight together; 0 = no key (never a real key)
+#pragma unroll
+        for (int u = 0; u < kHold; ++u) {
+            const int i = threadIdx.x + u * kThreads;
+            my[u] = i < n ? __ldcg(keys + i) : 0ull;
+        }
+    }
+    // visits every key of the list: from registers, or re-read from L2 eight at a time
+    auto for_each_key = [&](auto &&fn) {
+        if (kInRegs) {
+#pragma unroll
+            for (int u = 0; u < kHold; ++u)
+                if (my[u] != 0ull) fn(my[u]);
+        } else {
+            for (int base = 0; base < n; base += 8 * kThreads) {
+                u64 t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = base + u * kThreads + threadIdx.x;
+                    t[u] = i < n ? __ldcg(keys + i) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (t[u] != 0ull) fn(t[u]);
+            }
+        }
+    };
     unsigned lo = order_bits(score_thr_f) + 1u, hi = 0xFFFFFFFFu;  // undecided score-bit range (inclusive)
     int above = 0;                                                 // keys with score bits > hi: selected for sure
     const unsigned top = order_bits(1.0f);                         // scores are probabilities: <= 1
@@ -523,10 +548,10 @@ __device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, in
     for (int level = 0; level < 4; ++level) {
         for (int i = threadIdx.x; i < kBins; i += kThreads) hist[i] = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += kThreads) {
-            const unsigned sb = (unsigned)(__ldcg(keys + i) >> 32);
+        for_each_key([&](u64 key) {
+            const unsigned sb = (unsigned)(key >> 32);
             if (sb >= lo && sb <= hi) atomicAdd(&hist[min((sb - lo) >> shift, (unsigned)(kBins - 1))], 1);
-        }
+        });
         __syncthreads();
         int c[kPerThread], own = 0;
 #pragma unroll
@@ -566,10 +591,9 @@ __device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, in
         if (above_new + s_tb_cnt <= kCollectCap) {
             // collect every key at or above the threshold bin (>= k of them, <= kCollectCap)
             __syncthreads();  // all reads of hist / s_* done before buf and the counter are written
-            for (int i = threadIdx.x; i < n; i += kThreads) {
-                const u64 key = __ldcg(keys + i);
+            for_each_key([&](u64 key) {
                 if ((unsigned)(key >> 32) >= lo_new) sh.buf[atomicAdd(&sh.count, 1)] = key;
-            }
+            });
             __syncthreads();
             return true;
         }
@@ -612,7 +636,8 @@ __global__ void __launch_bounds__(kThreads) detect_from_candidates_kernel(SqdCan
         __syncthreads();
         have = true;
     } else {
-        have = hist_select_collect(sh, keys, n, k, score_thr_f);
+        have = n <= 16 * kThreads ? hist_select_collect<true>(sh, keys, n, k, score_thr_f)
+                                  : hist_select_collect<false>(sh, keys, n, k, score_thr_f);
     }
     if (have) {
         rank_sort(sh);  // descending: the first k entries are the top-k
@@ -742,22 +767,21 @@ SqdCand sqd_cand_layout(void *ws, int batch, int num_anchors) {
 // phase 1: pred -> candidate lists (cand.count must have been zeroed on the stream)
 int sqd_score_candidates(const float *d_pred, int batch, int num_anchors, int num_classes, double score_thresh,
                          SqdCand cand, cudaStream_t st) {
-    const long long total = (long long)batch * num_anchors;
-    SQD_REQUIRE(total < (1ll << 31), SQD_E_SHAPE, "detect: batch*num_anchors %lld does not fit 31 bits", total);
+    SQD_REQUIRE(batch <= 65535, SQD_E_SHAPE, "detect: batch %d > 65535 (split the call)", batch);
+    SQD_REQUIRE(((size_t)num_anchors * (num_classes + 5) * sizeof(float)) % 16 == 0, SQD_E_ALIGN,
+                "detect: an image of pred (%d x %d floats) is not a multiple of 16 bytes", num_anchors, num_classes + 5);
     const float sthr = (float)score_thresh;
-    const int max_grid = SQD_SM_COUNT * 8;
+    const int per_block = num_classes == 3 ? kScanThreads * kScanUnroll : kScanThreads;
+    const int gx = (num_anchors + per_block - 1) / per_block;   // one pass per block (the in-kernel loop is for safety)
+    const dim3 grid((unsigned)gx, (unsigned)batch);
     if (num_classes == 3) {
-        long long g = (total + kScanThreads * kScanUnroll - 1) / (kScanThreads * kScanUnroll);
-        const int grid = (int)(g < max_grid ? g : max_grid);
-        score_candidates_kernel<3><<<grid, kScanThreads, 0, st>>>(d_pred, (unsigned)total, (unsigned)num_anchors, 3, sthr, cand);
+        score_candidates_kernel<3><<<grid, kScanThreads, 0, st>>>(d_pred, num_anchors, 3, sthr, cand);
     } else {
-        long long g = (total + kScanThreads - 1) / kScanThreads;
-        const int grid = (int)(g < max_grid ? g : max_grid);
         const size_t smem = (size_t)kScanThreads * (num_classes + 5) * sizeof(float);
         if (num_classes == 8)
-            score_candidates_kernel<8><<<grid, kScanThreads, smem, st>>>(d_pred, (unsigned)total, (unsigned)num_anchors, 8, sthr, cand);
+            score_candidates_kernel<8><<<grid, kScanThreads, smem, st>>>(d_pred, num_anchors, 8, sthr, cand);
         else
-            score_candidates_kernel<0><<<grid, kScanThreads, smem, st>>>(d_pred, (unsigned)total, (unsigned)num_anchors, num_classes, sthr, cand);
+            score_candidates_kernel<0><<<grid, kScanThreads, smem, st>>>(d_pred, num_anchors, num_classes, sthr, cand);
     }
     SQD_LAUNCH_CHECK("score_candidates_kernel");
     return SQD_OK;

@@ -95,8 +95,9 @@ def convdet_forward(feat, weight, bias, packed=None, algo=CONV_TCGEN05_F16X3, nu
 
 
 # ---- a2-a7 -----------------------------------------------------------------------------------------
-def decode_scores(pred, anchors_f32, input_hw, num_classes, want=("class_ids", "scores", "boxes")):
-    """pred (B,A,C+5) -> dict with the requested keys among class_ids/scores/boxes/probs/logp/conf/deltas."""
+def decode_scores(pred, anchors_f32, input_hw, num_classes, want=("class_ids", "scores", "boxes"), out=None):
+    """pred (B,A,C+5) -> dict with the requested keys among class_ids/scores/boxes/probs/logp/conf/deltas.
+    out: a dict returned by an earlier call with the same shapes, to be overwritten (no allocation)."""
     lib = load()
     pred = pred.contiguous()
     B, A, NF = pred.shape
@@ -106,7 +107,8 @@ def decode_scores(pred, anchors_f32, input_hw, num_classes, want=("class_ids", "
     shapes = {"class_ids": ((B, A), torch.int64), "scores": ((B, A), torch.float32), "boxes": ((B, A, 4), torch.float32),
               "probs": ((B, A, num_classes), torch.float32), "logp": ((B, A, num_classes), torch.float32),
               "conf": ((B, A, 1), torch.float32), "deltas": ((B, A, 4), torch.float32)}
-    out = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], device=dev) for k in want}
+    if out is None:
+        out = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], device=dev) for k in want}
     g = lambda k: ptr(out[k]) if k in out else None  # noqa: E731
     check(lib.sqd_decode_scores(ptr(pred), ptr(anchors_f32), B, A, num_classes, int(input_hw[0]), int(input_hw[1]),
                                 g("class_ids"), g("scores"), g("boxes"), g("probs"), g("logp"), g("conf"), g("deltas"),
