@@ -228,6 +228,33 @@ SQD_API int sqd_loss_fwd_bwd(const float *d_pred, const float *d_gt, const float
 SQD_API int sqd_boxes_postprocess(float *d_boxes, const int32_t *d_count, const float *d_meta, int batch, int top_k,
                           void *stream);
 
+/* 8(f) rank 1, second half: result packing.  One (B, top_k, 6) fp32 array [class, score, x1, y1, x2, y2] (rows >= count:
+ * class -1, zeros) so that a batch crosses to the host with ONE copy (+ the counts); d_meta (B,10) as above applies
+ * boxes_postprocess on the way (NULL: boxes copied as they are).  Inputs are not modified.
+ * Replaces the per-image .cpu() calls and the host boxes_postprocess of src/engine/detector.py:37-40. */
+SQD_API int sqd_pack_results(const int32_t *d_count, const int32_t *d_class, const float *d_score, const float *d_box,
+                             const float *d_meta, int batch, int top_k, float *d_packed, void *stream);
+
+/* 8(f) rank 3  KITTI result writer (HOST function; src/datasets/kitti.py:78-97).  Formats the packed results of a
+ * batch as the evaluator's text lines
+ *     "{class} -1 -1 0 {x1:.2f} {y1:.2f} {x2:.2f} {y2:.2f} 0 0 0 0 0 0 0 {score:.3f}\n"
+ * into h_out; h_offsets (batch+1 entries, may be NULL) delimits the block of each image (an image that kept nothing
+ * has an empty block, like the reference's empty file).  class_names_lower: num_classes C strings.
+ * Returns the number of bytes needed (call with cap = 0 to size the buffer) or < 0 on a bad argument. */
+SQD_API long long sqd_format_kitti(const float *h_packed, const int32_t *h_count, int batch, int top_k,
+                                   const char *const *class_names_lower, int num_classes, char *h_out, size_t cap,
+                                   long long *h_offsets);
+
+/* 8(f) rank 4  input pre-processing: whiten, bilinear resize, HWC -> CHW in one pass.
+ *     Replaces whiten + resize of src/utils/image.py:9-19,77-88 (numpy + cv2.resize INTER_LINEAR on float32, whose
+ *     coordinate / weight arithmetic is reproduced) and the transpose of src/datasets/base.py:33 for eval-mode inputs
+ *     (no drift / flip).
+ *   d_images (B, src_h, src_w, 3) uint8 (dtype 0) or float32 (dtype 1), RGB interleaved as loaded
+ *   mean3 / std3: HOST pointers to the 3 channel means / stds (kitti.py:17-18)
+ *   d_out (B, 3, dst_h, dst_w) float32 ; image_meta['scales'] = (dst_h/src_h, dst_w/src_w) is the caller's to record */
+SQD_API int sqd_preprocess(const void *d_images, int dtype, int batch, int src_h, int src_w, const float *mean3,
+                           const float *std3, int dst_h, int dst_w, float *d_out, void *stream);
+
 /* Debug aid: synchronise `stream`, return 0 if the last tcgen05 ConvDet launch on this workspace
  * drained cleanly, else the role (1 TMA producer, 2 MMA issuer, 3 epilogue) whose bounded mbarrier
  * wait timed out.  The kernels never spin forever. */

@@ -331,11 +331,92 @@ def gen_postprocess():
     save("postprocess", n=np.array(len(cases)), **arrays)
 
 
+def _ref_kitti_module():
+    """The reference's datasets/kitti.py, imported by file path: the venv's HuggingFace `datasets` package shadows the
+    reference's (it has no __init__.py) and skimage is not installed -- both are stubbed, nothing else."""
+    import importlib
+    pkg = types.ModuleType("datasets")
+    pkg.__path__ = [os.path.join(REF, "src", "datasets")]
+    saved = {k: sys.modules.get(k) for k in ("datasets", "skimage", "skimage.io")}
+    sys.modules["datasets"] = pkg
+    sk, skio = types.ModuleType("skimage"), types.ModuleType("skimage.io")
+    sk.io = skio
+    sys.modules["skimage"], sys.modules["skimage.io"] = sk, skio
+    try:
+        return importlib.import_module("datasets.kitti"), importlib.import_module("datasets.base")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def gen_kitti_results():
+    """KITTI.save_results (kitti.py:78-97) run unmodified on seeded detections; the files' text is the golden."""
+    import tempfile
+    rk, _ = _ref_kitti_module()
+    rs = np.random.RandomState(11)
+    names = ("Car", "Pedestrian", "Cyclist")
+    results, counts = [], []
+    for b in range(6):
+        n = [5, 0, 1, 12, 64, 3][b]
+        counts.append(n)
+        meta = {"image_id": "%06d" % b}
+        if n == 0:
+            results.append({"image_meta": meta})
+            continue
+        cls = np.sort(rs.randint(0, 3, size=n)).astype(np.int64)
+        sc = rs.uniform(0.3, 1.0, size=n).astype(np.float32)
+        xy = rs.uniform(-3, 1240, size=(n, 2)).astype(np.float32)
+        wh = rs.uniform(0.004, 300, size=(n, 2)).astype(np.float32)
+        bx = np.concatenate([xy, xy + wh], axis=1).astype(np.float32)
+        bx[0] = np.round(bx[0] * 8) / 8 + np.float32(0.005)   # values sitting near a rounding boundary of %.2f
+        results.append({"class_ids": cls, "scores": sc, "boxes": bx, "image_meta": meta})
+    with tempfile.TemporaryDirectory() as tmp:
+        fake = types.SimpleNamespace(results_dir=tmp, class_names=names)
+        rk.KITTI.save_results(fake, results)
+        texts = [open(os.path.join(tmp, "data", "%06d.txt" % b)).read() for b in range(6)]
+    K = 64
+    packed = np.zeros((6, K, 6), np.float32)
+    packed[:, :, 0] = -1
+    for b, r in enumerate(results):
+        n = counts[b]
+        if n:
+            packed[b, :n, 0], packed[b, :n, 1], packed[b, :n, 2:] = r["class_ids"], r["scores"], r["boxes"]
+    save("kitti_results", packed=packed, count=np.array(counts, np.int32), texts=np.array(texts),
+         class_names=np.array(names))
+
+
+def preprocess_case(seed, h0, w0):
+    return np.random.RandomState(seed).randint(0, 256, size=(h0, w0, 3)).astype(np.uint8)
+
+
+def gen_preprocess():
+    """BaseDataset.preprocess (base.py:49-59: whiten -> drift/flip off in eval -> resize) + the transpose of base.py:33,
+    run unmodified on seeded uint8 images loaded like kitti.py:52 (.astype(float32))."""
+    rk, rb = _ref_kitti_module()
+    mean = np.array([93.877, 98.801, 95.923], dtype=np.float32).reshape(1, 1, 3)   # kitti.py:17-18
+    std = np.array([78.782, 80.130, 81.200], dtype=np.float32).reshape(1, 1, 3)
+    arrays = {}
+    cases = [(21, 47, 150, 48, 160), (22, 61, 97, 48, 160), (23, 48, 160, 48, 160), (24, 30, 333, 96, 160)]
+    for i, (seed, h0, w0, h, w) in enumerate(cases):
+        img = preprocess_case(seed, h0, w0).astype(np.float32)
+        fake = types.SimpleNamespace(cfg=types.SimpleNamespace(drift_prob=0.0, flip_prob=0.0, forbid_resize=False),
+                                     phase="val", rgb_mean=mean, rgb_std=std, input_size=(h, w))
+        meta = {"orig_size": np.array(img.shape, dtype=np.int32)}
+        out, meta, _ = rb.BaseDataset.preprocess(fake, img, meta, None)
+        arrays[f"case_{i}"] = np.array([seed, h0, w0, h, w])
+        arrays[f"out_{i}"] = np.ascontiguousarray(out.transpose(2, 0, 1)).astype(np.float32)
+        arrays[f"scales_{i}"] = meta["scales"]
+    save("preprocess", n=np.array(len(cases)), mean=mean.reshape(3), std=std.reshape(3), **arrays)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["anchors", "decode_filter", "nms", "matcher", "matcher_fallback", "loss", "head_e2e",
-                             "postprocess"]
+                             "postprocess", "kitti_results", "preprocess"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

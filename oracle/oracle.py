@@ -478,3 +478,46 @@ def boxes_postprocess(boxes, image_meta):
         b[:, [0, 2]] += image_meta["drifts"][1]
         b[:, [1, 3]] += image_meta["drifts"][0]
     return b
+
+
+# --------------------------------------------------------------------------------------
+# 8(f) rank 3: KITTI result lines
+# --------------------------------------------------------------------------------------
+def kitti_result_text(class_ids, scores, boxes, class_names):
+    """src/datasets/kitti.py:88-96: the content of one image's result file."""
+    out = []
+    for i in range(len(class_ids)):
+        out.append("{} -1 -1 0 {:.2f} {:.2f} {:.2f} {:.2f} 0 0 0 0 0 0 0 {:.3f}\n".format(
+            class_names[int(class_ids[i])].lower(), *boxes[i, :], scores[i]))
+    return "".join(out)
+
+
+# --------------------------------------------------------------------------------------
+# 8(f) rank 4: whiten + resize (+ HWC -> CHW)
+# --------------------------------------------------------------------------------------
+def preprocess_image(image_hwc, mean, std, out_hw):
+    """src/utils/image.py:9-19 (whiten) then :77-88 (cv2.resize, default INTER_LINEAR) then base.py:33 (transpose).
+    cv2's float32 bilinear restated: fx = float((d + .5) * scale - .5), s = floor, weights (1 - f, f), borders clamp
+    with a zero weight; horizontal pass per source row, then the vertical pass."""
+    img = (np.asarray(image_hwc, dtype=F32) - np.asarray(mean, F32).reshape(1, 1, 3)) / np.asarray(std, F32).reshape(1, 1, 3)
+    H0, W0 = img.shape[:2]
+    H, W = out_hw
+
+    def table(n_dst, n_src):
+        scale = 1.0 / (float(n_dst) / n_src)
+        d = np.arange(n_dst, dtype=np.float64)
+        f = ((d + 0.5) * scale - 0.5).astype(F32)
+        s = np.floor(f).astype(np.int64)
+        f = (f - s.astype(F32)).astype(F32)
+        lo = s < 0
+        f[lo], s[lo] = 0, 0
+        hi = s >= n_src - 1
+        f[hi], s[hi] = 0, n_src - 1
+        return s, np.minimum(s + 1, n_src - 1), f
+
+    x0, x1, fx = table(W, W0)
+    y0, y1, fy = table(H, H0)
+    a0 = (F32(1) - fx)[None, :, None]
+    rows = img[:, x0, :] * a0 + img[:, x1, :] * fx[None, :, None]           # (H0, W, 3)
+    out = rows[y0] * (F32(1) - fy)[:, None, None] + rows[y1] * fy[:, None, None]
+    return np.ascontiguousarray(out.astype(F32).transpose(2, 0, 1))

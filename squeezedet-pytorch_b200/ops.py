@@ -293,3 +293,54 @@ def boxes_postprocess_(det: Detections, meta: torch.Tensor):
     check(lib.sqd_boxes_postprocess(ptr(det.box), ptr(det.count), ptr(meta.contiguous()), B, K,
                                     stream_ptr(det.box.device)), "sqd_boxes_postprocess")
     return det
+
+
+def pack_results(det: Detections, meta: torch.Tensor = None) -> torch.Tensor:
+    """Detections (+ optional (B,10) postprocess records) -> (B, top_k, 6) [class, score, x1, y1, x2, y2]; det is
+    not modified.  One .cpu() of this tensor (and of det.count) brings a whole batch to the host."""
+    lib = load()
+    B, K, _ = det.box.shape
+    packed = torch.empty((B, K, 6), dtype=torch.float32, device=det.box.device)
+    check(lib.sqd_pack_results(ptr(det.count), ptr(det.cls), ptr(det.score), ptr(det.box),
+                               ptr(meta.contiguous()) if meta is not None else None, B, K, ptr(packed),
+                               stream_ptr(det.box.device)), "sqd_pack_results")
+    return packed
+
+
+def format_kitti(packed_host: torch.Tensor, count_host: torch.Tensor, class_names):
+    """HOST: packed (B,k,6) float32 + count (B,) int32 (CPU tensors) -> list of B strings, the content of the per-image
+    result files KITTI.save_results writes (kitti.py:78-97)."""
+    lib = load()
+    if packed_host.is_cuda or count_host.is_cuda:
+        raise _lib.SqdError("format_kitti formats HOST arrays (bring the packed results over with one .cpu())")
+    packed_host = packed_host.contiguous().float()
+    count_host = count_host.contiguous().to(torch.int32)
+    B, K, _ = packed_host.shape
+    names = (C.c_char_p * len(class_names))(*[n.lower().encode() for n in class_names])
+    hp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    need = lib.sqd_format_kitti(hp(packed_host), hp(count_host), B, K, names, len(class_names), None, 0, None)
+    if need < 0:
+        check(int(need), "sqd_format_kitti")
+    buf = C.create_string_buffer(int(need) + 1)
+    offs = (C.c_longlong * (B + 1))()
+    got = lib.sqd_format_kitti(hp(packed_host), hp(count_host), B, K, names, len(class_names), buf, int(need), offs)
+    if got < 0:
+        check(int(got), "sqd_format_kitti")
+    raw = buf.raw
+    return [raw[offs[b]:offs[b + 1]].decode() for b in range(B)]
+
+
+def preprocess_images(images: torch.Tensor, mean, std, out_hw) -> torch.Tensor:
+    """(B, H0, W0, 3) uint8 or float32 CUDA images (RGB, as loaded) -> (B, 3, H, W) float32 network input:
+    whiten + bilinear resize + HWC->CHW (image.py whiten/resize, base.py:33)."""
+    lib = load()
+    if images.dim() != 4 or images.shape[-1] != 3 or images.dtype not in (torch.uint8, torch.float32):
+        raise _lib.SqdError("preprocess_images needs (B, H, W, 3) uint8 or float32")
+    images = images.contiguous()
+    B, H0, W0, _ = images.shape
+    out = torch.empty((B, 3, int(out_hw[0]), int(out_hw[1])), dtype=torch.float32, device=images.device)
+    m = (C.c_float * 3)(*[float(x) for x in mean])
+    s = (C.c_float * 3)(*[float(x) for x in std])
+    check(lib.sqd_preprocess(ptr(images), 0 if images.dtype == torch.uint8 else 1, B, H0, W0, m, s, int(out_hw[0]),
+                             int(out_hw[1]), ptr(out), stream_ptr(images.device)), "sqd_preprocess")
+    return out

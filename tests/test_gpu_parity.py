@@ -428,3 +428,63 @@ def test_boxes_postprocess_vs_reference_golden(ops, golden):
         det.box[0, :n] = dev(boxes)
         ops.boxes_postprocess_(det, dev(rec))
         np.testing.assert_allclose(det.box[0, :n].cpu().numpy(), g[f"out_{i}"], rtol=1e-6, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------------
+# 8(f): result packing (+ KITTI text) and input pre-processing
+# ------------------------------------------------------------------------------------------------------
+def test_pack_results_and_kitti_text(ops):
+    """Detections -> one packed (B,k,6) array (+ boxes_postprocess on the device) -> the reference's per-image dicts and
+    the KITTI result text, against the oracle's filter / postprocess / formatter."""
+    from squeezedet_pytorch_b200 import results
+    shp = synth.KITTI
+    a64, a32 = anchors_dev(shp)
+    batch = 5
+    pred = synth.clustered_pred(shp, batch, 909, anchors=a64)
+    det = ops.detect_from_pred(dev(pred), a32, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh, shp.score_thresh)
+    metas = [{"orig_size": np.array([375, 1242, 3], np.int32), "scales": np.array([384 / 375., 1248 / 1242.], np.float32)}
+             for _ in range(batch)]
+    metas[2]["flipped"] = True
+    metas[3]["drifts"] = np.array([-7, 11], np.int32)
+    rec = np.zeros((batch, 10), np.float32)
+    rec[:, 0:2] = [m["scales"] for m in metas]
+    rec[2, 6] = 1242
+    rec[3, 7:9] = [-7, 11]
+    box_before = det.box.clone()
+    packed, count = results.to_host(det, dev(rec))
+    assert torch.equal(det.box, box_before)                      # inputs untouched
+    expect = orc.detect_filtered(pred, a64, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh, shp.score_thresh)
+    rows = results.unpack(packed, count, metas)
+    texts = results.kitti_texts(packed, count)
+    for b, (row, exp) in enumerate(zip(rows, expect)):
+        n = len(exp["anchor_idx"])
+        assert int(count[b]) == n
+        if n == 0:
+            assert set(row) == {"image_meta"} and texts[b] == ""
+            continue
+        assert np.array_equal(row["class_ids"], exp["class_ids"])
+        np.testing.assert_allclose(row["scores"], exp["scores"], rtol=RTOL, atol=1e-7)
+        want = orc.boxes_postprocess(exp["boxes"], metas[b])
+        np.testing.assert_allclose(row["boxes"], want, rtol=RTOL, atol=2e-3)
+        # the text is a pure function of the packed values
+        assert texts[b] == orc.kitti_result_text(row["class_ids"], row["scores"], row["boxes"], results.KITTI_CLASS_NAMES)
+        assert (packed[b, n:, 0] == -1).all()
+
+
+def test_preprocess_vs_reference_golden(ops, golden):
+    """whiten + cv2 bilinear resize + HWC->CHW on the GPU against BaseDataset.preprocess run unmodified (uint8 and
+    float32 inputs, down/up-scaling, identity size)."""
+    g = golden("preprocess")
+    for i in range(int(g["n"])):
+        seed, h0, w0, h, w = (int(v) for v in g[f"case_{i}"])
+        img = np.random.RandomState(seed).randint(0, 256, size=(h0, w0, 3)).astype(np.uint8)
+        for arr in (img, img.astype(np.float32)):
+            out = ops.preprocess_images(dev(arr[None]), g["mean"], g["std"], (h, w))
+            assert out.shape == (1, 3, h, w)
+            np.testing.assert_allclose(out[0].cpu().numpy(), g[f"out_{i}"], rtol=1e-5, atol=6e-5)  # IPP fp32 coordinates, see test_oracle_golden
+    # batched call == per-image calls, and the oracle agrees at the KITTI size (375x1242 -> 384x1248)
+    big = np.random.RandomState(5).randint(0, 256, size=(2, 375, 1242, 3)).astype(np.uint8)
+    out = ops.preprocess_images(dev(big), g["mean"], g["std"], synth.KITTI.input_hw).cpu().numpy()
+    for b in range(2):
+        np.testing.assert_allclose(out[b], orc.preprocess_image(big[b], g["mean"], g["std"], synth.KITTI.input_hw),
+                                   rtol=1e-5, atol=1e-5)
