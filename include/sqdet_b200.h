@@ -255,6 +255,21 @@ SQD_API long long sqd_format_kitti(const float *h_packed, const int32_t *h_count
 SQD_API int sqd_preprocess(const void *d_images, int dtype, int batch, int src_h, int src_w, const float *mean3,
                            const float *std3, int dst_h, int dst_w, float *d_out, void *stream);
 
+/* 8(f) rank 2 (first half)  ConvDet backward: gradient with respect to the Fire11 features and the bias.
+ *     Replaces autograd through nn.Conv2d (src/model/squeezedet.py:73-75; cuDNN dgrad in the reference).  The input
+ *     gradient is the forward implicit GEMM with roles swapped (3x3 convolution of d_gpred with flipped, transposed
+ *     weights), run on the same tcgen05 f16x3 kernel in slabs of 128 feature channels.
+ *   d_gpred      (B, gh, gw, Cout) fp32 -- gradient of pred in the library's (B, A, C+5) layout
+ *   d_gfeat_nhwc (B, gh, gw, Cin)  fp32 -- channels_last memory of the logical (B, Cin, gh, gw) gradient; Cin % 128 == 0
+ *   sqd_convdet_dgrad_pack_weights derives the flipped / transposed weight planes once per weight update.
+ *   The weight gradient is not provided yet (torch's conv2d_weight is used by the Python mirror). */
+SQD_API size_t sqd_convdet_dgrad_packed_bytes(int cout, int cin);
+SQD_API int sqd_convdet_dgrad_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, void *stream);
+SQD_API size_t sqd_convdet_dgrad_workspace_bytes(int batch, int cin, int gh, int gw, int cout);
+SQD_API int sqd_convdet_dgrad(const float *d_gpred, const void *d_dgrad_packed, int batch, int cin, int gh, int gw, int cout,
+                              float *d_gfeat_nhwc, void *d_workspace, size_t workspace_bytes, void *stream);
+SQD_API int sqd_convdet_bias_grad(const float *d_gpred, int batch, int gh, int gw, int cout, float *d_gbias, void *stream);
+
 /* Debug aid: synchronise `stream`, return 0 if the last tcgen05 ConvDet launch on this workspace
  * drained cleanly, else the role (1 TMA producer, 2 MMA issuer, 3 epilogue) whose bounded mbarrier
  * wait timed out.  The kernels never spin forever. */

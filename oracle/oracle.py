@@ -110,6 +110,22 @@ def convdet_forward_f64(feat_nchw, weight, bias, num_anchors, num_fields):
     return y.reshape(B, num_anchors, num_fields)
 
 
+def convdet_backward(feat_nchw, weight, gpred_nhwc, dtype=F32):
+    """Gradients of the ConvDet head for an upstream gradient of its (B,gh,gw,Cout) output: what autograd through
+    nn.Conv2d(pad 1) + permute (src/model/squeezedet.py:83-85) returns -- (d feat (B,Cin,gh,gw), d weight, d bias).
+    torch's CPU conv gradient routines do the contractions, as in the reference; dtype float64 = accuracy yardstick."""
+    import torch
+
+    td = torch.float64 if dtype == F64 else torch.float32
+    x = torch.from_numpy(np.ascontiguousarray(feat_nchw)).to(td)
+    w = torch.from_numpy(np.ascontiguousarray(weight)).to(td)
+    g = torch.from_numpy(np.ascontiguousarray(gpred_nhwc)).to(td).permute(0, 3, 1, 2).contiguous()
+    gx = torch.nn.grad.conv2d_input(x.shape, w, g, padding=1)
+    gw = torch.nn.grad.conv2d_weight(x, w.shape, g, padding=1)
+    gb = g.sum(dim=(0, 2, 3))
+    return gx.numpy(), gw.numpy(), gb.numpy()
+
+
 # --------------------------------------------------------------------------------------
 # a2-a6  PredictionResolver
 # --------------------------------------------------------------------------------------

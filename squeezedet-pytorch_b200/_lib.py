@@ -51,6 +51,11 @@ SIGNATURES = {
     "sqd_loss_workspace_bytes": (_sz, [_i, _i]),
     "sqd_loss_fwd_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), _vp, _vp, _vp, _vp, _sz, _vp]),
     "sqd_boxes_postprocess": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "sqd_convdet_dgrad_packed_bytes": (_sz, [_i, _i]),
+    "sqd_convdet_dgrad_pack_weights": (_i, [_vp, _i, _i, _vp, _vp]),
+    "sqd_convdet_dgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "sqd_convdet_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "sqd_convdet_bias_grad": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "sqd_pack_results": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "sqd_format_kitti": (C.c_longlong, [_vp, _vp, _i, _i, C.POINTER(C.c_char_p), _i, _vp, _sz, _vp]),
     "sqd_preprocess": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _vp, _vp]),

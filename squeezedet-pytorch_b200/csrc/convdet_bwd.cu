@@ -1,0 +1,210 @@
+// SURVEY 8(f) rank 2, first half: ConvDet backward with respect to the Fire11 features (dgrad) on the tcgen05
+// forward kernel, plus the bias gradient.  Reference: autograd through nn.Conv2d(768, 72, 3, padding=1)
+// (src/model/squeezedet.py:73-75,83-87; trainer.py:43-46 calls loss.backward()) -> cuDNN dgrad there.
+//
+// dX[b,y,x,c] = sum_{dy,dx,n} G[b, y+1-dy, x+1-dx, n] * W[n,c,dy,dx]
+//             = a 3x3 pad-1 convolution of G (the gradient of pred, NHWC with Cout = K*(C+5) channels) with the
+//               weights W2[c][n][dy'][dx'] = W[n][c][2-dy'][2-dx']   (taps flipped, channel roles swapped)
+// so it is the forward implicit GEMM with roles swapped: "input channels" = Cout padded to a multiple of 64 (72 -> 128),
+// "output channels" = Cin = 768 in slabs of 128 columns (six launches of convdet_f16_pair_kernel<128,0>, all reading the
+// same small fp16 planes of G, which stay in L2).  Same f16x3 numerics as the forward (fp32-grade products).
+// The result is written NHWC (B, gh, gw, Cin): the channels_last memory format of the logical (B, Cin, gh, gw) tensor.
+// The weight gradient (wgrad: a contraction over B*gh*gw pixels) is NOT native yet -- see DESIGN.md.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+size_t sqd_f16_packed_bytes(int cout, int cin);
+int sqd_f16_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, cudaStream_t st);
+size_t sqd_f16_split_bytes(int batch, int cin, int gh, int gw);
+size_t sqd_f16_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout);
+int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
+                         int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st,
+                         const SqdCandEmit *emit, int out_stride);
+
+namespace {
+
+constexpr int kSlab = 128;  // output columns (feature channels) per GEMM launch
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+int kpad_of(int cout) { return (cout + 63) / 64 * 64; }
+int nslab_of(int cin) { return (cin + kSlab - 1) / kSlab; }
+
+// W (cout, cin, 3, 3) -> W2 slab (kSlab, kp, 3, 3): W2[j][n][t] = W[n][s*kSlab + j][8 - t], zero outside
+__global__ void flip_transpose_weights_kernel(const float *__restrict__ w, int cout, int cin, int kp, int slab,
+                                              float *__restrict__ w2) {
+    const int total = kSlab * kp * 9;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int t = i % 9, n = (i / 9) % kp, j = i / (9 * kp);
+        const int c = slab * kSlab + j;
+        w2[i] = (n < cout && c < cin) ? w[((size_t)n * cin + c) * 9 + (8 - t)] : 0.f;
+    }
+}
+
+// power-of-two scale s with amax*s in [2^13, 2^14) -- must match convdet_f16.cu (the GEMM divides it out again)
+__device__ __forceinline__ float pow2_scale_for(float amax) {
+    if (!(amax > 0.f) || amax > 3.0e38f) return 1.f;
+    int ex;
+    frexpf(amax, &ex);
+    int e = 14 - ex;
+    e = e < -126 ? -126 : (e > 126 ? 126 : e);
+    return ldexpf(1.f, e);
+}
+
+// max |g| per (image, 64-channel block of the padded channel axis): one thread per cell walks the cell's channels
+// block by block (register maximum), a warp reduction and one shared atomic per warp and block follow
+__global__ void __launch_bounds__(256) gpred_absmax_kernel(const float *__restrict__ g, int P, int cout, int ncb,
+                                                           unsigned *__restrict__ amax_bits) {
+    extern __shared__ unsigned s_max[];   // ncb
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < ncb; i += blockDim.x) s_max[i] = 0u;
+    __syncthreads();
+    const float *src = g + (size_t)b * P * cout;
+    for (int cell0 = blockIdx.x * blockDim.x; cell0 < P; cell0 += gridDim.x * blockDim.x) {   // warp-uniform trip count
+        const int cell = cell0 + threadIdx.x;
+        for (int cb = 0; cb < ncb; ++cb) {
+            float m = 0.f;
+            if (cell < P) {
+                const int c1 = min(cout, (cb + 1) * 64);
+                for (int ch = cb * 64; ch < c1; ++ch) m = fmaxf(m, fabsf(__ldg(src + (size_t)cell * cout + ch)));
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if ((threadIdx.x & 31) == 0) atomicMax(&s_max[cb], __float_as_uint(m));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ncb; i += blockDim.x) atomicMax(amax_bits + (size_t)b * ncb + i, s_max[i]);
+}
+
+// G (B, P, cout) fp32 -> x1 / x2 fp16 planes (B, P, kp), channels >= cout zero; one thread per (cell, 4 channels)
+__global__ void __launch_bounds__(256) gpred_split_pad_kernel(const float *__restrict__ g, int P, int cout, int kp,
+                                                              const unsigned *__restrict__ amax_bits, uint2 *__restrict__ p1,
+                                                              uint2 *__restrict__ p2, size_t total) {
+    const int kq = kp >> 2, ncb = kp >> 6;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i % kq);
+        const size_t cell = i / kq;           // b*P + pixel
+        const int b = (int)(cell / P);
+        const float s = pow2_scale_for(__uint_as_float(amax_bits[(size_t)b * ncb + (q >> 4)]));
+        unsigned short h1[4], h2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int ch = 4 * q + e;
+            const float xs = ch < cout ? g[cell * cout + ch] * s : 0.f;
+            const __half a = __float2half_rn(xs);
+            const __half r = __float2half_rn((xs - __half2float(a)) * 2048.f);
+            h1[e] = __half_as_ushort(a);
+            h2[e] = __half_as_ushort(r);
+        }
+        p1[i] = make_uint2((unsigned)h1[0] | ((unsigned)h1[1] << 16), (unsigned)h1[2] | ((unsigned)h1[3] << 16));
+        p2[i] = make_uint2((unsigned)h2[0] | ((unsigned)h2[1] << 16), (unsigned)h2[2] | ((unsigned)h2[3] << 16));
+    }
+}
+
+// db[n] = sum over (b, pixel) of G[b, pixel, n]: fixed-order two-level sum (deterministic), double accumulation
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float *__restrict__ g, size_t rows, int cout,
+                                                        float *__restrict__ db) {
+    const int n = blockIdx.x;
+    double acc = 0.0;
+    for (size_t r = threadIdx.x; r < rows; r += blockDim.x) acc += (double)g[r * cout + n];
+    __shared__ double s[256];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) db[n] = (float)s[0];
+}
+
+struct DgradWs {
+    size_t planes_off, gemm_off, total;
+};
+DgradWs dgrad_ws(int batch, int cin, int gh, int gw, int cout) {
+    DgradWs w;
+    const int kp = kpad_of(cout);
+    w.planes_off = 0;
+    w.gemm_off = align256(sqd_f16_split_bytes(batch, kp, gh, gw));
+    w.total = w.gemm_off + align256(sqd_f16_workspace_bytes(batch, kp, gh, gw, kSlab, SQD_LAYOUT_SPLIT_NHWC));
+    (void)cin;
+    return w;
+}
+
+}  // namespace
+
+extern "C" size_t sqd_convdet_dgrad_packed_bytes(int cout, int cin) {
+    if (cout <= 0 || cin <= 0) return 0;
+    const int kp = kpad_of(cout);
+    return (size_t)nslab_of(cin) * align256(sqd_f16_packed_bytes(kSlab, kp)) + align256((size_t)kSlab * kp * 9 * sizeof(float));
+}
+
+extern "C" int sqd_convdet_dgrad_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, void *stream) {
+    SQD_REQUIRE(d_weight && d_packed, SQD_E_NULL, "sqd_convdet_dgrad_pack_weights: NULL pointer");
+    SQD_REQUIRE(cout >= 1 && cout <= 1024 && cin >= 1, SQD_E_SHAPE, "sqd_convdet_dgrad_pack_weights: bad shape (%d, %d)", cout, cin);
+    SQD_REQUIRE(sqd_aligned16(d_packed), SQD_E_ALIGN, "sqd_convdet_dgrad_pack_weights: buffer must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int kp = kpad_of(cout), ns = nslab_of(cin);
+    const size_t slab_bytes = align256(sqd_f16_packed_bytes(kSlab, kp));
+    char *base = static_cast<char *>(d_packed);
+    float *tmp = reinterpret_cast<float *>(base + (size_t)ns * slab_bytes);
+    for (int s = 0; s < ns; ++s) {
+        flip_transpose_weights_kernel<<<SQD_SM_COUNT, 256, 0, st>>>(d_weight, cout, cin, kp, s, tmp);
+        SQD_LAUNCH_CHECK("flip_transpose_weights_kernel");
+        int rc = sqd_f16_pack_weights(tmp, kSlab, kp, base + (size_t)s * slab_bytes, st);
+        if (rc) return rc;
+    }
+    return SQD_OK;
+}
+
+extern "C" size_t sqd_convdet_dgrad_workspace_bytes(int batch, int cin, int gh, int gw, int cout) {
+    if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0) return 256;
+    return dgrad_ws(batch, cin, gh, gw, cout).total;
+}
+
+extern "C" int sqd_convdet_dgrad(const float *d_gpred, const void *d_dgrad_packed, int batch, int cin, int gh, int gw,
+                                 int cout, float *d_gfeat_nhwc, void *d_workspace, size_t workspace_bytes, void *stream) {
+    if (batch == 0) return SQD_OK;
+    SQD_REQUIRE(d_gpred && d_dgrad_packed && d_gfeat_nhwc && d_workspace, SQD_E_NULL, "sqd_convdet_dgrad: NULL pointer");
+    SQD_REQUIRE(batch > 0 && batch <= 65535 && cin >= kSlab && cin % kSlab == 0 && gh > 0 && gw > 0 && cout >= 1 && cout <= 1024,
+                SQD_E_SHAPE, "sqd_convdet_dgrad: bad shape (Cin must be a multiple of %d)", kSlab);
+    SQD_REQUIRE(sqd_aligned16(d_gpred) && sqd_aligned16(d_gfeat_nhwc) && sqd_aligned16(d_workspace), SQD_E_ALIGN,
+                "sqd_convdet_dgrad: pointers must be 16-byte aligned");
+    const DgradWs w = dgrad_ws(batch, cin, gh, gw, cout);
+    SQD_REQUIRE(workspace_bytes >= w.total, SQD_E_WORKSPACE, "sqd_convdet_dgrad: workspace too small (%zu < %zu bytes)",
+                workspace_bytes, w.total);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int kp = kpad_of(cout), ncb = kp / 64, P = gh * gw, ns = nslab_of(cin);
+    char *ws = static_cast<char *>(d_workspace);
+    // 1. G -> zero-padded fp16 planes with per-(image, block) scales (G is 1/10 of the features: two small passes)
+    char *planes = ws + w.planes_off;
+    const size_t amax_bytes = align256((size_t)batch * ncb * sizeof(unsigned));
+    const size_t plane_bytes = align256((size_t)batch * P * kp * sizeof(unsigned short));
+    unsigned *amax = reinterpret_cast<unsigned *>(planes);
+    SQD_CUDA(cudaMemsetAsync(amax, 0, amax_bytes, st));
+    gpred_absmax_kernel<<<dim3(16, batch), 256, ncb * sizeof(unsigned), st>>>(d_gpred, P, cout, ncb, amax);
+    SQD_LAUNCH_CHECK("gpred_absmax_kernel");
+    const size_t total = (size_t)batch * P * (kp / 4);
+    int gx = (int)((total + 255) / 256);
+    if (gx > SQD_SM_COUNT * 16) gx = SQD_SM_COUNT * 16;
+    gpred_split_pad_kernel<<<gx, 256, 0, st>>>(d_gpred, P, cout, kp, amax, reinterpret_cast<uint2 *>(planes + amax_bytes),
+                                              reinterpret_cast<uint2 *>(planes + amax_bytes + plane_bytes), total);
+    SQD_LAUNCH_CHECK("gpred_split_pad_kernel");
+    // 2. one implicit GEMM per slab of 128 feature channels
+    const size_t slab_bytes = align256(sqd_f16_packed_bytes(kSlab, kp));
+    for (int s = 0; s < ns; ++s) {
+        int rc = sqd_convdet_f16_pair(reinterpret_cast<const float *>(planes), SQD_LAYOUT_SPLIT_NHWC,
+                                      static_cast<const char *>(d_dgrad_packed) + (size_t)s * slab_bytes, nullptr, batch, kp, gh,
+                                      gw, kSlab, d_gfeat_nhwc + (size_t)s * kSlab, ws + w.gemm_off, st, nullptr, cin);
+        if (rc) return rc;
+    }
+    return SQD_OK;
+}
+
+extern "C" int sqd_convdet_bias_grad(const float *d_gpred, int batch, int gh, int gw, int cout, float *d_gbias, void *stream) {
+    SQD_REQUIRE(d_gpred && d_gbias, SQD_E_NULL, "sqd_convdet_bias_grad: NULL pointer");
+    SQD_REQUIRE(batch >= 0 && gh > 0 && gw > 0 && cout >= 1, SQD_E_SHAPE, "sqd_convdet_bias_grad: bad shape");
+    bias_grad_kernel<<<cout, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_gpred, (size_t)batch * gh * gw, cout, d_gbias);
+    SQD_LAUNCH_CHECK("bias_grad_kernel");
+    return SQD_OK;
+}

@@ -813,6 +813,7 @@ struct PairParams {
     int *status;
     long long *trace;
     int trace_cta;
+    int out_stride;      // floats between consecutive cells of the output (== cout for pred; Cin for the dgrad slabs)
     // fused score epilogue (template CS > 0 only): candidates above the score threshold go to per-image lists
     SqdCand cand;        // cand.count == nullptr: no emission
     float score_thr;
@@ -932,7 +933,7 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
         tma_prefetch_desc(&map_a2);
         tma_prefetch_desc(&map_b);
     }
-    for (int i = threadIdx.x; i < NPAD; i += kThreads2) s_bias[i] = i < p.cout ? __ldg(p.bias + i) : 0.f;
+    for (int i = threadIdx.x; i < NPAD; i += kThreads2) s_bias[i] = (i < p.cout && p.bias) ? __ldg(p.bias + i) : 0.f;
     if (warp == kWarpMma2) tmem_alloc_2cta(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
@@ -1227,8 +1228,8 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
 #pragma unroll
             for (int n = 0; n < NPAD; ++n) acc[n] = fadd(fmul(acc[n], inv), s_bias[n]);
             if (inb) {
-                float *out = p.pred + (((size_t)it.img * p.gh + y) * p.gw + x) * p.cout;
-                if ((p.cout & 3) == 0) {
+                float *out = p.pred + (((size_t)it.img * p.gh + y) * p.gw + x) * p.out_stride;
+                if (((p.cout | p.out_stride) & 3) == 0) {
                     float4 *o4 = reinterpret_cast<float4 *>(out);
 #pragma unroll
                     for (int n = 0; n < NPAD; n += 4)
@@ -1243,7 +1244,7 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                 __syncwarp();
                 flush_pending();   // a previous tile not fully scored yet (short segments)
                 if (it.img < p.batch) {   // ghost tiles have nothing to score (warp-uniform)
-                    pend_row = inb ? p.pred + (((size_t)it.img * p.gh + y) * p.gw + x) * p.cout : nullptr;
+                    pend_row = inb ? p.pred + (((size_t)it.img * p.gh + y) * p.gw + x) * p.out_stride : nullptr;
                     pend_img = it.img;
                     pend_a0 = (y * p.gw + x) * p.anchors_per_cell;
                     pend_k = 0;
@@ -1404,7 +1405,7 @@ int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, 
 // an opt-in experiment (SQD_FUSED_SCORE=1), not the default.
 int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                          int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st,
-                         const SqdCandEmit *emit) {
+                         const SqdCandEmit *emit, int out_stride) {
     SQD_REQUIRE(cin % kBlockK == 0, SQD_E_SHAPE, "convdet (tcgen05): Cin %d must be a multiple of %d", cin, kBlockK);
     SQD_REQUIRE(cout >= 1 && cout <= 128, SQD_E_SHAPE, "convdet (tcgen05): Cout %d outside [1,128]", cout);
     EncodeTiledFn encode = get_encode_fn();
@@ -1449,6 +1450,7 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
 
     PairParams p;
     p.cin = cin; p.gh = gh; p.gw = gw; p.cout = cout; p.batch = batch;
+    p.out_stride = out_stride > 0 ? out_stride : cout;
     p.tiles_x = (gw + kTileX - 1) / kTileX;
     p.tiles_per_img = p.tiles_x * ((gh + kTileY - 1) / kTileY);
     const long long total_tiles = (long long)p.tiles_per_img * batch;

@@ -45,26 +45,31 @@ _ARCH = {
 
 
 class _ConvDetFn(torch.autograd.Function):
-    """ConvDet forward on the tcgen05 kernel; backward (not yet native) uses
-    torch's conv gradient routines so training keeps working."""
+    """ConvDet forward on the tcgen05 kernel.  Backward: the feature gradient runs on the same
+    tcgen05 kernel with swapped roles (ops.convdet_dgrad) and the bias gradient on a reduction kernel; the WEIGHT
+    gradient is not native yet and uses torch's conv2d_weight."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, packed, algo):
+    def forward(ctx, x, weight, bias, packed, algo, dgrad_packed_fn):
         ctx.save_for_backward(x, weight)
+        ctx.dgrad_packed_fn = dgrad_packed_fn
         return ops.convdet_forward(x, weight, bias, packed=packed, algo=algo)  # (B,gh,gw,Cout)
 
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
-        g_nchw = g.permute(0, 3, 1, 2)
         gx = gw = gb = None
+        g = g.contiguous()
         if ctx.needs_input_grad[0]:
-            gx = torch.nn.grad.conv2d_input(x.shape, weight, g_nchw, padding=1)
+            if weight.shape[1] % 128 == 0:
+                gx = ops.convdet_dgrad(g, weight, ctx.dgrad_packed_fn() if ctx.dgrad_packed_fn else None)
+            else:
+                gx = torch.nn.grad.conv2d_input(x.shape, weight, g.permute(0, 3, 1, 2), padding=1)
         if ctx.needs_input_grad[1]:
-            gw = torch.nn.grad.conv2d_weight(x, weight.shape, g_nchw, padding=1)
+            gw = torch.nn.grad.conv2d_weight(x, weight.shape, g.permute(0, 3, 1, 2), padding=1)
         if ctx.needs_input_grad[2]:
-            gb = g.sum(dim=(0, 1, 2))
-        return gx, gw, gb, None, None
+            gb = ops.convdet_bias_grad(g)
+        return gx, gw, gb, None, None, None
 
 
 class SqueezeDetBase(nn.Module):
@@ -87,6 +92,8 @@ class SqueezeDetBase(nn.Module):
         self.conv_algo = getattr(cfg, "conv_algo", CONV_TCGEN05_F16X3)
         self._packed = None
         self._packed_version = None
+        self._dgrad_packed = None
+        self._dgrad_packed_version = None
         self.init_weights()
 
     def init_weights(self):  # squeezedet.py:89-97
@@ -106,9 +113,19 @@ class SqueezeDetBase(nn.Module):
             self._packed_version = ver
         return self._packed
 
+    def dgrad_packed_weights(self):
+        """Flipped / transposed planes for the feature gradient; derived lazily, only when a backward pass needs them."""
+        w = self.convdet.weight
+        ver = (w._version, w.data_ptr(), str(w.device))
+        if self._dgrad_packed is None or self._dgrad_packed_version != ver:
+            self._dgrad_packed = ops.pack_convdet_dgrad_weights(w)
+            self._dgrad_packed_version = ver
+        return self._dgrad_packed
+
     def head(self, feat):
         """ConvDet + permute/view of squeezedet.py:83-87 on a Fire11 feature map."""
-        pred = _ConvDetFn.apply(feat, self.convdet.weight, self.convdet.bias, self.packed_weights(), self.conv_algo)
+        pred = _ConvDetFn.apply(feat, self.convdet.weight, self.convdet.bias, self.packed_weights(), self.conv_algo,
+                                self.dgrad_packed_weights)
         return pred.view(-1, self.num_anchors, self.num_classes + 5)
 
     def forward(self, x):

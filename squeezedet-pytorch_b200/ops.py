@@ -94,6 +94,43 @@ def convdet_forward(feat, weight, bias, packed=None, algo=CONV_TCGEN05_F16X3, nu
     return pred
 
 
+# ---- 8f.2 (first half): ConvDet backward w.r.t. features and bias ---------------------------------------
+def pack_convdet_dgrad_weights(weight: torch.Tensor) -> torch.Tensor:
+    """Flipped / transposed weight planes for convdet_dgrad; derived data, once per weight update."""
+    lib = load()
+    w = weight.detach().contiguous().float()
+    cout, cin = w.shape[0], w.shape[1]
+    packed = torch.empty(lib.sqd_convdet_dgrad_packed_bytes(cout, cin), dtype=torch.uint8, device=w.device)
+    check(lib.sqd_convdet_dgrad_pack_weights(ptr(w), cout, cin, ptr(packed), stream_ptr(w.device)),
+          "sqd_convdet_dgrad_pack_weights")
+    return packed
+
+
+def convdet_dgrad(gpred, weight, dgrad_packed=None):
+    """gpred (B,gh,gw,Cout) [gradient of convdet_forward's output] -> gradient of the features, logical shape
+    (B,Cin,gh,gw) in channels_last memory (a zero-copy permute of the kernel's NHWC output)."""
+    lib = load()
+    g = gpred.contiguous().float()
+    B, gh, gw, cout = g.shape
+    cin = weight.shape[1]
+    if dgrad_packed is None:
+        dgrad_packed = pack_convdet_dgrad_weights(weight)
+    ws = workspace().get("convdet_dgrad", lib.sqd_convdet_dgrad_workspace_bytes(B, cin, gh, gw, cout), g.device)
+    out = torch.empty((B, gh, gw, cin), dtype=torch.float32, device=g.device)
+    check(lib.sqd_convdet_dgrad(ptr(g), ptr(dgrad_packed), B, cin, gh, gw, cout, ptr(out), ptr(ws), ws.numel(),
+                                stream_ptr(g.device)), "sqd_convdet_dgrad")
+    return out.permute(0, 3, 1, 2)
+
+
+def convdet_bias_grad(gpred):
+    lib = load()
+    g = gpred.contiguous().float()
+    B, gh, gw, cout = g.shape
+    gb = torch.empty((cout,), dtype=torch.float32, device=g.device)
+    check(lib.sqd_convdet_bias_grad(ptr(g), B, gh, gw, cout, ptr(gb), stream_ptr(g.device)), "sqd_convdet_bias_grad")
+    return gb
+
+
 # ---- a2-a7 -----------------------------------------------------------------------------------------
 def decode_scores(pred, anchors_f32, input_hw, num_classes, want=("class_ids", "scores", "boxes"), out=None):
     """pred (B,A,C+5) -> dict with the requested keys among class_ids/scores/boxes/probs/logp/conf/deltas.

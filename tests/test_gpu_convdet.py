@@ -244,3 +244,57 @@ def test_split_grid_not_multiple_of_four(ops):
     tc = ops.convdet_forward(dev(feat), dev(w), dev(b), check_status=True)
     simt = ops.convdet_forward(dev(feat), dev(w), dev(b), algo=CONV_SIMT_FP32)
     assert torch.allclose(tc, simt, rtol=1e-4, atol=2e-5 * float(simt.abs().max())), float((tc - simt).abs().max())
+
+
+@pytest.mark.parametrize("name,batch", [("tiny_160x96", 3), ("kitti_1248x384", 2)])
+def test_convdet_dgrad_and_bias_grad(ops, name, batch):
+    """Feature and bias gradients of the head (tcgen05 kernel with swapped roles) against autograd's conv gradient
+    routines (torch CPU fp32 = the reference's arithmetic, and fp64 as the accuracy yardstick)."""
+    shp = {x.name: x for x in (synth.TINY, synth.KITTI)}[name]
+    feat = synth.features(shp, batch, 71)
+    w, _ = synth.convdet_params(shp, 72)
+    rs = np.random.RandomState(73)
+    g = (rs.standard_normal((batch, *shp.grid_hw, shp.out_channels)) * rs.uniform(0.01, 3.0, size=(batch, 1, 1, 1))).astype(np.float32)
+    g[:, :, :, 64:] *= 1e-3                                   # the second channel block gets its own scale
+    gx32, _, gb32 = orc.convdet_backward(feat, w, g)
+    gx64, _, gb64 = orc.convdet_backward(feat, w, g, dtype=np.float64)
+    got = ops.convdet_dgrad(dev(g), dev(w))
+    assert got.shape == (batch, shp.in_channels, *shp.grid_hw)
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    got = got.cpu().numpy()
+    scale = np.abs(gx64).mean()
+    e_ours, e_ref = np.abs(got - gx64).max() / scale, np.abs(gx32 - gx64).max() / scale
+    print(f"dgrad vs float64: ours max {e_ours:.2e}, torch-cpu fp32 max {e_ref:.2e} (relative to mean |dX|)")
+    np.testing.assert_allclose(got, gx32, rtol=1e-4, atol=1e-4 * scale)
+    assert e_ours < 4 * e_ref + 1e-6
+    gb = ops.convdet_bias_grad(dev(g)).cpu().numpy()
+    np.testing.assert_allclose(gb, gb64, rtol=1e-5, atol=1e-5 * np.abs(gb64).max())
+    np.testing.assert_allclose(gb, gb32, rtol=1e-4, atol=1e-4 * np.abs(gb64).max())
+
+
+def test_training_backward_uses_native_dgrad(ops):
+    """SqueezeDetBase.head: autograd through the mirror gives the same feature / bias gradients as autograd through a
+    stock nn.Conv2d with the same parameters (the reference's head), and a weight gradient (torch's routine for now)."""
+    from squeezedet_pytorch_b200 import config, model
+    shp = synth.TINY
+    cfg = config.make_config(shp, dropout_prob=0.0)
+    base = model.SqueezeDetBase(cfg).cuda()
+    w, b = synth.convdet_params(shp, 81)
+    with torch.no_grad():
+        base.convdet.weight.copy_(torch.from_numpy(w))
+        base.convdet.bias.copy_(torch.from_numpy(b))
+    feat = dev(synth.features(shp, 2, 82)).requires_grad_(True)
+    up = dev(np.random.RandomState(83).standard_normal((2, shp.num_anchors, shp.num_fields)).astype(np.float32))
+    (base.head(feat) * up).sum().backward()
+    g_feat, g_w, g_b = feat.grad.clone(), base.convdet.weight.grad.clone(), base.convdet.bias.grad.clone()
+    feat2 = feat.detach().clone().requires_grad_(True)
+    conv = torch.nn.Conv2d(shp.in_channels, shp.out_channels, 3, padding=1).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(base.convdet.weight)
+        conv.bias.copy_(base.convdet.bias)
+    torch.backends.cudnn.allow_tf32 = False
+    (conv(feat2).permute(0, 2, 3, 1).reshape(2, shp.num_anchors, shp.num_fields) * up).sum().backward()
+    s = float(feat2.grad.abs().mean())
+    assert torch.allclose(g_feat, feat2.grad, rtol=1e-4, atol=1e-4 * s)
+    assert torch.allclose(g_b, conv.bias.grad, rtol=1e-4, atol=1e-4 * float(conv.bias.grad.abs().max()))
+    assert torch.allclose(g_w, conv.weight.grad, rtol=1e-3, atol=1e-4 * float(conv.weight.grad.abs().max()))
