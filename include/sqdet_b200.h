@@ -262,12 +262,16 @@ SQD_API int sqd_preprocess(const void *d_images, int dtype, int batch, int src_h
  *   d_gpred      (B, gh, gw, Cout) fp32 -- gradient of pred in the library's (B, A, C+5) layout
  *   d_gfeat_nhwc (B, gh, gw, Cin)  fp32 -- channels_last memory of the logical (B, Cin, gh, gw) gradient; Cin % 128 == 0
  *   sqd_convdet_dgrad_pack_weights derives the flipped / transposed weight planes once per weight update.
- *   The weight gradient is not provided yet (torch's conv2d_weight is used by the Python mirror). */
+ *   sqd_convdet_wgrad: d_gweight (Cout, Cin, 3, 3) from the NCHW fp32 features and d_gpred -- an fp32 CUDA-core implicit
+ *   GEMM split over the pixel axis with a fixed-order reduction (deterministic); Cout <= 80.  Not a tensor-core kernel yet. */
 SQD_API size_t sqd_convdet_dgrad_packed_bytes(int cout, int cin);
 SQD_API int sqd_convdet_dgrad_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, void *stream);
 SQD_API size_t sqd_convdet_dgrad_workspace_bytes(int batch, int cin, int gh, int gw, int cout);
 SQD_API int sqd_convdet_dgrad(const float *d_gpred, const void *d_dgrad_packed, int batch, int cin, int gh, int gw, int cout,
                               float *d_gfeat_nhwc, void *d_workspace, size_t workspace_bytes, void *stream);
+SQD_API size_t sqd_convdet_wgrad_workspace_bytes(int batch, int cin, int gh, int gw, int cout);
+SQD_API int sqd_convdet_wgrad(const float *d_feat_nchw, const float *d_gpred, int batch, int cin, int gh, int gw, int cout,
+                              float *d_gweight, void *d_workspace, size_t workspace_bytes, void *stream);
 SQD_API int sqd_convdet_bias_grad(const float *d_gpred, int batch, int gh, int gw, int cout, float *d_gbias, void *stream);
 
 /* Debug aid: synchronise `stream`, return 0 if the last tcgen05 ConvDet launch on this workspace

@@ -55,6 +55,8 @@ SIGNATURES = {
     "sqd_convdet_dgrad_pack_weights": (_i, [_vp, _i, _i, _vp, _vp]),
     "sqd_convdet_dgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "sqd_convdet_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "sqd_convdet_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "sqd_convdet_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "sqd_convdet_bias_grad": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "sqd_pack_results": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "sqd_format_kitti": (C.c_longlong, [_vp, _vp, _i, _i, C.POINTER(C.c_char_p), _i, _vp, _sz, _vp]),

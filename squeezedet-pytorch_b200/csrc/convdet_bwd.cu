@@ -118,6 +118,90 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float *__restrict_
     if (threadIdx.x == 0) db[n] = (float)s[0];
 }
 
+// ---- weight gradient (fp32 CUDA-core implicit GEMM, split over the pixel axis) ---------------------------------------
+// dW[n,c,dy,dx] = sum_{b,y,x} G[b,y,x,n] * X[b,c,y+dy-1,x+dx-1]: M = Cout (72), N = 9*Cin (6912), K = B*gh*gw (37,440 at
+// KITTI B = 20).  A CTA owns (one tap, 128 input channels, all Cout <= 80 output channels) for a slice of the image rows
+// and walks it in 32-pixel row segments: X segment (128 ch x 32 px, NCHW rows are pixel-contiguous, shifted by the tap,
+// zero outside the image = the conv padding) and G segment (32 px x Cout, NHWC rows) staged in shared memory, each of
+// the 320 threads accumulating an 8 (channels) x 4 (outputs) register tile from three 16-byte shared loads per pixel.  Slices write fp32 partials that a second
+// kernel adds in a fixed order (deterministic; no atomics).  Not a tensor-core kernel: the tcgen05 version (pixel-major
+// operands, chunked TMEM accumulation per image) is round-2 work; this one removes the cuDNN dependency of the training
+// mirror and is the yardstick it will be checked against.
+constexpr int kWgC = 128, kWgN = 80, kWgPix = 32, kWgThreads = 320;  // 16 channel octets x 20 output quads
+constexpr int kWgXs = kWgC + 4;                                        // padded row: 16-byte aligned, conflict-free LDS.128
+
+__global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const float *__restrict__ x, const float *__restrict__ g,
+                                                                   int batch, int cin, int gh, int gw, int cout, int nslice,
+                                                                   float *__restrict__ partial) {
+    __shared__ __align__(16) float xs[kWgPix][kWgXs];  // [pixel][channel]
+    __shared__ __align__(16) float gs[kWgPix][kWgN];   // [pixel][output channel]
+    const int tap = blockIdx.x, cb = blockIdx.y, slice = blockIdx.z;
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const int c0 = cb * kWgC;
+    const int tc = threadIdx.x & 15, tn = threadIdx.x >> 4;   // channels 4*tc.. and 64+4*tc.., outputs 4*tn..
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int rows = batch * gh;                               // image rows in the whole batch
+    const int r_begin = (int)((long long)rows * slice / nslice), r_end = (int)((long long)rows * (slice + 1) / nslice);
+    for (int r = r_begin; r < r_end; ++r) {
+        const int b = r / gh, y = r - b * gh;
+        const int ys = y + dy;                                 // source row of X
+        for (int x0 = 0; x0 < gw; x0 += kWgPix) {
+            // stage X: 32 consecutive pixels of one channel row per warp-wide load (shifted by the tap, zero outside)
+            for (int i = threadIdx.x; i < kWgC * kWgPix; i += kWgThreads) {
+                const int c = i >> 5, l = i & 31;
+                const int xsrc = x0 + l + dx;
+                const bool ok = ys >= 0 && ys < gh && xsrc >= 0 && xsrc < gw && x0 + l < gw && c0 + c < cin;
+                xs[l][c] = ok ? __ldg(x + (((size_t)b * cin + c0 + c) * gh + ys) * gw + xsrc) : 0.f;
+            }
+            // stage G: 32 pixels x cout contiguous floats (row-major), zero beyond the row end / cout
+            const float *grow = g + (((size_t)b * gh + y) * gw + x0) * cout;
+            const int npix = min(kWgPix, gw - x0);
+            for (int i = threadIdx.x; i < kWgPix * kWgN; i += kWgThreads) {
+                const int p = i / kWgN, n = i - p * kWgN;
+                gs[p][n] = (p < npix && n < cout) ? __ldg(grow + (size_t)p * cout + n) : 0.f;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int p = 0; p < kWgPix; ++p) {
+                const float4 a = *reinterpret_cast<const float4 *>(&xs[p][4 * tc]);
+                const float4 a2 = *reinterpret_cast<const float4 *>(&xs[p][64 + 4 * tc]);
+                const float4 bq = *reinterpret_cast<const float4 *>(&gs[p][4 * tn]);
+                const float av[8] = {a.x, a.y, a.z, a.w, a2.x, a2.y, a2.z, a2.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+    // partial[slice][n][c][tap]  (the layout of the weight tensor, so the reduction is a plain strided sum)
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + (i < 4 ? 4 * tc + i : 64 + 4 * tc + i - 4), n = 4 * tn + j;
+            if (c < cin && n < cout) partial[(((size_t)slice * cout + n) * cin + c) * 9 + tap] = acc[i][j];
+        }
+}
+
+__global__ void wgrad_reduce_kernel(const float *__restrict__ partial, size_t n, int nslice, float *__restrict__ gw_out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < nslice; ++k) s += partial[(size_t)k * n + i];   // fixed order
+        gw_out[i] = s;
+    }
+}
+
+int wgrad_slices(int batch, int gh) {
+    int s = (batch * gh + 29) / 30;     // ~30 image rows per slice
+    return s < 1 ? 1 : (s > 32 ? 32 : s);
+}
+
 struct DgradWs {
     size_t planes_off, gemm_off, total;
 };
@@ -206,5 +290,29 @@ extern "C" int sqd_convdet_bias_grad(const float *d_gpred, int batch, int gh, in
     SQD_REQUIRE(batch >= 0 && gh > 0 && gw > 0 && cout >= 1, SQD_E_SHAPE, "sqd_convdet_bias_grad: bad shape");
     bias_grad_kernel<<<cout, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_gpred, (size_t)batch * gh * gw, cout, d_gbias);
     SQD_LAUNCH_CHECK("bias_grad_kernel");
+    return SQD_OK;
+}
+
+extern "C" size_t sqd_convdet_wgrad_workspace_bytes(int batch, int cin, int gh, int gw, int cout) {
+    if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0) return 256;
+    return align256((size_t)wgrad_slices(batch, gh) * cout * cin * 9 * sizeof(float));
+}
+
+extern "C" int sqd_convdet_wgrad(const float *d_feat_nchw, const float *d_gpred, int batch, int cin, int gh, int gw, int cout,
+                                 float *d_gweight, void *d_workspace, size_t workspace_bytes, void *stream) {
+    SQD_REQUIRE(d_feat_nchw && d_gpred && d_gweight && d_workspace, SQD_E_NULL, "sqd_convdet_wgrad: NULL pointer");
+    SQD_REQUIRE(batch >= 1 && cin >= 1 && gh > 0 && gw > 0 && cout >= 1 && cout <= kWgN, SQD_E_SHAPE,
+                "sqd_convdet_wgrad: bad shape (Cout <= %d)", kWgN);
+    SQD_REQUIRE(workspace_bytes >= sqd_convdet_wgrad_workspace_bytes(batch, cin, gh, gw, cout), SQD_E_WORKSPACE,
+                "sqd_convdet_wgrad: workspace too small (%zu bytes)", workspace_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int ns = wgrad_slices(batch, gh);
+    float *partial = static_cast<float *>(d_workspace);
+    const dim3 grid(9, (cin + kWgC - 1) / kWgC, ns);
+    wgrad_partial_kernel<<<grid, kWgThreads, 0, st>>>(d_feat_nchw, d_gpred, batch, cin, gh, gw, cout, ns, partial);
+    SQD_LAUNCH_CHECK("wgrad_partial_kernel");
+    const size_t n = (size_t)cout * cin * 9;
+    wgrad_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(partial, n, ns, d_gweight);
+    SQD_LAUNCH_CHECK("wgrad_reduce_kernel");
     return SQD_OK;
 }

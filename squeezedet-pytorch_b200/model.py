@@ -46,8 +46,9 @@ _ARCH = {
 
 class _ConvDetFn(torch.autograd.Function):
     """ConvDet forward on the tcgen05 kernel.  Backward: the feature gradient runs on the same
-    tcgen05 kernel with swapped roles (ops.convdet_dgrad) and the bias gradient on a reduction kernel; the WEIGHT
-    gradient is not native yet and uses torch's conv2d_weight."""
+    tcgen05 kernel with swapped roles (ops.convdet_dgrad), the weight gradient on an fp32 CUDA-core implicit GEMM
+    (ops.convdet_wgrad) and the bias gradient on a reduction kernel.  Shapes outside the kernels' limits (Cin not a
+    multiple of 128, Cout > 80) use torch's conv gradient routines."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, packed, algo, dgrad_packed_fn):
@@ -66,7 +67,10 @@ class _ConvDetFn(torch.autograd.Function):
             else:
                 gx = torch.nn.grad.conv2d_input(x.shape, weight, g.permute(0, 3, 1, 2), padding=1)
         if ctx.needs_input_grad[1]:
-            gw = torch.nn.grad.conv2d_weight(x, weight.shape, g.permute(0, 3, 1, 2), padding=1)
+            if weight.shape[0] <= 80:
+                gw = ops.convdet_wgrad(x, g)
+            else:
+                gw = torch.nn.grad.conv2d_weight(x, weight.shape, g.permute(0, 3, 1, 2), padding=1)
         if ctx.needs_input_grad[2]:
             gb = ops.convdet_bias_grad(g)
         return gx, gw, gb, None, None, None

@@ -122,6 +122,20 @@ def convdet_dgrad(gpred, weight, dgrad_packed=None):
     return out.permute(0, 3, 1, 2)
 
 
+def convdet_wgrad(feat, gpred):
+    """feat (B,Cin,gh,gw) NCHW fp32, gpred (B,gh,gw,Cout) -> gradient of the ConvDet weight (Cout,Cin,3,3)."""
+    lib = load()
+    x = feat.detach().contiguous().float()
+    g = gpred.contiguous().float()
+    B, cin, gh, gw = x.shape
+    cout = g.shape[-1]
+    ws = workspace().get("convdet_wgrad", lib.sqd_convdet_wgrad_workspace_bytes(B, cin, gh, gw, cout), g.device)
+    out = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=g.device)
+    check(lib.sqd_convdet_wgrad(ptr(x), ptr(g), B, cin, gh, gw, cout, ptr(out), ptr(ws), ws.numel(), stream_ptr(g.device)),
+          "sqd_convdet_wgrad")
+    return out
+
+
 def convdet_bias_grad(gpred):
     lib = load()
     g = gpred.contiguous().float()

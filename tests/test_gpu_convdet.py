@@ -270,11 +270,23 @@ def test_convdet_dgrad_and_bias_grad(ops, name, batch):
     gb = ops.convdet_bias_grad(dev(g)).cpu().numpy()
     np.testing.assert_allclose(gb, gb64, rtol=1e-5, atol=1e-5 * np.abs(gb64).max())
     np.testing.assert_allclose(gb, gb32, rtol=1e-4, atol=1e-4 * np.abs(gb64).max())
+    # weight gradient (fp32 CUDA-core kernel, fixed-order reduction): deterministic and as accurate as torch's fp32
+    _, gw32, _ = orc.convdet_backward(feat, w, g)
+    _, gw64, _ = orc.convdet_backward(feat, w, g, dtype=np.float64)
+    gw1 = ops.convdet_wgrad(dev(feat), dev(g))
+    gw2 = ops.convdet_wgrad(dev(feat), dev(g))
+    assert torch.equal(gw1, gw2)
+    gw1 = gw1.cpu().numpy()
+    wscale = np.abs(gw64).mean()
+    e_ours, e_ref = np.abs(gw1 - gw64).max() / wscale, np.abs(gw32 - gw64).max() / wscale
+    print(f"wgrad vs float64: ours max {e_ours:.2e}, torch-cpu fp32 max {e_ref:.2e} (relative to mean |dW|)")
+    np.testing.assert_allclose(gw1, gw32, rtol=1e-4, atol=1e-4 * wscale)
+    assert e_ours < 4 * e_ref + 1e-5
 
 
-def test_training_backward_uses_native_dgrad(ops):
+def test_training_backward_is_native(ops):
     """SqueezeDetBase.head: autograd through the mirror gives the same feature / bias gradients as autograd through a
-    stock nn.Conv2d with the same parameters (the reference's head), and a weight gradient (torch's routine for now)."""
+    stock nn.Conv2d with the same parameters (the reference's head): feature, weight and bias gradients."""
     from squeezedet_pytorch_b200 import config, model
     shp = synth.TINY
     cfg = config.make_config(shp, dropout_prob=0.0)
@@ -297,4 +309,4 @@ def test_training_backward_uses_native_dgrad(ops):
     s = float(feat2.grad.abs().mean())
     assert torch.allclose(g_feat, feat2.grad, rtol=1e-4, atol=1e-4 * s)
     assert torch.allclose(g_b, conv.bias.grad, rtol=1e-4, atol=1e-4 * float(conv.bias.grad.abs().max()))
-    assert torch.allclose(g_w, conv.weight.grad, rtol=1e-3, atol=1e-4 * float(conv.weight.grad.abs().max()))
+    assert torch.allclose(g_w, conv.weight.grad, rtol=1e-4, atol=1e-4 * float(conv.weight.grad.abs().mean()))
