@@ -3,17 +3,24 @@
 // np.argsort of A IoUs per GT box, in DataLoader workers) and BaseDataset.prepare_annotations,
 // src/datasets/base.py:61-76.
 //
-// One CTA per image; GT boxes are processed sequentially (the greedy assignment is order
-// dependent by definition), each one as a block-wide masked arg-max over the A anchors in
-// float64 with the reference's exact operation order (no FMA contraction), so equal IoUs are
-// bit-equal here exactly when they are in numpy.  Tie policy: lowest anchor index (a stable
-// argsort in the reference).  "Taken" anchors live in a shared-memory bitmask.
-// Bytes per image: G * A * 32 (float64 anchor table, L2-resident across the batch).
+// One thread-block CLUSTER per image (8 CTAs: the anchors are split between them, so a GT box costs 4 anchors per
+// thread instead of 66); GT boxes are processed sequentially (the greedy assignment is order dependent by
+// definition), each one as a masked arg-max over the A anchors in float64 with the reference's exact operation order
+// (no FMA contraction), so equal IoUs are bit-equal here exactly when they are in numpy: block arg-max per CTA, the
+// CTAs' candidates meet in rank 0 through distributed shared memory, and the winner is broadcast back.  Tie policy:
+// lowest anchor index (a stable argsort in the reference) -- the key (value, index) is totally ordered, so the result
+// does not depend on how the anchors are partitioned.  "Taken" anchors live in a shared-memory bitmask (each CTA keeps
+// the bits of its own anchors).  Bytes per image: G * A * 32 (float64 anchor table, L2-resident across the batch).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
+constexpr int kMaxCluster = 8;
 
 struct Best {
     double v;
@@ -62,18 +69,44 @@ __device__ Best block_reduce(Best x, Best *scratch) {
     return scratch[0];
 }
 
+// Cluster-wide arg-max / arg-min: every CTA contributes its block result, all CTAs get the winner.  `xchg` counts
+// the exchanges of this CTA (identical in all CTAs of the cluster): slots alternate so that two cluster barriers per
+// exchange are enough.  All threads of all CTAs of the cluster must call.
+template <bool kMax>
+__device__ Best cluster_reduce(Best mine, int cs, int rank, int &xchg, Best (*s_cand)[kMaxCluster], Best *s_win) {
+    if (cs == 1) return mine;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int slot = xchg & 1;
+    ++xchg;
+    if (threadIdx.x == 0) cluster.map_shared_rank(&s_cand[slot][0], 0)[rank] = mine;
+    cluster.sync();
+    if (rank == 0 && threadIdx.x == 0) {
+        Best w = s_cand[slot][0];
+        for (int r = 1; r < cs; ++r) w = kMax ? better_max(w, s_cand[slot][r]) : better_min(w, s_cand[slot][r]);
+        for (int r = 0; r < cs; ++r) *cluster.map_shared_rank(&s_win[slot], r) = w;
+    }
+    cluster.sync();
+    return s_win[slot];
+}
+
 __global__ void __launch_bounds__(kThreads) match_kernel(const float4 *gt_boxes, const int *gt_count, int gmax,
                                                          const double *anchors, int A, int *out_idx,
-                                                         float4 *out_deltas) {
-    extern __shared__ unsigned taken[];  // ceil(A/32) words
+                                                         float4 *out_deltas, int cs) {
+    extern __shared__ unsigned taken[];  // bits of this CTA's anchors [a_begin, a_end): ceil(chunk/32) words
     __shared__ Best scratch[kThreads / 32];
-    const int img = blockIdx.x;
+    __shared__ Best s_cand[2][kMaxCluster];
+    __shared__ Best s_win[2];
+    const int img = blockIdx.x / cs, rank = blockIdx.x - img * cs;
+    const int chunk = ((A + cs - 1) / cs + 31) & ~31;           // multiple of 32: bitmask words never straddle CTAs
+    const int a_begin = min(A, rank * chunk), a_end = min(A, a_begin + chunk);
     const int G = min(max(gt_count[img], 0), gmax);
-    for (int i = threadIdx.x; i < (A + 31) / 32; i += kThreads) taken[i] = 0u;
-    for (int g = G + threadIdx.x; g < gmax; g += kThreads) {
-        out_idx[(size_t)img * gmax + g] = -1;
-        out_deltas[(size_t)img * gmax + g] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    int xchg = 0;
+    for (int i = threadIdx.x; i < (chunk + 31) / 32; i += kThreads) taken[i] = 0u;
+    if (rank == 0)
+        for (int g = G + threadIdx.x; g < gmax; g += kThreads) {
+            out_idx[(size_t)img * gmax + g] = -1;
+            out_deltas[(size_t)img * gmax + g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     __syncthreads();
 
     for (int g = 0; g < G; ++g) {
@@ -88,8 +121,9 @@ __global__ void __launch_bounds__(kThreads) match_kernel(const float4 *gt_boxes,
 
         // pass 1: best IoU > 0 among untaken anchors (boxes.py:70-81,104-111)
         Best best{0.0, 0x7fffffff};
-        for (int a = threadIdx.x; a < A; a += kThreads) {
-            if ((taken[a >> 5] >> (a & 31)) & 1u) continue;
+        for (int a = a_begin + threadIdx.x; a < a_end; a += kThreads) {
+            const int la = a - a_begin;
+            if ((taken[la >> 5] >> (la & 31)) & 1u) continue;
             const double2 xy = *reinterpret_cast<const double2 *>(anchors + (size_t)a * 4);
             const double2 wh = *reinterpret_cast<const double2 *>(anchors + (size_t)a * 4 + 2);
             const double hw = d_mul(0.5, d_sub(wh.x, 1.0)), hh = d_mul(0.5, d_sub(wh.y, 1.0));
@@ -106,12 +140,14 @@ __global__ void __launch_bounds__(kThreads) match_kernel(const float4 *gt_boxes,
             }
         }
         best = block_reduce<true>(best, scratch);
+        best = cluster_reduce<true>(best, cs, rank, xchg, s_cand, s_win);
 
-        if (best.idx == 0x7fffffff) {
+        if (best.idx == 0x7fffffff) {   // cluster-uniform
             // pass 2: nearest untaken anchor in squared xywh distance (boxes.py:115-121)
             Best nb{0.0, 0x7fffffff};
-            for (int a = threadIdx.x; a < A; a += kThreads) {
-                if ((taken[a >> 5] >> (a & 31)) & 1u) continue;
+            for (int a = a_begin + threadIdx.x; a < a_end; a += kThreads) {
+                const int la = a - a_begin;
+                if ((taken[la >> 5] >> (la & 31)) & 1u) continue;
                 const double2 xy = *reinterpret_cast<const double2 *>(anchors + (size_t)a * 4);
                 const double2 wh = *reinterpret_cast<const double2 *>(anchors + (size_t)a * 4 + 2);
                 const double d0 = d_sub((double)gx, xy.x), d1 = d_sub((double)gy, xy.y);
@@ -122,28 +158,32 @@ __global__ void __launch_bounds__(kThreads) match_kernel(const float4 *gt_boxes,
                     nb.idx = a;
                 }
             }
-            best = block_reduce<false>(nb, scratch);
+            nb = block_reduce<false>(nb, scratch);
+            best = cluster_reduce<false>(nb, cs, rank, xchg, s_cand, s_win);
         }
 
         if (threadIdx.x == 0) {
             int j = best.idx;
-            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j != 0x7fffffff) {
-                taken[j >> 5] |= 1u << (j & 31);
-                const double ax = anchors[(size_t)j * 4], ay = anchors[(size_t)j * 4 + 1];
-                const double aw = anchors[(size_t)j * 4 + 2], ah = anchors[(size_t)j * 4 + 3];
-                d.x = (float)d_div(d_sub((double)gx, ax), aw);   // boxes.py:125-128, float64 then cast
-                d.y = (float)d_div(d_sub((double)gy, ay), ah);
-                d.z = (float)log(d_div((double)gw, aw));
-                d.w = (float)log(d_div((double)gh, ah));
-            } else {
-                j = A;  // more GT boxes than anchors: the reference leaves anchor_idx == num_anchors
+            if (j != 0x7fffffff && j >= a_begin && j < a_end) taken[(j - a_begin) >> 5] |= 1u << ((j - a_begin) & 31);
+            if (rank == 0) {
+                float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j != 0x7fffffff) {
+                    const double ax = anchors[(size_t)j * 4], ay = anchors[(size_t)j * 4 + 1];
+                    const double aw = anchors[(size_t)j * 4 + 2], ah = anchors[(size_t)j * 4 + 3];
+                    d.x = (float)d_div(d_sub((double)gx, ax), aw);   // boxes.py:125-128, float64 then cast
+                    d.y = (float)d_div(d_sub((double)gy, ay), ah);
+                    d.z = (float)log(d_div((double)gw, aw));
+                    d.w = (float)log(d_div((double)gh, ah));
+                } else {
+                    j = A;  // more GT boxes than anchors: the reference leaves anchor_idx == num_anchors
+                }
+                out_idx[(size_t)img * gmax + g] = j;
+                out_deltas[(size_t)img * gmax + g] = d;
             }
-            out_idx[(size_t)img * gmax + g] = j;
-            out_deltas[(size_t)img * gmax + g] = d;
         }
         __syncthreads();  // taken[] update visible before the next GT box
     }
+    if (cs > 1) cg::this_cluster().sync();   // nobody exits while a peer may still write its exchange slots
 }
 
 // scatter the matched rows into the (already zeroed) dense target, base.py:69-74
@@ -182,12 +222,31 @@ extern "C" int sqd_match_anchors(const float *d_gt_boxes, const int32_t *d_gt_co
                 num_anchors);
     SQD_REQUIRE(sqd_aligned16(d_gt_boxes) && sqd_aligned16(d_anchors64) && sqd_aligned16(d_deltas), SQD_E_ALIGN,
                 "sqd_match_anchors: gt_boxes/anchors/deltas must be 16-byte aligned");
-    const size_t smem = (size_t)((num_anchors + 31) / 32) * sizeof(unsigned);
+    // CTAs per image: enough to bring a GT box down to a few anchors per thread, not more than fills the GPU
+    int cs = kMaxCluster;
+    while (cs > 1 && (num_anchors / cs < 2 * kThreads || (long long)batch * cs > 4ll * SQD_SM_COUNT * 2)) cs >>= 1;
+    const int chunk = ((num_anchors + cs - 1) / cs + 31) & ~31;
+    const size_t smem = (size_t)((chunk + 31) / 32) * sizeof(unsigned);
     if (smem > 48 * 1024)
         SQD_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    match_kernel<<<batch, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float4 *>(d_gt_boxes), d_gt_count, gmax, d_anchors64, num_anchors, d_anchor_idx,
-        reinterpret_cast<float4 *>(d_deltas));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(batch * cs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, match_kernel, reinterpret_cast<const float4 *>(d_gt_boxes), d_gt_count, gmax,
+                                       d_anchors64, num_anchors, d_anchor_idx, reinterpret_cast<float4 *>(d_deltas), cs);
+    if (e != cudaSuccess) {
+        sqd_set_error("launch of match_kernel failed: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
     SQD_LAUNCH_CHECK("match_kernel");
     return SQD_OK;
 }
