@@ -469,11 +469,14 @@ __global__ void __launch_bounds__(kScanThreads) score_candidates_kernel(const fl
         extern __shared__ __align__(16) float slab[];
         const int Cn = CS > 0 ? CS : C;
         const int NF = Cn + 5;
-        const float *ipred = pred + (size_t)img * A * NF;   // 16-byte aligned (checked by the host wrapper)
+        const float *ipred = pred + (size_t)img * A * NF;
         for (int row0 = blockIdx.x * kScanThreads; row0 < A; row0 += gridDim.x * kScanThreads) {
             const int n = min(kScanThreads, A - row0);
             const float *src = ipred + (size_t)row0 * NF;
-            const int count = n * NF, nvec = count >> 2;  // slab start is 16-byte aligned: 256*NF*4 is a multiple of 16
+            // 16-byte loads when this image's rows start 16-byte aligned (256*NF*4 is a multiple of 16, so then every
+            // slab of the image is); otherwise (A*NF odd multiples of 4 bytes) plain 4-byte loads
+            const int count = n * NF;
+            const int nvec = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 ? count >> 2 : 0;
             const float4 *src4 = reinterpret_cast<const float4 *>(src);
             float4 *dst4 = reinterpret_cast<float4 *>(slab);
             for (int i = threadIdx.x; i < nvec; i += kScanThreads) dst4[i] = ld_stream_f4(src4 + i);
@@ -768,8 +771,6 @@ SqdCand sqd_cand_layout(void *ws, int batch, int num_anchors) {
 int sqd_score_candidates(const float *d_pred, int batch, int num_anchors, int num_classes, double score_thresh,
                          SqdCand cand, cudaStream_t st) {
     SQD_REQUIRE(batch <= 65535, SQD_E_SHAPE, "detect: batch %d > 65535 (split the call)", batch);
-    SQD_REQUIRE(((size_t)num_anchors * (num_classes + 5) * sizeof(float)) % 16 == 0, SQD_E_ALIGN,
-                "detect: an image of pred (%d x %d floats) is not a multiple of 16 bytes", num_anchors, num_classes + 5);
     const float sthr = (float)score_thresh;
     const int per_block = num_classes == 3 ? kScanThreads * kScanUnroll : kScanThreads;
     const int gx = (num_anchors + per_block - 1) / per_block;   // one pass per block (the in-kernel loop is for safety)

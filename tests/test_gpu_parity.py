@@ -488,3 +488,56 @@ def test_preprocess_vs_reference_golden(ops, golden):
     for b in range(2):
         np.testing.assert_allclose(out[b], orc.preprocess_image(big[b], g["mean"], g["std"], synth.KITTI.input_hw),
                                    rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------------
+# filter: maximum sizes, tie policy under massive exact ties, odd shapes (all three CUDA routes + the oracle)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,k,A,levels", [(3, 64, 5000, 3), (1, 1, 777, 2), (8, 256, 9000, 5), (32, 1024, 20000, 4),
+                                          (2, 7, 1031, 1), (20, 1024, 3000, 0)])
+def test_filter_ties_and_max_sizes(ops, C, k, A, levels):
+    """Logits quantised to a handful of values make thousands of anchors share EXACTLY the same score (levels = 1: every
+    anchor ties), so the declared tie policy (lower anchor index first) decides the top-k, the histogram select of the
+    two-phase tail overflows its buffer and falls back to the running-threshold radix select, and k = 1024 / C = 32
+    exercise the size limits.  levels = 0: continuous scores.  All routes must agree bit for bit; the oracle's filter
+    run on the CUDA dense outputs must give the same kept set."""
+    rs = np.random.RandomState(1000 + C * 7 + k)
+    B = 3
+    shp = synth.Shape("x", (96, 160), C, k)
+    pred = rs.standard_normal((B, A, C + 5)).astype(np.float32)
+    if levels:
+        pred[..., :C + 1] = np.round(pred[..., :C + 1] * levels / 2) * (2.0 / levels)
+        if levels == 1:
+            pred[..., :C + 1] = 0.5
+    pred[..., C] += 1.0                                                     # enough confidence to pass a 0.05 threshold
+    anchors = np.concatenate([rs.uniform(20, 140, (A, 1)), rs.uniform(20, 76, (A, 1)), rs.uniform(8, 60, (A, 2))], 1)
+    a32 = dev(anchors.astype(np.float32))
+    dp = dev(pred)
+    thr, nms = 0.05, 0.4
+    two = ops.detect_from_pred(dp, a32, shp.input_hw, C, k, nms, thr, two_phase=True)
+    one = ops.detect_from_pred(dp, a32, shp.input_hw, C, k, nms, thr, two_phase=False)
+    dense = ops.decode_scores(dp, a32, shp.input_hw, C)
+    unf = ops.topk_nms(dense["class_ids"], dense["scores"], dense["boxes"], C, k, nms, thr)
+    for f in ("count", "anchor", "cls", "score", "box"):
+        assert torch.equal(getattr(two, f), getattr(one, f)), f
+        assert torch.equal(getattr(two, f), getattr(unf, f)), f
+    ids, sc, bx = (dense[x].cpu().numpy() for x in ("class_ids", "scores", "boxes"))
+    expect = [orc.filter_image(ids[b], sc[b], bx[b], C, k, nms, thr) for b in range(B)]
+    _check_rows(dets_to_lists(two), expect, exact_values=True)
+    assert int(two.count.sum()) > 0
+
+
+def test_filter_nan_and_inf_inputs(ops):
+    """NaN / inf logits must not hang or corrupt anything: all CUDA routes still agree with each other."""
+    shp = synth.TINY
+    a64, a32 = anchors_dev(shp)
+    pred = synth.clustered_pred(shp, 4, 5, anchors=a64)
+    pred[0, 5, :] = np.nan
+    pred[1, 7, 3] = np.inf
+    pred[2, 9, 0] = -np.inf
+    pred[3, 11, 4:] = np.inf
+    dp = dev(pred)
+    two = ops.detect_from_pred(dp, a32, shp.input_hw, 3, shp.top_k, 0.4, 0.3, two_phase=True)
+    one = ops.detect_from_pred(dp, a32, shp.input_hw, 3, shp.top_k, 0.4, 0.3, two_phase=False)
+    assert torch.equal(two.count, one.count) and torch.equal(two.anchor, one.anchor)
+    assert int(two.count.max()) <= shp.top_k
