@@ -1,5 +1,6 @@
 // C-ABI glue: error plumbing, ConvDet algorithm dispatch, the fused head->detections entry point and
 // the boxes_postprocess epilogue.  See include/sqdet_b200.h for the contract of every symbol.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -21,7 +22,7 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
 size_t sqd_cand_bytes(int batch, int num_anchors);
 SqdCand sqd_cand_layout(void *ws, int batch, int num_anchors);
 int sqd_score_candidates(const float *d_pred, int batch, int num_anchors, int num_classes, double score_thresh,
-                         SqdCand cand, cudaStream_t st);
+                         SqdCand cand, cudaStream_t st, bool pdl);
 int sqd_detect_from_candidates(SqdCand cand, const float *d_pred, const float *d_anchors, int batch, int num_anchors,
                                int num_classes, int input_h, int input_w, int top_k, double nms_thresh,
                                double score_thresh, int32_t *d_count, int32_t *d_out_anchor, int32_t *d_out_class,
@@ -42,6 +43,11 @@ void sqd_set_error(const char *fmt, ...) {
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool sqd_pdl_enabled() {
+    const char *e = getenv("SQD_NO_PDL");
+    return !(e && atoi(e) != 0);
+}
 
 extern "C" int sqd_abi_version(void) { return SQD_ABI_VERSION; }
 extern "C" const char *sqd_last_error(void) { return g_err; }
@@ -170,7 +176,7 @@ int head_detect_impl(const float *d_feat, int layout, const void *d_packed, cons
     if (rc) return rc;
     if (ev) SQD_CUDA(cudaEventRecord(ev[0], st));
     if (!emitted) {
-        rc = sqd_score_candidates(pred, batch, A, num_classes, score_thresh, cand, st);
+        rc = sqd_score_candidates(pred, batch, A, num_classes, score_thresh, cand, st, /*pdl=*/algo != SQD_CONV_SIMT_FP32);
         if (rc) return rc;
     }
     // a8-a9 on the candidates

@@ -248,3 +248,29 @@ struct SqdCandEmit {
     float score_thr;
     int *done;   // host: set to 1 if the epilogue will emit, 0 if the caller must scan pred itself
 };
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// The path is a chain of kernels on one stream (pre-pass -> GEMM -> scan -> tail).  A kernel launched with the
+// programmatic-stream-serialization attribute may start while its predecessor is still running: its CTAs do their
+// set-up (barrier init, TMEM allocation, descriptor prefetch ...) and then block in sqd_pdl_wait() until the predecessor
+// grid has completed and its writes are visible.  The predecessor calls sqd_pdl_trigger() early to allow that.  Both
+// are no-ops for kernels launched the ordinary way.  Disabled with SQD_NO_PDL=1 (then every launch is fully serialised).
+__device__ __forceinline__ void sqd_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void sqd_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool sqd_pdl_enabled();   // api.cu (reads SQD_NO_PDL once per call)
+
+template <class K, class... Args>
+cudaError_t sqd_launch_dependent(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && sqd_pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}

@@ -440,6 +440,8 @@ __global__ void __launch_bounds__(kScanThreads) score_candidates_kernel(const fl
                                                                         float score_thr_f, SqdCand cand) {
     const u64 floor_key = score_floor_key(score_thr_f);
     const int img = blockIdx.y;
+    sqd_pdl_trigger();   // the tail kernel may be scheduled; it waits for this grid to complete
+    sqd_pdl_wait();      // pred (written by the preceding kernel of the chain) is complete and visible
     if (CS == 3) {
         // 32-byte rows: the four scoring fields are the first 16 bytes of a row
         const float4 *p4 = reinterpret_cast<const float4 *>(pred) + 2 * (size_t)img * A;
@@ -618,6 +620,7 @@ __global__ void __launch_bounds__(kThreads) detect_from_candidates_kernel(SqdCan
     __shared__ Shared sh;
     extern __shared__ __align__(16) unsigned char dyn[];
     const int img = blockIdx.x;
+    sqd_pdl_wait();      // candidate lists and pred are complete and visible
     const int n = min(cand.count[img], cand.stride);
     const u64 *keys = cand.keys + (size_t)img * cand.stride;
     FromPred<0> src;
@@ -768,23 +771,29 @@ SqdCand sqd_cand_layout(void *ws, int batch, int num_anchors) {
 }
 
 // phase 1: pred -> candidate lists (cand.count must have been zeroed on the stream)
+// pdl: the launch directly follows the kernel that produced d_pred on `st` (programmatic dependent launch)
 int sqd_score_candidates(const float *d_pred, int batch, int num_anchors, int num_classes, double score_thresh,
-                         SqdCand cand, cudaStream_t st) {
+                         SqdCand cand, cudaStream_t st, bool pdl) {
     SQD_REQUIRE(batch <= 65535, SQD_E_SHAPE, "detect: batch %d > 65535 (split the call)", batch);
     const float sthr = (float)score_thresh;
     const int per_block = num_classes == 3 ? kScanThreads * kScanUnroll : kScanThreads;
     const int gx = (num_anchors + per_block - 1) / per_block;   // one pass per block (the in-kernel loop is for safety)
     const dim3 grid((unsigned)gx, (unsigned)batch);
+    cudaError_t e;
     if (num_classes == 3) {
-        score_candidates_kernel<3><<<grid, kScanThreads, 0, st>>>(d_pred, num_anchors, 3, sthr, cand);
+        e = sqd_launch_dependent(score_candidates_kernel<3>, grid, dim3(kScanThreads), 0, st, pdl, d_pred, num_anchors, 3, sthr, cand);
     } else {
         const size_t smem = (size_t)kScanThreads * (num_classes + 5) * sizeof(float);
         if (num_classes == 8)
-            score_candidates_kernel<8><<<grid, kScanThreads, smem, st>>>(d_pred, num_anchors, 8, sthr, cand);
+            e = sqd_launch_dependent(score_candidates_kernel<8>, grid, dim3(kScanThreads), smem, st, pdl, d_pred, num_anchors, 8, sthr, cand);
         else
-            score_candidates_kernel<0><<<grid, kScanThreads, smem, st>>>(d_pred, num_anchors, num_classes, sthr, cand);
+            e = sqd_launch_dependent(score_candidates_kernel<0>, grid, dim3(kScanThreads), smem, st, pdl, d_pred, num_anchors,
+                                     num_classes, sthr, cand);
     }
-    SQD_LAUNCH_CHECK("score_candidates_kernel");
+    if (e != cudaSuccess) {
+        sqd_set_error("launch of score_candidates_kernel failed: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
     return SQD_OK;
 }
 
@@ -797,11 +806,15 @@ int sqd_detect_from_candidates(SqdCand cand, const float *d_pred, const float *d
     const size_t smem = dyn_smem_bytes(top_k);
     int rc = opt_in_smem(detect_from_candidates_kernel, smem);
     if (rc) return rc;
-    detect_from_candidates_kernel<<<batch, kThreads, smem, st>>>(cand, d_pred, reinterpret_cast<const float4 *>(d_anchors),
-                                                                 num_anchors, num_classes, (float)(input_w - 1),
-                                                                 (float)(input_h - 1), top_k, float_at_or_below(nms_thresh),
-                                                                 (float)score_thresh, o);
-    SQD_LAUNCH_CHECK("detect_from_candidates_kernel");
+    // always a dependent launch: its predecessor on the stream is the scan (or the GEMM whose epilogue scored)
+    cudaError_t e = sqd_launch_dependent(detect_from_candidates_kernel, dim3(batch), dim3(kThreads), smem, st, true, cand, d_pred,
+                                         reinterpret_cast<const float4 *>(d_anchors), num_anchors, num_classes,
+                                         (float)(input_w - 1), (float)(input_h - 1), top_k, float_at_or_below(nms_thresh),
+                                         (float)score_thresh, o);
+    if (e != cudaSuccess) {
+        sqd_set_error("launch of detect_from_candidates_kernel failed: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
     return SQD_OK;
 }
 
@@ -837,7 +850,7 @@ extern "C" int sqd_detect_from_pred(const float *d_pred, const float *d_anchors,
         SQD_REQUIRE(sqd_aligned16(d_workspace), SQD_E_ALIGN, "sqd_detect_from_pred: workspace must be 16-byte aligned");
         const SqdCand cand = sqd_cand_layout(d_workspace, batch, num_anchors);
         SQD_CUDA(cudaMemsetAsync(cand.count, 0, (size_t)batch * sizeof(int), st));
-        rc = sqd_score_candidates(d_pred, batch, num_anchors, num_classes, score_thresh, cand, st);
+        rc = sqd_score_candidates(d_pred, batch, num_anchors, num_classes, score_thresh, cand, st, false);  // follows a memset
         if (rc) return rc;
         return sqd_detect_from_candidates(cand, d_pred, d_anchors, batch, num_anchors, num_classes, input_h, input_w, top_k,
                                           nms_thresh, score_thresh, d_count, d_out_anchor, d_out_class, d_out_score,
