@@ -45,8 +45,9 @@ class Detector(object):
 
     # -- the fast path: features -> final detections, one host crossing ------------------------------
     @torch.no_grad()
-    def detect_batch(self, batch) -> ops.Detections:
-        """Device-side result for a batch {'image': (B,3,H,W)} (+ optional 'image_meta')."""
+    def detect_batch(self, batch, postprocess=True):
+        """Device-side result for a batch {'image': (B,3,H,W)} (+ optional 'image_meta'):
+        (Detections with the boxes still in network-input coordinates, (B,10) postprocess records or None)."""
         cfg = self.cfg
         base = self.model.base
         feat = base.features(batch["image"])
@@ -54,27 +55,29 @@ class Detector(object):
         det = ops.head_detect(feat, base.convdet.weight, base.convdet.bias, anchors, cfg.anchors_per_grid,
                               cfg.num_classes, cfg.input_size, cfg.keep_top_k, cfg.nms_thresh, cfg.score_thresh,
                               packed=base.packed_weights(), algo=base.conv_algo)
-        if "image_meta" in batch and batch["image_meta"]:
+        meta = None
+        if postprocess and "image_meta" in batch and batch["image_meta"]:
             meta = torch.from_numpy(_meta_record(batch["image_meta"], det.count.shape[0])).to(feat.device)
-            ops.boxes_postprocess_(det, meta)
-        return det
+        return det, meta
+
+    @torch.no_grad()
+    def detect_packed(self, batch):
+        """(packed (B,k,6) [class, score, x1,y1,x2,y2] with boxes_postprocess applied, count (B,)) on the HOST:
+        two device->host copies for the whole batch."""
+        from . import results
+        det, meta = self.detect_batch(batch)
+        return results.to_host(det, meta)
 
     @torch.no_grad()
     def detect(self, batch):
         """Reference contract, detector.py:20-50: list of {'class_ids','scores','boxes','image_meta'}
         (or {'image_meta'} only when an image keeps nothing)."""
-        det = self.detect_batch(batch)
-        rows = det.to_list()
-        results = []
+        from . import results
+        packed, count = self.detect_packed(batch)
         meta_in = batch.get("image_meta", {}) or {}
-        for b, row in enumerate(rows):
-            image_meta = {k: (v[b].cpu().numpy() if torch.is_tensor(v) else v[b]) for k, v in meta_in.items()}
-            if row is None:
-                results.append({"image_meta": image_meta})
-                continue
-            results.append({"class_ids": row["class_ids"].numpy(), "scores": row["scores"].numpy(),
-                            "boxes": row["boxes"].numpy(), "image_meta": image_meta})
-        return results
+        metas = [{k: (v[b].cpu().numpy() if torch.is_tensor(v) else v[b]) for k, v in meta_in.items()}
+                 for b in range(count.shape[0])]
+        return results.unpack(packed, count, metas)
 
     def detect_dataset(self, dataset):
         """detector.py:52-85: DataLoader loop with data / net timers (I/O glue, stock PyTorch)."""
