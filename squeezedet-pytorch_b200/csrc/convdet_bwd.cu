@@ -129,6 +129,38 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float *__restrict_
 // mirror and is the yardstick it will be checked against.
 constexpr int kWgC = 128, kWgN = 80, kWgPix = 32, kWgThreads = 320;  // 16 channel octets x 20 output quads
 constexpr int kWgXs = kWgC + 4;                                        // padded row: 16-byte aligned, conflict-free LDS.128
+constexpr int kWgXLoads = (kWgC * kWgPix + kWgThreads - 1) / kWgThreads;   // 13 scalar X loads per thread and segment
+constexpr int kWgGLoads = (kWgPix * (kWgN / 4) + kWgThreads - 1) / kWgThreads;  // 2 float4 G loads per thread and segment
+
+// Global -> register fetch of one 32-pixel segment (software pipelined: issued before the previous segment is
+// multiplied).  X: warp w covers channels w, w+10, ... of the CTA's 128, lane = pixel of the segment, shifted by the
+// tap and zero outside the image (= the conv padding).  G: 32 pixels x Cout floats as float4 (Cout % 4 == 0).
+struct WgFetch {
+    float x[kWgXLoads];
+    float4 g[kWgGLoads];
+};
+
+__device__ __forceinline__ void wg_fetch(WgFetch &f, const float *__restrict__ x, const float *__restrict__ g, int b, int y,
+                                         int x0, int dy, int dx, int c0, int cin, int gh, int gw, int cout) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ys = y + dy, xsrc = x0 + lane + dx;
+    const bool ok = ys >= 0 && ys < gh && xsrc >= 0 && xsrc < gw && x0 + lane < gw;
+    const float *xp = x + (((size_t)b * cin + c0 + warp) * gh + (ok ? ys : 0)) * gw + (ok ? xsrc : 0);
+    const size_t cstep = (size_t)(kWgThreads / 32) * gh * gw;
+#pragma unroll
+    for (int j = 0; j < kWgXLoads; ++j) {
+        const int c = warp + (kWgThreads / 32) * j;
+        f.x[j] = (ok && c < kWgC && c0 + c < cin) ? __ldg(xp + j * cstep) : 0.f;
+    }
+    const float4 *grow = reinterpret_cast<const float4 *>(g + (((size_t)b * gh + y) * gw + x0) * cout);
+    const int npix = min(kWgPix, gw - x0), q4 = cout >> 2;
+#pragma unroll
+    for (int j = 0; j < kWgGLoads; ++j) {
+        const int i = threadIdx.x + j * kWgThreads;
+        const int p = i / (kWgN / 4), q = i - p * (kWgN / 4);
+        f.g[j] = (p < npix && q < q4) ? __ldg(grow + (size_t)p * q4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
 
 __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const float *__restrict__ x, const float *__restrict__ g,
                                                                    int batch, int cin, int gh, int gw, int cout, int nslice,
@@ -139,6 +171,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const float *
     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
     const int c0 = cb * kWgC;
     const int tc = threadIdx.x & 15, tn = threadIdx.x >> 4;   // channels 4*tc.. and 64+4*tc.., outputs 4*tn..
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -146,38 +179,43 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const float *
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const int rows = batch * gh;                               // image rows in the whole batch
     const int r_begin = (int)((long long)rows * slice / nslice), r_end = (int)((long long)rows * (slice + 1) / nslice);
-    for (int r = r_begin; r < r_end; ++r) {
-        const int b = r / gh, y = r - b * gh;
-        const int ys = y + dy;                                 // source row of X
-        for (int x0 = 0; x0 < gw; x0 += kWgPix) {
-            // stage X: 32 consecutive pixels of one channel row per warp-wide load (shifted by the tap, zero outside)
-            for (int i = threadIdx.x; i < kWgC * kWgPix; i += kWgThreads) {
-                const int c = i >> 5, l = i & 31;
-                const int xsrc = x0 + l + dx;
-                const bool ok = ys >= 0 && ys < gh && xsrc >= 0 && xsrc < gw && x0 + l < gw && c0 + c < cin;
-                xs[l][c] = ok ? __ldg(x + (((size_t)b * cin + c0 + c) * gh + ys) * gw + xsrc) : 0.f;
-            }
-            // stage G: 32 pixels x cout contiguous floats (row-major), zero beyond the row end / cout
-            const float *grow = g + (((size_t)b * gh + y) * gw + x0) * cout;
-            const int npix = min(kWgPix, gw - x0);
-            for (int i = threadIdx.x; i < kWgPix * kWgN; i += kWgThreads) {
-                const int p = i / kWgN, n = i - p * kWgN;
-                gs[p][n] = (p < npix && n < cout) ? __ldg(grow + (size_t)p * cout + n) : 0.f;
-            }
-            __syncthreads();
-#pragma unroll 8
-            for (int p = 0; p < kWgPix; ++p) {
-                const float4 a = *reinterpret_cast<const float4 *>(&xs[p][4 * tc]);
-                const float4 a2 = *reinterpret_cast<const float4 *>(&xs[p][64 + 4 * tc]);
-                const float4 bq = *reinterpret_cast<const float4 *>(&gs[p][4 * tn]);
-                const float av[8] = {a.x, a.y, a.z, a.w, a2.x, a2.y, a2.z, a2.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+    const int segs_per_row = (gw + kWgPix - 1) / kWgPix;
+    const int nseg = (r_end - r_begin) * segs_per_row;
+    WgFetch f;
+    if (nseg > 0) wg_fetch(f, x, g, r_begin / gh, r_begin % gh, 0, dy, dx, c0, cin, gh, gw, cout);
+    for (int sgi = 0; sgi < nseg; ++sgi) {
+        const int r = r_begin + sgi / segs_per_row, x0 = (sgi % segs_per_row) * kWgPix;
+        const int npix = min(kWgPix, gw - x0);
+        // registers -> shared memory
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-            }
-            __syncthreads();
+        for (int j = 0; j < kWgXLoads; ++j) {
+            const int c = warp + (kWgThreads / 32) * j;
+            if (c < kWgC) xs[lane][c] = f.x[j];
         }
+#pragma unroll
+        for (int j = 0; j < kWgGLoads; ++j) {
+            const int i = threadIdx.x + j * kWgThreads;
+            const int p = i / (kWgN / 4), q = i - p * (kWgN / 4);
+            if (p < kWgPix) *reinterpret_cast<float4 *>(&gs[p][4 * q]) = f.g[j];
+        }
+        __syncthreads();
+        if (sgi + 1 < nseg) {   // next segment's loads fly while this one is multiplied
+            const int rn = r_begin + (sgi + 1) / segs_per_row;
+            wg_fetch(f, x, g, rn / gh, rn % gh, ((sgi + 1) % segs_per_row) * kWgPix, dy, dx, c0, cin, gh, gw, cout);
+        }
+#pragma unroll 2
+        for (int p = 0; p < npix; ++p) {
+            const float4 a = *reinterpret_cast<const float4 *>(&xs[p][4 * tc]);
+            const float4 a2 = *reinterpret_cast<const float4 *>(&xs[p][64 + 4 * tc]);
+            const float4 bq = *reinterpret_cast<const float4 *>(&gs[p][4 * tn]);
+            const float av[8] = {a.x, a.y, a.z, a.w, a2.x, a2.y, a2.z, a2.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+        (void)r;
     }
     // partial[slice][n][c][tap]  (the layout of the weight tensor, so the reduction is a plain strided sum)
 #pragma unroll
@@ -301,8 +339,9 @@ extern "C" size_t sqd_convdet_wgrad_workspace_bytes(int batch, int cin, int gh, 
 extern "C" int sqd_convdet_wgrad(const float *d_feat_nchw, const float *d_gpred, int batch, int cin, int gh, int gw, int cout,
                                  float *d_gweight, void *d_workspace, size_t workspace_bytes, void *stream) {
     SQD_REQUIRE(d_feat_nchw && d_gpred && d_gweight && d_workspace, SQD_E_NULL, "sqd_convdet_wgrad: NULL pointer");
-    SQD_REQUIRE(batch >= 1 && cin >= 1 && gh > 0 && gw > 0 && cout >= 1 && cout <= kWgN, SQD_E_SHAPE,
-                "sqd_convdet_wgrad: bad shape (Cout <= %d)", kWgN);
+    SQD_REQUIRE(batch >= 1 && cin >= 1 && gh > 0 && gw > 0 && cout >= 4 && cout <= kWgN && cout % 4 == 0, SQD_E_SHAPE,
+                "sqd_convdet_wgrad: bad shape (Cout a multiple of 4, <= %d)", kWgN);
+    SQD_REQUIRE(sqd_aligned16(d_gpred), SQD_E_ALIGN, "sqd_convdet_wgrad: gpred must be 16-byte aligned");
     SQD_REQUIRE(workspace_bytes >= sqd_convdet_wgrad_workspace_bytes(batch, cin, gh, gw, cout), SQD_E_WORKSPACE,
                 "sqd_convdet_wgrad: workspace too small (%zu bytes)", workspace_bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

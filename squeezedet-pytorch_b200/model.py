@@ -67,7 +67,7 @@ class _ConvDetFn(torch.autograd.Function):
             else:
                 gx = torch.nn.grad.conv2d_input(x.shape, weight, g.permute(0, 3, 1, 2), padding=1)
         if ctx.needs_input_grad[1]:
-            if weight.shape[0] <= 80:
+            if weight.shape[0] <= 80 and weight.shape[0] % 4 == 0:
                 gw = ops.convdet_wgrad(x, g)
             else:
                 gw = torch.nn.grad.conv2d_weight(x, weight.shape, g.permute(0, 3, 1, 2), padding=1)
