@@ -272,6 +272,14 @@ SQD_API int sqd_convdet_dgrad(const float *d_gpred, const void *d_dgrad_packed, 
 SQD_API size_t sqd_convdet_wgrad_workspace_bytes(int batch, int cin, int gh, int gw, int cout);
 SQD_API int sqd_convdet_wgrad(const float *d_feat_nchw, const float *d_gpred, int batch, int cin, int gh, int gw, int cout,
                               float *d_gweight, void *d_workspace, size_t workspace_bytes, void *stream);
+/* The same weight gradient on tcgen05 / TMEM (f16x3, fp32-grade): pixel-major fp16 planes of the features and of the
+ * transposed d_gpred are built in the workspace, the contraction over pixels runs as (128 channels x 80 outputs x 64
+ * pixels) MMAs with one TMEM accumulation chunk per image, slices of the batch are reduced in a fixed order.
+ * Cin % 64 == 0, Cout <= 80.  sqd_convdet_wgrad_tc_status: 0 if the last call drained cleanly (synchronises). */
+SQD_API size_t sqd_convdet_wgrad_tc_workspace_bytes(int batch, int cin, int gh, int gw, int cout);
+SQD_API int sqd_convdet_wgrad_tc(const float *d_feat_nchw, const float *d_gpred, int batch, int cin, int gh, int gw, int cout,
+                                 float *d_gweight, void *d_workspace, size_t workspace_bytes, void *stream);
+SQD_API int sqd_convdet_wgrad_tc_status(const void *d_workspace, void *stream);
 SQD_API int sqd_convdet_bias_grad(const float *d_gpred, int batch, int gh, int gw, int cout, float *d_gbias, void *stream);
 
 /* Debug aid: synchronise `stream`, return 0 if the last tcgen05 ConvDet launch on this workspace

@@ -57,6 +57,9 @@ SIGNATURES = {
     "sqd_convdet_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "sqd_convdet_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "sqd_convdet_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "sqd_convdet_wgrad_tc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "sqd_convdet_wgrad_tc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "sqd_convdet_wgrad_tc_status": (_i, [_vp, _vp]),
     "sqd_convdet_bias_grad": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "sqd_pack_results": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "sqd_format_kitti": (C.c_longlong, [_vp, _vp, _i, _i, C.POINTER(C.c_char_p), _i, _vp, _sz, _vp]),

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libsqdet_b200.so")
-SOURCES = ["api.cu", "io_kernels.cu", "decode.cu", "topk_nms.cu", "matcher.cu", "loss.cu", "convdet_simt.cu", "convdet_f16.cu", "convdet_bwd.cu"]
+SOURCES = ["api.cu", "io_kernels.cu", "decode.cu", "topk_nms.cu", "matcher.cu", "loss.cu", "convdet_simt.cu", "convdet_f16.cu", "convdet_bwd.cu", "convdet_wgrad_tc.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
          "-I", os.path.join(ROOT, "include"), "-I", HERE]

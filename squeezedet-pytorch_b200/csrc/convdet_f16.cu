@@ -1633,6 +1633,18 @@ int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, 
     return SQD_OK;
 }
 
+// max |x| of `nruns` contiguous runs of run_floats fp32 values (d_amax zeroed by the caller); used by the wgrad pre-pass
+int sqd_f16_absmax_runs(const float *d_in, size_t run_floats, int nruns, unsigned *d_amax, cudaStream_t st) {
+    SQD_REQUIRE(run_floats % 4 == 0 && nruns >= 1 && nruns <= 65535, SQD_E_SHAPE, "absmax: bad run shape");
+    const size_t n4 = run_floats / 4;
+    int bx = (int)((n4 + 256 * 8 - 1) / (256 * 8));
+    if (bx > 8) bx = 8;
+    if (bx < 1) bx = 1;
+    absmax_kernel<<<dim3(bx, nruns), 256, 0, st>>>(reinterpret_cast<const float4 *>(d_in), n4, d_amax);
+    SQD_LAUNCH_CHECK("absmax_kernel");
+    return SQD_OK;
+}
+
 size_t sqd_f16_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout) {
     return ws_layout(batch, cin, gh, gw, cout, layout).total;
 }

@@ -1,0 +1,520 @@
+// SURVEY 8(f) rank 2, second half: ConvDet WEIGHT gradient on tcgen05 / TMEM (sm_100a), f16x3 numerics.
+// Reference: autograd through nn.Conv2d(768, 72, 3, padding=1), src/model/squeezedet.py:73-75 (cuDNN wgrad there).
+//
+//   dW[n,c,dy,dx] = sum_{b,y,x} G[b,y,x,n] * X[b,c,y+dy-1,x+dx-1]
+// Per tap (dy,dx) this is a GEMM  D[c, n] = sum_pixels Xshift[c, pix] * G[pix, n]  whose contraction runs over PIXELS, so
+// both operands must be pixel-contiguous ("K-major" in UMMA terms), and TMA dictates how (measured, tools/micro/tma_box.cu:
+// with SWIZZLE_128B the innermost box extent must be the full 128 B, and the innermost start coordinate must be 16-byte
+// aligned -- a one-pixel tap shift cannot be a box origin):
+//   * every image plane is stored FLAT with rows padded by at least one zero column to gwp (a multiple of 8): pixel
+//     (y,x) -> j = y*gwp + x.  A K tile is 64 consecutive flat pixels.  Thanks to the zero pad columns a flat shift by
+//     (dy-1)*gwp + (dx-1) equals the 2-D shift with zero padding; shifts past either end are TMA out-of-bounds zeros.
+//   * A (M = 128 channels x K = 64 pixels): NCHW fp16 planes of the features, 3-D box {64 px, 128 ch, 1 img} at the
+//     aligned origin 64*t: 128 rows of 128 B = one SWIZZLE_128B K-major tile.  Never shifted.
+//   * B (N = 80 outputs x K = 64 pixels): G transposed to (B, 80, P_pad) planes; the tap moves G instead of X:
+//     G^T[n, q - off].  The row part of the shift, (dy-1)*gwp, is a multiple of 8 and goes into the box origin; the
+//     column part (dx-1) needs THREE pre-shifted copies of the (small) G^T planes.  [g2 | g1] are two boxes stacked.
+// Numerics as in the forward (convdet_f16.cu): x*s = x1 + x2/2^11, g*t = g1 + g2/2^11 with power-of-two scales per
+// (image, 64-channel block) and per (image, 64-output block); per K step of 16 pixels two MMAs
+//     D[:, 0:160] (+)= X1 * [g2 | g1]^T        D[:, 0:80] += X2 * g1^T
+// A TMEM accumulation chunk = the pixel tiles of ONE image (<= 30 tiles x 4 K steps): the scales are uniform inside it,
+// and the accumulate warps fold it into fp32 registers with the row's 1/s (channel block) and the column's 1/t.
+// Work item = (128-channel block, tap, slice of the batch's pixel tiles); slices write fp32 partials that a second
+// kernel adds in a fixed order (deterministic).  Both operands stream (no operand is reused across K), so the kernel
+// is L2 -> SM bound, not tensor bound: 52 KB per 64-pixel step per CTA.
+// Warp roles (192 threads): 0 TMA producer, 1 TMEM alloc + MMA issue, 2..5 accumulate.  Every wait is bounded.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+using namespace sqd_tc;
+
+constexpr int kMTile = 128;            // channels per work item (UMMA_M)
+constexpr int kNPad = 80;              // outputs, padded (Cout <= 80)
+constexpr int kPixTile = 64;            // K tile = 64 flat pixels = one 128-byte swizzle row of fp16
+constexpr int kABytes = kMTile * 128;  // one plane of one stage (16 KB)
+constexpr int kBBytes = kNPad * 128;   // one plane of G^T (10 KB)
+constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;   // x1 | x2 | g2 | g1 = 52 KB
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+constexpr int kAccCols = 2 * kNPad;    // [cross | main]
+constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+
+__device__ __forceinline__ float pow2_scale_for(float amax) {   // must match convdet_f16.cu
+    if (!(amax > 0.f) || amax > 3.0e38f) return 1.f;
+    int ex;
+    frexpf(amax, &ex);
+    int e = 14 - ex;
+    e = e < -126 ? -126 : (e > 126 ? 126 : e);
+    return ldexpf(1.f, e);
+}
+
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// ---- operand preparation ---------------------------------------------------------------------------------------------
+// X (B,Cin,gh,gw) fp32 -> x1 / x2 fp16 planes (B,Cin,gh,gwp), same NCHW order, rows zero-padded to gwp; scale per
+// (image, 64-channel block) from amax (computed by absmax over the contiguous slab).
+__global__ void __launch_bounds__(256) split_nchw_rows_kernel(const float *__restrict__ x, int cin, int gh, int gw, int gwp,
+                                                              const unsigned *__restrict__ amax_bits, __half *__restrict__ p1,
+                                                              __half *__restrict__ p2, size_t total_rows) {
+    // one warp per (b, c, y) row: lanes cover the gwp columns
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    const int lane = threadIdx.x & 31;
+    const size_t bc = row / gh;                      // b*cin + c
+    const int b = (int)(bc / cin), c = (int)(bc - (size_t)b * cin);
+    const float s = pow2_scale_for(__uint_as_float(amax_bits[(size_t)b * (cin >> 6) + (c >> 6)]));
+    const float *src = x + row * gw;
+    for (int col = lane; col < gwp; col += 32) {
+        const float xs = col < gw ? __ldg(src + col) * s : 0.f;
+        const __half h1 = __float2half_rn(xs);
+        const __half h2 = __float2half_rn((xs - __half2float(h1)) * kLoScale);
+        p1[row * gwp + col] = h1;
+        p2[row * gwp + col] = h2;
+    }
+}
+
+// max |g| per (image, 64-output block): grid (chunks, B)
+__global__ void __launch_bounds__(256) g_absmax_kernel(const float *__restrict__ g, int P, int cout, unsigned *__restrict__ amax_bits) {
+    __shared__ unsigned s_max[2];
+    if (threadIdx.x < 2) s_max[threadIdx.x] = 0u;
+    __syncthreads();
+    const int b = blockIdx.y;
+    const float *src = g + (size_t)b * P * cout;
+    float m0 = 0.f, m1 = 0.f;
+    for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < P; cell += gridDim.x * blockDim.x) {
+        for (int n = 0; n < cout; ++n) {
+            const float v = fabsf(__ldg(src + (size_t)cell * cout + n));
+            if (n < 64) m0 = fmaxf(m0, v); else m1 = fmaxf(m1, v);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&s_max[0], __float_as_uint(m0));
+        atomicMax(&s_max[1], __float_as_uint(m1));
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) atomicMax(amax_bits + (size_t)b * 2 + threadIdx.x, s_max[threadIdx.x]);
+}
+
+// G (B, gh*gw, cout) fp32 -> three column-shifted copies e = 0,1,2 (shift e-1) of the transposed fp16 planes
+// (3, B, 80, gh*gwp):  copy_e[b][n][j] = G^T[b][n][j - (e-1)]  (zero outside the image, in pad columns, for n >= cout)
+__global__ void __launch_bounds__(256) g_transpose_split_kernel(const float *__restrict__ g, int gh, int gw, int gwp, int cout,
+                                                                int batch, const unsigned *__restrict__ amax_bits,
+                                                                __half *__restrict__ p1, __half *__restrict__ p2, size_t total) {
+    const int ppad = gh * gwp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % ppad);
+        size_t r = i / ppad;
+        const int n = (int)(r % kNPad);
+        r /= kNPad;
+        const int b = (int)(r % batch), e = (int)(r / batch);
+        const int src = j - (e - 1);
+        float xs = 0.f;
+        if (n < cout && src >= 0 && src < ppad) {
+            const int y = src / gwp, col = src - y * gwp;
+            if (col < gw) {
+                const float t = pow2_scale_for(__uint_as_float(amax_bits[(size_t)b * 2 + (n >> 6)]));
+                xs = __ldg(g + (((size_t)b * gh + y) * gw + col) * cout + n) * t;
+            }
+        }
+        const __half h1 = __float2half_rn(xs);
+        const __half h2 = __float2half_rn((xs - __half2float(h1)) * kLoScale);
+        p1[i] = h1;
+        p2[i] = h2;
+    }
+}
+
+// ---- main kernel -----------------------------------------------------------------------------------------------------
+struct WgParams {
+    int cin, gh, gw, cout, batch;
+    int gwp, tiles_per_img;          // padded row length; 64-pixel tiles per image = ceil(gh*gwp / 64)
+    int total_tiles;                 // batch * tiles_per_img
+    int nslice;
+    int dbg;                         // debug (SQD_WG_DBG): 1 skip MMAs, 2 skip TMA loads, 4 skip TMEM drain, 8 skip partial store
+    const unsigned *amax_x;          // (B, Cin/64)
+    const unsigned *amax_g;          // (B, 2)
+    float *partial;                  // (nslice, 9, Cin, 80)
+    int *status;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
+                const __grid_constant__ CUtensorMap map_g1a, const __grid_constant__ CUtensorMap map_g1b,
+                const __grid_constant__ CUtensorMap map_g1c, const __grid_constant__ CUtensorMap map_g2a,
+                const __grid_constant__ CUtensorMap map_g2b, const __grid_constant__ CUtensorMap map_g2c, const WgParams p) {
+    constexpr uint32_t kIdescCat = umma_idesc_f16(128, 2 * kNPad);
+    constexpr uint32_t kIdescOne = umma_idesc_f16(128, kNPad);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *ctrl = smem + (size_t)kStages * kStageBytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ctrl);      // [4]
+    uint64_t *empty = full + 4;                               // [4]
+    uint64_t *tmem_full = empty + 4;                          // [2]
+    uint64_t *tmem_empty = tmem_full + 2;                     // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    volatile int *abort_flag = reinterpret_cast<volatile int *>(tmem_slot + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = blockIdx.x, tap = blockIdx.y, slice = blockIdx.z;
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const int k0 = (int)((long long)p.total_tiles * slice / p.nslice), k1 = (int)((long long)p.total_tiles * (slice + 1) / p.nslice);
+    const int ntiles = k1 - k0;
+
+    if (threadIdx.x == 0) {
+        *abort_flag = 0;
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tmem_full + b, 1);
+            mbar_init(tmem_empty + b, 4);
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    // the column part of the tap shift selects one of the three pre-shifted copies of G^T
+    const CUtensorMap *map_g1 = dx < 0 ? &map_g1a : (dx == 0 ? &map_g1b : &map_g1c);
+    const CUtensorMap *map_g2 = dx < 0 ? &map_g2a : (dx == 0 ? &map_g2b : &map_g2c);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x1);
+        tma_prefetch_desc(&map_x2);
+        tma_prefetch_desc(map_g1);
+        tma_prefetch_desc(map_g2);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: x1 | x2 (shifted by the tap) | g2 | g1 of one 64-pixel tile per stage =====
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < ntiles; ++i) {
+            const int kt = k0 + i;
+            const int img = kt / p.tiles_per_img, t = kt - img * p.tiles_per_img;
+            if (!mbar_wait_warp(empty + s, ph ^ 1u, abort_flag)) {
+                if (lane == 0) atomicCAS(p.status, 0, 1);
+                break;
+            }
+            if (elect_one_sync()) {
+                uint8_t *st = smem + (size_t)s * kStageBytes;
+                if (p.dbg & 2) {
+                    mbar_arrive(full + s);
+                    goto next_stage;
+                }
+                mbar_arrive_expect_tx(full + s, kStageBytes);
+                const int q0 = t * kPixTile;                 // flat pixel origin of the X tile (16-byte aligned)
+                const int g0 = q0 - dy * p.gwp;              // G^T origin: the row part of the tap shift (multiple of 8)
+                tma_load_3d(&map_x1, full + s, st, q0, mt * kMTile, img);
+                tma_load_3d(&map_x2, full + s, st + kABytes, q0, mt * kMTile, img);
+                tma_load_3d(map_g2, full + s, st + 2 * kABytes, g0, 0, img);
+                tma_load_3d(map_g1, full + s, st + 2 * kABytes + kBBytes, g0, 0, img);
+            }
+        next_stage:
+            __syncwarp();
+            if (++s == kStages) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: 8 MMAs per tile; a chunk (= the tiles of one image) accumulates in one TMEM buffer =====
+        int s = 0, chunk = 0;
+        uint32_t ph = 0;
+        bool fresh = true;
+        for (int i = 0; i < ntiles; ++i) {
+            const int kt = k0 + i;
+            const int img = kt / p.tiles_per_img;
+            const bool chunk_end = (i == ntiles - 1) || ((kt + 1) / p.tiles_per_img != img);
+            const int buf = chunk & 1;
+            if (fresh) {
+                if (!mbar_wait_warp(tmem_empty + buf, (((uint32_t)(chunk >> 1)) & 1u) ^ 1u, abort_flag)) {
+                    if (lane == 0) atomicCAS(p.status, 0, 4);
+                    break;
+                }
+            }
+            if (!mbar_wait_warp(full + s, ph, abort_flag)) {
+                if (lane == 0) atomicCAS(p.status, 0, 2);
+                break;
+            }
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)buf * kAccCols;
+            const uint32_t st = smem_u32(smem + (size_t)s * kStageBytes);
+            const uint64_t a1 = umma_desc_sw128(st), a2 = umma_desc_sw128(st + kABytes);
+            const uint64_t b_cat = umma_desc_sw128(st + 2 * kABytes), b_g1 = umma_desc_sw128(st + 2 * kABytes + kBBytes);
+            if (elect_one_sync()) {
+#pragma unroll
+                for (int ks = 0; ks < 4 && !(p.dbg & 1); ++ks) {
+                    const uint64_t adv = (uint64_t)((ks * 32) >> 4);   // +32 B per K step of 16 pixels
+                    umma_f16_ss(d_tmem, a1 + adv, b_cat + adv, kIdescCat, (fresh && ks == 0) ? 0u : 1u);
+                    umma_f16_ss(d_tmem, a2 + adv, b_g1 + adv, kIdescOne, 1u);
+                }
+                umma_commit(empty + s);
+                if (chunk_end) umma_commit(tmem_full + buf);
+            }
+            __syncwarp();
+            fresh = chunk_end;
+            if (chunk_end) ++chunk;
+            if (++s == kStages) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
+    } else {
+        // ===== accumulate warps: TMEM chunk -> fp32 registers with the image's scales divided out =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                 // channel inside the 128-channel block
+        const int c = mt * kMTile + row;
+        float acc[kNPad];
+#pragma unroll
+        for (int n = 0; n < kNPad; ++n) acc[n] = 0.f;
+        int chunk = 0;
+        for (int i = 0; i < ntiles; ++i) {
+            const int kt = k0 + i;
+            const int img = kt / p.tiles_per_img;
+            const bool chunk_end = (i == ntiles - 1) || ((kt + 1) / p.tiles_per_img != img);
+            if (!chunk_end) continue;
+            const int buf = chunk & 1;
+            const uint32_t ph = ((uint32_t)(chunk >> 1)) & 1u;
+            ++chunk;
+            if (!mbar_wait_warp(tmem_full + buf, ph, abort_flag)) {
+                if (lane == 0) atomicCAS(p.status, 0, 3);
+                break;
+            }
+            tc_fence_after();
+            __syncwarp();
+            const int ncb = p.cin >> 6;
+            const float inv_x = c < p.cin ? 1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_x + (size_t)img * ncb + (c >> 6)))) : 0.f;
+            const float inv_g0 = 1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_g + (size_t)img * 2)));
+            const float inv_g1 = 1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_g + (size_t)img * 2 + 1)));
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * kAccCols;
+#pragma unroll
+            for (int n0 = 0; n0 < kNPad && !(p.dbg & 4); n0 += 16) {
+                uint32_t v[16], w[16];
+                tmem_ld_x16(taddr + n0, v);            // x1*g2 + x2*g1   (x 2^11)
+                tmem_ld_x16(taddr + kNPad + n0, w);    // x1*g1
+                tmem_ld_wait();
+                const float inv_g = n0 < 64 ? inv_g0 : inv_g1;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float t = fmaf(__uint_as_float(v[k]), kLoInv, __uint_as_float(w[k])) * inv_x;   // exact scaling
+                    acc[n0 + k] = fmaf(t, inv_g, acc[n0 + k]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + buf);
+        }
+        if (c < p.cin && !(p.dbg & 8)) {
+            float4 *dst = reinterpret_cast<float4 *>(p.partial + (((size_t)slice * 9 + tap) * p.cin + c) * kNPad);
+#pragma unroll
+            for (int n = 0; n < kNPad; n += 4) dst[n >> 2] = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// dW[n][c][tap] = sum_slices partial[slice][tap][c][n]   (fixed order)
+__global__ void wgrad_tc_reduce_kernel(const float *__restrict__ partial, int nslice, int cin, int cout, float *__restrict__ gw_out) {
+    const size_t n_out = (size_t)cout * cin * 9;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (size_t)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % 9);
+        const size_t r = i / 9;
+        const int c = (int)(r % cin), n = (int)(r / cin);
+        float s = 0.f;
+        for (int k = 0; k < nslice; ++k) s += partial[(((size_t)k * 9 + tap) * cin + c) * kNPad + n];
+        gw_out[i] = s;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+    return fn;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+int gwp_of(int gw) { return (gw + 1 + 7) & ~7; }   // at least one zero pad column, rows a multiple of 16 bytes
+
+// debug aid (SQD_WG_SYNC=1): synchronise after every stage so that a faulting kernel is named
+int stage_check(const char *what, cudaStream_t st) {
+    const char *e = getenv("SQD_WG_SYNC");
+    if (!e || atoi(e) == 0) return SQD_OK;
+    cudaError_t err = cudaStreamSynchronize(st);
+    if (err == cudaSuccess) err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        sqd_set_error("wgrad_tc stage '%s' failed: %s", what, cudaGetErrorString(err));
+        return (int)err;
+    }
+    return SQD_OK;
+}
+
+struct WgWs {
+    size_t status_off, amax_x_off, amax_g_off, x1_off, x2_off, g1_off, g2_off, partial_off, total;
+    int nslice;
+};
+WgWs wg_ws(int batch, int cin, int gh, int gw) {
+    WgWs w;
+    const int gwp = gwp_of(gw);
+    const int tiles = batch * ((gh * gwp + kPixTile - 1) / kPixTile);
+    // slices: enough CTAs for ~3 waves of (Cin/128 x 9) work items, at least ~8 pixel tiles each
+    const int items = ((cin + kMTile - 1) / kMTile) * 9;
+    int ns = (3 * SQD_SM_COUNT + items - 1) / items;
+    if (ns > tiles / 8) ns = tiles / 8;
+    if (ns < 1) ns = 1;
+    w.nslice = ns;
+    size_t off = 0;
+    w.status_off = off;  off += 256;
+    w.amax_x_off = off;  off += align256((size_t)batch * (cin / 64) * sizeof(unsigned));
+    w.amax_g_off = off;  off += align256((size_t)batch * 2 * sizeof(unsigned));
+    const size_t xplane = align256((size_t)batch * cin * gh * gwp * sizeof(__half));
+    const size_t gplane = align256((size_t)3 * batch * kNPad * gh * gwp * sizeof(__half));   // three column shifts
+    w.x1_off = off;  off += xplane;
+    w.x2_off = off;  off += xplane;
+    w.g1_off = off;  off += gplane;
+    w.g2_off = off;  off += gplane;
+    w.partial_off = off;  off += align256((size_t)ns * 9 * cin * kNPad * sizeof(float));
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+
+// implemented in convdet_f16.cu: max |x| of contiguous runs (one per blockIdx.y)
+int sqd_f16_absmax_runs(const float *d_in, size_t run_floats, int nruns, unsigned *d_amax, cudaStream_t st);
+
+extern "C" size_t sqd_convdet_wgrad_tc_workspace_bytes(int batch, int cin, int gh, int gw, int cout) {
+    if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0) return 256;
+    return wg_ws(batch, cin, gh, gw).total;
+}
+
+extern "C" int sqd_convdet_wgrad_tc(const float *d_feat_nchw, const float *d_gpred, int batch, int cin, int gh, int gw, int cout,
+                                    float *d_gweight, void *d_workspace, size_t workspace_bytes, void *stream) {
+    SQD_REQUIRE(d_feat_nchw && d_gpred && d_gweight && d_workspace, SQD_E_NULL, "sqd_convdet_wgrad_tc: NULL pointer");
+    SQD_REQUIRE(batch >= 1 && cin >= 64 && cin % 64 == 0 && gh > 0 && gw > 0 && cout >= 1 && cout <= kNPad, SQD_E_SHAPE,
+                "sqd_convdet_wgrad_tc: bad shape (Cin a multiple of 64, Cout <= %d)", kNPad);
+    SQD_REQUIRE(sqd_aligned16(d_workspace), SQD_E_ALIGN, "sqd_convdet_wgrad_tc: workspace must be 16-byte aligned");
+    const WgWs w = wg_ws(batch, cin, gh, gw);
+    SQD_REQUIRE(workspace_bytes >= w.total, SQD_E_WORKSPACE, "sqd_convdet_wgrad_tc: workspace too small (%zu < %zu bytes)",
+                workspace_bytes, w.total);
+    EncodeTiledFn encode = get_encode_fn();
+    SQD_REQUIRE(encode != nullptr, SQD_E_DRIVER, "cuTensorMapEncodeTiled not available from the CUDA driver");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char *ws = static_cast<char *>(d_workspace);
+    const int gwp = gwp_of(gw), P = gh * gw, ncb = cin / 64;
+    unsigned *amax_x = reinterpret_cast<unsigned *>(ws + w.amax_x_off), *amax_g = reinterpret_cast<unsigned *>(ws + w.amax_g_off);
+    __half *x1 = reinterpret_cast<__half *>(ws + w.x1_off), *x2 = reinterpret_cast<__half *>(ws + w.x2_off);
+    __half *g1 = reinterpret_cast<__half *>(ws + w.g1_off), *g2 = reinterpret_cast<__half *>(ws + w.g2_off);
+    SQD_CUDA(cudaMemsetAsync(ws, 0, w.x1_off, st));   // status + both amax arrays
+
+    // 1. operands: pixel-major fp16 planes
+    int rc = sqd_f16_absmax_runs(d_feat_nchw, (size_t)64 * P, batch * ncb, amax_x, st);
+    if (rc) return rc;
+    if ((rc = stage_check("absmax x", st))) return rc;
+    {
+        const size_t rows = (size_t)batch * cin * gh;
+        split_nchw_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(d_feat_nchw, cin, gh, gw, gwp, amax_x, x1, x2, rows);
+        SQD_LAUNCH_CHECK("split_nchw_rows_kernel");
+        if ((rc = stage_check("split x", st))) return rc;
+    }
+    g_absmax_kernel<<<dim3(8, batch), 256, 0, st>>>(d_gpred, P, cout, amax_g);
+    SQD_LAUNCH_CHECK("g_absmax_kernel");
+    if ((rc = stage_check("absmax g", st))) return rc;
+    {
+        const size_t total = (size_t)3 * batch * kNPad * gh * gwp;
+        int gx = (int)((total + 255) / 256);
+        if (gx > SQD_SM_COUNT * 16) gx = SQD_SM_COUNT * 16;
+        g_transpose_split_kernel<<<gx, 256, 0, st>>>(d_gpred, gh, gw, gwp, cout, batch, amax_g, g1, g2, total);
+        SQD_LAUNCH_CHECK("g_transpose_split_kernel");
+        if ((rc = stage_check("transpose g", st))) return rc;
+    }
+
+    // 2. tensor maps over the flat planes: {padded pixel, channel / output, image}; maps 2..4 = g1 shifted -1,0,+1, 5..7 = g2
+    alignas(64) CUtensorMap maps[8];
+    const size_t ppad = (size_t)gh * gwp;
+    for (int i = 0; i < 8; ++i) {
+        const int chan = i < 2 ? cin : kNPad;
+        void *base = i == 0 ? (void *)x1 : i == 1 ? (void *)x2
+                   : i < 5 ? (void *)(g1 + (size_t)(i - 2) * batch * kNPad * ppad) : (void *)(g2 + (size_t)(i - 5) * batch * kNPad * ppad);
+        const cuuint64_t dims[3] = {(cuuint64_t)ppad, (cuuint64_t)chan, (cuuint64_t)batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)ppad * 2, (cuuint64_t)chan * ppad * 2};
+        const cuuint32_t box[3] = {kPixTile, (cuuint32_t)(i < 2 ? kMTile : kNPad), 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SQD_REQUIRE(r == CUDA_SUCCESS, SQD_E_DRIVER, "cuTensorMapEncodeTiled(wgrad operand %d) failed: CUresult %d", i, (int)r);
+    }
+
+    // 3. the GEMM and the fixed-order reduction
+    WgParams p;
+    p.cin = cin; p.gh = gh; p.gw = gw; p.cout = cout; p.batch = batch;
+    p.gwp = gwp;
+    p.tiles_per_img = (gh * gwp + kPixTile - 1) / kPixTile;
+    p.total_tiles = batch * p.tiles_per_img;
+    p.nslice = w.nslice;
+    p.dbg = getenv("SQD_WG_DBG") ? atoi(getenv("SQD_WG_DBG")) : 0;
+    p.amax_x = amax_x;
+    p.amax_g = amax_g;
+    p.partial = reinterpret_cast<float *>(ws + w.partial_off);
+    p.status = reinterpret_cast<int *>(ws + w.status_off);
+    const size_t smem = 1024 + (size_t)kStages * kStageBytes + 1024;
+    SQD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const dim3 grid((cin + kMTile - 1) / kMTile, 9, w.nslice);
+    wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
+    SQD_LAUNCH_CHECK("wgrad_tc_kernel");
+    if ((rc = stage_check("gemm", st))) return rc;
+    const size_t n_out = (size_t)cout * cin * 9;
+    wgrad_tc_reduce_kernel<<<(int)((n_out + 255) / 256), 256, 0, st>>>(p.partial, w.nslice, cin, cout, d_gweight);
+    SQD_LAUNCH_CHECK("wgrad_tc_reduce_kernel");
+    if ((rc = stage_check("reduce", st))) return rc;
+    return SQD_OK;
+}
+
+// 0 = the last sqd_convdet_wgrad_tc on this workspace drained cleanly (synchronises the stream)
+extern "C" int sqd_convdet_wgrad_tc_status(const void *d_workspace, void *stream) {
+    SQD_REQUIRE(d_workspace, SQD_E_NULL, "sqd_convdet_wgrad_tc_status: NULL workspace");
+    int h = -1;
+    SQD_CUDA(cudaMemcpyAsync(&h, d_workspace, sizeof(int), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    SQD_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    if (h != 0) sqd_set_error("tcgen05 wgrad pipeline timed out (role %d)", h);
+    return h;
+}

@@ -122,15 +122,23 @@ def convdet_dgrad(gpred, weight, dgrad_packed=None):
     return out.permute(0, 3, 1, 2)
 
 
-def convdet_wgrad(feat, gpred):
-    """feat (B,Cin,gh,gw) NCHW fp32, gpred (B,gh,gw,Cout) -> gradient of the ConvDet weight (Cout,Cin,3,3)."""
+def convdet_wgrad(feat, gpred, tensor_cores=True, check_status=False):
+    """feat (B,Cin,gh,gw) NCHW fp32, gpred (B,gh,gw,Cout) -> gradient of the ConvDet weight (Cout,Cin,3,3).
+    tensor_cores: the tcgen05 f16x3 kernel (Cin % 64 == 0); otherwise the fp32 CUDA-core kernel (Cout % 4 == 0)."""
     lib = load()
     x = feat.detach().contiguous().float()
     g = gpred.contiguous().float()
     B, cin, gh, gw = x.shape
     cout = g.shape[-1]
-    ws = workspace().get("convdet_wgrad", lib.sqd_convdet_wgrad_workspace_bytes(B, cin, gh, gw, cout), g.device)
     out = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=g.device)
+    if tensor_cores and cin % 64 == 0:
+        ws = workspace().get("convdet_wgrad_tc", lib.sqd_convdet_wgrad_tc_workspace_bytes(B, cin, gh, gw, cout), g.device)
+        check(lib.sqd_convdet_wgrad_tc(ptr(x), ptr(g), B, cin, gh, gw, cout, ptr(out), ptr(ws), ws.numel(),
+                                       stream_ptr(g.device)), "sqd_convdet_wgrad_tc")
+        if check_status:
+            check(lib.sqd_convdet_wgrad_tc_status(ptr(ws), stream_ptr(g.device)), "sqd_convdet_wgrad_tc_status")
+        return out
+    ws = workspace().get("convdet_wgrad", lib.sqd_convdet_wgrad_workspace_bytes(B, cin, gh, gw, cout), g.device)
     check(lib.sqd_convdet_wgrad(ptr(x), ptr(g), B, cin, gh, gw, cout, ptr(out), ptr(ws), ws.numel(), stream_ptr(g.device)),
           "sqd_convdet_wgrad")
     return out

@@ -273,15 +273,17 @@ def test_convdet_dgrad_and_bias_grad(ops, name, batch):
     # weight gradient (fp32 CUDA-core kernel, fixed-order reduction): deterministic and as accurate as torch's fp32
     _, gw32, _ = orc.convdet_backward(feat, w, g)
     _, gw64, _ = orc.convdet_backward(feat, w, g, dtype=np.float64)
-    gw1 = ops.convdet_wgrad(dev(feat), dev(g))
-    gw2 = ops.convdet_wgrad(dev(feat), dev(g))
-    assert torch.equal(gw1, gw2)
-    gw1 = gw1.cpu().numpy()
     wscale = np.abs(gw64).mean()
-    e_ours, e_ref = np.abs(gw1 - gw64).max() / wscale, np.abs(gw32 - gw64).max() / wscale
-    print(f"wgrad vs float64: ours max {e_ours:.2e}, torch-cpu fp32 max {e_ref:.2e} (relative to mean |dW|)")
-    np.testing.assert_allclose(gw1, gw32, rtol=1e-4, atol=1e-4 * wscale)
-    assert e_ours < 4 * e_ref + 1e-5
+    e_ref = np.abs(gw32 - gw64).max() / wscale
+    for tc in (False, True):   # fp32 CUDA-core kernel, tcgen05 f16x3 kernel
+        gw1 = ops.convdet_wgrad(dev(feat), dev(g), tensor_cores=tc, check_status=True)
+        gw2 = ops.convdet_wgrad(dev(feat), dev(g), tensor_cores=tc, check_status=True)
+        assert torch.equal(gw1, gw2)
+        gw1 = gw1.cpu().numpy()
+        e_ours = np.abs(gw1 - gw64).max() / wscale
+        print(f"wgrad ({'tcgen05' if tc else 'simt'}) vs float64: ours max {e_ours:.2e}, torch-cpu fp32 max {e_ref:.2e} (rel. to mean |dW|)")
+        np.testing.assert_allclose(gw1, gw32, rtol=1e-4, atol=1e-4 * wscale)
+        assert e_ours < 4 * e_ref + 1e-5
 
 
 def test_training_backward_is_native(ops):

@@ -39,11 +39,12 @@ pred, t_fwd = timed(lambda: ops.convdet_forward(feat, w, b, packed=packed, num_f
 (losses, dpred), t_loss = timed(lambda: ops.loss_fwd_bwd(pred, gt, a32, shp.input_hw, shp.num_classes, (1.0, 3.75, 100.0, 6.0)))
 g = dpred.view(B, *shp.grid_hw, shp.out_channels)
 _, t_dgrad = timed(lambda: ops.convdet_dgrad(g, w, dpacked))
-_, t_wgrad = timed(lambda: ops.convdet_wgrad(feat, g))
+_, t_wgrad = timed(lambda: ops.convdet_wgrad(feat, g, tensor_cores=False))
+_, t_wgrad_tc = timed(lambda: ops.convdet_wgrad(feat, g, tensor_cores=True))
 _, t_bgrad = timed(lambda: ops.convdet_bias_grad(g))
 gchw = g.permute(0, 3, 1, 2).contiguous()
 torch.backends.cudnn.allow_tf32 = False
 _, t_dgrad_t = timed(lambda: torch.nn.grad.conv2d_input(feat.shape, w, gchw, padding=1))
 _, t_wgrad_t = timed(lambda: torch.nn.grad.conv2d_weight(feat, w.shape, gchw, padding=1))
 print(f"batch {B} KITTI, us: matcher+targets {t_match:.1f} | convdet fwd {t_fwd:.1f} | loss fwd+bwd {t_loss:.1f} | "
-      f"dgrad {t_dgrad:.1f} (cuDNN fp32 {t_dgrad_t:.1f}) | wgrad {t_wgrad:.1f} (cuDNN fp32 {t_wgrad_t:.1f}) | bias grad {t_bgrad:.1f}")
+      f"dgrad {t_dgrad:.1f} (cuDNN fp32 {t_dgrad_t:.1f}) | wgrad simt {t_wgrad:.1f} / tcgen05 {t_wgrad_tc:.1f} (cuDNN fp32 {t_wgrad_t:.1f}) | bias grad {t_bgrad:.1f}")
