@@ -70,22 +70,24 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uin
 // X (B,Cin,gh,gw) fp32 -> x1 / x2 fp16 planes (B,Cin,gh,gwp), same NCHW order, rows zero-padded to gwp; scale per
 // (image, 64-channel block) from amax (computed by absmax over the contiguous slab).
 __global__ void __launch_bounds__(256) split_nchw_rows_kernel(const float *__restrict__ x, int cin, int gh, int gw, int gwp,
-                                                              const unsigned *__restrict__ amax_bits, __half *__restrict__ p1,
-                                                              __half *__restrict__ p2, size_t total_rows) {
-    // one warp per (b, c, y) row: lanes cover the gwp columns
-    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= total_rows) return;
-    const int lane = threadIdx.x & 31;
-    const size_t bc = row / gh;                      // b*cin + c
-    const int b = (int)(bc / cin), c = (int)(bc - (size_t)b * cin);
-    const float s = pow2_scale_for(__uint_as_float(amax_bits[(size_t)b * (cin >> 6) + (c >> 6)]));
-    const float *src = x + row * gw;
-    for (int col = lane; col < gwp; col += 32) {
-        const float xs = col < gw ? __ldg(src + col) * s : 0.f;
-        const __half h1 = __float2half_rn(xs);
-        const __half h2 = __float2half_rn((xs - __half2float(h1)) * kLoScale);
-        p1[row * gwp + col] = h1;
-        p2[row * gwp + col] = h2;
+                                                              const unsigned *__restrict__ amax_bits, __half2 *__restrict__ p1,
+                                                              __half2 *__restrict__ p2) {
+    // one block per (image, channel) plane; a thread per pair of columns (gw, gwp even: 8-byte loads, 4-byte stores)
+    const size_t plane = blockIdx.x;                     // b*cin + c
+    const int b = (int)(plane / cin), c = (int)(plane - (size_t)b * cin);
+    const float s = pow2_scale_for(__uint_as_float(__ldg(amax_bits + (size_t)b * (cin >> 6) + (c >> 6))));
+    const int hp = gwp >> 1, hw = gw >> 1;
+    const float2 *src = reinterpret_cast<const float2 *>(x + plane * gh * gw);
+    __half2 *d1 = p1 + plane * gh * hp, *d2 = p2 + plane * gh * hp;
+    for (int i = threadIdx.x; i < gh * hp; i += blockDim.x) {
+        const int y = i / hp, cp = i - y * hp;
+        float2 v = make_float2(0.f, 0.f);
+        if (cp < hw) v = __ldg(src + y * hw + cp);
+        const float x0 = v.x * s, x1 = v.y * s;
+        const __half2 h = __floats2half2_rn(x0, x1);
+        const float2 f = __half22float2(h);
+        d1[i] = h;
+        d2[i] = __floats2half2_rn((x0 - f.x) * kLoScale, (x1 - f.y) * kLoScale);
     }
 }
 
@@ -117,30 +119,36 @@ __global__ void __launch_bounds__(256) g_absmax_kernel(const float *__restrict__
 }
 
 // G (B, gh*gw, cout) fp32 -> three column-shifted copies e = 0,1,2 (shift e-1) of the transposed fp16 planes
-// (3, B, 80, gh*gwp):  copy_e[b][n][j] = G^T[b][n][j - (e-1)]  (zero outside the image, in pad columns, for n >= cout)
+// (3, B, 80, gh*gwp):  copy_e[b][n][y*gwp + col] = G[b][y][col - (e-1)][n]  (zero outside the row, for n >= cout).
+// One block per image row: the row's gw x cout floats are read coalesced into shared memory and written back
+// transposed, pixel-contiguous.  (A flat shift would pull column 0 of the next row into the last pad column of the
+// -1 copy; that position only ever meets a zero pad column of X, so writing zero there is equivalent.)
 __global__ void __launch_bounds__(256) g_transpose_split_kernel(const float *__restrict__ g, int gh, int gw, int gwp, int cout,
                                                                 int batch, const unsigned *__restrict__ amax_bits,
-                                                                __half *__restrict__ p1, __half *__restrict__ p2, size_t total) {
-    const int ppad = gh * gwp;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int j = (int)(i % ppad);
-        size_t r = i / ppad;
-        const int n = (int)(r % kNPad);
-        r /= kNPad;
-        const int b = (int)(r % batch), e = (int)(r / batch);
-        const int src = j - (e - 1);
+                                                                __half *__restrict__ p1, __half *__restrict__ p2) {
+    extern __shared__ float srow[];   // [gw][cout + 1]
+    const int b = blockIdx.y, y = blockIdx.x;
+    const int ld = cout + 1;
+    const float *src = g + ((size_t)b * gh + y) * gw * cout;
+    for (int i = threadIdx.x; i < gw * cout; i += blockDim.x) {
+        const int col = i / cout, n = i - col * cout;
+        srow[col * ld + n] = __ldg(src + i);
+    }
+    __syncthreads();
+    const float t0 = pow2_scale_for(__uint_as_float(__ldg(amax_bits + (size_t)b * 2)));
+    const float t1 = pow2_scale_for(__uint_as_float(__ldg(amax_bits + (size_t)b * 2 + 1)));
+    const size_t ppad = (size_t)gh * gwp;
+    const int total = kNPad * gwp, e = blockIdx.z;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int n = i / gwp, j = i - n * gwp;
+        const int col = j - (e - 1);
         float xs = 0.f;
-        if (n < cout && src >= 0 && src < ppad) {
-            const int y = src / gwp, col = src - y * gwp;
-            if (col < gw) {
-                const float t = pow2_scale_for(__uint_as_float(amax_bits[(size_t)b * 2 + (n >> 6)]));
-                xs = __ldg(g + (((size_t)b * gh + y) * gw + col) * cout + n) * t;
-            }
-        }
+        if (n < cout && col >= 0 && col < gw) xs = srow[col * ld + n] * (n < 64 ? t0 : t1);
         const __half h1 = __float2half_rn(xs);
         const __half h2 = __float2half_rn((xs - __half2float(h1)) * kLoScale);
-        p1[i] = h1;
-        p2[i] = h2;
+        const size_t o = (((size_t)e * batch + b) * kNPad + n) * ppad + (size_t)y * gwp + j;
+        p1[o] = h1;
+        p2[o] = h2;
     }
 }
 
@@ -343,16 +351,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
     }
 }
 
-// dW[n][c][tap] = sum_slices partial[slice][tap][c][n]   (fixed order)
+// dW[n][c][tap] = sum_slices partial[slice][tap][c][n]   (fixed order; reads coalesced along n, 4-byte scattered writes)
 __global__ void wgrad_tc_reduce_kernel(const float *__restrict__ partial, int nslice, int cin, int cout, float *__restrict__ gw_out) {
-    const size_t n_out = (size_t)cout * cin * 9;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (size_t)gridDim.x * blockDim.x) {
-        const int tap = (int)(i % 9);
-        const size_t r = i / 9;
-        const int c = (int)(r % cin), n = (int)(r / cin);
+    const size_t n_in = (size_t)9 * cin * kNPad;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += (size_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i % kNPad);
+        const size_t r = i / kNPad;
+        const int c = (int)(r % cin), tap = (int)(r / cin);
+        if (n >= cout) continue;
         float s = 0.f;
-        for (int k = 0; k < nslice; ++k) s += partial[(((size_t)k * 9 + tap) * cin + c) * kNPad + n];
-        gw_out[i] = s;
+        for (int k = 0; k < nslice; ++k) s += partial[(size_t)k * n_in + i];
+        gw_out[((size_t)n * cin + c) * 9 + tap] = s;
     }
 }
 
@@ -449,20 +458,20 @@ extern "C" int sqd_convdet_wgrad_tc(const float *d_feat_nchw, const float *d_gpr
     int rc = sqd_f16_absmax_runs(d_feat_nchw, (size_t)64 * P, batch * ncb, amax_x, st);
     if (rc) return rc;
     if ((rc = stage_check("absmax x", st))) return rc;
-    {
-        const size_t rows = (size_t)batch * cin * gh;
-        split_nchw_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(d_feat_nchw, cin, gh, gw, gwp, amax_x, x1, x2, rows);
-        SQD_LAUNCH_CHECK("split_nchw_rows_kernel");
-        if ((rc = stage_check("split x", st))) return rc;
-    }
+    SQD_REQUIRE(gw % 2 == 0, SQD_E_SHAPE, "sqd_convdet_wgrad_tc: grid width %d must be even", gw);
+    split_nchw_rows_kernel<<<(unsigned)((size_t)batch * cin), 256, 0, st>>>(d_feat_nchw, cin, gh, gw, gwp, amax_x,
+                                                                           reinterpret_cast<__half2 *>(x1),
+                                                                           reinterpret_cast<__half2 *>(x2));
+    SQD_LAUNCH_CHECK("split_nchw_rows_kernel");
+    if ((rc = stage_check("split x", st))) return rc;
     g_absmax_kernel<<<dim3(8, batch), 256, 0, st>>>(d_gpred, P, cout, amax_g);
     SQD_LAUNCH_CHECK("g_absmax_kernel");
     if ((rc = stage_check("absmax g", st))) return rc;
     {
-        const size_t total = (size_t)3 * batch * kNPad * gh * gwp;
-        int gx = (int)((total + 255) / 256);
-        if (gx > SQD_SM_COUNT * 16) gx = SQD_SM_COUNT * 16;
-        g_transpose_split_kernel<<<gx, 256, 0, st>>>(d_gpred, gh, gw, gwp, cout, batch, amax_g, g1, g2, total);
+        const size_t smem_g = (size_t)gw * (cout + 1) * sizeof(float);
+        if (smem_g > 48 * 1024)
+            SQD_CUDA(cudaFuncSetAttribute(g_transpose_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        g_transpose_split_kernel<<<dim3(gh, batch, 3), 256, smem_g, st>>>(d_gpred, gh, gw, gwp, cout, batch, amax_g, g1, g2);
         SQD_LAUNCH_CHECK("g_transpose_split_kernel");
         if ((rc = stage_check("transpose g", st))) return rc;
     }
@@ -502,8 +511,8 @@ extern "C" int sqd_convdet_wgrad_tc(const float *d_feat_nchw, const float *d_gpr
     wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
     SQD_LAUNCH_CHECK("wgrad_tc_kernel");
     if ((rc = stage_check("gemm", st))) return rc;
-    const size_t n_out = (size_t)cout * cin * 9;
-    wgrad_tc_reduce_kernel<<<(int)((n_out + 255) / 256), 256, 0, st>>>(p.partial, w.nslice, cin, cout, d_gweight);
+    const size_t n_in = (size_t)9 * cin * kNPad;
+    wgrad_tc_reduce_kernel<<<(int)((n_in + 255) / 256), 256, 0, st>>>(p.partial, w.nslice, cin, cout, d_gweight);
     SQD_LAUNCH_CHECK("wgrad_tc_reduce_kernel");
     if ((rc = stage_check("reduce", st))) return rc;
     return SQD_OK;
