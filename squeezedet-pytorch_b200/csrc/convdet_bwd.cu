@@ -20,7 +20,7 @@ size_t sqd_f16_split_bytes(int batch, int cin, int gh, int gw);
 size_t sqd_f16_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout);
 int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                          int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st,
-                         const SqdCandEmit *emit, int out_stride);
+                         const SqdCandEmit *emit, int out_stride, int ksteps_last);
 
 namespace {
 
@@ -312,12 +312,15 @@ extern "C" int sqd_convdet_dgrad(const float *d_gpred, const void *d_dgrad_packe
     gpred_split_pad_kernel<<<gx, 256, 0, st>>>(d_gpred, P, cout, kp, amax, reinterpret_cast<uint2 *>(planes + amax_bytes),
                                               reinterpret_cast<uint2 *>(planes + amax_bytes + plane_bytes), total);
     SQD_LAUNCH_CHECK("gpred_split_pad_kernel");
-    // 2. one implicit GEMM per slab of 128 feature channels
+    // 2. one implicit GEMM per slab of 128 feature channels; the zero-padded K steps of the last gradient-channel block
+    //    (72 channels: block 1 holds 8 real ones = one 16-channel step of four) are not issued
+    const int rem = cout % 64;
+    const int ksteps_last = rem == 0 ? 4 : (rem + 15) / 16;
     const size_t slab_bytes = align256(sqd_f16_packed_bytes(kSlab, kp));
     for (int s = 0; s < ns; ++s) {
         int rc = sqd_convdet_f16_pair(reinterpret_cast<const float *>(planes), SQD_LAYOUT_SPLIT_NHWC,
                                       static_cast<const char *>(d_dgrad_packed) + (size_t)s * slab_bytes, nullptr, batch, kp, gh,
-                                      gw, kSlab, d_gfeat_nhwc + (size_t)s * kSlab, ws + w.gemm_off, st, nullptr, cin);
+                                      gw, kSlab, d_gfeat_nhwc + (size_t)s * kSlab, ws + w.gemm_off, st, nullptr, cin, ksteps_last);
         if (rc) return rc;
     }
     return SQD_OK;

@@ -816,6 +816,7 @@ struct PairParams {
     int trace_cta;
     int out_stride;      // floats between consecutive cells of the output (== cout for pred; Cin for the dgrad slabs)
     int pdl;             // host only: launch as a programmatic dependent of the pre-pass kernel
+    int ksteps_last;     // PK kernels: valid 16-channel K steps of the last channel block (1..4)
     // fused score epilogue (template CS > 0 only): candidates above the score threshold go to per-image lists
     SqdCand cand;        // cand.count == nullptr: no emission
     float score_thr;
@@ -866,7 +867,9 @@ __device__ __forceinline__ bool pair_wait_warp(uint64_t *bar, uint32_t parity, v
 // fp32 logits -- class softmax x confidence sigmoid, first-max argmax, the same sqd_score_anchor every filter kernel
 // uses -- and appends the anchors above the score threshold to per-image candidate lists (SqdCand), so the filter
 // that follows never scans pred.
-template <int NPAD, int CS>
+// PK: the last 64-channel block is only partly filled (p.ksteps_last valid 16-channel K steps; the rest is zero padding,
+// e.g. the 72 -> 128 padded gradient channels of the dgrad GEMM): its all-zero K steps are not issued.
+template <int NPAD, int CS, bool PK = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                         const __grid_constant__ CUtensorMap map_b, const PairParams p) {
@@ -1002,6 +1005,7 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                 const uint32_t d1 = tmem_base + (uint32_t)buf * kAccCols, d2 = d1 + 2 * NPAD;
                 const uint32_t st = smem_u32(smem + (size_t)rs.s * kStageBytes);
                 const bool chunk_end = sc.chunk_ends(i, it.r, in_chunk, p.chunk_units);
+                const int nks = (PK && it.cb == p.cin / kBlockK - 1) ? p.ksteps_last : kBlockK / kUmmaK;
                 if (elect_one_sync()) {
                     if (!(p.dbg & 1)) {
 #pragma unroll
@@ -1012,6 +1016,7 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                             const uint64_t bw1 = umma_desc_sw128(st + kAStageBytes + dyi * kBTapBytes + kW1Offset);
 #pragma unroll
                             for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
+                                if (PK && ks >= nks) continue;
                                 const uint64_t adv = (uint64_t)((ks * kUmmaK * 2) >> 4);
                                 const uint32_t accum = (in_chunk | dyi | ks) ? 1u : 0u;
                                 umma_f16_ss_2cta(d1, a1 + adv, b + adv, kIdesc1, accum);
@@ -1393,12 +1398,12 @@ int pair_stages_for(int npad) {
     return (int)s;
 }
 
-template <int NPAD, int CS = 0>
+template <int NPAD, int CS = 0, bool PK = false>
 int launch_pair(const CUtensorMap *maps, const PairParams &p, int grid, cudaStream_t st) {
     const size_t smem = 1024 + (size_t)p.stages * (kAStageBytes + 3 * NPAD * kBlockK * 2) + kCtrlBytes;
-    SQD_CUDA(cudaFuncSetAttribute(convdet_f16_pair_kernel<NPAD, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SQD_CUDA(cudaFuncSetAttribute(convdet_f16_pair_kernel<NPAD, CS, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // dependent launch when the pre-pass kernel directly precedes it on the stream (p.pdl)
-    cudaError_t e = sqd_launch_dependent(convdet_f16_pair_kernel<NPAD, CS>, dim3(grid), dim3(kThreads2), smem, st, p.pdl != 0,
+    cudaError_t e = sqd_launch_dependent(convdet_f16_pair_kernel<NPAD, CS, PK>, dim3(grid), dim3(kThreads2), smem, st, p.pdl != 0,
                                          maps[0], maps[1], maps[2], p);
     if (e != cudaSuccess) {
         sqd_set_error("launch of convdet_f16_pair_kernel failed: %s", cudaGetErrorString(e));
@@ -1418,7 +1423,7 @@ int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, 
 // an opt-in experiment (SQD_FUSED_SCORE=1), not the default.
 int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                          int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st,
-                         const SqdCandEmit *emit, int out_stride) {
+                         const SqdCandEmit *emit, int out_stride, int ksteps_last) {
     SQD_REQUIRE(cin % kBlockK == 0, SQD_E_SHAPE, "convdet (tcgen05): Cin %d must be a multiple of %d", cin, kBlockK);
     SQD_REQUIRE(cout >= 1 && cout <= 128, SQD_E_SHAPE, "convdet (tcgen05): Cout %d outside [1,128]", cout);
     EncodeTiledFn encode = get_encode_fn();
@@ -1467,6 +1472,7 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
     p.cin = cin; p.gh = gh; p.gw = gw; p.cout = cout; p.batch = batch;
     p.out_stride = out_stride > 0 ? out_stride : cout;
     p.pdl = after_prepass ? 1 : 0;
+    p.ksteps_last = (ksteps_last >= 1 && ksteps_last < 4) ? ksteps_last : 4;
     p.tiles_x = (gw + kTileX - 1) / kTileX;
     p.tiles_per_img = p.tiles_x * ((gh + kTileY - 1) / kTileY);
     const long long total_tiles = (long long)p.tiles_per_img * batch;
@@ -1514,6 +1520,8 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
             return launch_pair<128, 8>(maps, p, grid, st);
         }
     }
+    if (p.ksteps_last < 4 && npad == 128) return launch_pair<128, 0, true>(maps, p, grid, st);   // the dgrad slabs
+    p.ksteps_last = 4;
     switch (npad / 16) {
         case 1: return launch_pair<16>(maps, p, grid, st);
         case 2: return launch_pair<32>(maps, p, grid, st);
