@@ -341,9 +341,9 @@ def main_ours(args):
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "note": "sqd_head_detect_host: pinned host features -> H2D in groups of %d images overlapped with the kernels "
                             "-> D2H of the detections, stream sync every step" % args.e2e_chunk},
-            "gpu_launches": 5 * K,
-            "kernels_per_step": ["absmax_kernel", "split_nchw_f16_kernel|split_nhwc_f16_kernel",
-                                 "convdet_f16_pair_kernel<80,0>", "score_candidates_kernel<3>", "detect_from_candidates_kernel"],
+            "gpu_launches": 4 * K,
+            "kernels_per_step": ["split_nchw_cluster_kernel (max|x| + fp16 split, one pass)", "convdet_f16_pair_kernel<80,0>",
+                                 "score_candidates_kernel<3>", "detect_from_candidates_kernel"],
             "kernel_ms": kern,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tflops"], "traffic": NCU_CONVDET_TRAFFIC_B20 if B == 20 else None,
