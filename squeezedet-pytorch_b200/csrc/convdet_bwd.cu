@@ -11,6 +11,7 @@
 // The result is written NHWC (B, gh, gw, Cin): the channels_last memory format of the logical (B, Cin, gh, gw) tensor.
 // The weight gradient (wgrad: a contraction over B*gh*gw pixels) is NOT native yet -- see DESIGN.md.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -20,7 +21,7 @@ size_t sqd_f16_split_bytes(int batch, int cin, int gh, int gw);
 size_t sqd_f16_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout);
 int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                          int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st,
-                         const SqdCandEmit *emit, int out_stride, int ksteps_last);
+                         const SqdCandEmit *emit, int out_stride, int ksteps_last, int slabs, size_t slab_stride);
 
 namespace {
 
@@ -316,13 +317,23 @@ extern "C" int sqd_convdet_dgrad(const float *d_gpred, const void *d_dgrad_packe
     //    (72 channels: block 1 holds 8 real ones = one 16-channel step of four) are not issued
     const int rem = cout % 64;
     const int ksteps_last = rem == 0 ? 4 : (rem + 15) / 16;
+    // ONE launch over all slabs: virtual image v = slab * B + b reads the planes of image b, the weights of `slab` and
+    // writes feature channels [slab*128, +128).  (Six launches of one slab each spend most of their time in prologue,
+    // pipeline fill and the last tile's epilogue: 2 tiles per CTA pair.)
     const size_t slab_bytes = align256(sqd_f16_packed_bytes(kSlab, kp));
-    for (int s = 0; s < ns; ++s) {
-        int rc = sqd_convdet_f16_pair(reinterpret_cast<const float *>(planes), SQD_LAYOUT_SPLIT_NHWC,
-                                      static_cast<const char *>(d_dgrad_packed) + (size_t)s * slab_bytes, nullptr, batch, kp, gh,
-                                      gw, kSlab, d_gfeat_nhwc + (size_t)s * kSlab, ws + w.gemm_off, st, nullptr, cin, ksteps_last);
-        if (rc) return rc;
+    if (getenv("SQD_DGRAD_PER_SLAB")) {
+        for (int s = 0; s < ns; ++s) {
+            int rc = sqd_convdet_f16_pair(reinterpret_cast<const float *>(planes), SQD_LAYOUT_SPLIT_NHWC,
+                                          static_cast<const char *>(d_dgrad_packed) + (size_t)s * slab_bytes, nullptr, batch, kp, gh,
+                                          gw, kSlab, d_gfeat_nhwc + (size_t)s * kSlab, ws + w.gemm_off, st, nullptr, cin, ksteps_last,
+                                          1, 0);
+            if (rc) return rc;
+        }
+        return SQD_OK;
     }
+    int rc = sqd_convdet_f16_pair(reinterpret_cast<const float *>(planes), SQD_LAYOUT_SPLIT_NHWC, d_dgrad_packed, nullptr, batch, kp,
+                                  gh, gw, kSlab, d_gfeat_nhwc, ws + w.gemm_off, st, nullptr, cin, ksteps_last, ns, slab_bytes);
+    if (rc) return rc;
     return SQD_OK;
 }
 

@@ -817,24 +817,56 @@ struct PairParams {
     int out_stride;      // floats between consecutive cells of the output (== cout for pred; Cin for the dgrad slabs)
     int pdl;             // host only: launch as a programmatic dependent of the pre-pass kernel
     int ksteps_last;     // PK kernels: valid 16-channel K steps of the last channel block (1..4)
+    // PK kernels (the dgrad GEMM): `slabs` weight matrices share the same input planes; the tile space is slab-major,
+    // tiles_per_slab (even) tiles per slab; slab s uses the weights of map_b's 3rd coordinate s (header `slab_stride`
+    // bytes further) and writes output columns [s*NPAD, +NPAD).
+    int slabs, tiles_per_slab;
+    size_t slab_stride;
     // fused score epilogue (template CS > 0 only): candidates above the score threshold go to per-image lists
     SqdCand cand;        // cand.count == nullptr: no emission
     float score_thr;
     int anchors_per_cell;
 };
 
-struct PairIter {  // like UnitIter, for the tile of one rank; img may run past the batch for a ghost tile
-    int r, cb, dxi, img, tx, ty;
-    __device__ __forceinline__ void seek(long long u, int tile_offset, const PairParams &p) {
-        const int pt = (int)(u / p.upt);
+// like UnitIter, for the tile of one rank; img == batch marks a ghost tile (loads zeros, stores nothing).
+//  PK = false: pair-tile j = tiles {j, j + pair_tiles}; `sel` = the rank's tile offset.
+//  PK = true (several weight slabs over the same images): the two ranks of a pair MUST work on the same slab (they share
+//  the B operand), so pair-tile j = the adjacent tiles {2j, 2j+1} of a slab-major tile space whose slabs are padded to
+//  an even tile count (tiles_per_slab); `sel` = the rank.
+template <bool PK>
+struct PairIterT {
+    int r, cb, dxi, img, tx, ty, slab, pt, sel;
+    __device__ __forceinline__ void locate(const PairParams &p) {
+        if (PK) {
+            const int tile = 2 * pt + sel;
+            slab = tile / p.tiles_per_slab;
+            const int local = tile - slab * p.tiles_per_slab;
+            if (slab >= p.slabs) {
+                slab = p.slabs - 1;
+                img = p.batch;
+                tx = ty = 0;
+                return;
+            }
+            img = local / p.tiles_per_img;       // == batch for the slab's padding tile
+            const int t = local - img * p.tiles_per_img;
+            ty = t / p.tiles_x;
+            tx = t - ty * p.tiles_x;
+        } else {
+            slab = 0;
+            const int tile = pt + sel;
+            img = tile / p.tiles_per_img;
+            const int t = tile - img * p.tiles_per_img;
+            ty = t / p.tiles_x;
+            tx = t - ty * p.tiles_x;
+        }
+    }
+    __device__ __forceinline__ void seek(long long u, int sel_, const PairParams &p) {
+        sel = sel_;
+        pt = (int)(u / p.upt);
         r = (int)(u - (long long)pt * p.upt);
         cb = r / 3;
         dxi = r - cb * 3;
-        const int tile = pt + tile_offset;
-        img = tile / p.tiles_per_img;
-        const int t = tile - img * p.tiles_per_img;
-        ty = t / p.tiles_x;
-        tx = t - ty * p.tiles_x;
+        locate(p);
     }
     __device__ __forceinline__ void next(const PairParams &p) {
         ++r;
@@ -845,7 +877,10 @@ struct PairIter {  // like UnitIter, for the tile of one rank; img may run past 
         if (r == p.upt) {
             r = 0;
             cb = 0;
-            if (++tx == p.tiles_x) {
+            ++pt;
+            if (PK) {
+                locate(p);
+            } else if (++tx == p.tiles_x) {
                 tx = 0;
                 if (++ty * p.tiles_x == p.tiles_per_img) {
                     ty = 0;
@@ -900,7 +935,8 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
     const int cta = blockIdx.x;
     const uint32_t rank = cluster_ctarank();
     const int pair = cta >> 1, npairs = gridDim.x >> 1;
-    const int tile_offset = rank ? p.pair_tiles : 0;
+    const int tile_offset = PK ? (int)rank : (rank ? p.pair_tiles : 0);
+    using PairIter = PairIterT<PK>;
     const bool spin = (p.dbg & 8) != 0;   // debug: 8 = poll mbarrier.test_wait instead of parking in try_wait (slower)
 
     // ---- this pair's slice of the (pair-tile, unit) space ----------------------------------------------------
@@ -965,15 +1001,21 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                 const int x = it.tx * kTileX + it.dxi - 1, y = it.ty * kTileY - 1;
                 const int bytes = ((p.dbg & 2) ? 0 : kAStageBytes) + ((p.dbg & 4) ? 0 : 3 * kBTapBytes);
                 if (rank == 0) mbar_arrive_expect_tx(full + rs.s, 2 * bytes);  // both CTAs' bytes
-                if (!(p.dbg & 2)) {
+                if (!(p.dbg & 2)) {   // ghost tile: image index == batch -> out of bounds -> zeros
                     tma_load_4d_2cta(&map_a1, full + rs.s, st, it.cb * kBlockK, x, y, it.img);
                     tma_load_4d_2cta(&map_a2, full + rs.s, st + kPlaneBytes, it.cb * kBlockK, x, y, it.img);
                 }
                 if (!(p.dbg & 4)) {
+                    const int slab = it.slab;
 #pragma unroll
-                    for (int dyi = 0; dyi < 3; ++dyi)
-                        tma_load_2d_2cta(&map_b, full + rs.s, st + kAStageBytes + dyi * kBTapBytes,
-                                         (dyi * 3 + it.dxi) * p.cin + it.cb * kBlockK, (int)rank * NPAD);
+                    for (int dyi = 0; dyi < 3; ++dyi) {
+                        if (PK)
+                            tma_load_3d_2cta(&map_b, full + rs.s, st + kAStageBytes + dyi * kBTapBytes,
+                                             (dyi * 3 + it.dxi) * p.cin + it.cb * kBlockK, (int)rank * NPAD, slab);
+                        else
+                            tma_load_2d_2cta(&map_b, full + rs.s, st + kAStageBytes + dyi * kBTapBytes,
+                                             (dyi * 3 + it.dxi) * p.cin + it.cb * kBlockK, (int)rank * NPAD);
+                    }
                 }
             }
             __syncwarp();
@@ -1237,11 +1279,15 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
             // whole tile in registers: x 1/(s_a*s_w), + bias -> pred   (ghost tile: img == batch, nothing stored)
             const int x = it.tx * kTileX + row % kTileX, y = it.ty * kTileY + row / kTileX;
             const bool inb = it.img < p.batch && y < p.gh && x < p.gw;
-            const float inv = inv_sw;   // the feature scales were divided out chunk by chunk
+            const int slab = it.slab;
+            // the feature scales were divided out chunk by chunk; the weight scale belongs to the slab
+            const float inv = PK ? reinterpret_cast<const PackedHeader *>(reinterpret_cast<const char *>(p.whdr) +
+                                                                          (size_t)slab * p.slab_stride)->inv_scale
+                                 : inv_sw;
 #pragma unroll
             for (int n = 0; n < NPAD; ++n) acc[n] = fadd(fmul(acc[n], inv), s_bias[n]);
             if (inb) {
-                float *out = p.pred + (((size_t)it.img * p.gh + y) * p.gw + x) * p.out_stride;
+                float *out = p.pred + (((size_t)it.img * p.gh + y) * p.gw + x) * p.out_stride + (PK ? slab * NPAD : 0);
                 if (((p.cout | p.out_stride) & 3) == 0) {
                     float4 *o4 = reinterpret_cast<float4 *>(out);
 #pragma unroll
@@ -1423,7 +1469,7 @@ int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, 
 // an opt-in experiment (SQD_FUSED_SCORE=1), not the default.
 int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                          int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st,
-                         const SqdCandEmit *emit, int out_stride, int ksteps_last) {
+                         const SqdCandEmit *emit, int out_stride, int ksteps_last, int slabs, size_t slab_stride) {
     SQD_REQUIRE(cin % kBlockK == 0, SQD_E_SHAPE, "convdet (tcgen05): Cin %d must be a multiple of %d", cin, kBlockK);
     SQD_REQUIRE(cout >= 1 && cout <= 128, SQD_E_SHAPE, "convdet (tcgen05): Cout %d outside [1,128]", cout);
     EncodeTiledFn encode = get_encode_fn();
@@ -1455,27 +1501,45 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SQD_REQUIRE(r == CUDA_SUCCESS, SQD_E_DRIVER, "cuTensorMapEncodeTiled(features) failed: CUresult %d", (int)r);
     }
+    if (slabs < 1) slabs = 1;
+    // the dgrad GEMM (PK kernel): several weight matrices over the same planes in one launch and / or a partly filled last
+    // channel block; it addresses the weights through a 3-D map {k, row, slab}
+    const bool multi = (slabs > 1 || (ksteps_last >= 1 && ksteps_last < 4)) && npad == 128;
+    SQD_REQUIRE(slabs == 1 || multi, SQD_E_UNSUPPORTED, "convdet (tcgen05): multi-slab launches need Cout == 128 per slab");
+    if (slabs == 1) slab_stride = 0;
     {
         const size_t ktot = (size_t)9 * cin;
         void *mat2 = const_cast<char *>(static_cast<const char *>(d_packed) + kHeaderBytes) + (size_t)2 * npad * ktot * sizeof(__half);
-        const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)(2 * npad)};
-        const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-        const cuuint32_t box[2] = {kBlockK, (cuuint32_t)npad};   // one CTA's half: npad rows
-        const cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&maps[2], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, mat2, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r;
+        if (multi) {
+            SQD_REQUIRE(slab_stride % 16 == 0, SQD_E_SHAPE, "convdet (tcgen05): bad slab layout");
+            const cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)(2 * npad), (cuuint64_t)slabs};
+            const cuuint64_t strides[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)(slabs > 1 ? slab_stride : (size_t)2 * npad * ktot * 2)};
+            const cuuint32_t box[3] = {kBlockK, (cuuint32_t)npad, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            r = encode(&maps[2], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, mat2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)(2 * npad)};
+            const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+            const cuuint32_t box[2] = {kBlockK, (cuuint32_t)npad};   // one CTA's half: npad rows
+            const cuuint32_t estr[2] = {1, 1};
+            r = encode(&maps[2], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, mat2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
         SQD_REQUIRE(r == CUDA_SUCCESS, SQD_E_DRIVER, "cuTensorMapEncodeTiled(weights) failed: CUresult %d", (int)r);
     }
 
     PairParams p;
     p.cin = cin; p.gh = gh; p.gw = gw; p.cout = cout; p.batch = batch;
+    p.slabs = slabs; p.slab_stride = slab_stride;
     p.out_stride = out_stride > 0 ? out_stride : cout;
     p.pdl = after_prepass ? 1 : 0;
     p.ksteps_last = (ksteps_last >= 1 && ksteps_last < 4) ? ksteps_last : 4;
     p.tiles_x = (gw + kTileX - 1) / kTileX;
     p.tiles_per_img = p.tiles_x * ((gh + kTileY - 1) / kTileY);
-    const long long total_tiles = (long long)p.tiles_per_img * batch;
+    p.tiles_per_slab = (p.tiles_per_img * batch + 1) & ~1;   // PK: slabs padded to an even tile count
+    const long long total_tiles = multi ? (long long)p.tiles_per_slab * slabs : (long long)p.tiles_per_img * batch;
     SQD_REQUIRE(total_tiles < (1ll << 30), SQD_E_SHAPE, "convdet (tcgen05): too many tiles");
     p.total_tiles = (int)total_tiles;
     p.pair_tiles = (int)((total_tiles + 1) / 2);
@@ -1520,7 +1584,7 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
             return launch_pair<128, 8>(maps, p, grid, st);
         }
     }
-    if (p.ksteps_last < 4 && npad == 128) return launch_pair<128, 0, true>(maps, p, grid, st);   // the dgrad slabs
+    if (multi) return launch_pair<128, 0, true>(maps, p, grid, st);   // the dgrad GEMM
     p.ksteps_last = 4;
     switch (npad / 16) {
         case 1: return launch_pair<16>(maps, p, grid, st);

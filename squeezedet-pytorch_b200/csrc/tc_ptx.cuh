@@ -209,6 +209,12 @@ __device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap *map, uint64_
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_2cta(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 // mbarrier (same offset in every CTA of `cta_mask`) arrives when all previously issued MMAs of this thread completed
 __device__ __forceinline__ void umma_commit_2cta(uint64_t *bar, uint16_t cta_mask) {
     asm volatile(

@@ -1,6 +1,8 @@
 """a1 ConvDet head on the GPU: tcgen05 3xTF32 kernel and the fp32 SIMT yardstick against the
 reference's conv (golden pred recorded from the reference, and the oracle = torch CPU conv2d),
 then the end-to-end kept-index parity features -> detections."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -259,6 +261,13 @@ def test_convdet_dgrad_and_bias_grad(ops, name, batch):
     gx32, _, gb32 = orc.convdet_backward(feat, w, g)
     gx64, _, gb64 = orc.convdet_backward(feat, w, g, dtype=np.float64)
     got = ops.convdet_dgrad(dev(g), dev(w))
+    os.environ["SQD_DGRAD_PER_SLAB"] = "1"       # six launches of one 128-channel slab each: same products; tiles that are
+    try:                                         # split between CTA pairs are cut elsewhere, so the last fp32 add may differ
+        per_slab = ops.convdet_dgrad(dev(g), dev(w))
+    finally:
+        del os.environ["SQD_DGRAD_PER_SLAB"]
+    assert torch.allclose(got, per_slab, rtol=1e-5, atol=2e-5 * float(per_slab.abs().mean()))   # both within 1.3e-5 of float64
+    assert torch.equal(got, ops.convdet_dgrad(dev(g), dev(w)))      # and each schedule is deterministic
     assert got.shape == (batch, shp.in_channels, *shp.grid_hw)
     assert got.is_contiguous(memory_format=torch.channels_last)
     got = got.cpu().numpy()
