@@ -321,3 +321,30 @@ def test_training_backward_is_native(ops):
     assert torch.allclose(g_feat, feat2.grad, rtol=1e-4, atol=1e-4 * s)
     assert torch.allclose(g_b, conv.bias.grad, rtol=1e-4, atol=1e-4 * float(conv.bias.grad.abs().max()))
     assert torch.allclose(g_w, conv.weight.grad, rtol=1e-4, atol=1e-4 * float(conv.weight.grad.abs().mean()))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_convdet_random_shapes_vs_fp32_kernel(ops, seed):
+    """Odd geometries: grids that are not multiples of the 8 x 16 tile (partial tiles in both directions, single-row /
+    single-column grids), odd tile counts (ghost tile of the CTA pair), few / many input channel blocks, every output
+    padding 16..128, batch 1: the tcgen05 kernel against the fp32 CUDA-core kernel, NCHW and channels_last."""
+    from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32
+    rs = np.random.RandomState(900 + seed)
+    gh, gw = int(rs.randint(1, 30)), int(rs.randint(1, 100))
+    if seed == 0:
+        gh, gw = 1, 1
+    if seed == 1:
+        gh, gw = 9, 17          # one cell past a tile edge in both directions
+    batch = int(rs.randint(1, 5))
+    cin = int(rs.choice([64, 128, 320, 768]))
+    cout = int(rs.choice([8, 13, 24, 40, 72, 96, 117, 128]))
+    x = rs.standard_normal((batch, cin, gh, gw)).astype(np.float32) * rs.uniform(1e-3, 30.0)
+    w = (rs.standard_normal((cout, cin, 3, 3)) * (1.5 / np.sqrt(9 * cin))).astype(np.float32)
+    b = rs.standard_normal(cout).astype(np.float32)
+    ref = ops.convdet_forward(dev(x), dev(w), dev(b), algo=CONV_SIMT_FP32)
+    tc = ops.convdet_forward(dev(x), dev(w), dev(b), check_status=True)
+    scale = float(ref.abs().mean())
+    assert tc.shape == (batch, gh, gw, cout)
+    assert torch.allclose(tc, ref, rtol=1e-4, atol=3e-5 * scale), (gh, gw, batch, cin, cout, float((tc - ref).abs().max()), scale)
+    cl = ops.convdet_forward(dev(x).contiguous(memory_format=torch.channels_last), dev(w), dev(b), check_status=True)
+    assert torch.equal(cl, tc) or gh * gw == 1   # 1x1 grids: torch cannot tell the layouts apart (both contiguous)
