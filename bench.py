@@ -322,6 +322,31 @@ def main_ours(args):
         info = run_cpu_arm(args, budget_s=15.0, warmup=2, steps=1000)
         cpu = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    # ---- the reference's OWN GPU path on this B200 (rank 0, N=1): cuDNN conv (TF32 off = the reference's fp32) + ATen
+    #      decode kernels + the per-image filter loop with torchvision nms, restated op for op in oracle/torch_port.py ----
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import torch_port
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        a_cpu = torch.from_numpy(synth.anchor_table(shp).astype(np.float32))[None]
+        run_ref = lambda f: torch_port.detect(f, weight, bias, a_cpu, shp.num_classes, shp.input_hw, shp.top_k,  # noqa: E731
+                                              shp.nms_thresh, shp.score_thresh)
+        for i in range(2):
+            run_ref(feats[i % R])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nref = 0
+        while nref < 5 or time.perf_counter() - t0 < 3.0:
+            run_ref(feats[nref % R])
+            nref += 1
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / nref
+        gpu_ref = {"value": B / dt, "unit": "images/s", "kind": "port of the reference's PyTorch CUDA path (oracle/torch_port.py): "
+                   "cuDNN fp32 conv + ATen decode + per-image argsort / torchvision.ops.nms loop with its host syncs",
+                   "sample": "%d passes over one batch of %d resident feature maps, wall clock" % (nref, B),
+                   "ms_per_step": dt * 1e3}
+
     if rank == 0:
         conv_s = kern["convdet_ms"] * 1e-3
         achieved = B * FLOP_PER_IMAGE / conv_s / 1e12
@@ -373,6 +398,8 @@ def main_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if gpu_ref is not None:
+            line["gpu_reference_baseline"] = gpu_ref
         sys.stdout.flush()
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -256,3 +256,30 @@ def test_preprocess_oracle_vs_reference_golden(golden):
         # the installed cv2 (4.13) resizes float images through Intel IPP, whose bilinear kernel evaluates the source
         # coordinates in fp32: up to 3e-3 on 0..255 pixel values = 4e-5 on whitened values (1.5e-5 of their range)
         np.testing.assert_allclose(out, g[f"out_{i}"], rtol=1e-5, atol=6e-5)
+
+
+@pytest.mark.parametrize("name", ["tiny_160x96", "kitti_1248x384"])
+def test_torch_port_of_reference_path_matches_golden(golden, name):
+    """oracle/torch_port.py (the op-for-op torch restatement bench.py times on the GPU as `gpu_reference_baseline`)
+    reproduces what the reference's own modules produced for the same features and weights."""
+    import torch
+    from oracle import torch_port
+    g = golden("head_e2e_" + name)
+    shp = SHAPES[name]
+    batch, seed = int(g["batch"]), int(g["seed"])
+    feat = synth.features(shp, batch, seed)
+    w, b = synth.convdet_params(shp, seed + 1)
+    a = torch.from_numpy(synth.anchor_table(shp).astype(np.float32))[None]
+    torch.set_num_threads(8)
+    out = torch_port.detect(torch.from_numpy(feat), torch.from_numpy(w), torch.from_numpy(b), a, shp.num_classes, shp.input_hw,
+                            shp.top_k, shp.nms_thresh, shp.score_thresh)
+    sc = split_ragged(g["kept_count"], g["kept_score"])
+    bx = split_ragged(g["kept_count"], g["kept_box"])
+    cl = split_ragged(g["kept_count"], g["kept_class"])
+    for i, row in enumerate(out):
+        if len(sc[i]) == 0:
+            assert row is None
+            continue
+        assert np.array_equal(row["class_ids"], cl[i])
+        np.testing.assert_allclose(row["scores"], sc[i], rtol=RTOL, atol=1e-7)
+        np.testing.assert_allclose(row["boxes"], bx[i], rtol=RTOL, atol=1e-3)
