@@ -10,8 +10,15 @@
 // CTAs' candidates meet in rank 0 through distributed shared memory, and the winner is broadcast back.  Tie policy:
 // lowest anchor index (a stable argsort in the reference) -- the key (value, index) is totally ordered, so the result
 // does not depend on how the anchors are partitioned.  "Taken" anchors live in a shared-memory bitmask (each CTA keeps
-// the bits of its own anchors).  Bytes per image: G * A * 32 (float64 anchor table, L2-resident across the batch).
+// the bits of its own anchors).
+// Batched rounds: the greedy order only matters when two boxes want the same anchor, which is rare.  A round computes the
+// best untaken anchor of up to 32 pending boxes in ONE pass (anchor geometry in registers, all candidates exchanged with
+// one pair of cluster barriers) and accepts them in annotation order up to the first box whose candidate was just
+// taken by an earlier box of the round (or that has no overlapping anchor: distance fallback, one box the old way);
+// the rest is recomputed in the next round.  Every round settles at least one box, so the result is the sequential
+// one by construction; typical images need one or two rounds instead of G.  Bytes per image: G * A * 32 (float64 anchor table, L2-resident across the batch).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -21,6 +28,7 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kMaxCluster = 8;
+constexpr int kRoundBoxes = 32;   // boxes settled per batched round
 
 struct Best {
     double v;
@@ -91,7 +99,7 @@ __device__ Best cluster_reduce(Best mine, int cs, int rank, int &xchg, Best (*s_
 
 __global__ void __launch_bounds__(kThreads) match_kernel(const float4 *gt_boxes, const int *gt_count, int gmax,
                                                          const double *anchors, int A, int *out_idx,
-                                                         float4 *out_deltas, int cs) {
+                                                         float4 *out_deltas, int cs, int no_batch) {
     extern __shared__ unsigned taken[];  // bits of this CTA's anchors [a_begin, a_end): ceil(chunk/32) words
     __shared__ Best scratch[kThreads / 32];
     __shared__ Best s_cand[2][kMaxCluster];
@@ -109,7 +117,138 @@ __global__ void __launch_bounds__(kThreads) match_kernel(const float4 *gt_boxes,
         }
     __syncthreads();
 
-    for (int g = 0; g < G; ++g) {
+    __shared__ Best s_wbest[kRoundBoxes][kThreads / 32];
+    __shared__ Best s_cand2[2][kRoundBoxes][kMaxCluster];
+    __shared__ Best s_final[2][kRoundBoxes];
+    __shared__ int s_nacc[2];
+    const bool batched = !no_batch;
+    int g_next = 0;      // boxes [0, g_next) are settled
+    int force_seq = 0;   // the next box must take the sequential path (distance fallback)
+    while (g_next < G) {
+        if (batched && !force_seq) {
+            // ---- one batched round over boxes [g_next, g_next + nb) ----
+            const int nb = min(kRoundBoxes, G - g_next);
+            const int slot = xchg & 1;
+            ++xchg;
+            constexpr int kMaxPer = 5;                      // anchors per thread kept in registers per pass (KITTI: 2112 per CTA)
+            for (int a0 = a_begin; a0 < a_end || a0 == a_begin; a0 += kThreads * kMaxPer) {
+                double ax1[kMaxPer], ay1[kMaxPer], ax2[kMaxPer], ay2[kMaxPer], aar[kMaxPer];
+                bool live[kMaxPer];
+#pragma unroll
+                for (int k = 0; k < kMaxPer; ++k) {
+                    const int a = a0 + k * kThreads + threadIdx.x;
+                    live[k] = a < a_end && !((taken[(a - a_begin) >> 5] >> ((a - a_begin) & 31)) & 1u);
+                    if (live[k]) {
+                        const double2 xy = *reinterpret_cast<const double2 *>(anchors + (size_t)a * 4);
+                        const double2 wh = *reinterpret_cast<const double2 *>(anchors + (size_t)a * 4 + 2);
+                        const double hw = d_mul(0.5, d_sub(wh.x, 1.0)), hh = d_mul(0.5, d_sub(wh.y, 1.0));
+                        ax1[k] = d_sub(xy.x, hw); ay1[k] = d_sub(xy.y, hh); ax2[k] = d_add(xy.x, hw); ay2[k] = d_add(xy.y, hh);
+                        aar[k] = d_mul(d_sub(ax2[k], ax1[k]), d_sub(ay2[k], ay1[k]));
+                    }
+                }
+                for (int j = 0; j < nb; ++j) {
+                    const float4 b = gt_boxes[(size_t)img * gmax + g_next + j];
+                    const double bx1 = b.x, by1 = b.y, bx2 = b.z, by2 = b.w;
+                    const double area_g = (double)fmul(fsub(b.z, b.x), fsub(b.w, b.y));
+                    Best best{0.0, 0x7fffffff};
+#pragma unroll
+                    for (int k = 0; k < kMaxPer; ++k) {
+                        if (!live[k]) continue;
+                        const double lr = fmax(d_sub(fmin(ax2[k], bx2), fmax(ax1[k], bx1)), 0.0);
+                        const double tb = fmax(d_sub(fmin(ay2[k], by2), fmax(ay1[k], by1)), 0.0);
+                        const double inter = d_mul(lr, tb);
+                        const double uni = d_sub(d_add(aar[k], area_g), inter);
+                        const double iou = d_div(inter, d_add(uni, 1e-10));
+                        if (iou > 0.0 && (best.idx == 0x7fffffff || iou > best.v)) {   // a ascends with k: first max kept
+                            best.v = iou;
+                            best.idx = a0 + k * kThreads + threadIdx.x;
+                        }
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        Best y;
+                        y.v = __shfl_down_sync(0xffffffffu, best.v, off);
+                        y.idx = __shfl_down_sync(0xffffffffu, best.idx, off);
+                        best = better_max(best, y);
+                    }
+                    if ((threadIdx.x & 31) == 0) {
+                        Best &dst = s_wbest[j][threadIdx.x >> 5];
+                        dst = a0 == a_begin ? best : better_max(dst, best);   // several passes when a CTA owns > 4096 anchors
+                    }
+                }
+                if (a0 + kThreads * kMaxPer >= a_end) break;
+            }
+            __syncthreads();
+            if ((int)threadIdx.x < nb) {   // block result of box j -> rank 0
+                Best w = s_wbest[threadIdx.x][0];
+                for (int k = 1; k < kThreads / 32; ++k) w = better_max(w, s_wbest[threadIdx.x][k]);
+                if (cs > 1) cg::this_cluster().map_shared_rank(&s_cand2[slot][threadIdx.x][0], 0)[rank] = w;
+                else s_cand2[slot][threadIdx.x][0] = w;
+            }
+            if (cs > 1) cg::this_cluster().sync(); else __syncthreads();
+            if (rank == 0) {
+                if ((int)threadIdx.x < nb) {
+                    Best w = s_cand2[slot][threadIdx.x][0];
+                    for (int r = 1; r < cs; ++r) w = better_max(w, s_cand2[slot][threadIdx.x][r]);
+                    s_final[slot][threadIdx.x] = w;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    // accept in annotation order up to the first box that has no candidate or collides with an accepted one
+                    int n_acc = 0;
+                    for (; n_acc < nb; ++n_acc) {
+                        const int c = s_final[slot][n_acc].idx;
+                        bool clash = c == 0x7fffffff;
+                        for (int q = 0; q < n_acc && !clash; ++q) clash = s_final[slot][q].idx == c;
+                        if (clash) break;
+                    }
+                    for (int r = 0; r < cs; ++r) {
+                        if (cs > 1) {
+                            Best *rf = cg::this_cluster().map_shared_rank(&s_final[slot][0], r);
+                            if (r) for (int q = 0; q < n_acc; ++q) rf[q] = s_final[slot][q];
+                            *cg::this_cluster().map_shared_rank(&s_nacc[slot], r) = n_acc;
+                        } else {
+                            s_nacc[slot] = n_acc;
+                        }
+                    }
+                }
+            }
+            if (cs > 1) cg::this_cluster().sync(); else __syncthreads();
+            const int n_acc = s_nacc[slot];
+            for (int q = threadIdx.x; q < n_acc; q += kThreads) {
+                const int j = s_final[slot][q].idx;
+                if (j >= a_begin && j < a_end) atomicOr(&taken[(j - a_begin) >> 5], 1u << ((j - a_begin) & 31));
+                if (rank == 0) {
+                    const float4 b = gt_boxes[(size_t)img * gmax + g_next + q];
+                    const float gx = fdiv(fadd(b.x, b.z), 2.0f), gy = fdiv(fadd(b.y, b.w), 2.0f);
+                    const float gw = fadd(fsub(b.z, b.x), 1.0f), gh = fadd(fsub(b.w, b.y), 1.0f);
+                    const double ax = anchors[(size_t)j * 4], ay = anchors[(size_t)j * 4 + 1];
+                    const double aw = anchors[(size_t)j * 4 + 2], ah = anchors[(size_t)j * 4 + 3];
+                    float4 d;
+                    d.x = (float)d_div(d_sub((double)gx, ax), aw);   // boxes.py:125-128, float64 then cast
+                    d.y = (float)d_div(d_sub((double)gy, ay), ah);
+                    d.z = (float)log(d_div((double)gw, aw));
+                    d.w = (float)log(d_div((double)gh, ah));
+                    out_idx[(size_t)img * gmax + g_next + q] = j;
+                    out_deltas[(size_t)img * gmax + g_next + q] = d;
+                }
+            }
+            __syncthreads();
+            g_next += n_acc;
+            // the box that stopped the round: no overlapping untaken anchor -> distance fallback (sequential path);
+            // a clash -> simply recomputed by the next round
+            if (n_acc < nb && s_final[slot][n_acc].idx == 0x7fffffff && rank == 0) force_seq = 1;
+            if (cs > 1) {   // make the verdict cluster-uniform (only rank 0 holds the un-accepted candidates)
+                __shared__ int s_force[2];
+                if (rank == 0 && threadIdx.x == 0)
+                    for (int r = 0; r < cs; ++r) *cg::this_cluster().map_shared_rank(&s_force[slot], r) = force_seq;
+                cg::this_cluster().sync();
+                force_seq = s_force[slot];
+            }
+            continue;
+        }
+        force_seq = 0;
+        const int g = g_next++;
         const float4 b = gt_boxes[(size_t)img * gmax + g];
         // float32 scalar arithmetic of boxes.py:17-22 (xyxy_to_xywh on the float32 GT array)
         const float gx = fdiv(fadd(b.x, b.z), 2.0f);
@@ -242,7 +381,8 @@ extern "C" int sqd_match_anchors(const float *d_gt_boxes, const int32_t *d_gt_co
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, match_kernel, reinterpret_cast<const float4 *>(d_gt_boxes), d_gt_count, gmax,
-                                       d_anchors64, num_anchors, d_anchor_idx, reinterpret_cast<float4 *>(d_deltas), cs);
+                                       d_anchors64, num_anchors, d_anchor_idx, reinterpret_cast<float4 *>(d_deltas), cs,
+                                       getenv("SQD_MATCH_SEQUENTIAL") ? 1 : 0);
     if (e != cudaSuccess) {
         sqd_set_error("launch of match_kernel failed: %s", cudaGetErrorString(e));
         return (int)e;

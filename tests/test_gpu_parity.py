@@ -541,3 +541,35 @@ def test_filter_nan_and_inf_inputs(ops):
     one = ops.detect_from_pred(dp, a32, shp.input_hw, 3, shp.top_k, 0.4, 0.3, two_phase=False)
     assert torch.equal(two.count, one.count) and torch.equal(two.anchor, one.anchor)
     assert int(two.count.max()) <= shp.top_k
+
+
+def test_matcher_batched_rounds_equal_sequential(monkeypatch):
+    """The batched rounds (many boxes per pass, accepted up to the first clash) against the box-by-box kernel and the
+    oracle, on inputs built to clash: duplicated boxes (same best anchor), shifted near-duplicates, boxes with no
+    overlapping anchor in between (distance fallback), more boxes than a round holds."""
+    from squeezedet_pytorch_b200 import targets
+    shp = synth.KITTI
+    anchors = synth.anchor_table(shp)
+    m = targets.AnchorMatcher(anchors, shp.num_classes)
+    rs = np.random.RandomState(77)
+    boxes_l = []
+    for i in range(6):
+        _, bx = synth.gt_boxes(shp, 400 + i)
+        bx = np.concatenate([bx, bx[:3], bx[:2] + np.float32(0.25)])            # exact and near duplicates -> clashes
+        if i % 2 == 0:
+            tiny = np.array([[3.0, 3.0, 3.5, 3.4], [1240.0, 380.0, 1240.4, 380.3]], np.float32)   # overlap nothing? (fallback)
+            bx = np.concatenate([bx[:2], tiny, bx[2:]])
+        if i == 5:
+            bx = np.concatenate([bx] * 4)[:70]                                  # more than two rounds of 32
+        boxes_l.append(np.ascontiguousarray(bx, dtype=np.float32))
+    gb, _, gc = m.pack(boxes_l)
+    monkeypatch.delenv("SQD_MATCH_SEQUENTIAL", raising=False)
+    idx_b, del_b = m.match(gb, gc)
+    monkeypatch.setenv("SQD_MATCH_SEQUENTIAL", "1")
+    idx_s, del_s = m.match(gb, gc)
+    monkeypatch.delenv("SQD_MATCH_SEQUENTIAL", raising=False)
+    assert torch.equal(idx_b, idx_s) and torch.equal(del_b, del_s)
+    for i, bx in enumerate(boxes_l):
+        exp_del, exp_idx = orc.match_anchors(bx, anchors)
+        assert np.array_equal(idx_b[i, :len(bx)].cpu().numpy(), exp_idx), i
+        np.testing.assert_allclose(del_b[i, :len(bx)].cpu().numpy(), exp_del, rtol=1e-6, atol=1e-6)
