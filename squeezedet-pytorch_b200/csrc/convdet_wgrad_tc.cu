@@ -158,7 +158,6 @@ struct WgParams {
     int gwp, tiles_per_img;          // padded row length; 64-pixel tiles per image = ceil(gh*gwp / 64)
     int total_tiles;                 // batch * tiles_per_img
     int nslice;
-    int dbg;                         // debug (SQD_WG_DBG): 1 skip MMAs, 2 skip TMA loads, 4 skip TMEM drain, 8 skip partial store
     const unsigned *amax_x;          // (B, Cin/64)
     const unsigned *amax_g;          // (B, 2)
     float *partial;                  // (nslice, 9, Cin, 80)
@@ -229,10 +228,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
             }
             if (elect_one_sync()) {
                 uint8_t *st = smem + (size_t)s * kStageBytes;
-                if (p.dbg & 2) {
-                    mbar_arrive(full + s);
-                    goto next_stage;
-                }
                 mbar_arrive_expect_tx(full + s, kStageBytes);
                 const int q0 = t * kPixTile;                 // flat pixel origin of the X tile (16-byte aligned)
                 const int g0 = q0 - dy * p.gwp;              // G^T origin: the row part of the tap shift (multiple of 8)
@@ -241,7 +236,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
                 tma_load_3d(map_g2, full + s, st + 2 * kABytes, g0, 0, img);
                 tma_load_3d(map_g1, full + s, st + 2 * kABytes + kBBytes, g0, 0, img);
             }
-        next_stage:
             __syncwarp();
             if (++s == kStages) {
                 s = 0;
@@ -275,7 +269,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
             const uint64_t b_cat = umma_desc_sw128(st + 2 * kABytes), b_g1 = umma_desc_sw128(st + 2 * kABytes + kBBytes);
             if (elect_one_sync()) {
 #pragma unroll
-                for (int ks = 0; ks < 4 && !(p.dbg & 1); ++ks) {
+                for (int ks = 0; ks < 4; ++ks) {
                     const uint64_t adv = (uint64_t)((ks * 32) >> 4);   // +32 B per K step of 16 pixels
                     umma_f16_ss(d_tmem, a1 + adv, b_cat + adv, kIdescCat, (fresh && ks == 0) ? 0u : 1u);
                     umma_f16_ss(d_tmem, a2 + adv, b_g1 + adv, kIdescOne, 1u);
@@ -320,7 +314,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
             const float inv_g1 = 1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_g + (size_t)img * 2 + 1)));
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * kAccCols;
 #pragma unroll
-            for (int n0 = 0; n0 < kNPad && !(p.dbg & 4); n0 += 16) {
+            for (int n0 = 0; n0 < kNPad; n0 += 16) {
                 uint32_t v[16], w[16];
                 tmem_ld_x16(taddr + n0, v);            // x1*g2 + x2*g1   (x 2^11)
                 tmem_ld_x16(taddr + kNPad + n0, w);    // x1*g1
@@ -336,7 +330,199 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + buf);
         }
-        if (c < p.cin && !(p.dbg & 8)) {
+        if (c < p.cin) {
+            float4 *dst = reinterpret_cast<float4 *>(p.partial + (((size_t)slice * 9 + tap) * p.cin + c) * kNPad);
+#pragma unroll
+            for (int n = 0; n < kNPad; n += 4) dst[n >> 2] = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---- three taps per CTA ---------------------------------------------------------------------------------------------
+// The feature tile is the same for all nine taps (only G moves), and the single-tap kernel above is L2 -> SM bound
+// (tensor pipe 39 % active).  Here a CTA owns (128-channel block, column shift dx, slice) and runs the THREE row shifts
+// dy against one load of the feature tile: 32 KB of X + 3 x 20 KB of G per 64-pixel step instead of 3 x 52 KB.  Three
+// accumulators of 160 TMEM columns (single buffered: the issuer waits for the twelve accumulate warps once per image),
+// 14 warps: TMA producer, MMA issuer, 3 groups of 4 accumulate warps (group t owns the accumulator of dy = t - 1).
+constexpr int kTaps3 = 3;
+constexpr int kStage3Bytes = 2 * kABytes + kTaps3 * 2 * kBBytes;   // 92 KB
+constexpr int kStages3 = 2;
+constexpr int kThreads3 = 64 + kTaps3 * 128;                       // 448
+
+__global__ void __launch_bounds__(kThreads3, 1)
+wgrad_tc3_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
+                 const __grid_constant__ CUtensorMap map_g1a, const __grid_constant__ CUtensorMap map_g1b,
+                 const __grid_constant__ CUtensorMap map_g1c, const __grid_constant__ CUtensorMap map_g2a,
+                 const __grid_constant__ CUtensorMap map_g2b, const __grid_constant__ CUtensorMap map_g2c, const WgParams p) {
+    constexpr uint32_t kIdescCat = umma_idesc_f16(128, 2 * kNPad);
+    constexpr uint32_t kIdescOne = umma_idesc_f16(128, kNPad);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *ctrl = smem + (size_t)kStages3 * kStage3Bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ctrl);      // [2]
+    uint64_t *empty = full + 2;                               // [2]
+    uint64_t *tmem_full = empty + 2;                          // [1]
+    uint64_t *tmem_empty = tmem_full + 1;                     // [1]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+    volatile int *abort_flag = reinterpret_cast<volatile int *>(tmem_slot + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = blockIdx.x, dxi = blockIdx.y, slice = blockIdx.z;   // dxi = dx + 1
+    const int k0 = (int)((long long)p.total_tiles * slice / p.nslice), k1 = (int)((long long)p.total_tiles * (slice + 1) / p.nslice);
+    const int ntiles = k1 - k0;
+
+    if (threadIdx.x == 0) {
+        *abort_flag = 0;
+        for (int s = 0; s < kStages3; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4 * kTaps3);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    const CUtensorMap *map_g1 = dxi == 0 ? &map_g1a : (dxi == 1 ? &map_g1b : &map_g1c);
+    const CUtensorMap *map_g2 = dxi == 0 ? &map_g2a : (dxi == 1 ? &map_g2b : &map_g2c);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x1);
+        tma_prefetch_desc(&map_x2);
+        tma_prefetch_desc(map_g1);
+        tma_prefetch_desc(map_g2);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < ntiles; ++i) {
+            const int kt = k0 + i;
+            const int img = kt / p.tiles_per_img, t = kt - img * p.tiles_per_img;
+            if (!mbar_wait_warp(empty + s, ph ^ 1u, abort_flag)) {
+                if (lane == 0) atomicCAS(p.status, 0, 1);
+                break;
+            }
+            if (elect_one_sync()) {
+                uint8_t *st = smem + (size_t)s * kStage3Bytes;
+                mbar_arrive_expect_tx(full + s, kStage3Bytes);
+                const int q0 = t * kPixTile;
+                tma_load_3d(&map_x1, full + s, st, q0, mt * kMTile, img);
+                tma_load_3d(&map_x2, full + s, st + kABytes, q0, mt * kMTile, img);
+#pragma unroll
+                for (int ti = 0; ti < kTaps3; ++ti) {   // dy = ti - 1: G^T origin q0 - dy*gwp
+                    uint8_t *bt = st + 2 * kABytes + ti * 2 * kBBytes;
+                    tma_load_3d(map_g2, full + s, bt, q0 - (ti - 1) * p.gwp, 0, img);
+                    tma_load_3d(map_g1, full + s, bt + kBBytes, q0 - (ti - 1) * p.gwp, 0, img);
+                }
+            }
+            __syncwarp();
+            if (++s == kStages3) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
+    } else if (warp == 1) {
+        int s = 0, chunk = 0;
+        uint32_t ph = 0;
+        bool fresh = true;
+        for (int i = 0; i < ntiles; ++i) {
+            const int kt = k0 + i;
+            const int img = kt / p.tiles_per_img;
+            const bool chunk_end = (i == ntiles - 1) || ((kt + 1) / p.tiles_per_img != img);
+            if (fresh) {   // single accumulator set: wait until the previous image has been drained
+                if (!mbar_wait_warp(tmem_empty, ((uint32_t)chunk & 1u) ^ 1u, abort_flag)) {
+                    if (lane == 0) atomicCAS(p.status, 0, 4);
+                    break;
+                }
+            }
+            if (!mbar_wait_warp(full + s, ph, abort_flag)) {
+                if (lane == 0) atomicCAS(p.status, 0, 2);
+                break;
+            }
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + (size_t)s * kStage3Bytes);
+            const uint64_t a1 = umma_desc_sw128(st), a2 = umma_desc_sw128(st + kABytes);
+            if (elect_one_sync()) {
+#pragma unroll
+                for (int ti = 0; ti < kTaps3; ++ti) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)ti * kAccCols;
+                    const uint64_t b_cat = umma_desc_sw128(st + 2 * kABytes + ti * 2 * kBBytes);
+                    const uint64_t b_g1 = umma_desc_sw128(st + 2 * kABytes + ti * 2 * kBBytes + kBBytes);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+                        umma_f16_ss(d_tmem, a1 + adv, b_cat + adv, kIdescCat, (fresh && ks == 0) ? 0u : 1u);
+                        umma_f16_ss(d_tmem, a2 + adv, b_g1 + adv, kIdescOne, 1u);
+                    }
+                }
+                umma_commit(empty + s);
+                if (chunk_end) umma_commit(tmem_full);
+            }
+            __syncwarp();
+            fresh = chunk_end;
+            if (chunk_end) ++chunk;
+            if (++s == kStages3) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
+    } else {
+        const int ti = (warp - 2) >> 2;                // accumulator / dy of this group
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const int c = mt * kMTile + row;
+        float acc[kNPad];
+#pragma unroll
+        for (int n = 0; n < kNPad; ++n) acc[n] = 0.f;
+        int chunk = 0;
+        for (int i = 0; i < ntiles; ++i) {
+            const int kt = k0 + i;
+            const int img = kt / p.tiles_per_img;
+            const bool chunk_end = (i == ntiles - 1) || ((kt + 1) / p.tiles_per_img != img);
+            if (!chunk_end) continue;
+            const uint32_t ph = (uint32_t)chunk & 1u;
+            ++chunk;
+            if (!mbar_wait_warp(tmem_full, ph, abort_flag)) {
+                if (lane == 0) atomicCAS(p.status, 0, 3);
+                break;
+            }
+            tc_fence_after();
+            __syncwarp();
+            const int ncb = p.cin >> 6;
+            const float inv_x = c < p.cin ? 1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_x + (size_t)img * ncb + (c >> 6)))) : 0.f;
+            const float inv_g0 = 1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_g + (size_t)img * 2)));
+            const float inv_g1 = 1.f / pow2_scale_for(__uint_as_float(__ldg(p.amax_g + (size_t)img * 2 + 1)));
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ti * kAccCols;
+#pragma unroll
+            for (int n0 = 0; n0 < kNPad; n0 += 16) {
+                uint32_t v[16], w[16];
+                tmem_ld_x16(taddr + n0, v);
+                tmem_ld_x16(taddr + kNPad + n0, w);
+                tmem_ld_wait();
+                const float inv_g = n0 < 64 ? inv_g0 : inv_g1;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float t = fmaf(__uint_as_float(v[k]), kLoInv, __uint_as_float(w[k])) * inv_x;
+                    acc[n0 + k] = fmaf(t, inv_g, acc[n0 + k]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+        }
+        if (c < p.cin) {
+            const int tap = ti * 3 + dxi;              // dy-major tap index of the weight tensor
             float4 *dst = reinterpret_cast<float4 *>(p.partial + (((size_t)slice * 9 + tap) * p.cin + c) * kNPad);
 #pragma unroll
             for (int n = 0; n < kNPad; n += 4) dst[n >> 2] = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
@@ -404,9 +590,9 @@ WgWs wg_ws(int batch, int cin, int gh, int gw) {
     WgWs w;
     const int gwp = gwp_of(gw);
     const int tiles = batch * ((gh * gwp + kPixTile - 1) / kPixTile);
-    // slices: enough CTAs for ~3 waves of (Cin/128 x 9) work items, at least ~8 pixel tiles each
-    const int items = ((cin + kMTile - 1) / kMTile) * 9;
-    int ns = (3 * SQD_SM_COUNT + items - 1) / items;
+    // slices: three waves of work items (channel block x taps), at least ~8 pixel tiles each
+    const int items = ((cin + kMTile - 1) / kMTile) * (getenv("SQD_WG_SINGLE_TAP") ? 9 : 3);
+    int ns = (3 * SQD_SM_COUNT) / items;   // <= 3 full waves of one CTA per SM (a 4th, nearly empty wave costs a full wave time)
     if (ns > tiles / 8) ns = tiles / 8;
     if (ns < 1) ns = 1;
     w.nslice = ns;
@@ -500,16 +686,24 @@ extern "C" int sqd_convdet_wgrad_tc(const float *d_feat_nchw, const float *d_gpr
     p.tiles_per_img = (gh * gwp + kPixTile - 1) / kPixTile;
     p.total_tiles = batch * p.tiles_per_img;
     p.nslice = w.nslice;
-    p.dbg = getenv("SQD_WG_DBG") ? atoi(getenv("SQD_WG_DBG")) : 0;
     p.amax_x = amax_x;
     p.amax_g = amax_g;
     p.partial = reinterpret_cast<float *>(ws + w.partial_off);
     p.status = reinterpret_cast<int *>(ws + w.status_off);
-    const size_t smem = 1024 + (size_t)kStages * kStageBytes + 1024;
-    SQD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const dim3 grid((cin + kMTile - 1) / kMTile, 9, w.nslice);
-    wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
-    SQD_LAUNCH_CHECK("wgrad_tc_kernel");
+    if (!getenv("SQD_WG_SINGLE_TAP")) {
+        // three row shifts per CTA: a third of the feature-tile traffic
+        const size_t smem3 = 1024 + (size_t)kStages3 * kStage3Bytes + 1024;
+        SQD_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        const dim3 grid3((cin + kMTile - 1) / kMTile, 3, w.nslice);
+        wgrad_tc3_kernel<<<grid3, kThreads3, smem3, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
+        SQD_LAUNCH_CHECK("wgrad_tc3_kernel");
+    } else {
+        const size_t smem = 1024 + (size_t)kStages * kStageBytes + 1024;
+        SQD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const dim3 grid((cin + kMTile - 1) / kMTile, 9, w.nslice);
+        wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
+        SQD_LAUNCH_CHECK("wgrad_tc_kernel");
+    }
     if ((rc = stage_check("gemm", st))) return rc;
     const size_t n_in = (size_t)9 * cin * kNPad;
     wgrad_tc_reduce_kernel<<<(int)((n_in + 255) / 256), 256, 0, st>>>(p.partial, w.nslice, cin, cout, d_gweight);

@@ -284,13 +284,18 @@ def test_convdet_dgrad_and_bias_grad(ops, name, batch):
     _, gw64, _ = orc.convdet_backward(feat, w, g, dtype=np.float64)
     wscale = np.abs(gw64).mean()
     e_ref = np.abs(gw32 - gw64).max() / wscale
-    for tc in (False, True):   # fp32 CUDA-core kernel, tcgen05 f16x3 kernel
-        gw1 = ops.convdet_wgrad(dev(feat), dev(g), tensor_cores=tc, check_status=True)
-        gw2 = ops.convdet_wgrad(dev(feat), dev(g), tensor_cores=tc, check_status=True)
+    for tc in (False, True, "single-tap"):   # fp32 CUDA-core kernel, tcgen05 f16x3 (3 taps per CTA), tcgen05 (1 tap per CTA)
+        if tc == "single-tap":
+            os.environ["SQD_WG_SINGLE_TAP"] = "1"
+        try:
+            gw1 = ops.convdet_wgrad(dev(feat), dev(g), tensor_cores=bool(tc), check_status=True)
+            gw2 = ops.convdet_wgrad(dev(feat), dev(g), tensor_cores=bool(tc), check_status=True)
+        finally:
+            os.environ.pop("SQD_WG_SINGLE_TAP", None)
         assert torch.equal(gw1, gw2)
         gw1 = gw1.cpu().numpy()
         e_ours = np.abs(gw1 - gw64).max() / wscale
-        print(f"wgrad ({'tcgen05' if tc else 'simt'}) vs float64: ours max {e_ours:.2e}, torch-cpu fp32 max {e_ref:.2e} (rel. to mean |dW|)")
+        print(f"wgrad ({tc if isinstance(tc, str) else 'tcgen05' if tc else 'simt'}) vs float64: ours max {e_ours:.2e}, torch-cpu fp32 max {e_ref:.2e} (rel. to mean |dW|)")
         np.testing.assert_allclose(gw1, gw32, rtol=1e-4, atol=1e-4 * wscale)
         assert e_ours < 4 * e_ref + 1e-5
 
