@@ -139,6 +139,15 @@ def run_cpu_arm(args, budget_s, warmup, steps):
     return info
 
 
+_RESULT_OUT = None
+
+
+def emit_result(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -155,7 +164,7 @@ def main_reference(args):
         "e2e": {"value": info["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_result(line)
     return 0
 
 
@@ -400,8 +409,7 @@ def main_ours(args):
             line["cpu_baseline"] = cpu
         if gpu_ref is not None:
             line["gpu_reference_baseline"] = gpu_ref
-        sys.stdout.flush()
-        print(json.dumps(line), flush=True)
+        emit_result(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -420,6 +428,13 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: one e2e step only (the JSON line is then not a bench result)")
     ap.add_argument("--e2e-chunk", type=int, default=5, help="images per H2D/compute pipeline group of the e2e call")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result.  Libraries print there too (NCCL's "NCCL version" banner
+    # under NCCL_DEBUG=VERSION is a C printf), so file descriptor 1 is pointed at stderr for the whole run and the
+    # result goes to a private duplicate of the original stdout.
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return main_reference(args)
     return main_ours(args)

@@ -24,8 +24,9 @@ def init_from_env(backend=None):
         if backend == "nccl":
             torch.cuda.set_device(local)
             kw["device_id"] = torch.device("cuda", local)   # binds the communicator to this rank's GPU (no guessing)
-            if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-                os.environ["NCCL_DEBUG"] = "WARN"           # the version banner goes to stdout, which carries the JSON line
+            # NCCL writes its debug output (the "NCCL version" banner included, at any level >= VERSION) to stdout,
+            # which carries bench.py's one JSON line: route it to stderr instead of silencing it.
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, world, local
 
