@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SQD_ABI_VERSION 2
+#define SQD_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SQD_API __attribute__((visibility("default")))
@@ -173,7 +173,12 @@ SQD_API int sqd_head_detect_profile(const float *d_feat, int layout, const void 
  * asynchronous); the call enqueues, per group of `chunk_images` images, the H2D copy on `copy_stream` and the kernels
  * on `stream`, so the copy of group g+1 overlaps the compute of group g, then the D2H copies of the five output
  * arrays on `stream`.  The caller synchronises `stream` before reading the outputs.  copy_stream NULL = no overlap;
- * chunk_images <= 0 = one group.  The workspace holds the device staging of features and outputs. */
+ * chunk_images <= 0 = one group.  The workspace holds the device staging of features and outputs.
+ * flags: 0, or SQD_HOST_NO_STAGING_FENCE when the caller guarantees that nothing enqueued earlier on `stream` still
+ * reads THIS workspace (a serving loop that alternates two workspaces and has read call i's results before issuing
+ * call i+2): the first H2D copy then starts as soon as copy_stream is free instead of after `stream`'s earlier
+ * kernels, which keeps the PCIe link busy across calls. */
+#define SQD_HOST_NO_STAGING_FENCE 1
 SQD_API size_t sqd_head_detect_host_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int top_k, int layout,
                                                     int algo, int chunk_images);
 SQD_API int sqd_head_detect_host(const float *h_feat, int layout, const void *d_packed, const float *d_weight,
@@ -181,7 +186,8 @@ SQD_API int sqd_head_detect_host(const float *h_feat, int layout, const void *d_
                                  int anchors_per_grid, int num_classes, int input_h, int input_w, int top_k,
                                  double nms_thresh, double score_thresh, int32_t *h_count, int32_t *h_out_anchor,
                                  int32_t *h_out_class, float *h_out_score, float *h_out_box, void *d_workspace,
-                                 size_t workspace_bytes, int algo, int chunk_images, void *stream, void *copy_stream);
+                                 size_t workspace_bytes, int algo, int chunk_images, void *stream, void *copy_stream,
+                                 int flags);
 
 /* ---------------------------------------------------------------------------------------------
  * a11-a12  compute_deltas: greedy sequential anchor<->ground-truth matching in float64.

@@ -45,7 +45,7 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, C.POINTER(C.c_float)]),
     "sqd_head_detect_host_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i, _i]),
     "sqd_head_detect_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _d,
-                                  _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp, _vp]),
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _i]),
     "sqd_match_anchors": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "sqd_build_targets": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "sqd_loss_workspace_bytes": (_sz, [_i, _i]),

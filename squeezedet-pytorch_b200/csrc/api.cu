@@ -283,8 +283,11 @@ extern "C" int sqd_head_detect_host(const float *h_feat, int layout, const void 
                                     int anchors_per_grid, int num_classes, int input_h, int input_w, int top_k,
                                     double nms_thresh, double score_thresh, int32_t *h_count, int32_t *h_out_anchor,
                                     int32_t *h_out_class, float *h_out_score, float *h_out_box, void *d_workspace,
-                                    size_t workspace_bytes, int algo, int chunk_images, void *stream, void *copy_stream) {
+                                    size_t workspace_bytes, int algo, int chunk_images, void *stream, void *copy_stream,
+                                    int flags) {
     if (batch == 0) return SQD_OK;
+    SQD_REQUIRE((flags & ~SQD_HOST_NO_STAGING_FENCE) == 0, SQD_E_UNSUPPORTED, "sqd_head_detect_host: unknown flags 0x%x",
+                flags);
     SQD_REQUIRE(h_feat && h_count && h_out_anchor && h_out_class && h_out_score && h_out_box && d_workspace, SQD_E_NULL,
                 "sqd_head_detect_host: NULL pointer");
     SQD_REQUIRE(layout == SQD_LAYOUT_NCHW || layout == SQD_LAYOUT_NHWC, SQD_E_SHAPE, "sqd_head_detect_host: bad layout %d",
@@ -309,7 +312,7 @@ extern "C" int sqd_head_detect_host(const float *h_feat, int layout, const void 
     const size_t img_elems = (size_t)cin * gh * gw;
     const int nchunks = (batch + chunk - 1) / chunk;
     cudaEvent_t ev = nullptr;
-    if (cst != st) {
+    if (cst != st && !(flags & SQD_HOST_NO_STAGING_FENCE)) {
         // the staging buffer may still be read by kernels of the previous call on `stream`
         SQD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         SQD_CUDA(cudaEventRecord(ev, st));

@@ -258,8 +258,17 @@ class HostDetections:
         self.cls = torch.empty((batch, top_k), dtype=torch.int32).pin_memory()
         self.score = torch.empty((batch, top_k), dtype=torch.float32).pin_memory()
         self.box = torch.empty((batch, top_k, 4), dtype=torch.float32).pin_memory()
+        self.ready = None     # CUDA event of the call that last wrote these buffers (head_detect_host(sync=False))
+
+    def wait(self):
+        """Block until the call that fills these buffers has finished (no-op after a sync=True call)."""
+        if self.ready is not None:
+            self.ready.synchronize()
+            self.ready = None
+        return self
 
     def to_list(self):
+        self.wait()
         return Detections(self.count, self.anchor, self.cls, self.score, self.box).to_list()
 
 
@@ -268,9 +277,13 @@ _copy_streams = {}
 
 def head_detect_host(host_feat, weight, bias, anchors_f32, anchors_per_grid, num_classes, input_hw, top_k, nms_thresh,
                      score_thresh, packed=None, algo=CONV_TCGEN05_F16X3, out: HostDetections = None, chunk_images=5,
-                     overlap=True, sync=True) -> HostDetections:
+                     overlap=True, sync=True, slot=None) -> HostDetections:
     """HOST feature maps (B,Cin,gh,gw) fp32 (pinned, NCHW-contiguous) -> HOST detections through ONE ABI call that
-    pipelines H2D copies with the kernels (sqd_head_detect_host).  `weight`/`bias`/`anchors` live on the device."""
+    pipelines H2D copies with the kernels (sqd_head_detect_host).  `weight`/`bias`/`anchors` live on the device.
+
+    Serving loop (keeps the PCIe link busy across calls): pass sync=False and alternate slot=0,1 with one
+    HostDetections per slot; call `.wait()` on call i's result before issuing call i+2 (which reuses its slot).  Each
+    slot has its own device workspace, so call i+1's copies start while call i's kernels still run."""
     lib = load()
     if host_feat.is_cuda or not host_feat.is_contiguous() or host_feat.dtype != torch.float32:
         raise _lib.SqdError("head_detect_host needs a contiguous fp32 HOST tensor (B,Cin,gh,gw)")
@@ -282,8 +295,11 @@ def head_detect_host(host_feat, weight, bias, anchors_f32, anchors_per_grid, num
     if packed is None:
         packed = pack_convdet_weights(w)
     nbytes = lib.sqd_head_detect_host_workspace_bytes(B, cin, gh, gw, cout, top_k, LAYOUT_NCHW, algo, chunk_images)
-    ws = workspace().get("head_detect_host", nbytes, dev)
+    ws = workspace().get("head_detect_host" if slot is None else "head_detect_host/%d" % slot, nbytes, dev)
     det = out if out is not None else HostDetections(B, top_k)
+    if det.ready is not None:
+        raise _lib.SqdError("head_detect_host: the output buffers still belong to an unfinished call; .wait() on them first")
+    flags = 0 if slot is None else 1     # SQD_HOST_NO_STAGING_FENCE: per-slot workspaces, reuse guarded by .wait()
     cst = None
     if overlap:
         key = torch.device(dev).index
@@ -295,9 +311,12 @@ def head_detect_host(host_feat, weight, bias, anchors_f32, anchors_per_grid, num
                                    gw, anchors_per_grid, num_classes, int(input_hw[0]), int(input_hw[1]), top_k,
                                    float(nms_thresh), float(score_thresh), hp(det.count), hp(det.anchor), hp(det.cls),
                                    hp(det.score), hp(det.box), ptr(ws), ws.numel(), algo, int(chunk_images),
-                                   stream_ptr(dev), cst), "sqd_head_detect_host")
+                                   stream_ptr(dev), cst, flags), "sqd_head_detect_host")
     if sync:
         torch.cuda.current_stream(dev).synchronize()
+    else:
+        det.ready = torch.cuda.Event()
+        det.ready.record(torch.cuda.current_stream(dev))
     return det
 
 

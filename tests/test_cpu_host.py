@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/sqdet_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared          # the ctypes table covers the whole header
-    assert lib.sqd_abi_version() == 2
+    assert lib.sqd_abi_version() == 3
 
 
 def test_size_queries_need_no_gpu():

@@ -180,6 +180,41 @@ def test_head_detect_host_equals_device_call(ops, chunk):
         assert torch.equal(getattr(ref, f).cpu(), getattr(host, f)), f
 
 
+def test_head_detect_host_serving_loop(ops):
+    """sync=False with two alternating slots (SQD_HOST_NO_STAGING_FENCE): calls overlap on the device, every call's
+    result equals the blocking call on the same input, and buffers of an unfinished call are refused."""
+    from squeezedet_pytorch_b200._lib import SqdError
+    shp = synth.KITTI
+    w, b = synth.convdet_params(shp, 22)
+    a32 = dev(synth.anchor_table(shp).astype(np.float32))
+    args = (dev(w), dev(b), a32, 9, 3, shp.input_hw, shp.top_k, shp.nms_thresh, shp.score_thresh)
+    feats = [torch.from_numpy(synth.features(shp, 4, 40 + i)).pin_memory() for i in range(5)]
+    want = []
+    for f in feats:
+        d = ops.head_detect_host(f, *args, chunk_images=2)
+        want.append({k: getattr(d, k).clone() for k in ("count", "anchor", "cls", "score", "box")})
+    outs = [ops.HostDetections(4, shp.top_k) for _ in range(2)]
+    pending, got = None, []
+
+    def read(d):
+        d.wait()
+        got.append({k: getattr(d, k).clone() for k in ("count", "anchor", "cls", "score", "box")})
+
+    for i, f in enumerate(feats):
+        d = ops.head_detect_host(f, *args, chunk_images=2, out=outs[i % 2], sync=False, slot=i % 2)
+        if i == 0:
+            with pytest.raises(SqdError):
+                ops.head_detect_host(f, *args, chunk_images=2, out=outs[0], sync=False, slot=0)
+        if pending is not None:
+            read(pending)
+        pending = d
+    read(pending)
+    assert len(got) == len(want)
+    for g, w_ in zip(got, want):
+        for k in g:
+            assert torch.equal(g[k], w_[k]), k
+
+
 @pytest.mark.parametrize("name,batch", [("tiny_160x96", 3), ("kitti_1248x384", 7)])
 def test_pair_kernel_matches_single_cta_kernel(ops, name, batch):
     """The production CTA-pair kernel (cta_group::2, odd tile counts -> ghost tile, split tiles across pairs) against
