@@ -10,6 +10,7 @@
 // same small fp16 planes of G, which stay in L2).  Same f16x3 numerics as the forward (fp32-grade products).
 // The result is written NHWC (B, gh, gw, Cin): the channels_last memory format of the logical (B, Cin, gh, gw) tensor.
 // The weight gradient (wgrad: a contraction over B*gh*gw pixels) is NOT native yet -- see DESIGN.md.
+#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -78,6 +79,36 @@ __global__ void __launch_bounds__(256) gpred_absmax_kernel(const float *__restri
     for (int i = threadIdx.x; i < ncb; i += blockDim.x) atomicMax(amax_bits + (size_t)b * ncb + i, s_max[i]);
 }
 
+// The same maxima for cout % 4 == 0 (KITTI: 72): an image's (P, cout) block read as a flat run of 16-byte quads, fully
+// coalesced; a quad never straddles a pixel or a 64-channel block.  Grid (chunks, B); at most 2 blocks (cout <= 128).
+__global__ void __launch_bounds__(256) gpred_absmax_flat_kernel(const float4 *__restrict__ g, int quads_per_image, int qpp,
+                                                                int ncb, unsigned *__restrict__ amax_bits) {
+    __shared__ unsigned s_max[2];
+    if (threadIdx.x < 2) s_max[threadIdx.x] = 0u;
+    __syncthreads();
+    const int b = blockIdx.y;
+    const float4 *src = g + (size_t)b * quads_per_image;
+    float m0 = 0.f, m1 = 0.f;
+    const int stride = gridDim.x * blockDim.x;
+#pragma unroll 4
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < quads_per_image; q += stride) {
+        const float4 v = __ldg(src + q);
+        const float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+        if ((q % qpp) < 16) m0 = fmaxf(m0, m); else m1 = fmaxf(m1, m);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&s_max[0], __float_as_uint(m0));
+        atomicMax(&s_max[1], __float_as_uint(m1));
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < ncb) atomicMax(amax_bits + (size_t)b * ncb + threadIdx.x, s_max[threadIdx.x]);
+}
+
 // G (B, P, cout) fp32 -> x1 / x2 fp16 planes (B, P, kp), channels >= cout zero; one thread per (cell, 4 channels)
 __global__ void __launch_bounds__(256) gpred_split_pad_kernel(const float *__restrict__ g, int P, int cout, int kp,
                                                               const unsigned *__restrict__ amax_bits, uint2 *__restrict__ p1,
@@ -117,6 +148,47 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float *__restrict_
         __syncthreads();
     }
     if (threadIdx.x == 0) db[n] = (float)s[0];
+}
+
+// The same sums for cout % 4 == 0: coalesced 16-byte loads instead of one strided column per CTA.  A cluster of 8 CTAs
+// owns a group of 6 quads (24 columns, 96 B = three whole sectors of every 4*cout-byte row) and splits the rows; a
+// thread sums one quad over every 170th row in double, the CTA adds its 170 row lanes in lane order, CTA 0 of the
+// cluster adds the 8 CTA sums in rank order through distributed shared memory: a fixed order, deterministic, no scratch.
+constexpr int kBgThreads = 1024, kBgQuads = 6, kBgCluster = 8, kBgLanes = kBgThreads / kBgQuads;   // 170 row lanes
+__global__ void __cluster_dims__(kBgCluster, 1, 1) __launch_bounds__(kBgThreads)
+    bias_grad_cluster_kernel(const float4 *__restrict__ g, size_t rows, int qpp, float *__restrict__ db) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double s_lane[kBgLanes][kBgQuads * 4];
+    __shared__ double s_cta[kBgCluster][kBgQuads * 4];
+    const int rank = (int)cluster.block_rank(), group = blockIdx.x / kBgCluster;
+    const int q0 = group * kBgQuads, nq = min(kBgQuads, qpp - q0);
+    const int lq = threadIdx.x % kBgQuads, lr = threadIdx.x / kBgQuads;
+    const size_t per = (rows + kBgCluster - 1) / kBgCluster;
+    const size_t r0 = (size_t)rank * per, r1 = r0 + per < rows ? r0 + per : rows;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (lr < kBgLanes && lq < nq) {
+#pragma unroll 8
+        for (size_t r = r0 + lr; r < r1; r += kBgLanes) {
+            const float4 v = __ldg(g + r * qpp + q0 + lq);
+            a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+        }
+    }
+    if (lr < kBgLanes) {
+        s_lane[lr][lq * 4 + 0] = a0; s_lane[lr][lq * 4 + 1] = a1; s_lane[lr][lq * 4 + 2] = a2; s_lane[lr][lq * 4 + 3] = a3;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < kBgQuads * 4) {
+        double t = 0.0;
+        for (int l = 0; l < kBgLanes; ++l) t += s_lane[l][threadIdx.x];
+        cluster.map_shared_rank(&s_cta[0][0], 0)[rank * kBgQuads * 4 + threadIdx.x] = t;
+    }
+    cluster.sync();
+    if (rank == 0 && (int)threadIdx.x < nq * 4) {
+        double t = 0.0;
+        for (int r = 0; r < kBgCluster; ++r) t += s_cta[r][threadIdx.x];
+        db[q0 * 4 + threadIdx.x] = (float)t;
+    }
 }
 
 // ---- weight gradient (fp32 CUDA-core implicit GEMM, split over the pixel axis) ---------------------------------------
@@ -280,6 +352,20 @@ extern "C" int sqd_convdet_dgrad_pack_weights(const float *d_weight, int cout, i
     return SQD_OK;
 }
 
+// max |G| per (image, 64-channel block of the channel axis padded to a multiple of 64) into amax_bits (zeroed by the
+// caller; image stride ncb >= ceil(cout / 64)): the scale granularity of both the dgrad planes and the wgrad G^T copies.
+int sqd_gpred_absmax(const float *d_gpred, int batch, int P, int cout, int ncb, unsigned *amax_bits, cudaStream_t st) {
+    if (cout % 4 == 0 && cout <= 128 && ncb <= 2 && !getenv("SQD_BWD_OLD_PREPASS")) {
+        gpred_absmax_flat_kernel<<<dim3(16, batch), 256, 0, st>>>(reinterpret_cast<const float4 *>(d_gpred), P * (cout / 4),
+                                                                 cout / 4, ncb, amax_bits);
+        SQD_LAUNCH_CHECK("gpred_absmax_flat_kernel");
+    } else {
+        gpred_absmax_kernel<<<dim3(16, batch), 256, ncb * sizeof(unsigned), st>>>(d_gpred, P, cout, ncb, amax_bits);
+        SQD_LAUNCH_CHECK("gpred_absmax_kernel");
+    }
+    return SQD_OK;
+}
+
 extern "C" size_t sqd_convdet_dgrad_workspace_bytes(int batch, int cin, int gh, int gw, int cout) {
     if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0) return 256;
     return dgrad_ws(batch, cin, gh, gw, cout).total;
@@ -305,8 +391,10 @@ extern "C" int sqd_convdet_dgrad(const float *d_gpred, const void *d_dgrad_packe
     const size_t plane_bytes = align256((size_t)batch * P * kp * sizeof(unsigned short));
     unsigned *amax = reinterpret_cast<unsigned *>(planes);
     SQD_CUDA(cudaMemsetAsync(amax, 0, amax_bytes, st));
-    gpred_absmax_kernel<<<dim3(16, batch), 256, ncb * sizeof(unsigned), st>>>(d_gpred, P, cout, ncb, amax);
-    SQD_LAUNCH_CHECK("gpred_absmax_kernel");
+    {
+        int rc = sqd_gpred_absmax(d_gpred, batch, P, cout, ncb, amax, st);
+        if (rc) return rc;
+    }
     const size_t total = (size_t)batch * P * (kp / 4);
     int gx = (int)((total + 255) / 256);
     if (gx > SQD_SM_COUNT * 16) gx = SQD_SM_COUNT * 16;
@@ -340,7 +428,15 @@ extern "C" int sqd_convdet_dgrad(const float *d_gpred, const void *d_dgrad_packe
 extern "C" int sqd_convdet_bias_grad(const float *d_gpred, int batch, int gh, int gw, int cout, float *d_gbias, void *stream) {
     SQD_REQUIRE(d_gpred && d_gbias, SQD_E_NULL, "sqd_convdet_bias_grad: NULL pointer");
     SQD_REQUIRE(batch >= 0 && gh > 0 && gw > 0 && cout >= 1, SQD_E_SHAPE, "sqd_convdet_bias_grad: bad shape");
-    bias_grad_kernel<<<cout, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_gpred, (size_t)batch * gh * gw, cout, d_gbias);
+    const size_t rows = (size_t)batch * gh * gw;
+    if (cout % 4 == 0 && sqd_aligned16(d_gpred) && !getenv("SQD_BWD_OLD_PREPASS")) {
+        const int qpp = cout / 4, groups = (qpp + kBgQuads - 1) / kBgQuads;
+        bias_grad_cluster_kernel<<<groups * kBgCluster, kBgThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const float4 *>(d_gpred), rows, qpp, d_gbias);
+        SQD_LAUNCH_CHECK("bias_grad_cluster_kernel");
+        return SQD_OK;
+    }
+    bias_grad_kernel<<<cout, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_gpred, rows, cout, d_gbias);
     SQD_LAUNCH_CHECK("bias_grad_kernel");
     return SQD_OK;
 }

@@ -91,33 +91,6 @@ __global__ void __launch_bounds__(256) split_nchw_rows_kernel(const float *__res
     }
 }
 
-// max |g| per (image, 64-output block): grid (chunks, B)
-__global__ void __launch_bounds__(256) g_absmax_kernel(const float *__restrict__ g, int P, int cout, unsigned *__restrict__ amax_bits) {
-    __shared__ unsigned s_max[2];
-    if (threadIdx.x < 2) s_max[threadIdx.x] = 0u;
-    __syncthreads();
-    const int b = blockIdx.y;
-    const float *src = g + (size_t)b * P * cout;
-    float m0 = 0.f, m1 = 0.f;
-    for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < P; cell += gridDim.x * blockDim.x) {
-        for (int n = 0; n < cout; ++n) {
-            const float v = fabsf(__ldg(src + (size_t)cell * cout + n));
-            if (n < 64) m0 = fmaxf(m0, v); else m1 = fmaxf(m1, v);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMax(&s_max[0], __float_as_uint(m0));
-        atomicMax(&s_max[1], __float_as_uint(m1));
-    }
-    __syncthreads();
-    if (threadIdx.x < 2) atomicMax(amax_bits + (size_t)b * 2 + threadIdx.x, s_max[threadIdx.x]);
-}
-
 // G (B, gh*gw, cout) fp32 -> three column-shifted copies e = 0,1,2 (shift e-1) of the transposed fp16 planes
 // (3, B, 80, gh*gwp):  copy_e[b][n][y*gwp + col] = G[b][y][col - (e-1)][n]  (zero outside the row, for n >= cout).
 // One block per image row: the row's gw x cout floats are read coalesced into shared memory and written back
@@ -615,6 +588,7 @@ WgWs wg_ws(int batch, int cin, int gh, int gw) {
 
 // implemented in convdet_f16.cu: max |x| of contiguous runs (one per blockIdx.y)
 int sqd_f16_absmax_runs(const float *d_in, size_t run_floats, int nruns, unsigned *d_amax, cudaStream_t st);
+int sqd_gpred_absmax(const float *d_gpred, int batch, int P, int cout, int ncb, unsigned *amax_bits, cudaStream_t st);
 
 extern "C" size_t sqd_convdet_wgrad_tc_workspace_bytes(int batch, int cin, int gh, int gw, int cout) {
     if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0) return 256;
@@ -650,8 +624,7 @@ extern "C" int sqd_convdet_wgrad_tc(const float *d_feat_nchw, const float *d_gpr
                                                                            reinterpret_cast<__half2 *>(x2));
     SQD_LAUNCH_CHECK("split_nchw_rows_kernel");
     if ((rc = stage_check("split x", st))) return rc;
-    g_absmax_kernel<<<dim3(8, batch), 256, 0, st>>>(d_gpred, P, cout, amax_g);
-    SQD_LAUNCH_CHECK("g_absmax_kernel");
+    if ((rc = sqd_gpred_absmax(d_gpred, batch, P, cout, 2, amax_g, st))) return rc;
     if ((rc = stage_check("absmax g", st))) return rc;
     {
         const size_t smem_g = (size_t)gw * (cout + 1) * sizeof(float);
