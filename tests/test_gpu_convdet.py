@@ -180,6 +180,34 @@ def test_head_detect_host_equals_device_call(ops, chunk):
         assert torch.equal(getattr(ref, f).cpu(), getattr(host, f)), f
 
 
+@pytest.mark.parametrize("batch", [1, 6])
+def test_head_detect_is_cuda_graph_capturable(ops, batch):
+    """The whole step (pre-pass, GEMM, scan, tail; programmatic dependent launches included) records into a CUDA graph:
+    no allocation, synchronisation or host read inside the ABI call.  Replays on new inputs in the captured buffers
+    give exactly what the eager call gives."""
+    shp = synth.KITTI
+    w, b = synth.convdet_params(shp, 22)
+    a32 = dev(synth.anchor_table(shp).astype(np.float32))
+    dw, db = dev(w), dev(b)
+    packed = ops.pack_convdet_weights(dw)
+    args = (dw, db, a32, 9, 3, shp.input_hw, shp.top_k, shp.nms_thresh, shp.score_thresh)
+    feats = [dev(synth.features(shp, batch, 60 + i)) for i in range(3)]
+    want = [ops.head_detect(f, *args, packed=packed) for f in feats]          # also sizes the workspace before capture
+    static_in = feats[0].clone()
+    static_out = ops._alloc_detections(batch, shp.top_k, static_in.device)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ops.head_detect(static_in, *args, packed=packed, out=static_out)
+    for f, ref in zip(feats[::-1], want[::-1]):
+        static_in.copy_(f)
+        graph.replay()
+        torch.cuda.synchronize()
+        for k in ("count", "anchor", "cls", "score", "box"):
+            assert torch.equal(getattr(static_out, k), getattr(ref, k)), k
+    assert int(static_out.count.sum()) > 0
+
+
 def test_head_detect_host_serving_loop(ops):
     """sync=False with two alternating slots (SQD_HOST_NO_STAGING_FENCE): calls overlap on the device, every call's
     result equals the blocking call on the same input, and buffers of an unfinished call are refused."""
