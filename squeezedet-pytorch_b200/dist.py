@@ -58,10 +58,19 @@ def shard_batch(batch, rank, world):
 
 
 class GradBucket:
-    """All parameter gradients as views into one flat fp32 buffer -> one all-reduce per step."""
+    """All parameter gradients as views into one flat fp32 buffer -> one all-reduce per step.
 
-    def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
+    `early`: the parameters whose gradients autograd finishes FIRST -- the ConvDet head (its wgrad / bias-grad kernels
+    run before anything of the backbone's backward).  They sit at the front of the buffer and the
+    all-reduce of that segment is launched (async) from the hook of the last of them, so it travels over NVLink while
+    the backbone's backward still runs; `allreduce_mean` then reduces the rest and waits for both.  The result is the
+    same as one all-reduce of the whole buffer (sum, then 1/world)."""
+
+    def __init__(self, params, early=()):
+        early = [p for p in early if p.requires_grad]
+        seen = {id(p) for p in early}
+        self.params = early + [p for p in params if p.requires_grad and id(p) not in seen]
+        self.early_numel = sum(p.numel() for p in early)
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else "cpu"
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -69,17 +78,60 @@ class GradBucket:
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        self._n_early, self._pending, self._early_work = len(early), 0, None
+        for p in early:
+            p.register_post_accumulate_grad_hook(self._early_ready)
+
+    def _early_ready(self, _param):
+        if self._pending <= 0:
+            return                  # not armed (zero() was not called for this step) or already launched
+        self._pending -= 1
+        if self._pending == 0 and dist.is_initialized() and dist.get_world_size() > 1:
+            self._early_work = dist.all_reduce(self.flat[:self.early_numel], op=dist.ReduceOp.SUM, async_op=True)
 
     def zero(self):
+        """Start of a step: clear the gradients and arm the early all-reduce."""
         self.flat.zero_()
+        self._pending, self._early_work = self._n_early, None
 
-    def allreduce_mean(self, world=None, async_op=False):
+    def allreduce_mean(self, world=None):
         """sum over ranks then scale by 1/world (each rank's loss is its local per-image mean)."""
         if not dist.is_initialized() or dist.get_world_size() == 1:
             return None
         world = world or dist.get_world_size()
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
-        if async_op:
-            return work
+        if self._early_work is not None:
+            rest = self.flat[self.early_numel:]
+            work = dist.all_reduce(rest, op=dist.ReduceOp.SUM, async_op=True) if rest.numel() else None
+            self._early_work.wait()
+            if work is not None:
+                work.wait()
+            self._early_work = None
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        self._pending = 0
         self.flat.mul_(1.0 / world)
         return None
+
+
+def bucket_for(model):
+    """GradBucket of a SqueezeDetWithLoss / SqueezeDetBase-holding module with the ConvDet head as the early segment."""
+    base = model.base if hasattr(model, "base") else model
+    return GradBucket(model.parameters(), early=base.convdet.parameters())
+
+
+def train_step(model, batch, bucket, optimizer=None, grad_norm=None):
+    """One data-parallel step on this rank's shard of the batch: the body of Trainer.run_epoch (src/engine/
+    trainer.py:42-48) with the reference's per-step parameter broadcast + gradient reduce-to-GPU-0
+    (src/utils/data_parallel.py:93-101) replaced by the bucket's all-reduce.  `optimizer.zero_grad()` is
+    `bucket.zero()` here (the gradients are views into the bucket and must stay allocated).
+    Returns (mean loss of the shard, the per-image loss statistics dict)."""
+    bucket.zero()
+    loss, stats = model(batch)
+    loss = loss.mean()
+    loss.backward()                 # the head's all-reduce is launched from inside, as soon as its gradients exist
+    bucket.allreduce_mean()
+    if grad_norm:
+        torch.nn.utils.clip_grad_norm_(bucket.params, grad_norm)
+    if optimizer is not None:
+        optimizer.step()
+    return loss.detach(), stats

@@ -127,6 +127,30 @@ assert torch.allclose(bucket.flat, flat_ref, rtol=1e-5, atol=1e-6), (bucket.flat
 gathered = [torch.zeros_like(bucket.flat) for _ in range(world)]
 dist.all_gather(gathered, bucket.flat)
 assert torch.equal(gathered[0], gathered[1])
+# early segment: the "head" parameters are reduced from a gradient hook while backward is still running
+torch.manual_seed(1)
+net = torch.nn.Sequential(torch.nn.Linear(8, 6), torch.nn.ReLU(), torch.nn.Linear(6, 4))
+head = list(net[2].parameters())
+b2 = sdist.GradBucket(net.parameters(), early=head)
+assert b2.early_numel == 6 * 4 + 4 and b2.params[0] is head[0]
+launched = []
+orig = dist.all_reduce
+def spy(t, *a, **k):
+    launched.append(t.numel())
+    return orig(t, *a, **k)
+dist.all_reduce = spy
+for step in range(2):
+    b2.zero()
+    net(mine["image"] / 80.0).mean().backward()
+    assert launched[-1] == b2.early_numel and len(launched) == 3 * step + 1     # fired from the hook, before the call below
+    b2.allreduce_mean()
+    assert launched[-1] == b2.flat.numel() - b2.early_numel and len(launched) == 3 * step + 2
+    launched.append(0)
+dist.all_reduce = orig
+ref2 = torch.nn.Sequential(torch.nn.Linear(8, 6), torch.nn.ReLU(), torch.nn.Linear(6, 4)); ref2.load_state_dict(net.state_dict())
+ref2(batch["image"] / 80.0).mean().backward()
+want = torch.cat([p.grad.flatten() for p in list(ref2[2].parameters()) + list(ref2[0].parameters())])
+assert torch.allclose(b2.flat, want, rtol=1e-5, atol=1e-7), (b2.flat, want)
 dist.destroy_process_group()
 print("OK", rank)
 '''

@@ -180,6 +180,37 @@ def test_head_detect_host_equals_device_call(ops, chunk):
         assert torch.equal(getattr(ref, f).cpu(), getattr(host, f)), f
 
 
+def test_train_step_with_gradient_bucket(ops):
+    """dist.train_step (the body of Trainer.run_epoch, trainer.py:42-48, for one rank): gradients land in the flat bucket
+    with the ConvDet head as its leading (early all-reduce) segment and equal a plain loss.mean().backward()."""
+    from squeezedet_pytorch_b200 import config, model, targets, dist as sdist
+    shp = synth.TINY
+    cfg = config.make_config(shp, dropout_prob=0.0)
+    torch.manual_seed(3)
+    net = model.SqueezeDetWithLoss(cfg).cuda()
+    w, b = synth.convdet_params(shp, 3)
+    with torch.no_grad():
+        net.base.convdet.weight.copy_(torch.from_numpy(w))
+        net.base.convdet.bias.copy_(torch.from_numpy(b))
+    img = torch.randn(4, 3, *shp.input_hw, generator=torch.Generator().manual_seed(1)).cuda()
+    m = targets.AnchorMatcher(cfg.anchors, shp.num_classes)
+    cls_l, box_l = zip(*[synth.gt_boxes(shp, 70 + i) for i in range(4)])
+    batch = {"image": img, "gt": m.dense_targets(*m.pack(list(box_l), list(cls_l)))}
+    loss, _ = net(batch)
+    loss.mean().backward()
+    want = {n: p.grad.clone() for n, p in net.named_parameters()}
+    for p in net.parameters():
+        p.grad = None
+    bucket = sdist.bucket_for(net)
+    assert bucket.params[0] is net.base.convdet.weight and bucket.early_numel == w.size + b.size
+    opt = torch.optim.SGD(net.parameters(), lr=0.0)
+    for _ in range(2):                                          # the second step checks zero() / re-arming
+        l, stats = sdist.train_step(net, batch, bucket, optimizer=opt, grad_norm=1e9)
+    assert torch.isfinite(l) and set(stats) == {"loss", "class_loss", "score_loss", "bbox_loss"}
+    for n, p in net.named_parameters():
+        assert p.grad.data_ptr() >= bucket.flat.data_ptr() and torch.allclose(p.grad, want[n], rtol=1e-4, atol=1e-7), n
+
+
 @pytest.mark.parametrize("batch", [1, 6])
 def test_head_detect_is_cuda_graph_capturable(ops, batch):
     """The whole step (pre-pass, GEMM, scan, tail; programmatic dependent launches included) records into a CUDA graph:
