@@ -172,3 +172,69 @@ def test_gloo_world_size_2_shard_and_gradient_allreduce(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "OK" in o
+
+
+def _abi_call(lib, name, ptr_value, int_value, size_value=0):
+    """Call an int-returning entry point with every pointer = ptr_value, every int = int_value, doubles 0.5."""
+    import ctypes as C
+    from squeezedet_pytorch_b200 import _lib
+    _, args = _lib.SIGNATURES[name]
+    vals = []
+    for a in args:
+        if a is C.c_void_p:
+            vals.append(ptr_value)
+        elif hasattr(a, "_type_") and not isinstance(a._type_, str):       # POINTER(...)
+            vals.append(C.cast(ptr_value, a) if ptr_value else None)
+        elif a is C.c_double:
+            vals.append(0.5)
+        elif a is C.c_size_t:
+            vals.append(size_value)
+        else:
+            vals.append(int_value)
+    rc = getattr(lib, name)(*vals)
+    return rc, lib.sqd_last_error().decode()
+
+
+def test_abi_rejects_bad_arguments_before_touching_the_device():
+    """Error behaviour of the boundary (int return codes, message through sqd_last_error(), never throw,
+    never crash): every compute entry point refuses NULL pointers with SQD_E_NULL and nonsense shapes with a negative
+    code, naming itself in the message -- decided on the host, so it runs here without a GPU.  Entry points that get
+    past validation report the CUDA error (> 0) instead of computing on the CPU: there is no fallback."""
+    import ctypes as C
+    from squeezedet_pytorch_b200 import _lib
+    lib = _lib.load()
+    compute = [n for n, (res, args) in _lib.SIGNATURES.items() if res is C.c_int and args]
+    assert len(compute) >= 20
+    for name in compute:
+        rc, msg = _abi_call(lib, name, None, 1)
+        assert rc == -1, (name, rc, msg)                                    # SQD_E_NULL
+        assert msg.startswith(name), (name, msg)
+        rc, msg = _abi_call(lib, name, 0x10000, -1)
+        if name.endswith("_status"):                                        # one pointer, no shape: goes to the device
+            assert rc > 0, (name, rc, msg)
+            continue
+        assert rc in (-2, -5), (name, rc, msg)                              # SQD_E_SHAPE / SQD_E_UNSUPPORTED
+        assert msg.startswith(name), (name, msg)
+    # specific contracts
+    kitti = dict(batch=2, cin=768, gh=24, gw=78, cout=72)
+    need = lib.sqd_head_detect_workspace_bytes(kitti["batch"], kitti["cin"], kitti["gh"], kitti["gw"], kitti["cout"], 0, _lib.CONV_TCGEN05_F16X3)
+    assert need > 2 * 768 * 24 * 78 * 4                                     # at least the two fp16 planes of the features
+    p = C.c_void_p(0x10000)
+    rc = lib.sqd_head_detect_fused(p, 0, p, p, p, p, 2, 768, 24, 78, 9, 3, 384, 1248, 64, 0.4, 0.3, p, p, p, p, p, p, need - 1,
+                                   _lib.CONV_TCGEN05_F16X3, None)
+    assert rc == -3 and b"workspace too small" in lib.sqd_last_error()       # SQD_E_WORKSPACE
+    rc = lib.sqd_head_detect_fused(p, 0, p, p, p, p, 2, 768, 24, 78, 9, 3, 384, 1248, 64, 0.4, 0.3, p, p, p, p, p,
+                                   C.c_void_p(0x10004), need, _lib.CONV_TCGEN05_F16X3, None)
+    assert rc in (-3, -4), rc                                               # misaligned workspace
+    rc = lib.sqd_convdet_pack_weights(p, 72, 700, p, None)                  # Cin not a multiple of 64
+    assert rc == -2 and b"multiple of 64" in lib.sqd_last_error()
+    rc = lib.sqd_match_anchors(p, p, 1, 257, p, 100, p, p, None)            # more ground-truth boxes than the kernel holds
+    assert rc == -2 and b"gmax" in lib.sqd_last_error()
+    rc = lib.sqd_preprocess(p, 7, 1, 10, 10, C.cast(p, C.POINTER(C.c_float)), C.cast(p, C.POINTER(C.c_float)), 5, 5, p, None)
+    assert rc == -5 and b"dtype" in lib.sqd_last_error()                    # SQD_E_UNSUPPORTED
+    # an empty batch is legal everywhere and enqueues nothing (pointers may be NULL)
+    for name in ("sqd_decode_scores", "sqd_topk_nms", "sqd_detect_from_pred", "sqd_boxes_postprocess", "sqd_pack_results",
+                 "sqd_preprocess"):
+        _, args = _lib.SIGNATURES[name]
+        rc, msg = _abi_call(lib, name, None, 0)
+        assert rc == 0, (name, rc, msg)
