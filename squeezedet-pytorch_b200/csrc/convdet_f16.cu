@@ -70,6 +70,7 @@ struct PackedHeader {
     float scale;         // s_w = 2^e
     float inv_scale;     // 1 / s_w
     int npad, cin;
+    int hr;              // output channels per CTA in the CTA-pair layout (pair_hr_of)
 };
 
 // power-of-two scale s with amax*s in [2^13, 2^14); exponent clamped so that s and 1/s are normal floats
@@ -324,9 +325,10 @@ __global__ void weight_absmax_kernel(const float *__restrict__ w, size_t n, Pack
 
 // (Cout,Cin,3,3) fp32 -> two fp16 matrices [2*npad][9*cin]:
 //   mat  (1-CTA kernel): rows [0,npad) = w2 (scaled residual), rows [npad,2npad) = w1
-//   mat2 (CTA-pair kernel), H = npad/2: rows [r*npad, r*npad+H) = w2 of channels [r*H,(r+1)*H), the next H rows = w1 of
-//        the same channels, for pair rank r = 0,1 -- each CTA of a pair loads its own contiguous npad rows
-__global__ void pack_weights_f16_kernel(const float *__restrict__ w, int cout, int cin, int npad, PackedHeader *hdr,
+//   mat2 (CTA-pair kernel), hr = output channels per CTA of the pair: rows [r*2hr, r*2hr+hr) = w1 of channels
+//        [r*hr,(r+1)*hr), the next hr rows = w2 of the same channels, for pair rank r = 0,1 -- each CTA of a pair loads
+//        its own contiguous 2*hr rows.  hr = npad/2, or 36 for Cout <= 72 (KITTI): 144 instead of 160 B rows per MMA.
+__global__ void pack_weights_f16_kernel(const float *__restrict__ w, int cout, int cin, int npad, int hr, PackedHeader *hdr,
                                         __half *__restrict__ mat, __half *__restrict__ mat2) {
     const float s = pow2_scale_for(__uint_as_float(hdr->amax_bits));
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -334,6 +336,7 @@ __global__ void pack_weights_f16_kernel(const float *__restrict__ w, int cout, i
         hdr->inv_scale = 1.f / s;
         hdr->npad = npad;
         hdr->cin = cin;
+        hdr->hr = hr;
     }
     const size_t ktot = (size_t)9 * cin, total = (size_t)npad * ktot;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -346,9 +349,11 @@ __global__ void pack_weights_f16_kernel(const float *__restrict__ w, int cout, i
         split_f16(v * s, h1, h2);
         mat[i] = h2;
         mat[total + i] = h1;
-        const int H = npad >> 1, r = n / H, j = n - r * H;
-        mat2[((size_t)(r * npad + j)) * ktot + k] = h2;
-        mat2[((size_t)(r * npad + H + j)) * ktot + k] = h1;
+        if (n < 2 * hr) {   // channels >= 2*hr are padding beyond Cout and have no row in the pair layout
+            const int r = n / hr, j = n - r * hr;
+            mat2[((size_t)(r * 2 * hr + j)) * ktot + k] = h1;
+            mat2[((size_t)(r * 2 * hr + hr + j)) * ktot + k] = h2;
+        }
     }
 }
 
@@ -773,11 +778,13 @@ convdet_f16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
 //
 //  * pair-tile j = tiles {j, j + PT} (PT = ceil(tiles/2)); rank r of the pair owns tile j + r*PT.  A ghost tile
 //    (odd tile count) loads zeros (TMA out-of-bounds image index) and is never stored.
-//  * B tile of one tap in CTA r: rows [0,H) = w2 of channels [rH,(r+1)H), rows [H,2H) = w1 of the same channels.
-//        MMA1: D[:, 0:2N)   (+)= A1 * B^T        -> columns [cross(0:H) | main(0:H) | cross(H:2H) | main(H:2H)]
-//        MMA2: D[:, 2N:3N)  (+)= A2 * B[H:2H)^T  -> columns [cross2(0:H) | cross2(H:2H)]   (own columns: the N halves
-//              of the pair do not line up with MMA1's cross columns)
-//  * unit-granular stages: one stage = the unit's two A patches + its three B tiles (70 KB at Npad = 80, 3 stages).
+//  * B tile of one tap in CTA r (HR = output channels per CTA): rows [0,HR) = w1 of channels [r*HR,(r+1)*HR), rows
+//    [HR,2HR) = w2 (the scaled residual) of the same channels.
+//        MMA1: D[:, 0:4HR)      (+)= A1 * B^T           -> columns [main(r=0) | cross(r=0) | main(r=1) | cross(r=1)]
+//        MMA2: D[:, 4HR:+2*N2H) (+)= A2 * B[0:N2H)^T    -> columns [cross2(r=0) | cross2(r=1)], N2H = round8(HR); its
+//              columns HR..N2H-1 of each half are A2 * w2 products nobody reads
+//    HR = Npad/2 in general; HR = 36 for Cout <= 72 (KITTI's 72 channels): N = 144 + 80 instead of 160 + 80 per K step.
+//  * unit-granular stages: one stage = the unit's two A patches + its three B tiles (67 KB at Cout = 72, 3 stages).
 //    Per unit the issuing thread does two barrier waits, 24 MMAs and two multicast commits:
 //        full[s]   leader only: both CTAs' TMA bytes of stage s landed (cta_group::2 TMA credits the leader's barrier)
 //        sfree[s]  both CTAs  : the MMAs reading stage s completed            (tcgen05.commit multicast)
@@ -904,20 +911,23 @@ __device__ __forceinline__ bool pair_wait_warp(uint64_t *bar, uint32_t parity, v
 // that follows never scans pred.
 // PK: the last 64-channel block is only partly filled (p.ksteps_last valid 16-channel K steps; the rest is zero padding,
 // e.g. the 72 -> 128 padded gradient channels of the dgrad GEMM): its all-zero K steps are not issued.
-template <int NPAD, int CS, bool PK = false>
+template <int NPAD, int CS, bool PK = false, int HR = NPAD / 2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                         const __grid_constant__ CUtensorMap map_b, const PairParams p) {
-    constexpr int H = NPAD / 2;
-    constexpr int kBTapBytes = NPAD * kBlockK * 2;          // this CTA's half of one tap: [w2 H rows | w1 H rows]
-    constexpr int kW1Offset = H * kBlockK * 2;              // multiple of 1024 (H is a multiple of 8)
+    // This CTA's half of one tap is [w1: HR rows | w2: HR rows] for its HR output channels.  MMA1 = A1 x all 2*HR rows
+    // (N = 4*HR across the pair), MMA2 = A2 x the first N2H = round8(HR) rows (w1, plus up to 4 w2 rows whose columns
+    // nobody reads): both B descriptors start at row 0, so HR only has to be a multiple of 4.
+    constexpr int N1H = 2 * HR, N2H = (HR + 7) / 8 * 8;
+    static_assert(HR % 4 == 0 && 2 * HR <= NPAD && N2H <= N1H, "pair layout");
+    constexpr int kBTapBytes = N1H * kBlockK * 2;           // multiple of 1024: N1H is a multiple of 8
     constexpr int kStageBytes = kAStageBytes + 3 * kBTapBytes;
-    constexpr int kAccCols = 3 * NPAD;                      // [MMA1: 2*NPAD | MMA2: NPAD]
+    constexpr int kAccCols = 2 * N1H + 2 * N2H;             // [MMA1: 4*HR | MMA2: 2*N2H]
     constexpr int kAccBufs = (2 * kAccCols <= 512) ? 2 : 1;
     constexpr uint32_t kTmemCols = 512;
-    constexpr uint32_t kIdesc1 = umma_idesc_f16(256, 2 * NPAD);
-    constexpr uint32_t kIdesc2 = umma_idesc_f16(256, NPAD);
-    static_assert(kAccCols <= 512, "TMEM budget");
+    constexpr uint32_t kIdesc1 = umma_idesc_f16(256, 2 * N1H);
+    constexpr uint32_t kIdesc2 = umma_idesc_f16(256, 2 * N2H);
+    static_assert(kAccCols <= 512 && (2 * N1H) % 16 == 0 && (2 * N2H) % 16 == 0, "TMEM budget / UMMA N");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1011,10 +1021,10 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                     for (int dyi = 0; dyi < 3; ++dyi) {
                         if (PK)
                             tma_load_3d_2cta(&map_b, full + rs.s, st + kAStageBytes + dyi * kBTapBytes,
-                                             (dyi * 3 + it.dxi) * p.cin + it.cb * kBlockK, (int)rank * NPAD, slab);
+                                             (dyi * 3 + it.dxi) * p.cin + it.cb * kBlockK, (int)rank * N1H, slab);
                         else
                             tma_load_2d_2cta(&map_b, full + rs.s, st + kAStageBytes + dyi * kBTapBytes,
-                                             (dyi * 3 + it.dxi) * p.cin + it.cb * kBlockK, (int)rank * NPAD);
+                                             (dyi * 3 + it.dxi) * p.cin + it.cb * kBlockK, (int)rank * N1H);
                     }
                 }
             }
@@ -1044,7 +1054,7 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                 }
                 SQD_TRACE2(3, i);
                 tc_fence_after();
-                const uint32_t d1 = tmem_base + (uint32_t)buf * kAccCols, d2 = d1 + 2 * NPAD;
+                const uint32_t d1 = tmem_base + (uint32_t)buf * kAccCols, d2 = d1 + 2 * N1H;
                 const uint32_t st = smem_u32(smem + (size_t)rs.s * kStageBytes);
                 const bool chunk_end = sc.chunk_ends(i, it.r, in_chunk, p.chunk_units);
                 const int nks = (PK && it.cb == p.cin / kBlockK - 1) ? p.ksteps_last : kBlockK / kUmmaK;
@@ -1055,7 +1065,7 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                             const uint64_t a1 = umma_desc_sw128(st + dyi * kDyBytes);
                             const uint64_t a2 = umma_desc_sw128(st + kPlaneBytes + dyi * kDyBytes);
                             const uint64_t b = umma_desc_sw128(st + kAStageBytes + dyi * kBTapBytes);
-                            const uint64_t bw1 = umma_desc_sw128(st + kAStageBytes + dyi * kBTapBytes + kW1Offset);
+                            const uint64_t bw1 = b;   // the w1 rows come first
 #pragma unroll
                             for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
                                 if (PK && ks >= nks) continue;
@@ -1215,16 +1225,18 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                for (int j0 = 0; j0 < H; j0 += 8) {
+                for (int j0 = 0; j0 < HR; j0 += 8) {
                     uint32_t c1[8], mn[8], c2[8];
-                    tmem_ld_x8(taddr + h * NPAD + j0, c1);             // a1*w2
-                    tmem_ld_x8(taddr + h * NPAD + H + j0, mn);         // a1*w1
-                    tmem_ld_x8(taddr + 2 * NPAD + h * H + j0, c2);     // a2*w1
+                    tmem_ld_x8(taddr + h * N1H + j0, mn);              // a1*w1
+                    tmem_ld_x8(taddr + h * N1H + HR + j0, c1);         // a1*w2
+                    tmem_ld_x8(taddr + 2 * N1H + h * N2H + j0, c2);    // a2*w1
                     tmem_ld_wait();
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const float cross = fadd(__uint_as_float(c1[k]), __uint_as_float(c2[k]));
-                        acc[h * H + j0 + k] = fmaf(fmaf(cross, kLoInv, __uint_as_float(mn[k])), inv_a, acc[h * H + j0 + k]);
+                        if (j0 + k < HR) {   // HR % 8 == 4: the last group's upper half belongs to the neighbouring block
+                            const float cross = fadd(__uint_as_float(c1[k]), __uint_as_float(c2[k]));
+                            acc[h * HR + j0 + k] = fmaf(fmaf(cross, kLoInv, __uint_as_float(mn[k])), inv_a, acc[h * HR + j0 + k]);
+                        }
                     }
                 }
             }
@@ -1345,6 +1357,13 @@ EncodeTiledFn get_encode_fn() {
 }
 
 int npad_of(int cout) { return (cout + 15) / 16 * 16; }
+// output channels per CTA of a pair (see pack_weights_f16_kernel / convdet_f16_pair_kernel)
+int pair_hr_of(int cout) {
+    const int npad = npad_of(cout);
+    if (npad == 80 && cout <= 72) return 36;      // KITTI: 9 anchors x (3 + 5)
+    if (npad == 128 && cout <= 120) return 60;    // stress shape: 9 x (8 + 5) = 117
+    return npad / 2;
+}
 
 constexpr size_t kSmemLimit = 227 * 1024;
 constexpr size_t kCtrlBytes = 1024;
@@ -1428,15 +1447,15 @@ int sqd_f16_pack_weights(const float *d_weight, int cout, int cin, void *d_packe
     const size_t n = (size_t)cout * cin * 9;
     weight_absmax_kernel<<<SQD_SM_COUNT, 256, 0, st>>>(d_weight, n, hdr);
     SQD_LAUNCH_CHECK("weight_absmax_kernel");
-    pack_weights_f16_kernel<<<SQD_SM_COUNT * 4, 256, 0, st>>>(d_weight, cout, cin, npad_of(cout), hdr, mat,
+    pack_weights_f16_kernel<<<SQD_SM_COUNT * 4, 256, 0, st>>>(d_weight, cout, cin, npad_of(cout), pair_hr_of(cout), hdr, mat,
                                                               mat + (size_t)2 * npad_of(cout) * 9 * cin);
     SQD_LAUNCH_CHECK("pack_weights_f16_kernel");
     return SQD_OK;
 }
 
 namespace {
-int pair_stages_for(int npad) {
-    const size_t stage = (size_t)kAStageBytes + (size_t)3 * npad * kBlockK * 2;
+int pair_stages_for(int n1h) {
+    const size_t stage = (size_t)kAStageBytes + (size_t)3 * n1h * kBlockK * 2;
     size_t s = (kSmemLimit - 1024 - kCtrlBytes) / stage;
     if (s > 4) s = 4;
     const int cap = env_int("SQD_F16_PAIR_STAGES", 4);
@@ -1444,12 +1463,12 @@ int pair_stages_for(int npad) {
     return (int)s;
 }
 
-template <int NPAD, int CS = 0, bool PK = false>
+template <int NPAD, int CS = 0, bool PK = false, int HR = NPAD / 2>
 int launch_pair(const CUtensorMap *maps, const PairParams &p, int grid, cudaStream_t st) {
-    const size_t smem = 1024 + (size_t)p.stages * (kAStageBytes + 3 * NPAD * kBlockK * 2) + kCtrlBytes;
-    SQD_CUDA(cudaFuncSetAttribute(convdet_f16_pair_kernel<NPAD, CS, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = 1024 + (size_t)p.stages * (kAStageBytes + 3 * 2 * HR * kBlockK * 2) + kCtrlBytes;
+    SQD_CUDA(cudaFuncSetAttribute(convdet_f16_pair_kernel<NPAD, CS, PK, HR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // dependent launch when the pre-pass kernel directly precedes it on the stream (p.pdl)
-    cudaError_t e = sqd_launch_dependent(convdet_f16_pair_kernel<NPAD, CS, PK>, dim3(grid), dim3(kThreads2), smem, st, p.pdl != 0,
+    cudaError_t e = sqd_launch_dependent(convdet_f16_pair_kernel<NPAD, CS, PK, HR>, dim3(grid), dim3(kThreads2), smem, st, p.pdl != 0,
                                          maps[0], maps[1], maps[2], p);
     if (e != cudaSuccess) {
         sqd_set_error("launch of convdet_f16_pair_kernel failed: %s", cudaGetErrorString(e));
@@ -1474,7 +1493,7 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
     SQD_REQUIRE(cout >= 1 && cout <= 128, SQD_E_SHAPE, "convdet (tcgen05): Cout %d outside [1,128]", cout);
     EncodeTiledFn encode = get_encode_fn();
     SQD_REQUIRE(encode != nullptr, SQD_E_DRIVER, "cuTensorMapEncodeTiled not available from the CUDA driver");
-    const int npad = npad_of(cout);
+    const int npad = npad_of(cout), n1h = 2 * pair_hr_of(cout);
     const WsLayout w = ws_layout(batch, cin, gh, gw, cout, layout);
     char *ws = static_cast<char *>(d_workspace);
     SQD_CUDA(cudaMemsetAsync(ws, 0, w.partial_off, st));  // status + flags
@@ -1513,16 +1532,16 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
         CUresult r;
         if (multi) {
             SQD_REQUIRE(slab_stride % 16 == 0, SQD_E_SHAPE, "convdet (tcgen05): bad slab layout");
-            const cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)(2 * npad), (cuuint64_t)slabs};
+            const cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)(2 * n1h), (cuuint64_t)slabs};
             const cuuint64_t strides[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)(slabs > 1 ? slab_stride : (size_t)2 * npad * ktot * 2)};
-            const cuuint32_t box[3] = {kBlockK, (cuuint32_t)npad, 1};
+            const cuuint32_t box[3] = {kBlockK, (cuuint32_t)n1h, 1};
             const cuuint32_t estr[3] = {1, 1, 1};
             r = encode(&maps[2], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, mat2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         } else {
-            const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)(2 * npad)};
+            const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)(2 * n1h)};
             const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-            const cuuint32_t box[2] = {kBlockK, (cuuint32_t)npad};   // one CTA's half: npad rows
+            const cuuint32_t box[2] = {kBlockK, (cuuint32_t)n1h};    // one CTA's half: 2*hr rows
             const cuuint32_t estr[2] = {1, 1};
             r = encode(&maps[2], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, mat2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1559,7 +1578,7 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
         upp = p.upt / 2;
     }
     p.units_per_pair = (int)upp;
-    p.stages = pair_stages_for(npad);
+    p.stages = pair_stages_for(n1h);
     SQD_REQUIRE(p.stages >= 2, SQD_E_SHAPE, "convdet (tcgen05): shared memory too small for two stages");
     p.chunk_units = env_int("SQD_F16_CHUNK", 3);   // one 64-channel block (3 dx units) per TMEM chunk
     if (p.chunk_units < 1) p.chunk_units = 1;
@@ -1589,8 +1608,8 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
             p.score_thr = emit->score_thr;
             p.anchors_per_cell = cout / nf;
             *emit->done = 1;
-            if (npad == 80) return launch_pair<80, 3>(maps, p, grid, st);
-            return launch_pair<128, 8>(maps, p, grid, st);
+            if (npad == 80) return n1h == 72 ? launch_pair<80, 3, false, 36>(maps, p, grid, st) : launch_pair<80, 3>(maps, p, grid, st);
+            return n1h == 120 ? launch_pair<128, 8, false, 60>(maps, p, grid, st) : launch_pair<128, 8>(maps, p, grid, st);
         }
     }
     if (multi) return launch_pair<128, 0, true>(maps, p, grid, st);   // the dgrad GEMM
@@ -1600,10 +1619,10 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
         case 2: return launch_pair<32>(maps, p, grid, st);
         case 3: return launch_pair<48>(maps, p, grid, st);
         case 4: return launch_pair<64>(maps, p, grid, st);
-        case 5: return launch_pair<80>(maps, p, grid, st);
+        case 5: return n1h == 72 ? launch_pair<80, 0, false, 36>(maps, p, grid, st) : launch_pair<80>(maps, p, grid, st);
         case 6: return launch_pair<96>(maps, p, grid, st);
         case 7: return launch_pair<112>(maps, p, grid, st);
-        case 8: return launch_pair<128>(maps, p, grid, st);
+        case 8: return n1h == 120 ? launch_pair<128, 0, false, 60>(maps, p, grid, st) : launch_pair<128>(maps, p, grid, st);
     }
     SQD_REQUIRE(false, SQD_E_SHAPE, "convdet (tcgen05): unsupported Cout %d", cout);
 }
