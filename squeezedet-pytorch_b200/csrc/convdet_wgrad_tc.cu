@@ -24,6 +24,7 @@
 // is L2 -> SM bound, not tensor bound: 52 KB per 64-pixel step per CTA.
 // Warp roles (192 threads): 0 TMA producer, 1 TMEM alloc + MMA issue, 2..5 accumulate.  Every wait is bounded.
 #include <cuda.h>
+#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -91,6 +92,76 @@ __global__ void __launch_bounds__(256) split_nchw_rows_kernel(const float *__res
     }
 }
 
+// The same planes AND the block maxima in ONE pass over X: a cluster of 8 CTAs owns one (image, 64-channel block) slab,
+// CTA r its channels [8r, 8r+8) = one contiguous run of 8*gh*gw floats held in REGISTERS, the block maximum goes round
+// the cluster through distributed shared memory, then every thread scales, splits and stores what it holds.  A thread
+// item is one 16-byte chunk of an output row (8 columns: four 8-byte loads, the last chunk of a row ends in the zero
+// padding) -> one 16-byte store per plane.  4 B read + 4 B written per element instead of 8 + 4.  Up to 4 items per
+// thread (KITTI: 8 channels x 24 rows x 10 chunks = 1920 items per CTA); larger grids take the two kernels above.
+constexpr int kXsThreads = 512, kXsCluster = 8, kXsItems = 4, kXsChan = 64 / kXsCluster;
+__global__ void __cluster_dims__(kXsCluster, 1, 1) __launch_bounds__(kXsThreads)
+    split_nchw_rows_cluster_kernel(const float *__restrict__ x, int cin, int gh, int gw, int gwp, unsigned *__restrict__ amax_bits,
+                                   uint4 *__restrict__ p1, uint4 *__restrict__ p2) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float s_red[kXsThreads / 32];
+    __shared__ unsigned s_cmax[kXsCluster];
+    const int rank = (int)cluster.block_rank(), slab = blockIdx.x / kXsCluster, ncb = cin >> 6;
+    const int b = slab / ncb, cb = slab - b * ncb;
+    const size_t plane0 = (size_t)b * cin + cb * 64 + rank * kXsChan;
+    const int cpr = gwp >> 3, rows = kXsChan * gh, total = rows * cpr;       // chunks per row, rows and chunks of this CTA
+    const float2 *src = reinterpret_cast<const float2 *>(x + plane0 * gh * gw);
+    const int hw = gw >> 1;
+    float2 v[kXsItems][4];
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < kXsItems; ++i) {
+        const int q = threadIdx.x + i * kXsThreads;
+        const int r = q / cpr, k = q - r * cpr;                              // r = channel * gh + y: rows are contiguous in X
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int pc = 4 * k + e;                                        // column pair inside the row
+            v[i][e] = (q < total && pc < hw) ? __ldg(src + (size_t)r * hw + pc) : make_float2(0.f, 0.f);
+            m = fmaxf(m, fmaxf(fabsf(v[i][e].x), fabsf(v[i][e].y)));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < kXsThreads / 32 ? s_red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((int)threadIdx.x < kXsCluster) cluster.map_shared_rank(s_cmax, threadIdx.x)[rank] = __float_as_uint(m);
+    }
+    cluster.sync();
+    unsigned mb = 0u;
+#pragma unroll
+    for (int r = 0; r < kXsCluster; ++r) mb = max(mb, s_cmax[r]);
+    if (rank == 0 && threadIdx.x == 0) amax_bits[slab] = mb;
+    const float s = pow2_scale_for(__uint_as_float(mb));
+    uint4 *d1 = p1 + plane0 * gh * cpr, *d2 = p2 + plane0 * gh * cpr;
+#pragma unroll
+    for (int i = 0; i < kXsItems; ++i) {
+        const int q = threadIdx.x + i * kXsThreads;
+        if (q < total) {
+            unsigned h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float x0 = v[i][e].x * s, x1 = v[i][e].y * s;
+                const __half2 hh = __floats2half2_rn(x0, x1);
+                const float2 f = __half22float2(hh);
+                const __half2 ll = __floats2half2_rn((x0 - f.x) * kLoScale, (x1 - f.y) * kLoScale);
+                h[e] = *reinterpret_cast<const unsigned *>(&hh);
+                l[e] = *reinterpret_cast<const unsigned *>(&ll);
+            }
+            d1[q] = make_uint4(h[0], h[1], h[2], h[3]);                      // chunk q of the CTA's rows == chunk q of its planes
+            d2[q] = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+    }
+}
+
 // G (B, gh*gw, cout) fp32 -> three column-shifted copies e = 0,1,2 (shift e-1) of the transposed fp16 planes
 // (3, B, 80, gh*gwp):  copy_e[b][n][y*gwp + col] = G[b][y][col - (e-1)][n]  (zero outside the row, for n >= cout).
 // One block per image row: the row's gw x cout floats are read coalesced into shared memory and written back
@@ -101,7 +172,7 @@ __global__ void __launch_bounds__(256) g_transpose_split_kernel(const float *__r
                                                                 __half *__restrict__ p1, __half *__restrict__ p2) {
     extern __shared__ float srow[];   // [gw][cout + 1]
     const int b = blockIdx.y, y = blockIdx.x;
-    const int ld = cout + 1;
+    const int ld = cout + 1;          // odd for even cout: the strided reads below are bank-conflict free
     const float *src = g + ((size_t)b * gh + y) * gw * cout;
     for (int i = threadIdx.x; i < gw * cout; i += blockDim.x) {
         const int col = i / cout, n = i - col * cout;
@@ -111,17 +182,29 @@ __global__ void __launch_bounds__(256) g_transpose_split_kernel(const float *__r
     const float t0 = pow2_scale_for(__uint_as_float(__ldg(amax_bits + (size_t)b * 2)));
     const float t1 = pow2_scale_for(__uint_as_float(__ldg(amax_bits + (size_t)b * 2 + 1)));
     const size_t ppad = (size_t)gh * gwp;
-    const int total = kNPad * gwp, e = blockIdx.z;
+    // one item = 8 consecutive columns of one output channel of one shifted copy: one 16-byte store per plane
+    const int cpr = gwp >> 3, per_copy = kNPad * cpr, total = 3 * per_copy;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int n = i / gwp, j = i - n * gwp;
-        const int col = j - (e - 1);
-        float xs = 0.f;
-        if (n < cout && col >= 0 && col < gw) xs = srow[col * ld + n] * (n < 64 ? t0 : t1);
-        const __half h1 = __float2half_rn(xs);
-        const __half h2 = __float2half_rn((xs - __half2float(h1)) * kLoScale);
-        const size_t o = (((size_t)e * batch + b) * kNPad + n) * ppad + (size_t)y * gwp + j;
-        p1[o] = h1;
-        p2[o] = h2;
+        const int e = i / per_copy, r = i - e * per_copy, n = r / cpr, k = r - n * cpr;
+        const float t = n < 64 ? t0 : t1;
+        unsigned h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float xs[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int col = 8 * k + 2 * q + u - (e - 1);
+                xs[u] = (n < cout && col >= 0 && col < gw) ? srow[col * ld + n] * t : 0.f;
+            }
+            const __half2 hh = __floats2half2_rn(xs[0], xs[1]);
+            const float2 f = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn((xs[0] - f.x) * kLoScale, (xs[1] - f.y) * kLoScale);
+            h[q] = *reinterpret_cast<const unsigned *>(&hh);
+            l[q] = *reinterpret_cast<const unsigned *>(&ll);
+        }
+        const size_t o = (((size_t)e * batch + b) * kNPad + n) * ppad + (size_t)y * gwp + 8 * k;   // multiple of 8 halfs
+        *reinterpret_cast<uint4 *>(p1 + o) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(p2 + o) = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
@@ -615,14 +698,21 @@ extern "C" int sqd_convdet_wgrad_tc(const float *d_feat_nchw, const float *d_gpr
     SQD_CUDA(cudaMemsetAsync(ws, 0, w.x1_off, st));   // status + both amax arrays
 
     // 1. operands: pixel-major fp16 planes
-    int rc = sqd_f16_absmax_runs(d_feat_nchw, (size_t)64 * P, batch * ncb, amax_x, st);
-    if (rc) return rc;
-    if ((rc = stage_check("absmax x", st))) return rc;
+    int rc = SQD_OK;
     SQD_REQUIRE(gw % 2 == 0, SQD_E_SHAPE, "sqd_convdet_wgrad_tc: grid width %d must be even", gw);
-    split_nchw_rows_kernel<<<(unsigned)((size_t)batch * cin), 256, 0, st>>>(d_feat_nchw, cin, gh, gw, gwp, amax_x,
-                                                                           reinterpret_cast<__half2 *>(x1),
-                                                                           reinterpret_cast<__half2 *>(x2));
-    SQD_LAUNCH_CHECK("split_nchw_rows_kernel");
+    if (kXsChan * gh * (gwp / 8) <= kXsItems * kXsThreads && !getenv("SQD_BWD_OLD_PREPASS")) {
+        split_nchw_rows_cluster_kernel<<<(unsigned)(batch * ncb * kXsCluster), kXsThreads, 0, st>>>(
+            d_feat_nchw, cin, gh, gw, gwp, amax_x, reinterpret_cast<uint4 *>(x1), reinterpret_cast<uint4 *>(x2));
+        SQD_LAUNCH_CHECK("split_nchw_rows_cluster_kernel");
+    } else {
+        rc = sqd_f16_absmax_runs(d_feat_nchw, (size_t)64 * P, batch * ncb, amax_x, st);
+        if (rc) return rc;
+        if ((rc = stage_check("absmax x", st))) return rc;
+        split_nchw_rows_kernel<<<(unsigned)((size_t)batch * cin), 256, 0, st>>>(d_feat_nchw, cin, gh, gw, gwp, amax_x,
+                                                                               reinterpret_cast<__half2 *>(x1),
+                                                                               reinterpret_cast<__half2 *>(x2));
+        SQD_LAUNCH_CHECK("split_nchw_rows_kernel");
+    }
     if ((rc = stage_check("split x", st))) return rc;
     if ((rc = sqd_gpred_absmax(d_gpred, batch, P, cout, 2, amax_g, st))) return rc;
     if ((rc = stage_check("absmax g", st))) return rc;
@@ -630,7 +720,7 @@ extern "C" int sqd_convdet_wgrad_tc(const float *d_feat_nchw, const float *d_gpr
         const size_t smem_g = (size_t)gw * (cout + 1) * sizeof(float);
         if (smem_g > 48 * 1024)
             SQD_CUDA(cudaFuncSetAttribute(g_transpose_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-        g_transpose_split_kernel<<<dim3(gh, batch, 3), 256, smem_g, st>>>(d_gpred, gh, gw, gwp, cout, batch, amax_g, g1, g2);
+        g_transpose_split_kernel<<<dim3(gh, batch), 256, smem_g, st>>>(d_gpred, gh, gw, gwp, cout, batch, amax_g, g1, g2);
         SQD_LAUNCH_CHECK("g_transpose_split_kernel");
         if ((rc = stage_check("transpose g", st))) return rc;
     }

@@ -387,6 +387,19 @@ def test_convdet_dgrad_and_bias_grad(ops, name, batch):
         finally:
             os.environ.pop("SQD_WG_SINGLE_TAP", None)
         assert torch.equal(gw1, gw2)
+        if tc is True:
+            # the one-pass pre-passes (cluster X split, flat max|G|, cluster bias sums) against the kernels they replaced:
+            # same scales and planes -> the same gradient bit for bit; the bias sums only differ in summation order
+            os.environ["SQD_BWD_OLD_PREPASS"] = "1"
+            try:
+                gw_old = ops.convdet_wgrad(dev(feat), dev(g), tensor_cores=True, check_status=True)
+                gb_old = ops.convdet_bias_grad(dev(g))
+                gx_old = ops.convdet_dgrad(dev(g), dev(w))
+            finally:
+                del os.environ["SQD_BWD_OLD_PREPASS"]
+            assert torch.equal(gw1, gw_old)
+            assert torch.equal(gx_old.cpu(), torch.from_numpy(got))
+            assert torch.allclose(gb_old.cpu(), torch.from_numpy(gb), rtol=1e-6, atol=1e-6 * float(np.abs(gb64).max()))
         gw1 = gw1.cpu().numpy()
         e_ours = np.abs(gw1 - gw64).max() / wscale
         print(f"wgrad ({tc if isinstance(tc, str) else 'tcgen05' if tc else 'simt'}) vs float64: ours max {e_ours:.2e}, torch-cpu fp32 max {e_ref:.2e} (rel. to mean |dW|)")
