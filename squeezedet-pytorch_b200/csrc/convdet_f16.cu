@@ -219,10 +219,12 @@ __global__ void __launch_bounds__(kSplitThreads) split_nchw_cluster_kernel(const
     namespace cgx = cooperative_groups;
     cgx::cluster_group cluster = cgx::this_cluster();
     const int rank = (int)cluster.block_rank();
-    const int slab = blockIdx.x / cs, ncb = cin >> 6;
+    // index arithmetic without integer divisions (they were a quarter of this kernel's instructions): cs is a power of two
+    const int csh = 31 - __clz(cs);
+    const int slab = blockIdx.x >> csh, ncb = cin >> 6;
     const int b = slab / ncb, cb = slab - b * ncb, c0 = cb << 6;
     const int n4 = P >> 2;
-    const int q4b = (int)((long long)rank * n4 / cs), q4e = (int)((long long)(rank + 1) * n4 / cs), nq4 = q4e - q4b;
+    const int q4b = (rank * n4) >> csh, q4e = ((rank + 1) * n4) >> csh, nq4 = q4e - q4b;
     const float4 *src = reinterpret_cast<const float4 *>(in + ((size_t)b * cin + c0) * P) + q4b;
     sqd_pdl_trigger();   // the GEMM behind this kernel may be scheduled as SMs drain; it waits for this grid to complete
 
@@ -253,13 +255,16 @@ __global__ void __launch_bounds__(kSplitThreads) split_nchw_cluster_kernel(const
         }
     } else {
         const int total = 64 * nq4;
+        // idx / nq4 as a multiply-high: exact for idx < 2^16 and nq4 < 256 (idx < 64 * nq4 here)
+        const bool use_magic = nq4 < 256;
+        const unsigned magic = use_magic ? (unsigned)(0xFFFFFFFFu / (unsigned)nq4) + 1u : 0u;
         for (int base = 0; base < total; base += 4 * kSplitThreads) {
             float4 v[4];
             int cc[4], jj[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int idx = base + u * kSplitThreads + threadIdx.x;
-                cc[u] = idx / nq4;
+                cc[u] = use_magic ? (int)__umulhi((unsigned)idx, magic) : idx / nq4;
                 jj[u] = idx - cc[u] * nq4;
                 v[u] = idx < total ? ld_stream_f4(src + (size_t)cc[u] * n4 + jj[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
