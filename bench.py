@@ -35,7 +35,7 @@ METRIC = "images/sec head+decode+NMS @1248x384 (whole job; per-GPU = value / n_g
 FLOP_PER_IMAGE = 2 * 1872 * 72 * 6912          # 1,863,254,016
 PRED_BYTES_PER_IMAGE = 16848 * 8 * 4           # 539,136
 FEAT_BYTES_PER_IMAGE = 768 * 24 * 78 * 4       # 5,750,784
-NCU_CONVDET_TRAFFIC_B20 = 126333440 + 7085568  # bytes per launch at B = 20 (ncu --set full capture, see profiles/)
+NCU_CONVDET_TRAFFIC_B20 = 125986560 + 5881088  # bytes per launch at B = 20 (ncu --set full capture, profiles/r01_ncu_b20_final2.txt)
 DENSE_BYTES_PER_IMAGE = 16848 * (8 + 4 + 16)   # 471,744 (int64 id, score, box)
 
 
@@ -396,14 +396,14 @@ def main_ours(args):
                             "-> D2H of the detections; serving loop with two slots: step i+1 is issued before step i's "
                             "result is waited for and read on the host, every step's result is read" % args.e2e_chunk},
             "gpu_launches": 4 * K,
-            "kernels_per_step": ["split_nchw_cluster_kernel (max|x| + fp16 split, one pass)", "convdet_f16_pair_kernel<80,0>",
+            "kernels_per_step": ["split_nchw_cluster_kernel (max|x| + fp16 split, one pass)", "convdet_f16_pair_kernel<80,0,false,36>",
                                  "score_candidates_kernel<3>", "detect_from_candidates_kernel"],
             "kernel_ms": kern,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tflops"], "traffic": NCU_CONVDET_TRAFFIC_B20 if B == 20 else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, "
-                                           "profiles/r01_ncu_b20_pair_chunk3_split_cluster.txt (B = 20 only)",
-                         "kernel": "convdet_f16_pair_kernel<80,0>",
+                                           "profiles/r01_ncu_b20_final2.txt (B = 20 only)",
+                         "kernel": "convdet_f16_pair_kernel<80,0,false,36>",
                          "peak_source": peaks["source"] + ", dense bf16 burst",
                          "note": "algorithmic FLOPs 2*1872*72*6912 per image; the kernel issues 3 fp16 passes on N padded "
                                  "to 80 for fp32-level accuracy, so frac <= 1/3 * 72/80 = 0.30 by construction"},
