@@ -17,7 +17,8 @@ int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, 
 size_t sqd_f16_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout);
 int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                          int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st,
-                         const SqdCandEmit *emit, int out_stride, int ksteps_last, int slabs, size_t slab_stride);
+                         const SqdCandEmit *emit, int out_stride, int ksteps_last, int slabs, size_t slab_stride,
+                         int image_scales);
 // implemented in topk_nms.cu
 size_t sqd_cand_bytes(int batch, int num_anchors);
 SqdCand sqd_cand_layout(void *ws, int batch, int num_anchors);
@@ -96,7 +97,7 @@ static int convdet_forward_impl(const float *d_feat, int layout, const void *d_p
                 "sqd_convdet_forward: unknown algo %d", algo);
     SQD_REQUIRE(d_packed, SQD_E_NULL, "sqd_convdet_forward: tcgen05 algorithm needs packed weights");
     if (algo == SQD_CONV_TCGEN05_F16X3)
-        return sqd_convdet_f16_pair(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st, emit, 0, 0, 1, 0);
+        return sqd_convdet_f16_pair(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st, emit, 0, 0, 1, 0, 0);
     return sqd_convdet_f16(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
 }
 

@@ -22,7 +22,8 @@ size_t sqd_f16_split_bytes(int batch, int cin, int gh, int gw);
 size_t sqd_f16_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout);
 int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                          int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st,
-                         const SqdCandEmit *emit, int out_stride, int ksteps_last, int slabs, size_t slab_stride);
+                         const SqdCandEmit *emit, int out_stride, int ksteps_last, int slabs, size_t slab_stride,
+                         int image_scales);
 
 namespace {
 
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256) gpred_absmax_kernel(const float *__restri
 // The same maxima for cout % 4 == 0 (KITTI: 72): an image's (P, cout) block read as a flat run of 16-byte quads, fully
 // coalesced; a quad never straddles a pixel or a 64-channel block.  Grid (chunks, B); at most 2 blocks (cout <= 128).
 __global__ void __launch_bounds__(256) gpred_absmax_flat_kernel(const float4 *__restrict__ g, int quads_per_image, int qpp,
-                                                                int ncb, unsigned *__restrict__ amax_bits) {
+                                                                int ncb, unsigned *__restrict__ amax_bits, int per_image) {
     __shared__ unsigned s_max[2];
     if (threadIdx.x < 2) s_max[threadIdx.x] = 0u;
     __syncthreads();
@@ -106,7 +107,10 @@ __global__ void __launch_bounds__(256) gpred_absmax_flat_kernel(const float4 *__
         atomicMax(&s_max[1], __float_as_uint(m1));
     }
     __syncthreads();
-    if ((int)threadIdx.x < ncb) atomicMax(amax_bits + (size_t)b * ncb + threadIdx.x, s_max[threadIdx.x]);
+    // per_image: every block of the image gets the image maximum (one scale per image: the GEMM may then accumulate a
+    // whole tile in TMEM before folding it)
+    if ((int)threadIdx.x < ncb)
+        atomicMax(amax_bits + (size_t)b * ncb + threadIdx.x, per_image ? max(s_max[0], s_max[1]) : s_max[threadIdx.x]);
 }
 
 // G (B, P, cout) fp32 -> x1 / x2 fp16 planes (B, P, kp), channels >= cout zero; one thread per (cell, 4 channels)
@@ -354,10 +358,11 @@ extern "C" int sqd_convdet_dgrad_pack_weights(const float *d_weight, int cout, i
 
 // max |G| per (image, 64-channel block of the channel axis padded to a multiple of 64) into amax_bits (zeroed by the
 // caller; image stride ncb >= ceil(cout / 64)): the scale granularity of both the dgrad planes and the wgrad G^T copies.
-int sqd_gpred_absmax(const float *d_gpred, int batch, int P, int cout, int ncb, unsigned *amax_bits, cudaStream_t st) {
-    if (cout % 4 == 0 && cout <= 128 && ncb <= 2 && !getenv("SQD_BWD_OLD_PREPASS")) {
+int sqd_gpred_absmax(const float *d_gpred, int batch, int P, int cout, int ncb, unsigned *amax_bits, cudaStream_t st,
+                     int per_image) {
+    if (cout % 4 == 0 && cout <= 128 && ncb <= 2 && (per_image || !getenv("SQD_BWD_OLD_PREPASS"))) {
         gpred_absmax_flat_kernel<<<dim3(16, batch), 256, 0, st>>>(reinterpret_cast<const float4 *>(d_gpred), P * (cout / 4),
-                                                                 cout / 4, ncb, amax_bits);
+                                                                 cout / 4, ncb, amax_bits, per_image);
         SQD_LAUNCH_CHECK("gpred_absmax_flat_kernel");
     } else {
         gpred_absmax_kernel<<<dim3(16, batch), 256, ncb * sizeof(unsigned), st>>>(d_gpred, P, cout, ncb, amax_bits);
@@ -384,6 +389,10 @@ extern "C" int sqd_convdet_dgrad(const float *d_gpred, const void *d_dgrad_packe
                 workspace_bytes, w.total);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int kp = kpad_of(cout), ncb = kp / 64, P = gh * gw, ns = nslab_of(cin);
+    // ONE scale per image for G when the flat max kernel applies (72 channels = 2 blocks): a tile of the dgrad GEMM is
+    // then a single TMEM chunk (one drain of the 384-column accumulator per tile instead of two).  fp16 keeps 11
+    // significant bits down to 2^-27 of the image maximum, so a per-block scale buys nothing for a gradient tensor.
+    const int image_scales = (cout % 4 == 0 && cout <= 128 && ncb == 2 && !getenv("SQD_DGRAD_BLOCK_SCALES")) ? 1 : 0;
     char *ws = static_cast<char *>(d_workspace);
     // 1. G -> zero-padded fp16 planes with per-(image, block) scales (G is 1/10 of the features: two small passes)
     char *planes = ws + w.planes_off;
@@ -392,7 +401,7 @@ extern "C" int sqd_convdet_dgrad(const float *d_gpred, const void *d_dgrad_packe
     unsigned *amax = reinterpret_cast<unsigned *>(planes);
     SQD_CUDA(cudaMemsetAsync(amax, 0, amax_bytes, st));
     {
-        int rc = sqd_gpred_absmax(d_gpred, batch, P, cout, ncb, amax, st);
+        int rc = sqd_gpred_absmax(d_gpred, batch, P, cout, ncb, amax, st, image_scales);
         if (rc) return rc;
     }
     const size_t total = (size_t)batch * P * (kp / 4);
@@ -414,13 +423,13 @@ extern "C" int sqd_convdet_dgrad(const float *d_gpred, const void *d_dgrad_packe
             int rc = sqd_convdet_f16_pair(reinterpret_cast<const float *>(planes), SQD_LAYOUT_SPLIT_NHWC,
                                           static_cast<const char *>(d_dgrad_packed) + (size_t)s * slab_bytes, nullptr, batch, kp, gh,
                                           gw, kSlab, d_gfeat_nhwc + (size_t)s * kSlab, ws + w.gemm_off, st, nullptr, cin, ksteps_last,
-                                          1, 0);
+                                          1, 0, image_scales);
             if (rc) return rc;
         }
         return SQD_OK;
     }
     int rc = sqd_convdet_f16_pair(reinterpret_cast<const float *>(planes), SQD_LAYOUT_SPLIT_NHWC, d_dgrad_packed, nullptr, batch, kp,
-                                  gh, gw, kSlab, d_gfeat_nhwc, ws + w.gemm_off, st, nullptr, cin, ksteps_last, ns, slab_bytes);
+                                  gh, gw, kSlab, d_gfeat_nhwc, ws + w.gemm_off, st, nullptr, cin, ksteps_last, ns, slab_bytes, image_scales);
     if (rc) return rc;
     return SQD_OK;
 }

@@ -411,6 +411,7 @@ struct F16Params {
 struct Sched {  // the permuted unit sequence of one CTA: [whole tiles + head segment][deferred tail segment]
     long long u0;
     int n, main_len, upt;
+    int blk = 3;   // units per scale block: 3 (one 64-channel block); upt when every block of an image shares one scale
     __device__ __forceinline__ long long unit(int i) const {
         const int len_tail = n - main_len;
         return i < main_len ? u0 + len_tail + i : u0 + (i - main_len);
@@ -419,7 +420,7 @@ struct Sched {  // the permuted unit sequence of one CTA: [whole tiles + head se
     // (end of a tile, end of the main part, end of the CTA's range).  in_chunk = units already in the chunk.
     // A chunk never crosses a 64-channel block (r = cb*3 + dx): the block's feature scale is applied per chunk.
     __device__ __forceinline__ bool chunk_ends(int i, int r, int in_chunk, int chunk_units) const {
-        return in_chunk + 1 >= chunk_units || r % 3 == 2 || i == n - 1 || i == main_len - 1 || r == upt - 1;
+        return in_chunk + 1 >= chunk_units || r % blk == blk - 1 || i == n - 1 || i == main_len - 1 || r == upt - 1;
     }
 };
 
@@ -815,7 +816,8 @@ struct PairParams {
     int upt;             // units per tile = (cin/64) * 3
     int units_per_pair;  // even cut of pair_tiles*upt over the pairs (>= upt)
     int stages;
-    int chunk_units;     // units accumulated inside TMEM before the sum moves to registers (1 or 2)
+    int chunk_units;     // units accumulated inside TMEM before the sum moves to registers
+    int chunk_blk;       // units that share one feature scale: 3 (a 64-channel block) or upt (one scale per image)
     int dbg;
     const float *bias;
     const unsigned *amax_bits;
@@ -958,6 +960,7 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
     const long long total_units = (long long)p.pair_tiles * p.upt;
     Sched sc;
     sc.upt = p.upt;
+    sc.blk = p.chunk_blk;
     sc.u0 = (long long)pair * p.units_per_pair;
     {
         long long u1 = sc.u0 + p.units_per_pair;
@@ -1493,7 +1496,8 @@ int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, 
 // an opt-in experiment (SQD_FUSED_SCORE=1), not the default.
 int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                          int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st,
-                         const SqdCandEmit *emit, int out_stride, int ksteps_last, int slabs, size_t slab_stride) {
+                         const SqdCandEmit *emit, int out_stride, int ksteps_last, int slabs, size_t slab_stride,
+                         int image_scales) {
     SQD_REQUIRE(cin % kBlockK == 0, SQD_E_SHAPE, "convdet (tcgen05): Cin %d must be a multiple of %d", cin, kBlockK);
     SQD_REQUIRE(cout >= 1 && cout <= 128, SQD_E_SHAPE, "convdet (tcgen05): Cout %d outside [1,128]", cout);
     EncodeTiledFn encode = get_encode_fn();
@@ -1587,6 +1591,11 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
     SQD_REQUIRE(p.stages >= 2, SQD_E_SHAPE, "convdet (tcgen05): shared memory too small for two stages");
     p.chunk_units = env_int("SQD_F16_CHUNK", 3);   // one 64-channel block (3 dx units) per TMEM chunk
     if (p.chunk_units < 1) p.chunk_units = 1;
+    p.chunk_blk = 3;
+    if (image_scales && p.upt <= 6) {              // every block of an image shares one scale: a whole tile per chunk
+        p.chunk_blk = p.upt;
+        p.chunk_units = p.upt;
+    }
     p.dbg = env_int("SQD_F16_DBG", 0);
     p.bias = d_bias;
     p.amax_bits = reinterpret_cast<const unsigned *>(planes);

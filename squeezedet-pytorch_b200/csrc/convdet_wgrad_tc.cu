@@ -671,7 +671,8 @@ WgWs wg_ws(int batch, int cin, int gh, int gw) {
 
 // implemented in convdet_f16.cu: max |x| of contiguous runs (one per blockIdx.y)
 int sqd_f16_absmax_runs(const float *d_in, size_t run_floats, int nruns, unsigned *d_amax, cudaStream_t st);
-int sqd_gpred_absmax(const float *d_gpred, int batch, int P, int cout, int ncb, unsigned *amax_bits, cudaStream_t st);
+int sqd_gpred_absmax(const float *d_gpred, int batch, int P, int cout, int ncb, unsigned *amax_bits, cudaStream_t st,
+                     int per_image);
 
 extern "C" size_t sqd_convdet_wgrad_tc_workspace_bytes(int batch, int cin, int gh, int gw, int cout) {
     if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0) return 256;
@@ -714,7 +715,7 @@ extern "C" int sqd_convdet_wgrad_tc(const float *d_feat_nchw, const float *d_gpr
         SQD_LAUNCH_CHECK("split_nchw_rows_kernel");
     }
     if ((rc = stage_check("split x", st))) return rc;
-    if ((rc = sqd_gpred_absmax(d_gpred, batch, P, cout, 2, amax_g, st))) return rc;
+    if ((rc = sqd_gpred_absmax(d_gpred, batch, P, cout, 2, amax_g, st, 0))) return rc;
     if ((rc = stage_check("absmax g", st))) return rc;
     {
         const size_t smem_g = (size_t)gw * (cout + 1) * sizeof(float);
