@@ -907,6 +907,9 @@ struct PairIterT {
 
 #define SQD_TRACE2(slot, i) \
     do { if (p.trace && cta == p.trace_cta && lane == 0 && (i) < 512) p.trace[(i) * 32 + (slot)] = clock64(); } while (0)
+// kernel phases (thread 0 of the traced CTA): row 511 of the trace buffer
+#define SQD_TRACE_PH(slot) \
+    do { if (p.trace && blockIdx.x == (unsigned)p.trace_cta && threadIdx.x == 0) p.trace[511 * 32 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ bool pair_wait_warp(uint64_t *bar, uint32_t parity, volatile int *abort_flag, bool spin) {
     return spin ? mbar_spin_warp(bar, parity, abort_flag) : mbar_wait_warp(bar, parity, abort_flag);
@@ -955,6 +958,7 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
     const int tile_offset = PK ? (int)rank : (rank ? p.pair_tiles : 0);
     using PairIter = PairIterT<PK>;
     const bool spin = (p.dbg & 8) != 0;   // debug: 8 = poll mbarrier.test_wait instead of parking in try_wait (slower)
+    SQD_TRACE_PH(0);
 
     // ---- this pair's slice of the (pair-tile, unit) space ----------------------------------------------------
     const long long total_units = (long long)p.pair_tiles * p.upt;
@@ -993,15 +997,19 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
         tma_prefetch_desc(&map_b);
     }
     for (int i = threadIdx.x; i < NPAD; i += kThreads2) s_bias[i] = (i < p.cout && p.bias) ? __ldg(p.bias + i) : 0.f;
+    SQD_TRACE_PH(1);
     if (warp == kWarpMma2) tmem_alloc_2cta(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
+    SQD_TRACE_PH(2);
     cluster_sync_all();  // both CTAs: barriers initialised, TMEM allocated, before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    SQD_TRACE_PH(3);
     // Programmatic dependent launch: everything above ran while the pre-pass kernel was still finishing; from here on
     // its outputs (fp16 planes, block maxima) are needed.
     sqd_pdl_wait();
+    SQD_TRACE_PH(4);
 
     if (warp == kWarpTma2) {
         // ===== producer: this CTA's A patches (own tile) and its half of the three B tiles of one unit =====
@@ -1335,10 +1343,13 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
             flush_pending();
         }
     }
+    SQD_TRACE_PH(5);     // the producer warp is through (thread 0 is its lane 0)
     tc_fence_before();
     __syncthreads();
+    SQD_TRACE_PH(6);
     cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still touch its shared memory / barriers
     tc_fence_after();
+    SQD_TRACE_PH(7);
     if (warp == kWarpMma2) {
         __syncwarp();
         tmem_dealloc_2cta(tmem_base, kTmemCols);

@@ -51,6 +51,12 @@ for setting in (sys.argv[1:] or [""]):
     n = int((t[:, 10] > 0).sum())
     t0 = t[0, 0]
     print(f"==== {setting or 'default'}: {n} units traced")
+    ph = t[511, :8]
+    if ph[0] > 0:
+        names = ["entry", "setup done (barriers, bias, tensormap prefetch)", "tmem alloc + __syncthreads", "cluster sync", "pdl wait",
+                 "producer warp done", "__syncthreads (all warps done)", "final cluster sync"]
+        print("kernel phases of the traced CTA, cycles after entry: " + " | ".join(f"{nm} {int(v - ph[0])}" for nm, v in zip(names, ph)))
+        print(f"first TMA issue {int(t0 - ph[0])} after entry; last acc_done {int(t[:n, 12].max() - ph[0])}")
     print("unit " + " ".join(f"{x:>9s}" for x in NAMES))
     for i in list(range(0, 5)) + list(range(36, 40)) + list(range(n - 3, n)):
         print(f"{i:4d} " + " ".join(f"{int(v - t0):9d}" for v in t[i][:13]))
