@@ -446,7 +446,8 @@ def main_ours(args):
                                      "note": "between the stage events of sqd_head_detect_profile: the events serialise the "
                                              "chain, so this includes the launch ramp that the real step overlaps"},
                          "note": "algorithmic FLOPs 2*1872*72*6912 per image; the kernel issues 3 fp16 passes (MMAs N = 144 + 80 "
-                                 "for the 72 channels) for fp32-level accuracy, so frac <= 72/224 = 0.32 by construction"},
+                                 "for the 72 channels, 116.2 tensor cycles per K step measured: profiles/r01_umma_rate_2cta.txt) for "
+                                 "fp32-level accuracy, so frac <= 0.31 by construction"},
             "roofline_decode_nms": {"bound": "hbm", "achieved": Bd * PRED_BYTES_PER_IMAGE / det_s / 1e9,
                                     "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": Bd * PRED_BYTES_PER_IMAGE / det_s / 1e9 / peaks["hbm_gbs"], "traffic": None,
