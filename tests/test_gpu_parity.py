@@ -588,3 +588,48 @@ def test_filter_randomised_differential(ops):
     rs = np.random.RandomState(20260)
     kept = sum(fuzz.one_case(rs, torch.device("cuda"))["kept"] for _ in range(60))
     assert kept > 0
+
+
+def test_matcher_randomised_differential():
+    """Random annotation sets against the oracle's sequential matcher: 1..200 boxes per image (more boxes than a batched
+    round holds), tiny boxes far from every anchor (distance fallback), exact duplicates and boxes sitting exactly on
+    anchors (IoU ties -> lowest anchor index), crowded scenes where boxes compete for the same anchors."""
+    from squeezedet_pytorch_b200 import targets
+    rs = np.random.RandomState(777)
+    for shp in (synth.TINY, synth.KITTI):
+        anchors = synth.anchor_table(shp)
+        a_xyxy = orc.anchors_xyxy_f64(anchors)
+        m = targets.AnchorMatcher(anchors, shp.num_classes)
+        H, W = shp.input_hw
+        for trial in range(6):
+            boxes_l = []
+            for _ in range(4):
+                n = int(rs.choice([1, 2, 7, 33, 64, 120, 200]))
+                kind = rs.randint(0, 4)
+                if kind == 0:      # generic boxes
+                    cx, cy = rs.uniform(0, W, n), rs.uniform(0, H, n)
+                    w, h = rs.uniform(2, W / 3, n), rs.uniform(2, H / 2, n)
+                elif kind == 1:    # tiny boxes: many have IoU 0 with every anchor after the first few are taken
+                    cx, cy = rs.uniform(0, W, n), rs.uniform(0, H, n)
+                    w, h = rs.uniform(1.01, 2.5, n), rs.uniform(1.01, 2.5, n)
+                elif kind == 2:    # crowded: all boxes around one point
+                    cx, cy = rs.normal(W / 2, 10, n), rs.normal(H / 2, 6, n)
+                    w, h = rs.uniform(20, 60, n), rs.uniform(20, 60, n)
+                else:              # exactly on anchors, with duplicates
+                    pick = rs.randint(0, len(anchors), n)
+                    pick[n // 2:] = pick[:n - n // 2]
+                    bx = a_xyxy[pick]
+                    cx, cy = (bx[:, 0] + bx[:, 2]) / 2, (bx[:, 1] + bx[:, 3]) / 2
+                    w, h = bx[:, 2] - bx[:, 0] + 1, bx[:, 3] - bx[:, 1] + 1
+                b = np.stack([cx - (w - 1) / 2, cy - (h - 1) / 2, cx + (w - 1) / 2, cy + (h - 1) / 2], 1).astype(np.float32)
+                b = b[(b[:, 2] > b[:, 0]) & (b[:, 3] > b[:, 1])]                    # boxes.py:14-15
+                boxes_l.append(b if len(b) else np.array([[1, 1, 9, 9]], np.float32))
+            gb, _, gc = m.pack(boxes_l)
+            idx, deltas = m.match(gb, gc)
+            idx, deltas = idx.cpu().numpy(), deltas.cpu().numpy()
+            for i, b in enumerate(boxes_l):
+                n = len(b)
+                o_d, o_i = orc.match_anchors(b, anchors)
+                assert np.array_equal(o_i, idx[i, :n]), (shp.name, trial, i)
+                assert len(set(idx[i, :n].tolist())) == n                            # every box its own anchor
+                np.testing.assert_allclose(deltas[i, :n], o_d, rtol=1e-6, atol=1e-6)
