@@ -633,3 +633,32 @@ def test_matcher_randomised_differential():
                 assert np.array_equal(o_i, idx[i, :n]), (shp.name, trial, i)
                 assert len(set(idx[i, :n].tolist())) == n                            # every box its own anchor
                 np.testing.assert_allclose(deltas[i, :n], o_d, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("C", [1, 2, 3, 5, 8, 20])
+def test_loss_randomised_shapes_vs_oracle(ops, C):
+    """Loss forward + backward for class counts with and without specialised kernels, random loss weights, random
+    per-image upstream gradients, images with 1 object and with many: the four per-image terms and dpred against the
+    oracle (numpy float32 restatement of Loss.forward and of its autograd backward)."""
+    rs = np.random.RandomState(40 + C)
+    shp = synth.Shape("rnd", (int(rs.choice([96, 192])), int(rs.choice([160, 320]))), C, 16)
+    anchors = synth.anchor_table(shp)
+    B = 4
+    pred = (rs.standard_normal((B, shp.num_anchors, C + 5)) * rs.uniform(0.3, 2.0)).astype(np.float32)
+    gts = []
+    for b in range(B):
+        cls, boxes = synth.gt_boxes(shp, 5000 + 10 * C + b, lo=1, hi=1 if b == 0 else 20)
+        gts.append(orc.dense_targets(cls % C, boxes, anchors, C))
+    gt = np.stack(gts)
+    weights = tuple(float(x) for x in rs.uniform(0.5, 100.0, 4))
+    gl = rs.uniform(0.1, 2.0, B)
+    exp = orc.loss_forward(pred, gt, anchors, shp.input_hw, C, weights)
+    exp_d = orc.loss_backward(pred, gt, anchors, shp.input_hw, C, gl, weights)
+    grad = torch.from_numpy(np.repeat(gl[:, None], 4, 1).astype(np.float32)).cuda()
+    losses, dpred = ops.loss_fwd_bwd(dev(pred), dev(gt), dev(anchors.astype(np.float32)), shp.input_hw, C, weights, grad_loss=grad)
+    losses = losses.cpu().numpy()
+    np.testing.assert_allclose(losses[:, 0], exp["class_loss"], rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(losses[:, 1] + losses[:, 2], exp["score_loss"], rtol=RTOL)
+    np.testing.assert_allclose(losses[:, 3], exp["bbox_loss"], rtol=RTOL)
+    np.testing.assert_allclose(losses.sum(1), exp["loss"], rtol=RTOL)
+    np.testing.assert_allclose(dpred.cpu().numpy(), exp_d, rtol=1e-3, atol=2e-6 * np.abs(exp_d).max())
