@@ -932,11 +932,18 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
     static_assert(HR % 4 == 0 && 2 * HR <= NPAD && N2H <= N1H, "pair layout");
     constexpr int kBTapBytes = N1H * kBlockK * 2;           // multiple of 1024: N1H is a multiple of 8
     constexpr int kStageBytes = kAStageBytes + 3 * kBTapBytes;
-    constexpr int kAccCols = 2 * N1H + 2 * N2H;             // [MMA1: 4*HR | MMA2: 2*N2H]
+    // PK (the dgrad GEMM, HR = 64): THREE MMAs of N = 2*HR per K step instead -- A1 x w1 -> main columns, A1 x w2 and
+    // A2 x w1 -> the SAME cross columns (both carry the 2^-11 scale).  Same tensor time in the linear regime of the MMA
+    // rate (128 + 64 = 3 x 64 cycles), but 4*HR = 256 accumulator columns instead of 384: two TMEM buffers fit and the
+    // drain of a tile overlaps the MMAs of the next.  (For the forward's N = 72 the three MMAs would sit on the ~45-cycle
+    // instruction floor: 135 vs 116 cycles per K step.)
+    constexpr bool k3 = PK && HR % 8 == 0;
+    constexpr int kAccCols = k3 ? 4 * HR : 2 * N1H + 2 * N2H;   // [MMA1: 4*HR | MMA2: 2*N2H]  or  [main 2*HR | cross 2*HR]
     constexpr int kAccBufs = (2 * kAccCols <= 512) ? 2 : 1;
     constexpr uint32_t kTmemCols = 512;
     constexpr uint32_t kIdesc1 = umma_idesc_f16(256, 2 * N1H);
     constexpr uint32_t kIdesc2 = umma_idesc_f16(256, 2 * N2H);
+    constexpr uint32_t kIdesc3 = umma_idesc_f16(256, 2 * HR);
     static_assert(kAccCols <= 512 && (2 * N1H) % 16 == 0 && (2 * N2H) % 16 == 0, "TMEM budget / UMMA N");
 
     extern __shared__ uint8_t smem_raw[];
@@ -1082,13 +1089,20 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                             const uint64_t a2 = umma_desc_sw128(st + kPlaneBytes + dyi * kDyBytes);
                             const uint64_t b = umma_desc_sw128(st + kAStageBytes + dyi * kBTapBytes);
                             const uint64_t bw1 = b;   // the w1 rows come first
+                            const uint64_t bw2 = umma_desc_sw128(st + kAStageBytes + dyi * kBTapBytes + HR * kBlockK * 2);
 #pragma unroll
                             for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
                                 if (PK && ks >= nks) continue;
                                 const uint64_t adv = (uint64_t)((ks * kUmmaK * 2) >> 4);
                                 const uint32_t accum = (in_chunk | dyi | ks) ? 1u : 0u;
-                                umma_f16_ss_2cta(d1, a1 + adv, b + adv, kIdesc1, accum);
-                                umma_f16_ss_2cta(d2, a2 + adv, bw1 + adv, kIdesc2, accum);
+                                if (k3) {
+                                    umma_f16_ss_2cta(d1, a1 + adv, bw1 + adv, kIdesc3, accum);            // main  = a1*w1
+                                    umma_f16_ss_2cta(d1 + 2 * HR, a1 + adv, bw2 + adv, kIdesc3, accum);   // cross = a1*w2
+                                    umma_f16_ss_2cta(d1 + 2 * HR, a2 + adv, bw1 + adv, kIdesc3, 1u);      //       + a2*w1
+                                } else {
+                                    umma_f16_ss_2cta(d1, a1 + adv, b + adv, kIdesc1, accum);
+                                    umma_f16_ss_2cta(d2, a2 + adv, bw1 + adv, kIdesc2, accum);
+                                }
                             }
                         }
                     }
@@ -1242,6 +1256,17 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
             for (int h = 0; h < 2; ++h) {
 #pragma unroll
                 for (int j0 = 0; j0 < HR; j0 += 8) {
+                    if (k3) {
+                        uint32_t mn[8], cr[8];
+                        tmem_ld_x8(taddr + h * HR + j0, mn);                 // a1*w1
+                        tmem_ld_x8(taddr + 2 * HR + h * HR + j0, cr);        // a1*w2 + a2*w1
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            acc[h * HR + j0 + k] = fmaf(fmaf(__uint_as_float(cr[k]), kLoInv, __uint_as_float(mn[k])), inv_a,
+                                                        acc[h * HR + j0 + k]);
+                        continue;
+                    }
                     uint32_t c1[8], mn[8], c2[8];
                     tmem_ld_x8(taddr + h * N1H + j0, mn);              // a1*w1
                     tmem_ld_x8(taddr + h * N1H + HR + j0, c1);         // a1*w2
