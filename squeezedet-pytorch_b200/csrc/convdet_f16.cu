@@ -921,7 +921,7 @@ __device__ __forceinline__ bool pair_wait_warp(uint64_t *bar, uint32_t parity, v
 // that follows never scans pred.
 // PK: the last 64-channel block is only partly filled (p.ksteps_last valid 16-channel K steps; the rest is zero padding,
 // e.g. the 72 -> 128 padded gradient channels of the dgrad GEMM): its all-zero K steps are not issued.
-template <int NPAD, int CS, bool PK = false, int HR = NPAD / 2>
+template <int NPAD, int CS, bool PK = false, int HR = NPAD / 2, bool K3 = (NPAD >= 96)>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                         const __grid_constant__ CUtensorMap map_b, const PairParams p) {
@@ -932,12 +932,12 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
     static_assert(HR % 4 == 0 && 2 * HR <= NPAD && N2H <= N1H, "pair layout");
     constexpr int kBTapBytes = N1H * kBlockK * 2;           // multiple of 1024: N1H is a multiple of 8
     constexpr int kStageBytes = kAStageBytes + 3 * kBTapBytes;
-    // PK (the dgrad GEMM, HR = 64): THREE MMAs of N = 2*HR per K step instead -- A1 x w1 -> main columns, A1 x w2 and
-    // A2 x w1 -> the SAME cross columns (both carry the 2^-11 scale).  Same tensor time in the linear regime of the MMA
-    // rate (128 + 64 = 3 x 64 cycles), but 4*HR = 256 accumulator columns instead of 384: two TMEM buffers fit and the
-    // drain of a tile overlaps the MMAs of the next.  (For the forward's N = 72 the three MMAs would sit on the ~45-cycle
-    // instruction floor: 135 vs 116 cycles per K step.)
-    constexpr bool k3 = PK && HR % 8 == 0;
+    // K3 (Npad >= 96: the stress shape's 117 channels, the dgrad GEMM's 128): THREE MMAs of N = 2*HR per K step instead --
+    // A1 x w1 -> main columns, A1 x w2 and A2 x w1 -> the SAME cross columns (both carry the 2^-11 scale).  Same tensor
+    // time in the linear regime of the MMA rate (N >= 96: 128 + 64 = 3 x 64 cycles), but 4*HR accumulator columns instead
+    // of 6*HR: two TMEM buffers fit and the drain of a chunk overlaps the MMAs of the next.  (For KITTI's N = 72 the three
+    // MMAs would sit on the ~45-cycle instruction floor: 135 vs 116 cycles per K step; 2 x 224 columns fit anyway.)
+    constexpr bool k3 = K3 && HR % 8 == 0;
     constexpr int kAccCols = k3 ? 4 * HR : 2 * N1H + 2 * N2H;   // [MMA1: 4*HR | MMA2: 2*N2H]  or  [main 2*HR | cross 2*HR]
     constexpr int kAccBufs = (2 * kAccCols <= 512) ? 2 : 1;
     constexpr uint32_t kTmemCols = 512;
@@ -1400,22 +1400,21 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 int npad_of(int cout) { return (cout + 15) / 16 * 16; }
 // output channels per CTA of a pair (see pack_weights_f16_kernel / convdet_f16_pair_kernel)
 int pair_hr_of(int cout) {
     const int npad = npad_of(cout);
     if (npad == 80 && cout <= 72) return 36;      // KITTI: 9 anchors x (3 + 5)
-    if (npad == 128 && cout <= 120) return 60;    // stress shape: 9 x (8 + 5) = 117
     return npad / 2;
 }
 
 constexpr size_t kSmemLimit = 227 * 1024;
 constexpr size_t kCtrlBytes = 1024;
-
-int env_int(const char *name, int dflt) {
-    const char *e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
 
 int a_stages_for(int npad) {
     int s = env_int("SQD_F16_A_STAGES", 2);
@@ -1507,12 +1506,12 @@ int pair_stages_for(int n1h) {
     return (int)s;
 }
 
-template <int NPAD, int CS = 0, bool PK = false, int HR = NPAD / 2>
+template <int NPAD, int CS = 0, bool PK = false, int HR = NPAD / 2, bool K3 = (NPAD >= 96)>
 int launch_pair(const CUtensorMap *maps, const PairParams &p, int grid, cudaStream_t st) {
     const size_t smem = 1024 + (size_t)p.stages * (kAStageBytes + 3 * 2 * HR * kBlockK * 2) + kCtrlBytes;
-    SQD_CUDA(cudaFuncSetAttribute(convdet_f16_pair_kernel<NPAD, CS, PK, HR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SQD_CUDA(cudaFuncSetAttribute(convdet_f16_pair_kernel<NPAD, CS, PK, HR, K3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // dependent launch when the pre-pass kernel directly precedes it on the stream (p.pdl)
-    cudaError_t e = sqd_launch_dependent(convdet_f16_pair_kernel<NPAD, CS, PK, HR>, dim3(grid), dim3(kThreads2), smem, st, p.pdl != 0,
+    cudaError_t e = sqd_launch_dependent(convdet_f16_pair_kernel<NPAD, CS, PK, HR, K3>, dim3(grid), dim3(kThreads2), smem, st, p.pdl != 0,
                                          maps[0], maps[1], maps[2], p);
     if (e != cudaSuccess) {
         sqd_set_error("launch of convdet_f16_pair_kernel failed: %s", cudaGetErrorString(e));
@@ -1659,7 +1658,7 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
             p.anchors_per_cell = cout / nf;
             *emit->done = 1;
             if (npad == 80) return n1h == 72 ? launch_pair<80, 3, false, 36>(maps, p, grid, st) : launch_pair<80, 3>(maps, p, grid, st);
-            return n1h == 120 ? launch_pair<128, 8, false, 60>(maps, p, grid, st) : launch_pair<128, 8>(maps, p, grid, st);
+            return launch_pair<128, 8>(maps, p, grid, st);
         }
     }
     if (multi) return launch_pair<128, 0, true>(maps, p, grid, st);   // the dgrad GEMM
@@ -1672,7 +1671,7 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
         case 5: return n1h == 72 ? launch_pair<80, 0, false, 36>(maps, p, grid, st) : launch_pair<80>(maps, p, grid, st);
         case 6: return launch_pair<96>(maps, p, grid, st);
         case 7: return launch_pair<112>(maps, p, grid, st);
-        case 8: return n1h == 120 ? launch_pair<128, 0, false, 60>(maps, p, grid, st) : launch_pair<128>(maps, p, grid, st);
+        case 8: return launch_pair<128>(maps, p, grid, st);
     }
     SQD_REQUIRE(false, SQD_E_SHAPE, "convdet (tcgen05): unsupported Cout %d", cout);
 }
