@@ -797,7 +797,11 @@ convdet_f16_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
 //        tfull[b]  both CTAs  : TMEM accumulator b holds a finished unit      (tcgen05.commit multicast)
 //        tempty[b] leader only: all 8 accumulate warps of the pair drained accumulator b (remote mbarrier arrives)
 //  * 192 threads: warp 0 TMA producer, warp 1 TMEM alloc (+ MMA issue in the leader), warps 2..5 accumulate/epilogue.
+constexpr size_t kSmemLimit = 227 * 1024;
+constexpr size_t kCtrlBytes = 1024;
 constexpr int kThreads2 = 192;
+constexpr int kEpiPitch = 68;                                  // floats per staged pixel row: 64 channels + 4 (bank spread)
+constexpr size_t kEpiStageBytes = (size_t)4 * 32 * kEpiPitch * 4;   // PK kernel only: one staging tile per accumulate warp
 constexpr int kWarpTma2 = 0, kWarpMma2 = 1, kWarpAcc2 = 2;
 
 __device__ __forceinline__ void umma_f16_ss_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -1339,7 +1343,34 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                                  : inv_sw;
 #pragma unroll
             for (int n = 0; n < NPAD; ++n) acc[n] = fadd(fmul(acc[n], inv), s_bias[n]);
-            if (inb) {
+            if (PK && NPAD == 128) {
+                // The dgrad GEMM writes 512 B per pixel.  One thread per pixel row (the TMEM lane layout) makes every store
+                // instruction touch 32 different lines -- ncu: 16 % of all stall samples are LSU throttling on these stores.
+                // Transpose through a warp-private staging tile instead (64 channels per round): a store instruction then
+                // covers two pixels x 256 contiguous bytes.
+                float *stg = reinterpret_cast<float *>(ctrl + kCtrlBytes) + (size_t)q * (32 * kEpiPitch);
+                const float *my_out = inb ? p.pred + (((size_t)it.img * p.gh + y) * p.gw + x) * p.out_stride + slab * NPAD : nullptr;
+                const unsigned long long my_bits = reinterpret_cast<unsigned long long>(my_out);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    __syncwarp();
+#pragma unroll
+                    for (int n4 = 0; n4 < 16; ++n4)
+                        *reinterpret_cast<float4 *>(stg + lane * kEpiPitch + 4 * n4) =
+                            make_float4(acc[half * 64 + 4 * n4], acc[half * 64 + 4 * n4 + 1], acc[half * 64 + 4 * n4 + 2],
+                                        acc[half * 64 + 4 * n4 + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int itp = 0; itp < 16; ++itp) {
+                        const int pp = 2 * itp + (lane >> 4), q4 = lane & 15;
+                        const float4 v = *reinterpret_cast<const float4 *>(stg + pp * kEpiPitch + 4 * q4);
+                        const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)my_bits, pp);
+                        const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(my_bits >> 32), pp);
+                        float *dst = reinterpret_cast<float *>(((unsigned long long)hi << 32) | lo);
+                        if (dst != nullptr) *reinterpret_cast<float4 *>(dst + half * 64 + 4 * q4) = v;
+                    }
+                }
+            } else if (inb) {
                 float *out = p.pred + (((size_t)it.img * p.gh + y) * p.gw + x) * p.out_stride + (PK ? slab * NPAD : 0);
                 if (((p.cout | p.out_stride) & 3) == 0) {
                     float4 *o4 = reinterpret_cast<float4 *>(out);
@@ -1413,8 +1444,6 @@ int pair_hr_of(int cout) {
     return npad / 2;
 }
 
-constexpr size_t kSmemLimit = 227 * 1024;
-constexpr size_t kCtrlBytes = 1024;
 
 int a_stages_for(int npad) {
     int s = env_int("SQD_F16_A_STAGES", 2);
@@ -1508,7 +1537,8 @@ int pair_stages_for(int n1h) {
 
 template <int NPAD, int CS = 0, bool PK = false, int HR = NPAD / 2, bool K3 = (NPAD >= 96)>
 int launch_pair(const CUtensorMap *maps, const PairParams &p, int grid, cudaStream_t st) {
-    const size_t smem = 1024 + (size_t)p.stages * (kAStageBytes + 3 * 2 * HR * kBlockK * 2) + kCtrlBytes;
+    const size_t smem = 1024 + (size_t)p.stages * (kAStageBytes + 3 * 2 * HR * kBlockK * 2) + kCtrlBytes + (PK ? kEpiStageBytes : 0);
+    SQD_REQUIRE(smem <= kSmemLimit, SQD_E_SHAPE, "convdet (tcgen05): shared memory budget exceeded (%zu bytes)", smem);
     SQD_CUDA(cudaFuncSetAttribute(convdet_f16_pair_kernel<NPAD, CS, PK, HR, K3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // dependent launch when the pre-pass kernel directly precedes it on the stream (p.pdl)
     cudaError_t e = sqd_launch_dependent(convdet_f16_pair_kernel<NPAD, CS, PK, HR, K3>, dim3(grid), dim3(kThreads2), smem, st, p.pdl != 0,
