@@ -492,10 +492,11 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         int s = 0, chunk = 0;
         uint32_t ph = 0;
         bool fresh = true;
+        int rem = k0 % p.tiles_per_img;   // tile inside the image, stepped without divisions
         for (int i = 0; i < ntiles; ++i) {
-            const int kt = k0 + i;
-            const int img = kt / p.tiles_per_img;
-            const bool chunk_end = (i == ntiles - 1) || ((kt + 1) / p.tiles_per_img != img);
+            const bool last_of_img = rem == p.tiles_per_img - 1;
+            rem = last_of_img ? 0 : rem + 1;
+            const bool chunk_end = (i == ntiles - 1) || last_of_img;
             if (fresh) {   // single accumulator set: wait until the previous image has been drained
                 if (!mbar_wait_warp(tmem_empty, ((uint32_t)chunk & 1u) ^ 1u, abort_flag)) {
                     if (lane == 0) atomicCAS(p.status, 0, 4);
@@ -542,10 +543,19 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
 #pragma unroll
         for (int n = 0; n < kNPad; ++n) acc[n] = 0.f;
         int chunk = 0;
+        // (image, tile inside the image) stepped incrementally: two integer divisions per K tile and warp were a third of
+        // this kernel's instructions
+        int img_it = k0 / p.tiles_per_img, rem = k0 - img_it * p.tiles_per_img;
         for (int i = 0; i < ntiles; ++i) {
-            const int kt = k0 + i;
-            const int img = kt / p.tiles_per_img;
-            const bool chunk_end = (i == ntiles - 1) || ((kt + 1) / p.tiles_per_img != img);
+            const int img = img_it;
+            const bool last_of_img = rem == p.tiles_per_img - 1;
+            if (last_of_img) {
+                rem = 0;
+                ++img_it;
+            } else {
+                ++rem;
+            }
+            const bool chunk_end = (i == ntiles - 1) || last_of_img;
             if (!chunk_end) continue;
             const uint32_t ph = (uint32_t)chunk & 1u;
             ++chunk;
