@@ -420,7 +420,9 @@ struct Sched {  // the permuted unit sequence of one CTA: [whole tiles + head se
     // (end of a tile, end of the main part, end of the CTA's range).  in_chunk = units already in the chunk.
     // A chunk never crosses a 64-channel block (r = cb*3 + dx): the block's feature scale is applied per chunk.
     __device__ __forceinline__ bool chunk_ends(int i, int r, int in_chunk, int chunk_units) const {
-        return in_chunk + 1 >= chunk_units || r % blk == blk - 1 || i == n - 1 || i == main_len - 1 || r == upt - 1;
+        // blk is 3 or upt (r < upt): keep the modulo a compile-time constant
+        return in_chunk + 1 >= chunk_units || (blk == 3 ? r % 3 == 2 : r == blk - 1) || i == n - 1 || i == main_len - 1 ||
+               r == upt - 1;
     }
 };
 
