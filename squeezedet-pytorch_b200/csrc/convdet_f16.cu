@@ -1304,9 +1304,10 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
             const bool from_start = seg_r0 == 0, to_end = r == p.upt - 1;
             if (from_start && !to_end) {
                 // head of a split pair-tile: publish for the same rank of the next pair
-                float4 *dst = reinterpret_cast<float4 *>(p.partial + ((size_t)cta * 128 + row) * NPAD);
+                // quad-major layout [n/4][row]: the 32 lanes (rows) of a warp write 512 contiguous bytes per instruction
+                float4 *dst = reinterpret_cast<float4 *>(p.partial + (size_t)cta * 128 * NPAD) + row;
 #pragma unroll
-                for (int n = 0; n < NPAD; n += 4) dst[n >> 2] = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+                for (int n = 0; n < NPAD; n += 4) dst[(n >> 2) * 128] = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
                 __threadfence();
                 epi_bar();
                 if (et == 0) st_release(p.flags + cta, 1);
@@ -1324,10 +1325,10 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                     }
                 }
                 epi_bar();
-                const float4 *src = reinterpret_cast<const float4 *>(p.partial + ((size_t)(cta - 2) * 128 + row) * NPAD);
+                const float4 *src = reinterpret_cast<const float4 *>(p.partial + (size_t)(cta - 2) * 128 * NPAD) + row;
 #pragma unroll
                 for (int n = 0; n < NPAD; n += 4) {
-                    const float4 hd = __ldcg(src + (n >> 2));
+                    const float4 hd = __ldcg(src + (n >> 2) * 128);
                     acc[n] = fadd(hd.x, acc[n]); acc[n + 1] = fadd(hd.y, acc[n + 1]);
                     acc[n + 2] = fadd(hd.z, acc[n + 2]); acc[n + 3] = fadd(hd.w, acc[n + 3]);
                 }
