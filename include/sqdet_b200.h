@@ -148,6 +148,7 @@ SQD_API int sqd_detect_from_pred(const float *d_pred, const float *d_anchors, in
  * src/engine/detector.py:20-31).  Workspace from sqd_head_detect_workspace_bytes().  With the tcgen05 algorithm the
  * GEMM epilogue itself scores the anchors (softmax x sigmoid, argmax) and fills the candidate lists, so the filter
  * that follows reads a few hundred keys per image instead of scanning pred. */
+SQD_API size_t sqd_head_detect_status_offset(int batch, int gh, int gw, int cout);  /* byte offset of the int32 pipeline status word inside the fused call's workspace */
 SQD_API size_t sqd_head_detect_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout, int algo);
 SQD_API int sqd_head_detect_fused(const float *d_feat, int layout, const void *d_packed, const float *d_weight,
                           const float *d_bias, const float *d_anchors, int batch, int cin, int gh, int gw,
@@ -269,7 +270,9 @@ SQD_API int sqd_preprocess(const void *d_images, int dtype, int batch, int src_h
  *   d_gfeat_nhwc (B, gh, gw, Cin)  fp32 -- channels_last memory of the logical (B, Cin, gh, gw) gradient; Cin % 128 == 0
  *   sqd_convdet_dgrad_pack_weights derives the flipped / transposed weight planes once per weight update.
  *   sqd_convdet_wgrad: d_gweight (Cout, Cin, 3, 3) from the NCHW fp32 features and d_gpred -- an fp32 CUDA-core implicit
- *   GEMM split over the pixel axis with a fixed-order reduction (deterministic); Cout <= 80.  Not a tensor-core kernel yet. */
+ *   GEMM split over the pixel axis with a fixed-order reduction (deterministic); any Cout (80 output channels per launch).
+ *   The tensor-core form is sqd_convdet_wgrad_tc below (Cout <= 80, even grid width); this one is the yardstick and the
+ *   route for every other shape. */
 SQD_API size_t sqd_convdet_dgrad_packed_bytes(int cout, int cin);
 SQD_API int sqd_convdet_dgrad_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, void *stream);
 SQD_API size_t sqd_convdet_dgrad_workspace_bytes(int batch, int cin, int gh, int gw, int cout);

@@ -261,7 +261,12 @@ def gen_loss():
         loss_mod = ref_model.Loss(cfg)
         loss, stats = loss_mod(pred, gt)
         loss.mean().backward()                              # trainer.py:43,47
-        save(f"loss_{shp.name}", seed=np.array(seed), batch=np.array(batch),
+        # float64 yardstick: the reference's own graph evaluated in double (same module, double inputs) -- tells which
+        # side of an fp32 comparison is the noisy one (VERDICT r1 "What's weak" 3)
+        pred64 = pred.detach().double().requires_grad_(True)
+        loss64, _ = ref_model.Loss(cfg)(pred64, gt.double())
+        loss64.mean().backward()
+        save(f"loss_{shp.name}", seed=np.array(seed), batch=np.array(batch), dpred_f64=pred64.grad.numpy(),
              loss=loss.detach().numpy(), class_loss=stats["class_loss"].detach().numpy(),
              score_loss=stats["score_loss"].detach().numpy(), bbox_loss=stats["bbox_loss"].detach().numpy(),
              dpred=pred.grad.numpy())
@@ -301,6 +306,74 @@ def gen_head_e2e():
         save(f"head_e2e_{shp.name}", seed=np.array(seed), batch=np.array(batch), pred=pred.numpy(),
              kept_count=cnt, kept_anchor=kidx, kept_class=kcls, kept_score=ksc, kept_box=kbx)
         print("   kept per image:", cnt.tolist(), "pred std", float(pred.std()))
+
+
+def gen_head_e2e_full():
+    """The same reference run as gen_head_e2e at the sizes the GEMM really runs: KITTI batch 20
+    (BASELINE configs[1]) and the stress shape (configs[4]: 2496x768, C = 8, Cout = 117, top-256) batch 2.  To keep the
+    fixtures small only the kept rows, a strided sample of the reference's pred (every 61st value) and per-image
+    moments are stored; inputs are regenerated from the seed."""
+    for shp, batch, seed, tag in ((synth.KITTI, 20, 132, "b20"), (synth.STRESS, 2, 133, "b2")):
+        cfg = ref_cfg(shp)
+        net = ref_model.SqueezeDet(cfg)
+        net.base.features = torch.nn.Identity()
+        w, b = synth.convdet_params(shp, seed + 1)
+        with torch.no_grad():
+            net.base.convdet.weight.copy_(torch.from_numpy(w))
+            net.base.convdet.bias.copy_(torch.from_numpy(b))
+        det = ref_detector.Detector(net, cfg)
+        feat = torch.from_numpy(synth.features(shp, batch, seed))
+        with torch.no_grad():
+            pred = net.base(feat)
+            dets = net({"image": feat})
+        kept = [tracked_filter(det, {k: v[i] for k, v in dets.items()}) for i in range(batch)]
+        cnt, kidx = pack_ragged([k[0] for k in kept], np.int64)
+        _, kcls = pack_ragged([k[1] for k in kept], np.int64)
+        _, ksc = pack_ragged([k[2] for k in kept], np.float32)
+        _, kbx = pack_ragged([k[3] for k in kept], np.float32, 4)
+        p = pred.numpy()
+        flat = p.reshape(batch, -1)
+        save(f"head_e2e_{shp.name}_{tag}", seed=np.array(seed), batch=np.array(batch), pred_stride=np.array(61),
+             pred_sample=np.ascontiguousarray(flat[:, ::61]), pred_sum=flat.astype(np.float64).sum(1),
+             pred_abs_sum=np.abs(flat.astype(np.float64)).sum(1),
+             kept_count=cnt, kept_anchor=kidx, kept_class=kcls, kept_score=ksc, kept_box=kbx)
+        print("   kept per image:", cnt.tolist(), "pred std", float(pred.std()))
+
+
+def gen_nonfinite():
+    """Reference behaviour on NaN / inf class and confidence logits (VERDICT r1 "What's weak" 5): torch sorts NaN
+    scores FIRST (argsort descending, and the sort inside torchvision's nms), so a NaN-scored anchor enters the top-k,
+    can suppress its neighbours in NMS and is only dropped by the final `score > thresh`.  Non-finite DELTAS make the
+    reference assert (modules.py:18) -- recorded as such."""
+    for shp, seed in ((synth.TINY, 5), (synth.KITTI, 6)):
+        cfg = ref_cfg(shp)
+        pred = synth.nonfinite_pred(shp, seed, anchors=cfg.anchors)
+        res = ref_model.PredictionResolver(cfg, log_softmax=False)
+        with torch.no_grad():
+            probs, _, conf, _, boxes = res(torch.from_numpy(pred))
+            p2 = probs.clone()
+            p2 *= conf
+            ids = torch.argmax(p2, dim=2)
+            scores = torch.max(p2, dim=2)[0]
+        det = ref_detector.Detector(torch.nn.Identity(), cfg)
+        rows = []
+        for b in range(pred.shape[0]):
+            out = det.filter({"class_ids": ids[b], "scores": scores[b], "boxes": boxes[b]})
+            rows.append(None if out is None else {k: v.numpy() for k, v in out.items()})
+        cnt, kcls = pack_ragged([r["class_ids"] if r else [] for r in rows], np.int64)
+        _, ksc = pack_ragged([r["scores"] if r else [] for r in rows], np.float32)
+        _, kbx = pack_ragged([r["boxes"] if r else np.zeros((0, 4), np.float32) for r in rows], np.float32, 4)
+        bad = torch.from_numpy(pred.copy())
+        bad[0, 3, shp.num_classes + 3] = float("nan")
+        try:
+            res(bad)
+            asserted = False
+        except AssertionError:
+            asserted = True
+        save(f"nonfinite_{shp.name}", seed=np.array(seed), kept_count=cnt, kept_class=kcls, kept_score=ksc, kept_box=kbx,
+             nan_scores_per_image=np.isnan(scores.numpy()).sum(1), reference_asserts_on_nan_delta=np.array(asserted))
+        print("   kept per image:", cnt.tolist(), "NaN scores per image:", np.isnan(scores.numpy()).sum(1).tolist(),
+              "asserts on NaN delta:", asserted)
 
 
 def gen_postprocess():
@@ -416,7 +489,7 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["anchors", "decode_filter", "nms", "matcher", "matcher_fallback", "loss", "head_e2e",
-                             "postprocess", "kitti_results", "preprocess"]
+                             "head_e2e_full", "nonfinite", "postprocess", "kitti_results", "preprocess"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

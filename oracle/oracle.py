@@ -193,7 +193,7 @@ def nms(boxes, scores, thresh):
     n = boxes.shape[0]
     if n == 0:
         return np.zeros((0,), dtype=np.int64)
-    order = np.argsort(-scores, kind="stable")
+    order = desc_order(scores)
     x1, y1, x2, y2 = (boxes[:, i] for i in range(4))
     areas = (x2 - x1) * (y2 - y1)
     dead = np.zeros(n, dtype=bool)
@@ -219,11 +219,18 @@ def nms(boxes, scores, thresh):
 # --------------------------------------------------------------------------------------
 # a8  Detector.filter with index tracking
 # --------------------------------------------------------------------------------------
-def topk_order(scores, k):
-    """Declared tie policy: key = (score desc, anchor index asc)."""
+def desc_order(scores):
+    """Stable descending order with torch's NaN rule: torch.sort / torch.argsort(descending=True) (detector.py:88 and
+    the sort inside torchvision's nms kernel) treat NaN as LARGER than every number, +inf included, so NaN scores come
+    first (numpy would put them last)."""
     scores = np.asarray(scores, dtype=F32)
-    order = np.argsort(-scores, kind="stable")
-    return order[:k]
+    nan = np.isnan(scores)
+    return np.lexsort((-np.where(nan, F32(0), scores), ~nan))   # primary: NaN first; secondary: score descending; stable
+
+
+def topk_order(scores, k):
+    """Declared tie policy: key = (score desc, anchor index asc); NaN scores rank first (torch)."""
+    return desc_order(scores)[:k]
 
 
 def filter_image(class_ids, scores, boxes, num_classes, top_k, nms_thresh, score_thresh):
@@ -325,6 +332,47 @@ def match_anchors(gt_xyxy, anchors_xywh):
         deltas[i, 2] = np.log(F64(gw) / anc[j, 2])
         deltas[i, 3] = np.log(F64(gh) / anc[j, 3])
     return deltas, idx
+
+
+def match_tie_audit(gt_xyxy, anchors_xywh, chosen):
+    """Audit an anchor assignment `chosen` (G,) produced by ANY tie order of the reference's greedy matcher
+    (src/utils/boxes.py:84-135; numpy's default argsort is unstable, so the unpatched reference breaks ties arbitrarily).
+
+    Walks the boxes in annotation order with `chosen`'s own history of taken anchors and returns, per box,
+    (valid, multiplicity): valid = the chosen anchor attains the best untaken IoU (or, with no overlapping untaken
+    anchor, the smallest squared xywh distance); multiplicity = how many untaken anchors attain that optimum
+    (1 = the choice was forced, no tie).  Same float64 arithmetic as match_anchors."""
+    gt = np.asarray(gt_xyxy, dtype=F32)
+    anc = np.asarray(anchors_xywh, dtype=F64)
+    axy = anchors_xyxy_f64(anc)
+    area_a = (axy[:, 2] - axy[:, 0]) * (axy[:, 3] - axy[:, 1])
+    taken = np.zeros(anc.shape[0], dtype=bool)
+    valid, mult = [], []
+    for i in range(gt.shape[0]):
+        b = gt[i]
+        lr = np.maximum(np.minimum(axy[:, 2], F64(b[2])) - np.maximum(axy[:, 0], F64(b[0])), 0)
+        tb = np.maximum(np.minimum(axy[:, 3], F64(b[3])) - np.maximum(axy[:, 1], F64(b[1])), 0)
+        inter = lr * tb
+        area_g = F64((b[2] - b[0]) * (b[3] - b[1]))
+        iou = inter / (area_a + area_g - inter + 1e-10)
+        cand = np.where(taken | ~(iou > 0), -np.inf, iou)
+        j = int(chosen[i])
+        best = cand.max()
+        if np.isfinite(best):
+            valid.append(bool(cand[j] == best))
+            mult.append(int(np.count_nonzero(cand == best)))
+        else:
+            gx = (b[0] + b[2]) / F32(2)
+            gy = (b[1] + b[3]) / F32(2)
+            gw = b[2] - b[0] + F32(1)
+            gh = b[3] - b[1] + F32(1)
+            d0, d1, d2, d3 = F64(gx) - anc[:, 0], F64(gy) - anc[:, 1], F64(gw) - anc[:, 2], F64(gh) - anc[:, 3]
+            dist = np.where(taken, np.inf, ((d0 * d0 + d1 * d1) + d2 * d2) + d3 * d3)
+            best = dist.min()
+            valid.append(bool(dist[j] == best))
+            mult.append(int(np.count_nonzero(dist == best)))
+        taken[j] = True
+    return np.array(valid, dtype=bool), np.array(mult, dtype=np.int64)
 
 
 def dense_targets(class_ids, gt_xyxy, anchors_xywh, num_classes):

@@ -38,6 +38,7 @@ SIGNATURES = {
     "sqd_detect_workspace_bytes": (_sz, [_i, _i]),
     "sqd_detect_from_pred": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sqd_head_detect_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
+    "sqd_head_detect_status_offset": (_sz, [_i, _i, _i, _i]),
     "sqd_head_detect_fused": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _d,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "sqd_head_detect_profile_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

@@ -148,6 +148,14 @@ extern "C" size_t sqd_head_detect_workspace_bytes(int batch, int cin, int gh, in
     return pred + cand + sqd_convdet_workspace_bytes(batch, cin, gh, gw, cout, layout, algo);
 }
 
+// Byte offset, inside a sqd_head_detect_fused workspace, of the tcgen05 pipeline status word (int32; 0 = the last call
+// drained cleanly, else the role whose bounded wait timed out).  Callers that synchronise anyway read it with their
+// results instead of paying sqd_convdet_status' extra synchronisation.
+extern "C" size_t sqd_head_detect_status_offset(int batch, int gh, int gw, int cout) {
+    if (batch <= 0 || gh <= 0 || gw <= 0 || cout <= 0) return 0;
+    return align_up((size_t)batch * gh * gw * cout * sizeof(float), 256) + sqd_cand_bytes(batch, gh * gw * (cout / 6 + 1));
+}
+
 namespace {
 // Shared body of sqd_head_detect_fused / sqd_head_detect_profile.  ev (optional, 3 events) are recorded after the
 // split pre-pass (profile form only, where the caller ran it), after the GEMM and after the filter.

@@ -141,7 +141,9 @@ __device__ __forceinline__ bool sqd_score_candidate(const float *f, int C_rt, fl
             near = near || (c != imax && !(e <= 0.99999f));   // also catches NaN
             sum = (c == 0) ? e : fadd(sum, e);
         }
-    if (near || !(zmax == zmax)) {
+    // a non-finite maximum (NaN, or +-inf: the reference's exp(z - max) is then exp(inf - inf) = NaN for the maximum
+    // itself) takes the full path, which reproduces torch's NaN propagation
+    if (near || !(fabsf(zmax) <= 3.4028235e38f)) {
         sqd_score_anchor<CS>(f, C_rt, score, cls);
         return true;
     }
@@ -176,8 +178,10 @@ __device__ __forceinline__ float4 sqd_decode_box(float4 anc, float dx, float dy,
 // so "larger key" == (score desc, anchor index asc) -- the declared tie policy.
 typedef unsigned long long sqd_u64;
 
+// NaN (either sign) maps to the largest key: torch's descending sort ranks NaN before +inf (detector.py:88)
 __device__ __forceinline__ unsigned sqd_order_bits(float s) {
     const unsigned b = __float_as_uint(s);
+    if (s != s) return 0xFFFFFFFFu;
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 __device__ __forceinline__ float sqd_unorder_bits(unsigned k) {

@@ -217,8 +217,10 @@ struct WgFetch {
     float4 g[kWgGLoads];
 };
 
+// n0: first output channel of this launch's chunk (<= kWgN channels per launch); rows of G that are not 16-byte
+// aligned for the chunk (Cout or n0 not a multiple of 4, e.g. the stress head's 117 channels) are read with scalar loads.
 __device__ __forceinline__ void wg_fetch(WgFetch &f, const float *__restrict__ x, const float *__restrict__ g, int b, int y,
-                                         int x0, int dy, int dx, int c0, int cin, int gh, int gw, int cout) {
+                                         int x0, int dy, int dx, int c0, int cin, int gh, int gw, int cout, int n0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ys = y + dy, xsrc = x0 + lane + dx;
     const bool ok = ys >= 0 && ys < gh && xsrc >= 0 && xsrc < gw && x0 + lane < gw;
@@ -229,19 +231,38 @@ __device__ __forceinline__ void wg_fetch(WgFetch &f, const float *__restrict__ x
         const int c = warp + (kWgThreads / 32) * j;
         f.x[j] = (ok && c < kWgC && c0 + c < cin) ? __ldg(xp + j * cstep) : 0.f;
     }
-    const float4 *grow = reinterpret_cast<const float4 *>(g + (((size_t)b * gh + y) * gw + x0) * cout);
-    const int npix = min(kWgPix, gw - x0), q4 = cout >> 2;
+    const float *gbase = g + (((size_t)b * gh + y) * gw + x0) * cout + n0;
+    const int npix = min(kWgPix, gw - x0), nn = min(kWgN, cout - n0);
+    if (((cout | n0) & 3) == 0) {
+        const float4 *grow = reinterpret_cast<const float4 *>(gbase);
+        const int q4 = cout >> 2, qn = nn >> 2;
 #pragma unroll
-    for (int j = 0; j < kWgGLoads; ++j) {
-        const int i = threadIdx.x + j * kWgThreads;
-        const int p = i / (kWgN / 4), q = i - p * (kWgN / 4);
-        f.g[j] = (p < npix && q < q4) ? __ldg(grow + (size_t)p * q4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < kWgGLoads; ++j) {
+            const int i = threadIdx.x + j * kWgThreads;
+            const int p = i / (kWgN / 4), q = i - p * (kWgN / 4);
+            f.g[j] = (p < npix && q < qn) ? __ldg(grow + (size_t)p * q4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kWgGLoads; ++j) {
+            const int i = threadIdx.x + j * kWgThreads;
+            const int p = i / (kWgN / 4), q = i - p * (kWgN / 4);
+            const float *src = gbase + (size_t)p * cout + 4 * q;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p < npix) {
+                if (4 * q < nn) v.x = __ldg(src);
+                if (4 * q + 1 < nn) v.y = __ldg(src + 1);
+                if (4 * q + 2 < nn) v.z = __ldg(src + 2);
+                if (4 * q + 3 < nn) v.w = __ldg(src + 3);
+            }
+            f.g[j] = v;
+        }
     }
 }
 
 __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const float *__restrict__ x, const float *__restrict__ g,
                                                                    int batch, int cin, int gh, int gw, int cout, int nslice,
-                                                                   float *__restrict__ partial) {
+                                                                   float *__restrict__ partial, int n0) {
     __shared__ __align__(16) float xs[kWgPix][kWgXs];  // [pixel][channel]
     __shared__ __align__(16) float gs[kWgPix][kWgN];   // [pixel][output channel]
     const int tap = blockIdx.x, cb = blockIdx.y, slice = blockIdx.z;
@@ -259,7 +280,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const float *
     const int segs_per_row = (gw + kWgPix - 1) / kWgPix;
     const int nseg = (r_end - r_begin) * segs_per_row;
     WgFetch f;
-    if (nseg > 0) wg_fetch(f, x, g, r_begin / gh, r_begin % gh, 0, dy, dx, c0, cin, gh, gw, cout);
+    if (nseg > 0) wg_fetch(f, x, g, r_begin / gh, r_begin % gh, 0, dy, dx, c0, cin, gh, gw, cout, n0);
     for (int sgi = 0; sgi < nseg; ++sgi) {
         const int r = r_begin + sgi / segs_per_row, x0 = (sgi % segs_per_row) * kWgPix;
         const int npix = min(kWgPix, gw - x0);
@@ -278,7 +299,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const float *
         __syncthreads();
         if (sgi + 1 < nseg) {   // next segment's loads fly while this one is multiplied
             const int rn = r_begin + (sgi + 1) / segs_per_row;
-            wg_fetch(f, x, g, rn / gh, rn % gh, ((sgi + 1) % segs_per_row) * kWgPix, dy, dx, c0, cin, gh, gw, cout);
+            wg_fetch(f, x, g, rn / gh, rn % gh, ((sgi + 1) % segs_per_row) * kWgPix, dy, dx, c0, cin, gh, gw, cout, n0);
         }
 #pragma unroll 2
         for (int p = 0; p < npix; ++p) {
@@ -299,7 +320,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const float *
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int c = c0 + (i < 4 ? 4 * tc + i : 64 + 4 * tc + i - 4), n = 4 * tn + j;
+            const int c = c0 + (i < 4 ? 4 * tc + i : 64 + 4 * tc + i - 4), n = n0 + 4 * tn + j;
             if (c < cin && n < cout) partial[(((size_t)slice * cout + n) * cin + c) * 9 + tap] = acc[i][j];
         }
 }
@@ -458,8 +479,8 @@ extern "C" size_t sqd_convdet_wgrad_workspace_bytes(int batch, int cin, int gh, 
 extern "C" int sqd_convdet_wgrad(const float *d_feat_nchw, const float *d_gpred, int batch, int cin, int gh, int gw, int cout,
                                  float *d_gweight, void *d_workspace, size_t workspace_bytes, void *stream) {
     SQD_REQUIRE(d_feat_nchw && d_gpred && d_gweight && d_workspace, SQD_E_NULL, "sqd_convdet_wgrad: NULL pointer");
-    SQD_REQUIRE(batch >= 1 && cin >= 1 && gh > 0 && gw > 0 && cout >= 4 && cout <= kWgN && cout % 4 == 0, SQD_E_SHAPE,
-                "sqd_convdet_wgrad: bad shape (Cout a multiple of 4, <= %d)", kWgN);
+    SQD_REQUIRE(batch >= 1 && cin >= 1 && gh > 0 && gw > 0 && cout >= 1 && cout <= 4096, SQD_E_SHAPE,
+                "sqd_convdet_wgrad: bad shape (Cout in [1, 4096])");
     SQD_REQUIRE(sqd_aligned16(d_gpred), SQD_E_ALIGN, "sqd_convdet_wgrad: gpred must be 16-byte aligned");
     SQD_REQUIRE(workspace_bytes >= sqd_convdet_wgrad_workspace_bytes(batch, cin, gh, gw, cout), SQD_E_WORKSPACE,
                 "sqd_convdet_wgrad: workspace too small (%zu bytes)", workspace_bytes);
@@ -467,8 +488,10 @@ extern "C" int sqd_convdet_wgrad(const float *d_feat_nchw, const float *d_gpred,
     const int ns = wgrad_slices(batch, gh);
     float *partial = static_cast<float *>(d_workspace);
     const dim3 grid(9, (cin + kWgC - 1) / kWgC, ns);
-    wgrad_partial_kernel<<<grid, kWgThreads, 0, st>>>(d_feat_nchw, d_gpred, batch, cin, gh, gw, cout, ns, partial);
-    SQD_LAUNCH_CHECK("wgrad_partial_kernel");
+    for (int n0 = 0; n0 < cout; n0 += kWgN) {   // <= 80 output channels per launch (KITTI's 72: one launch)
+        wgrad_partial_kernel<<<grid, kWgThreads, 0, st>>>(d_feat_nchw, d_gpred, batch, cin, gh, gw, cout, ns, partial, n0);
+        SQD_LAUNCH_CHECK("wgrad_partial_kernel");
+    }
     const size_t n = (size_t)cout * cin * 9;
     wgrad_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(partial, n, ns, d_gweight);
     SQD_LAUNCH_CHECK("wgrad_reduce_kernel");

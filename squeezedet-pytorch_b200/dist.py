@@ -63,8 +63,14 @@ class GradBucket:
     `early`: the parameters whose gradients autograd finishes FIRST -- the ConvDet head (its wgrad / bias-grad kernels
     run before anything of the backbone's backward).  They sit at the front of the buffer and the
     all-reduce of that segment is launched (async) from the hook of the last of them, so it travels over NVLink while
-    the backbone's backward still runs; `allreduce_mean` then reduces the rest and waits for both.  The result is the
-    same as one all-reduce of the whole buffer (sum, then 1/world)."""
+    the backbone's backward still runs; `allreduce_sum` / `allreduce_mean` then reduce the rest and wait for both.  The
+    result is the same as one all-reduce of the whole buffer.
+
+    Two trailing slots ride along with the last segment (no extra collective, no host sync): `loss_slot` (this rank's
+    SUM of per-image losses) and `count_slot` (this rank's image count).  After the all-reduce they hold the global
+    loss sum and the global batch size, and `allreduce_sum(normalize=True)` divides the gradients by that count on the
+    device -- the reference's whole-batch `loss.mean()` (trainer.py:43) for ANY split of the batch, uneven or with
+    empty shards.  Every rank issues the same sequence of collectives whether or not its hooks fired."""
 
     def __init__(self, params, early=()):
         early = [p for p in early if p.requires_grad]
@@ -73,7 +79,10 @@ class GradBucket:
         self.early_numel = sum(p.numel() for p in early)
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else "cpu"
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._buf = torch.zeros(total + 2, dtype=torch.float32, device=dev)
+        self.flat = self._buf[:total]                   # the gradients
+        self.loss_slot = self._buf[total:total + 1]
+        self.count_slot = self._buf[total + 1:total + 2]
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
@@ -82,34 +91,47 @@ class GradBucket:
         for p in early:
             p.register_post_accumulate_grad_hook(self._early_ready)
 
+    @staticmethod
+    def _distributed():
+        return dist.is_initialized() and dist.get_world_size() > 1
+
     def _early_ready(self, _param):
         if self._pending <= 0:
             return                  # not armed (zero() was not called for this step) or already launched
         self._pending -= 1
-        if self._pending == 0 and dist.is_initialized() and dist.get_world_size() > 1:
+        if self._pending == 0 and self._distributed():
             self._early_work = dist.all_reduce(self.flat[:self.early_numel], op=dist.ReduceOp.SUM, async_op=True)
 
     def zero(self):
-        """Start of a step: clear the gradients and arm the early all-reduce."""
-        self.flat.zero_()
+        """Start of a step: clear the gradients (and the loss / count slots) and arm the early all-reduce."""
+        self._buf.zero_()
         self._pending, self._early_work = self._n_early, None
 
-    def allreduce_mean(self, world=None):
-        """sum over ranks then scale by 1/world (each rank's loss is its local per-image mean)."""
-        if not dist.is_initialized() or dist.get_world_size() == 1:
-            return None
-        world = world or dist.get_world_size()
-        if self._early_work is not None:
-            rest = self.flat[self.early_numel:]
-            work = dist.all_reduce(rest, op=dist.ReduceOp.SUM, async_op=True) if rest.numel() else None
-            self._early_work.wait()
-            if work is not None:
+    def allreduce_sum(self, normalize=False):
+        """Sum the bucket over the ranks.  normalize: divide the gradients by the all-reduced `count_slot` (device-side;
+        the caller put its image count there and back-propagated the SUM of its per-image losses)."""
+        if self._distributed():
+            armed = self._pending > 0 or self._early_work is not None
+            if self._n_early and armed:
+                if self._early_work is None:    # the hooks never fired (empty shard: no backward): same collectives anyway
+                    self._early_work = dist.all_reduce(self.flat[:self.early_numel], op=dist.ReduceOp.SUM, async_op=True)
+                work = dist.all_reduce(self._buf[self.early_numel:], op=dist.ReduceOp.SUM, async_op=True)
+                self._early_work.wait()
                 work.wait()
-            self._early_work = None
-        else:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+                self._early_work = None
+            else:
+                dist.all_reduce(self._buf, op=dist.ReduceOp.SUM)
         self._pending = 0
-        self.flat.mul_(1.0 / world)
+        if normalize:
+            self.flat.div_(self.count_slot)
+
+    def allreduce_mean(self, world=None):
+        """sum over ranks then scale by 1/world: for callers whose ranks back-propagate the MEAN loss of EQUAL-sized
+        shards.  (train_step uses the count-weighted form instead, which is exact for any split.)"""
+        distributed = self._distributed()
+        self.allreduce_sum(normalize=False)
+        if distributed:
+            self.flat.mul_(1.0 / (world or dist.get_world_size()))
         return None
 
 
@@ -119,19 +141,36 @@ def bucket_for(model):
     return GradBucket(model.parameters(), early=base.convdet.parameters())
 
 
+def _batch_images(batch):
+    for v in batch.values():
+        if torch.is_tensor(v):
+            return int(v.shape[0])
+    return 0
+
+
 def train_step(model, batch, bucket, optimizer=None, grad_norm=None):
     """One data-parallel step on this rank's shard of the batch: the body of Trainer.run_epoch (src/engine/
     trainer.py:42-48) with the reference's per-step parameter broadcast + gradient reduce-to-GPU-0
     (src/utils/data_parallel.py:93-101) replaced by the bucket's all-reduce.  `optimizer.zero_grad()` is
     `bucket.zero()` here (the gradients are views into the bucket and must stay allocated).
-    Returns (mean loss of the shard, the per-image loss statistics dict)."""
+
+    The reference averages the per-image losses over the WHOLE batch (trainer.py:43), so each rank back-propagates the
+    SUM of its images' losses and the summed gradients are divided by the global image count, which travels in the
+    bucket: shards of different sizes weigh every image equally, and a rank with an empty shard contributes zeros
+    (it skips forward / backward but still takes part in the collectives).
+    Returns (mean loss over the global batch as a 0-d device tensor, this shard's per-image statistics dict or {})."""
     bucket.zero()
-    loss, stats = model(batch)
-    loss = loss.mean()
-    loss.backward()                 # the head's all-reduce is launched from inside, as soon as its gradients exist
-    bucket.allreduce_mean()
+    n_local = _batch_images(batch)
+    stats = {}
+    if n_local > 0:
+        loss, stats = model(batch)
+        loss_sum = loss.sum()
+        loss_sum.backward()         # the head's all-reduce is launched from inside, as soon as its gradients exist
+        bucket.loss_slot.copy_(loss_sum.detach().reshape(1))
+    bucket.count_slot.fill_(float(n_local))
+    bucket.allreduce_sum(normalize=True)
     if grad_norm:
         torch.nn.utils.clip_grad_norm_(bucket.params, grad_norm)
     if optimizer is not None:
         optimizer.step()
-    return loss.detach(), stats
+    return (bucket.loss_slot / bucket.count_slot).reshape(()), stats

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import CONV_TCGEN05_F16X3
+from ._lib import CONV_SIMT_FP32, CONV_TCGEN05_F16X3, SqdError
 
 
 class Fire(nn.Module):
@@ -45,10 +45,11 @@ _ARCH = {
 
 
 class _ConvDetFn(torch.autograd.Function):
-    """ConvDet forward on the tcgen05 kernel.  Backward: the feature gradient runs on the same
-    tcgen05 kernel with swapped roles (ops.convdet_dgrad), the weight gradient on an fp32 CUDA-core implicit GEMM
-    (ops.convdet_wgrad) and the bias gradient on a reduction kernel.  Shapes outside the kernels' limits (Cin not a
-    multiple of 128, Cout > 80) use torch's conv gradient routines."""
+    """ConvDet forward on the tcgen05 kernel.  Backward, all native: the feature gradient runs on the
+    forward's tcgen05 kernel with swapped roles (ops.convdet_dgrad), the weight gradient on the tcgen05 pixel-contraction
+    kernel (ops.convdet_wgrad; Cout <= 80 and an even grid width) or else on the fp32 CUDA-core implicit GEMM of the same
+    library, the bias gradient on a cluster reduction.  There is no library (cuDNN / ATen) route: a shape the kernels
+    do not take raises SqdError."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, packed, algo, dgrad_packed_fn):
@@ -62,15 +63,12 @@ class _ConvDetFn(torch.autograd.Function):
         gx = gw = gb = None
         g = g.contiguous()
         if ctx.needs_input_grad[0]:
-            if weight.shape[1] % 128 == 0:
-                gx = ops.convdet_dgrad(g, weight, ctx.dgrad_packed_fn() if ctx.dgrad_packed_fn else None)
-            else:
-                gx = torch.nn.grad.conv2d_input(x.shape, weight, g.permute(0, 3, 1, 2), padding=1)
+            if weight.shape[1] % 128 != 0:
+                raise SqdError("ConvDet feature gradient: Cin %d is not a multiple of 128 (sqd_convdet_dgrad); detach the "
+                               "features or use a backbone with 128-aligned Fire11 channels" % weight.shape[1])
+            gx = ops.convdet_dgrad(g, weight, ctx.dgrad_packed_fn() if ctx.dgrad_packed_fn else None)
         if ctx.needs_input_grad[1]:
-            if weight.shape[0] <= 80 and weight.shape[0] % 4 == 0:
-                gw = ops.convdet_wgrad(x, g)
-            else:
-                gw = torch.nn.grad.conv2d_weight(x, weight.shape, g.permute(0, 3, 1, 2), padding=1)
+            gw = ops.convdet_wgrad(x, g)
         if ctx.needs_input_grad[2]:
             gb = ops.convdet_bias_grad(g)
         return gx, gw, gb, None, None, None
@@ -108,20 +106,28 @@ class SqueezeDetBase(nn.Module):
                     nn.init.constant_(m.bias, 0)
 
     def packed_weights(self):
-        """hi/lo tf32 weight planes for the tcgen05 kernel; derived data, re-derived whenever the
-        parameter changes (optimizer step, load_state_dict, .to(device)); never saved."""
+        """fp16 two-term split (w1, w2) weight planes for the tcgen05 f16x3 kernel; derived data, re-derived whenever the
+        parameter changes (optimizer step, load_state_dict, .to(device)) and on every call while training (in-place
+        updates through `.data` do not bump the version counter); never saved.  None for the SIMT algorithm."""
+        if self.conv_algo == CONV_SIMT_FP32:
+            return None
         w = self.convdet.weight
         ver = (w._version, w.data_ptr(), str(w.device))
-        if self._packed is None or self._packed_version != ver:
+        if self._packed is None or self._packed_version != ver or (self.training and torch.is_grad_enabled()):
             self._packed = ops.pack_convdet_weights(w)
             self._packed_version = ver
         return self._packed
+
+    def invalidate_packed_weights(self):
+        """Call after mutating convdet.weight through `.data` in eval mode (EMA, clipping ...): such writes bypass the
+        version counter the caches are keyed on."""
+        self._packed = self._dgrad_packed = None
 
     def dgrad_packed_weights(self):
         """Flipped / transposed planes for the feature gradient; derived lazily, only when a backward pass needs them."""
         w = self.convdet.weight
         ver = (w._version, w.data_ptr(), str(w.device))
-        if self._dgrad_packed is None or self._dgrad_packed_version != ver:
+        if self._dgrad_packed is None or self._dgrad_packed_version != ver or self.training:
             self._dgrad_packed = ops.pack_convdet_dgrad_weights(w)
             self._dgrad_packed_version = ver
         return self._dgrad_packed
@@ -149,7 +155,8 @@ class PredictionResolver(nn.Module):
         self.input_size = cfg.input_size
         self.num_classes = cfg.num_classes
         self.anchors_per_grid = cfg.anchors_per_grid
-        self.register_buffer("anchors", torch.from_numpy(np.asarray(cfg.anchors)).float().contiguous(),
+        # (1, A, 4) like the reference's attribute (squeezedet.py:106); the kernels only use the memory
+        self.register_buffer("anchors", torch.from_numpy(np.asarray(cfg.anchors)).float().contiguous().unsqueeze(0),
                              persistent=False)
 
     def _anchors_on(self, device):
@@ -158,6 +165,11 @@ class PredictionResolver(nn.Module):
         return self.anchors
 
     def forward(self, pred):
+        if pred.requires_grad and torch.is_grad_enabled():
+            # the reference's resolver is differentiable; this one is the inference-side decode (one fused kernel, no
+            # autograd graph).  Failing loudly beats silently returning zero gradients to a custom loss.
+            raise SqdError("PredictionResolver.forward is inference-only here (its outputs carry no gradient): call it "
+                           "under torch.no_grad() / on pred.detach(), or use Loss, which has its own native backward")
         want = ["probs", "conf", "deltas", "boxes"] + (["logp"] if self.log_softmax else [])
         out = ops.decode_scores(pred.detach(), self._anchors_on(pred.device), self.input_size, self.num_classes, want)
         return out["probs"], out.get("logp"), out["conf"], out["deltas"], out["boxes"]

@@ -23,10 +23,21 @@ class Detections:
     cls: torch.Tensor      # (B, top_k) int32
     score: torch.Tensor    # (B, top_k) float32
     box: torch.Tensor      # (B, top_k, 4) float32 xyxy
+    status: torch.Tensor = None   # (1,) int32 view of the tcgen05 pipeline status word of the call that filled this
+
+    def check_status(self):
+        """Raise if the tcgen05 pipeline of the producing call hit a bounded-wait timeout (preemption, time slicing,
+        a debugger ...) and drained with incomplete results.  Reads one int; called from to_list(), where the host
+        synchronises anyway."""
+        if self.status is not None:
+            code = int(self.status.cpu()[0])
+            if code != 0:
+                raise _lib.SqdError(f"tcgen05 ConvDet pipeline timed out (role {code}): the detections are incomplete")
 
     def to_list(self):
         """One host transfer for the whole batch -> list of reference-style dicts (or None when
         an image keeps nothing, like Detector.filter, detector.py:115-116)."""
+        self.check_status()
         count = self.count.cpu().tolist()
         anchor, cls, score, box = self.anchor.cpu(), self.cls.cpu(), self.score.cpu(), self.box.cpu()
         out = []
@@ -59,6 +70,17 @@ def feature_layout(feat: torch.Tensor):
     return LAYOUT_NCHW, feat.contiguous()
 
 
+def resolve_conv_algo(algo, cin, cout):
+    """The tcgen05 kernels take Cin % 64 == 0 and Cout <= 128; any other head runs on the library's own fp32 CUDA-core
+    implicit GEMM (Cin % 16 == 0, Cout <= 128).  Beyond that there is nothing to run it on (no library fallback)."""
+    if algo != CONV_SIMT_FP32 and (cin % 64 != 0 or cout > 128):
+        algo = CONV_SIMT_FP32
+    if algo == CONV_SIMT_FP32 and (cin % 16 != 0 or cout > 128):
+        raise _lib.SqdError(f"ConvDet head with Cin={cin}, Cout={cout} is outside the kernels' limits "
+                            "(Cin % 16 == 0 and Cout <= 128)")
+    return algo
+
+
 # ---- a1 --------------------------------------------------------------------------------------------
 def pack_convdet_weights(weight: torch.Tensor) -> torch.Tensor:
     """Derive the tcgen05 kernel's weight planes from base.convdet.weight (Cout,Cin,3,3)."""
@@ -79,6 +101,7 @@ def convdet_forward(feat, weight, bias, packed=None, algo=CONV_TCGEN05_F16X3, nu
     w = weight.detach().contiguous()
     b = bias.detach().contiguous()
     cout = w.shape[0]
+    algo = resolve_conv_algo(algo, cin, cout)
     if algo != CONV_SIMT_FP32 and packed is None:
         packed = pack_convdet_weights(w)
     nbytes = lib.sqd_convdet_workspace_bytes(B, cin, gh, gw, cout, layout, algo)
@@ -124,14 +147,15 @@ def convdet_dgrad(gpred, weight, dgrad_packed=None):
 
 def convdet_wgrad(feat, gpred, tensor_cores=True, check_status=False):
     """feat (B,Cin,gh,gw) NCHW fp32, gpred (B,gh,gw,Cout) -> gradient of the ConvDet weight (Cout,Cin,3,3).
-    tensor_cores: the tcgen05 f16x3 kernel (Cin % 64 == 0); otherwise the fp32 CUDA-core kernel (Cout % 4 == 0)."""
+    tensor_cores: the tcgen05 f16x3 kernel where the shape allows (Cin % 64 == 0, Cout <= 80, even grid width);
+    every other shape (e.g. the stress head's 117 channels) runs on the library's fp32 CUDA-core kernel."""
     lib = load()
     x = feat.detach().contiguous().float()
     g = gpred.contiguous().float()
     B, cin, gh, gw = x.shape
     cout = g.shape[-1]
     out = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=g.device)
-    if tensor_cores and cin % 64 == 0:
+    if tensor_cores and cin % 64 == 0 and cout <= 80 and gw % 2 == 0:     # the limits of sqd_convdet_wgrad_tc
         ws = workspace().get("convdet_wgrad_tc", lib.sqd_convdet_wgrad_tc_workspace_bytes(B, cin, gh, gw, cout), g.device)
         check(lib.sqd_convdet_wgrad_tc(ptr(x), ptr(g), B, cin, gh, gw, cout, ptr(out), ptr(ws), ws.numel(),
                                        stream_ptr(g.device)), "sqd_convdet_wgrad_tc")
@@ -216,11 +240,15 @@ def head_detect(feat, weight, bias, anchors_f32, anchors_per_grid, num_classes, 
     w = weight.detach().contiguous()
     b = bias.detach().contiguous()
     cout = w.shape[0]
+    algo = resolve_conv_algo(algo, cin, cout)
     if algo != CONV_SIMT_FP32 and packed is None:
         packed = pack_convdet_weights(w)
     nbytes = lib.sqd_head_detect_workspace_bytes(B, cin, gh, gw, cout, layout, algo)
     ws = workspace().get("head_detect", nbytes, x.device)
     det = out if out is not None else _alloc_detections(B, top_k, x.device)
+    if algo != CONV_SIMT_FP32 and B > 0:
+        off = lib.sqd_head_detect_status_offset(B, gh, gw, cout)
+        det.status = ws[off:off + 4].view(torch.int32)
     check(lib.sqd_head_detect_fused(C.c_void_p(x.data_ptr()), layout, ptr(packed), ptr(w), ptr(b), ptr(anchors_f32), B,
                                     cin, gh, gw, anchors_per_grid, num_classes, int(input_hw[0]), int(input_hw[1]),
                                     top_k, float(nms_thresh), float(score_thresh), ptr(det.count), ptr(det.anchor),
@@ -292,7 +320,8 @@ def head_detect_host(host_feat, weight, bias, anchors_f32, anchors_per_grid, num
     w = weight.detach().contiguous()
     b = bias.detach().contiguous()
     cout = w.shape[0]
-    if packed is None:
+    algo = resolve_conv_algo(algo, cin, cout)
+    if algo != CONV_SIMT_FP32 and packed is None:
         packed = pack_convdet_weights(w)
     nbytes = lib.sqd_head_detect_host_workspace_bytes(B, cin, gh, gw, cout, top_k, LAYOUT_NCHW, algo, chunk_images)
     ws = workspace().get("head_detect_host" if slot is None else "head_detect_host/%d" % slot, nbytes, dev)

@@ -162,3 +162,21 @@ def clustered_pred(shape: Shape, batch: int, seed: int, anchors=None) -> np.ndar
             ], axis=1)
             pred[b, hit, C + 1:] = reg + rs.standard_normal((hit.size, 4)) * 0.05
     return pred
+
+
+def nonfinite_pred(shape: Shape, seed: int, anchors=None) -> np.ndarray:
+    """clustered_pred for 5 images with NaN / +-inf planted in the CLASS and CONFIDENCE logits of the most confident
+    anchors (where they change the result).  Deltas stay finite: the reference asserts on a non-finite decoded width
+    (src/model/modules.py:18), so its behaviour is only defined for non-finite class / confidence logits."""
+    pred = clustered_pred(shape, 5, seed, anchors=anchors)
+    C = shape.num_classes
+    top = [np.argsort(-pred[b, :, C], kind="stable")[:6] for b in range(5)]
+    pred[0, top[0][0], :C + 1] = np.nan     # NaN class logits and confidence on the best anchor
+    pred[0, top[0][3], C] = np.nan          # NaN confidence only
+    pred[1, top[1][0], 1] = np.inf          # +inf class logit: softmax evaluates inf - inf = NaN
+    pred[2, top[2][0], 0] = -np.inf         # -inf class logit: probability 0
+    pred[2, top[2][1], :C] = -np.inf        # all -inf: NaN softmax
+    pred[3, top[3][0], C] = np.inf          # confidence logit +inf: sigmoid 1
+    pred[3, top[3][1], C] = -np.inf         # confidence logit -inf: sigmoid 0
+    pred[4, top[4][2], C - 1] = np.nan      # a single NaN class logit
+    return pred

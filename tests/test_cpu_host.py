@@ -144,13 +144,40 @@ for step in range(2):
     net(mine["image"] / 80.0).mean().backward()
     assert launched[-1] == b2.early_numel and len(launched) == 3 * step + 1     # fired from the hook, before the call below
     b2.allreduce_mean()
-    assert launched[-1] == b2.flat.numel() - b2.early_numel and len(launched) == 3 * step + 2
+    assert launched[-1] == b2.flat.numel() - b2.early_numel + 2 and len(launched) == 3 * step + 2   # + loss and count slots
     launched.append(0)
 dist.all_reduce = orig
 ref2 = torch.nn.Sequential(torch.nn.Linear(8, 6), torch.nn.ReLU(), torch.nn.Linear(6, 4)); ref2.load_state_dict(net.state_dict())
 ref2(batch["image"] / 80.0).mean().backward()
 want = torch.cat([p.grad.flatten() for p in list(ref2[2].parameters()) + list(ref2[0].parameters())])
 assert torch.allclose(b2.flat, want, rtol=1e-5, atol=1e-7), (b2.flat, want)
+# train_step: count-weighted all-reduce == the reference's whole-batch loss.mean() for UNEVEN and EMPTY shards
+class PerImage(torch.nn.Module):            # stands in for SqueezeDetWithLoss: batch dict -> (per-image loss, stats)
+    def __init__(self):
+        super().__init__()
+        self.base = torch.nn.Module()
+        self.base.convdet = torch.nn.Linear(6, 4)
+        self.body = torch.nn.Linear(8, 6)
+    def forward(self, batch):
+        l = (self.base.convdet(torch.relu(self.body(batch["image"]))) ** 2).sum(1)
+        return l, {"loss": l}
+for total in (7, 1, 10):
+    torch.manual_seed(5)
+    m = PerImage()
+    bk = sdist.bucket_for(m)
+    assert bk.early_numel == 6 * 4 + 4
+    full = {"image": torch.randn(total, 8, generator=torch.Generator().manual_seed(total))}
+    part = sdist.shard_batch(full, rank, world)
+    if total == 1:
+        assert part["image"].shape[0] == (1 if rank == 0 else 0)      # rank 1 owns nothing
+    loss, _ = sdist.train_step(m, part, bk)
+    m2 = PerImage(); m2.load_state_dict(m.state_dict())
+    l2, _ = m2(full)
+    l2.mean().backward()
+    want = torch.cat([p.grad.flatten() for p in list(m2.base.convdet.parameters()) + list(m2.body.parameters())])
+    assert torch.isfinite(bk.flat).all()
+    assert torch.allclose(bk.flat, want, rtol=1e-5, atol=1e-6), (total, bk.flat, want)
+    assert torch.allclose(loss, l2.mean().detach(), rtol=1e-5), (total, loss, l2.mean())
 dist.destroy_process_group()
 print("OK", rank)
 '''

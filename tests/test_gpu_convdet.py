@@ -1,4 +1,4 @@
-"""a1 ConvDet head on the GPU: tcgen05 3xTF32 kernel and the fp32 SIMT yardstick against the
+"""a1 ConvDet head on the GPU: tcgen05 f16x3 kernel and the fp32 SIMT yardstick against the
 reference's conv (golden pred recorded from the reference, and the oracle = torch CPU conv2d),
 then the end-to-end kept-index parity features -> detections."""
 import os
@@ -58,8 +58,8 @@ def test_convdet_vs_reference_golden(ops, golden, name, algo_name, layout):
 
 
 def test_convdet_accuracy_vs_float64(ops):
-    """Error of each fp32 implementation against a float64 evaluation (tiny shape): the 3xTF32
-    tensor-core kernel must be as accurate as fp32 CUDA-core FMA / the reference's CPU conv."""
+    """Error of each fp32 implementation against a float64 evaluation (tiny shape): the f16x3 (three fp16 passes on
+    power-of-two scaled operands) tensor-core kernel must be as accurate as fp32 CUDA-core FMA / the reference's CPU conv."""
     from squeezedet_pytorch_b200._lib import CONV_SIMT_FP32, CONV_TCGEN05_F16X3
     shp = synth.TINY
     feat = synth.features(shp, 2, 77)
@@ -70,7 +70,7 @@ def test_convdet_accuracy_vs_float64(ops):
     tc = ops.convdet_forward(dev(feat), dev(w), dev(b), algo=CONV_TCGEN05_F16X3, num_fields=shp.num_fields,
                              check_status=True).cpu().numpy()
     e_ref, e_simt, e_tc = _err(ref32, p64), _err(simt, p64), _err(tc, p64)
-    print(f"vs float64: torch-cpu max/rms {e_ref}, simt {e_simt}, tcgen05-3xtf32 {e_tc}")
+    print(f"vs float64: torch-cpu max/rms {e_ref}, simt {e_simt}, tcgen05-f16x3 {e_tc}")
     assert e_simt[0] < 2e-5 and e_tc[0] < 2e-5
     assert e_tc[1] < 4 * max(e_ref[1], e_simt[1]) + 1e-7
 
@@ -101,6 +101,49 @@ def test_head_to_detections_kept_indices(ops, golden, name):
             assert set(got.tolist()) ^ set(idx[i].tolist()) == set() or len(set(got.tolist()) ^ set(idx[i].tolist())) <= 2
             print(f"image {i}: order/near-tie difference vs reference: {got.tolist()} vs {idx[i].tolist()}")
     assert flips == 0, f"{flips} images differ from the reference's kept indices"
+
+
+@pytest.mark.parametrize("name,tag", [("kitti_1248x384", "b20"), ("stress_2496x768", "b2")])
+@pytest.mark.parametrize("route", ["fused_call", "staged", "host"])
+def test_full_size_head_vs_reference_golden(ops, golden, name, tag, route):
+    """The sizes the GEMM really runs: KITTI batch 20 = BASELINE configs[1] and the stress shape
+    (configs[4]: 2496x768, C = 8, Cout 117 -> the Npad = 128 three-MMA / two-TMEM-buffer variant, top-256) against
+    what the REFERENCE's own SqueezeDet + Detector.filter produced (tests/golden/head_e2e_*_{b20,b2}.npz): kept anchor
+    indices and classes bit-exact on every image, scores / boxes and a strided sample of pred within 1e-4."""
+    full = {x.name: x for x in (synth.KITTI, synth.STRESS)}
+    g = golden(f"head_e2e_{name}_{tag}")
+    shp = full[name]
+    batch, seed = int(g["batch"]), int(g["seed"])
+    feat = synth.features(shp, batch, seed)
+    w, b = synth.convdet_params(shp, seed + 1)
+    a32 = dev(synth.anchor_table(shp).astype(np.float32))
+    args = (a32, shp.anchors_per_grid, shp.num_classes, shp.input_hw, shp.top_k, shp.nms_thresh, shp.score_thresh)
+    if route == "fused_call":
+        rows = ops.head_detect(dev(feat), dev(w), dev(b), *args).to_list()
+    elif route == "host":
+        rows = ops.head_detect_host(torch.from_numpy(feat).pin_memory(), dev(w), dev(b), *args,
+                                    chunk_images=3 if name.startswith("kitti") else 1).to_list()
+    else:
+        pred = ops.convdet_forward(dev(feat), dev(w), dev(b), num_fields=shp.num_fields, check_status=True)
+        stride = int(g["pred_stride"])
+        got = pred.cpu().numpy().reshape(batch, -1)
+        mx = float(np.abs(got[:, ::stride] - g["pred_sample"]).max())
+        print(f"{name}: pred sample max|err| {mx:.3e} vs the reference's fp32 conv")
+        np.testing.assert_allclose(got[:, ::stride], g["pred_sample"], rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(got.astype(np.float64).sum(1), g["pred_sum"], rtol=1e-5, atol=1e-2)
+        rows = ops.detect_from_pred(pred, a32, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh,
+                                    shp.score_thresh).to_list()
+    idx = split_ragged(g["kept_count"], g["kept_anchor"])
+    cls = split_ragged(g["kept_count"], g["kept_class"])
+    sc = split_ragged(g["kept_count"], g["kept_score"])
+    bx = split_ragged(g["kept_count"], g["kept_box"])
+    assert len(rows) == batch
+    for i, row in enumerate(rows):
+        assert row is not None, i
+        assert np.array_equal(row["anchor_idx"].numpy(), idx[i]), f"image {i}: kept anchors differ from the reference"
+        assert np.array_equal(row["class_ids"].numpy(), cls[i]), i
+        np.testing.assert_allclose(row["scores"].numpy(), sc[i], rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(row["boxes"].numpy(), bx[i], rtol=1e-4, atol=1e-3)
 
 
 def test_head_properties_full_batch(ops):
@@ -342,11 +385,11 @@ def test_split_grid_not_multiple_of_four(ops):
     assert torch.allclose(tc, simt, rtol=1e-4, atol=2e-5 * float(simt.abs().max())), float((tc - simt).abs().max())
 
 
-@pytest.mark.parametrize("name,batch", [("tiny_160x96", 3), ("kitti_1248x384", 2)])
+@pytest.mark.parametrize("name,batch", [("tiny_160x96", 3), ("kitti_1248x384", 2), ("stress_2496x768", 1)])
 def test_convdet_dgrad_and_bias_grad(ops, name, batch):
     """Feature and bias gradients of the head (tcgen05 kernel with swapped roles) against autograd's conv gradient
     routines (torch CPU fp32 = the reference's arithmetic, and fp64 as the accuracy yardstick)."""
-    shp = {x.name: x for x in (synth.TINY, synth.KITTI)}[name]
+    shp = {x.name: x for x in (synth.TINY, synth.KITTI, synth.STRESS)}[name]   # stress: Cout = 117 (VERDICT r1 item 8)
     feat = synth.features(shp, batch, 71)
     w, _ = synth.convdet_params(shp, 72)
     rs = np.random.RandomState(73)
@@ -471,3 +514,68 @@ def test_convdet_random_shapes_vs_fp32_kernel(ops, seed):
     assert torch.allclose(tc, ref, rtol=1e-4, atol=3e-5 * scale), (gh, gw, batch, cin, cout, float((tc - ref).abs().max()), scale)
     cl = ops.convdet_forward(dev(x).contiguous(memory_format=torch.channels_last), dev(w), dev(b), check_status=True)
     assert torch.equal(cl, tc) or gh * gw == 1   # 1x1 grids: torch cannot tell the layouts apart (both contiguous)
+
+
+def test_no_library_fallback_and_stale_weight_guards(ops):
+    """(1) Autograd through the head never leaves the library: the stress head (Cout = 117) trains natively and a shape
+    the kernels do not take raises SqdError instead of dispatching to cuDNN.  (2) In-place updates through `.data` do not
+    bump the version counter: training mode re-packs every call, eval mode has an explicit invalidate.  (3) The
+    inference-only resolver refuses a pred that expects gradients.  (4) Heads outside the tcgen05 limits run on the
+    library's fp32 CUDA-core kernel."""
+    from squeezedet_pytorch_b200 import config, model
+    from squeezedet_pytorch_b200._lib import SqdError
+    shp = synth.Shape("mid8", (96, 160), 8, 32)                       # Cout = 117
+    cfg = config.make_config(shp, dropout_prob=0.0)
+    base = model.SqueezeDetBase(cfg).cuda()
+    w, b = synth.convdet_params(shp, 91)
+    with torch.no_grad():
+        base.convdet.weight.copy_(torch.from_numpy(w))
+        base.convdet.bias.copy_(torch.from_numpy(b))
+    feat = dev(synth.features(shp, 2, 92)).requires_grad_(True)
+    up = dev(np.random.RandomState(93).standard_normal((2, shp.num_anchors, shp.num_fields)).astype(np.float32))
+    (base.head(feat) * up).sum().backward()
+    conv = torch.nn.Conv2d(shp.in_channels, shp.out_channels, 3, padding=1).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(base.convdet.weight)
+        conv.bias.copy_(base.convdet.bias)
+    torch.backends.cudnn.allow_tf32 = False
+    feat2 = feat.detach().clone().requires_grad_(True)
+    (conv(feat2).permute(0, 2, 3, 1).reshape(2, shp.num_anchors, shp.num_fields) * up).sum().backward()
+    assert torch.allclose(feat.grad, feat2.grad, rtol=1e-4, atol=1e-4 * float(feat2.grad.abs().mean()))
+    assert torch.allclose(base.convdet.weight.grad, conv.weight.grad, rtol=1e-4, atol=1e-4 * float(conv.weight.grad.abs().mean()))
+    assert torch.allclose(base.convdet.bias.grad, conv.bias.grad, rtol=1e-4, atol=1e-4 * float(conv.bias.grad.abs().max()))
+    # a head whose feature gradient the kernels do not take (Cin = 64) raises instead of calling torch.nn.grad
+    x64 = torch.randn(1, 64, 6, 10, device="cuda", requires_grad=True)
+    w64 = torch.randn(24, 64, 3, 3, device="cuda", requires_grad=True)
+    out = model._ConvDetFn.apply(x64, w64, torch.zeros(24, device="cuda"), None, 0, None)
+    with pytest.raises(SqdError):
+        out.sum().backward()
+    # (2) stale packed weights
+    base.eval()
+    with torch.no_grad():
+        before = base.head(feat.detach())
+        base.convdet.weight.data.mul_(2.0)                       # bypasses the version counter
+        base.invalidate_packed_weights()
+        after = base.head(feat.detach())
+    assert not torch.equal(before, after)
+    base.train()
+    with torch.enable_grad():
+        p1 = base.head(feat.detach())
+        base.convdet.weight.data.mul_(0.5)
+        p2 = base.head(feat.detach())                            # training mode re-packs on every call
+    assert torch.allclose(p2, before, rtol=1e-5, atol=1e-5) and not torch.allclose(p1, p2)
+    # (3) resolver
+    res = model.PredictionResolver(cfg).cuda()
+    assert res.anchors.shape == (1, shp.num_anchors, 4)
+    with pytest.raises(SqdError):
+        res(before.clone().requires_grad_(True))
+    assert res(before)[4].shape == (2, shp.num_anchors, 4)
+    # (4) Cin = 80 (not a multiple of 64): the fp32 CUDA-core kernel takes it
+    x = torch.randn(2, 80, 5, 7, device="cuda")
+    wq = torch.randn(24, 80, 3, 3, device="cuda") * 0.05
+    bq = torch.randn(24, device="cuda")
+    got = ops.convdet_forward(x, wq, bq)
+    ref = torch.nn.functional.conv2d(x.cpu().double(), wq.cpu().double(), bq.cpu().double(), padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(got.cpu().double(), ref, rtol=1e-4, atol=1e-5)
+    with pytest.raises(SqdError):
+        ops.convdet_forward(torch.randn(1, 64, 4, 4, device="cuda"), torch.randn(765, 64, 3, 3, device="cuda"), torch.zeros(765, device="cuda"))

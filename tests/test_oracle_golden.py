@@ -115,6 +115,7 @@ def test_matcher_indices_bit_exact(golden, name):
     dl = split_ragged(g["count"], g["deltas"])
     idx_u = split_ragged(g["count"], g["anchor_idx_unpatched"])
     fallback_seen = False
+    n_box = n_tied = n_agree = n_forced = 0
     for i in range(int(g["n_img"])):
         cls, boxes = synth.gt_boxes(shp, int(g["seed0"]) + i)
         if i % 6 == 5:  # the crowd case of gen_golden.gen_matcher
@@ -126,8 +127,30 @@ def test_matcher_indices_bit_exact(golden, name):
         assert a.dtype == np.int32 and np.array_equal(a, idx[i]), f"image {i}"
         np.testing.assert_allclose(d, dl[i], rtol=1e-6, atol=1e-7)
         assert len(set(a.tolist())) == len(a)  # an anchor is never assigned twice
-        # where the unpatched reference differs it must be an equal-IoU tie, never a better anchor
+        # The unpatched reference (numpy's unstable argsort) may differ ONLY by how it broke an exact tie: under its own
+        # history of taken anchors every one of its choices must attain the optimum, and so must ours.
         assert len(idx_u[i]) == len(a)
+        ok_u, mult_u = orc.match_tie_audit(boxes, anchors, idx_u[i])
+        ok_s, mult_s = orc.match_tie_audit(boxes, anchors, a)
+        assert ok_u.all(), f"image {i}: the unpatched reference chose a non-optimal anchor?"
+        assert ok_s.all(), f"image {i}: the stable policy chose a non-optimal anchor"
+        n_box += len(a)
+        n_tied += int(np.count_nonzero(mult_s > 1))
+        # Tie-free subset: a box is FORCED when both histories agree up to it and its optimum is attained
+        # once; there the unpatched reference and the stable policy must pick the same anchor.
+        same_so_far = True
+        for j in range(len(a)):
+            if same_so_far and mult_s[j] == 1:
+                n_forced += 1
+                assert a[j] == idx_u[i][j], f"image {i} box {j}: forced choice differs from the unpatched reference"
+            if a[j] != idx_u[i][j]:
+                assert not same_so_far or (mult_u[j] > 1 and mult_s[j] > 1), f"image {i} box {j}: first disagreement is not a tie"
+                same_so_far = False
+        n_agree += int(np.count_nonzero(a == idx_u[i]))
+    print(f"matcher {name}: {n_box} GT boxes, tie rate {n_tied / max(n_box, 1):.3f}; agreement with the UNPATCHED reference: "
+          f"{n_agree / max(n_box, 1):.3f} overall, {n_forced}/{n_forced} on the tie-free (forced) subset; every choice of "
+          f"either policy attains the optimum under its own history")
+    assert n_forced > 0
     assert fallback_seen or int(g["n_img"]) < 6
 
 
@@ -177,9 +200,16 @@ def test_loss_forward_backward_matches_reference_autograd(golden, name):
     dpred = orc.loss_backward(pred, gt, anchors, shp.input_hw, shp.num_classes, np.full((B,), 1.0 / B))
     ref = g["dpred"]
     scale = np.abs(ref).max()
-    np.testing.assert_allclose(dpred, ref, rtol=1e-3, atol=1e-6 * scale)
+    np.testing.assert_allclose(dpred, ref, rtol=1e-4, atol=1e-6 * scale)   # SURVEY 8c tolerance; measured 3.5e-6
     # gradient flows through the IoU target into the deltas of matched anchors (not detached)
     assert np.abs(ref[..., shp.num_classes + 1:]).sum() > 0
+    # float64 yardstick (the reference's own graph run in double): the oracle is no further from it than the
+    # reference's fp32 autograd is
+    r64 = g["dpred_f64"]
+    rel = lambda a: float(np.max(np.abs(a.astype(np.float64) - r64) / (np.abs(r64) + 1e-6 * scale)))  # noqa: E731
+    e_ref, e_orc = rel(ref), rel(dpred)
+    print(f"dpred vs float64 yardstick ({name}): reference fp32 autograd {e_ref:.2e}, oracle {e_orc:.2e}")
+    assert e_orc <= 1.5 * e_ref + 1e-6
 
 
 def test_loss_zero_objects_is_nan(golden):
@@ -212,6 +242,54 @@ def test_head_end_to_end_matches_reference(golden, name):
     if name == "tiny_160x96":
         p64 = orc.convdet_forward_f64(feat, w, b, shp.num_anchors, shp.num_fields)
         np.testing.assert_allclose(pred, p64, rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("name,tag", [("kitti_1248x384", "b20"), ("stress_2496x768", "b2")])
+def test_head_end_to_end_full_size_matches_reference(golden, name, tag):
+    """BASELINE configs[1] (KITTI, batch 20) and configs[4] (stress: C = 8, Cout = 117, top-256): the oracle's conv +
+    decode + filter against what the reference's own SqueezeDet + Detector.filter produced (kept anchors bit-exact on
+    every image, a strided sample of pred within 1e-4)."""
+    g = golden(f"head_e2e_{name}_{tag}")
+    shp = SHAPES[name]
+    anchors = synth.anchor_table(shp)
+    batch, seed = int(g["batch"]), int(g["seed"])
+    feat = synth.features(shp, batch, seed)
+    w, b = synth.convdet_params(shp, seed + 1)
+    pred = orc.convdet_forward(feat, w, b, shp.num_anchors, shp.num_fields)
+    stride = int(g["pred_stride"])
+    np.testing.assert_allclose(pred.reshape(batch, -1)[:, ::stride], g["pred_sample"], rtol=RTOL, atol=1e-5)
+    np.testing.assert_allclose(pred.reshape(batch, -1).astype(np.float64).sum(1), g["pred_sum"], rtol=1e-5, atol=1e-2)
+    outs = orc.detect_filtered(pred, anchors, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh, shp.score_thresh)
+    idx = split_ragged(g["kept_count"], g["kept_anchor"])
+    cls = split_ragged(g["kept_count"], g["kept_class"])
+    sc = split_ragged(g["kept_count"], g["kept_score"])
+    bx = split_ragged(g["kept_count"], g["kept_box"])
+    assert len(outs) == batch
+    for i, o in enumerate(outs):
+        assert np.array_equal(o["anchor_idx"], idx[i]), i
+        assert np.array_equal(o["class_ids"], cls[i]), i
+        np.testing.assert_allclose(o["scores"], sc[i], rtol=RTOL, atol=1e-7)
+        np.testing.assert_allclose(o["boxes"], bx[i], rtol=RTOL, atol=1e-3)
+
+
+@pytest.mark.parametrize("name", ["tiny_160x96", "kitti_1248x384"])
+def test_nonfinite_logits_match_reference(golden, name):
+    """NaN / inf class and confidence logits: torch ranks NaN scores first, so they enter the top-k, may suppress in
+    NMS and are dropped by the final threshold; the oracle must reproduce the reference's kept rows exactly."""
+    g = golden("nonfinite_" + name)
+    shp = SHAPES[name]
+    anchors = synth.anchor_table(shp)
+    pred = synth.nonfinite_pred(shp, int(g["seed"]), anchors=anchors)
+    with np.errstate(invalid="ignore"):
+        outs = orc.detect_filtered(pred, anchors, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh, shp.score_thresh)
+    cls = split_ragged(g["kept_count"], g["kept_class"])
+    sc = split_ragged(g["kept_count"], g["kept_score"])
+    bx = split_ragged(g["kept_count"], g["kept_box"])
+    assert bool(g["reference_asserts_on_nan_delta"]) and int(g["nan_scores_per_image"].sum()) >= 4
+    for i, o in enumerate(outs):
+        assert np.array_equal(o["class_ids"], cls[i]), i
+        np.testing.assert_allclose(o["scores"], sc[i], rtol=RTOL, atol=1e-7)
+        np.testing.assert_allclose(o["boxes"], bx[i], rtol=RTOL, atol=1e-3)
 
 
 def test_boxes_postprocess(golden):
