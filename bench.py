@@ -325,6 +325,125 @@ def main_ours(args):
         assert int(det_big.count.min()) > 0
         del pred_big, dense, det_big
 
+
+    # ---- the other BASELINE.json configurations, driver-run at every rank count (max over ranks, whole-job values) -----
+    def timed_steps(fn, n, warm):
+        for i in range(warm):
+            fn(i)
+        torch.cuda.synchronize()
+        barrier()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            fn(i)
+        b_.record()
+        torch.cuda.synchronize()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b_)) / n
+
+    extra = {}
+    if not args.skip_extra:
+        # configs[2]: 2048 KITTI images sharded by image over the ranks (strong scaling: total work fixed), no collective
+        lo, hi = sdist.shard_range(args.config3_images, rank, world)
+        B3 = hi - lo
+        gen3 = torch.Generator(device=dev).manual_seed(4321 + rank)
+        feat3 = torch.empty((B3, shp.in_channels, *shp.grid_hw), device=dev)
+        for s0 in range(0, B3, 64):
+            feat3[s0:s0 + 64] = torch.relu(torch.randn((min(64, B3 - s0), shp.in_channels, *shp.grid_hw), generator=gen3, device=dev))
+        det3 = ops._alloc_detections(B3, shp.top_k, dev)
+        ms3 = timed_steps(lambda i: ops.head_detect(feat3, weight, bias, anchors, shp.anchors_per_grid, shp.num_classes,
+                                                    shp.input_hw, shp.top_k, shp.nms_thresh, shp.score_thresh, packed=packed,
+                                                    out=det3), 3, 2)
+        det3.check_status()
+        assert int(det3.count.min()) >= 0
+        extra["config3"] = {"workload": "BASELINE configs[2]: %d KITTI 1248x384 images sharded by image over %d GPU(s), "
+                                        "features resident (%.1f GB per GPU > L2), no collective" % (args.config3_images, world, B3 * FEAT_BYTES_PER_IMAGE / 1e9),
+                            "images_per_s": args.config3_images / (ms3 * 1e-3), "per_gpu": args.config3_images / (ms3 * 1e-3) / world,
+                            "ms_per_step": ms3, "images_per_gpu": B3, "scaling": "strong", "steps": 3, "warmup": 2}
+        del feat3, det3
+        ops.workspace().clear()
+        torch.cuda.empty_cache()
+
+        # configs[4]: the high-density stress shape, 512 images over 8 GPUs = 64 per GPU (weak: 64 per rank at any N)
+        sshp = synth.STRESS
+        B5 = args.stress_batch
+        gen5 = torch.Generator(device=dev).manual_seed(99 + rank)
+        feat5 = [torch.relu(torch.randn((B5, sshp.in_channels, *sshp.grid_hw), generator=gen5, device=dev)) for _ in range(2)]
+        w5_np, b5_np = synth.convdet_params(sshp, 4321)
+        w5, b5 = torch.from_numpy(w5_np).to(dev), torch.from_numpy(b5_np).to(dev)
+        packed5 = ops.pack_convdet_weights(w5)
+        anchors5 = torch.from_numpy(synth.anchor_table(sshp).astype(np.float32)).to(dev)
+        det5 = ops._alloc_detections(B5, sshp.top_k, dev)
+        ms5 = timed_steps(lambda i: ops.head_detect(feat5[i % 2], w5, b5, anchors5, sshp.anchors_per_grid, sshp.num_classes,
+                                                    sshp.input_hw, sshp.top_k, sshp.nms_thresh, sshp.score_thresh,
+                                                    packed=packed5, out=det5), 6, 3)
+        det5.check_status()
+        flop5 = 2 * sshp.grid_hw[0] * sshp.grid_hw[1] * sshp.out_channels * 9 * sshp.in_channels
+        extra["config5_stress"] = {"workload": "BASELINE configs[4]: 2496x768 input (67,392 anchors), 8 classes, top-256 per-class NMS, "
+                                               "%d images per GPU (512 over 8 GPUs)" % B5,
+                                   "images_per_s": world * B5 / (ms5 * 1e-3), "per_gpu": B5 / (ms5 * 1e-3), "ms_per_step": ms5,
+                                   "images_per_gpu": B5, "scaling": "weak", "steps": 6, "warmup": 3,
+                                   "tflops_algorithmic_per_gpu": B5 * flop5 / (ms5 * 1e-3) / 1e12,
+                                   "kept_per_image_mean": float(det5.count.float().mean())}
+        del feat5, det5, packed5
+        ops.workspace().clear()
+        torch.cuda.empty_cache()
+
+        # configs[3]: the training step of the path, batch 20 per GPU: anchor matching + dense targets (a10-a13), ConvDet
+        # forward (a1), loss forward + analytic backward (a14-a16), native wgrad / bias grad / dgrad (8f.2) and the NCCL
+        # all-reduce of the flat gradient bucket (8e row 2; the full model's 2,082,120 floats, the head's segment launched
+        # from the ConvDet backward before the dgrad GEMM is enqueued).  The backbone's own forward / backward is stock
+        # PyTorch and out of scope: the step starts at the Fire11 features (which require grad, so the dgrad GEMM runs).
+        from squeezedet_pytorch_b200 import config as sconfig, model as smodel, targets as stargets
+        cfg = sconfig.make_config(shp, device=str(dev), dropout_prob=0.0)
+        net = smodel.SqueezeDetWithLoss(cfg).to(dev)
+        with torch.no_grad():
+            net.base.convdet.weight.copy_(weight)
+            net.base.convdet.bias.copy_(bias)
+        net.train()
+
+        class HeadWithLoss(torch.nn.Module):      # SqueezeDetWithLoss.forward (squeezedet.py:184-187) from the features on
+            def __init__(self, full):
+                super().__init__()
+                self.base, self.loss = full.base, full.loss
+
+            def forward(self, batch):
+                return self.loss(self.base.head(batch["features"]), batch["gt"])
+
+        head = HeadWithLoss(net)
+        bucket = sdist.bucket_for(net)
+        matcher = stargets.AnchorMatcher(cfg.anchors, shp.num_classes, device=dev)
+        cls_l, box_l = zip(*[synth.gt_boxes(shp, 100 + 1000 * rank + i) for i in range(B)])
+        gt_packed = matcher.pack(list(box_l), list(cls_l))
+        tfeat = feats[0].detach().clone().requires_grad_(True)
+
+        def train_iter(_i):
+            tfeat.grad = None
+            gt = matcher.dense_targets(*gt_packed)
+            return sdist.train_step(head, {"features": tfeat, "gt": gt}, bucket)
+
+        ms_train = timed_steps(train_iter, max(10, min(K, 50)), 5)
+        loss_val = float(train_iter(0)[0])
+        assert np.isfinite(loss_val), loss_val
+        real_distributed = bucket._distributed
+        bucket._distributed = lambda: False           # the same step without the collective: the difference is what the
+        ms_train_local = timed_steps(train_iter, max(10, min(K, 50)), 3)   # all-reduce costs the step (its exposed time)
+        bucket._distributed = real_distributed
+        ar_ms = None
+        if world > 1:
+            def ar_only(_i):
+                dist.all_reduce(bucket._buf, op=dist.ReduceOp.SUM)
+            ar_ms = timed_steps(ar_only, 20, 5)
+        extra["train_step"] = {"workload": "BASELINE configs[3]: training step of the path at KITTI batch %d per GPU: matcher + targets, "
+                                           "ConvDet forward, loss fwd+bwd, native wgrad/bias/dgrad, all-reduce of the flat gradient "
+                                           "bucket (%d floats, head segment %d launched before the dgrad GEMM)" % (B, bucket.flat.numel(), bucket.early_numel),
+                               "ms_per_step": ms_train, "images_per_s": world * B / (ms_train * 1e-3),
+                               "ms_per_step_without_allreduce": ms_train_local,
+                               "exposed_allreduce_ms": max(0.0, ms_train - ms_train_local) if world > 1 else 0.0,
+                               "allreduce_alone_ms": ar_ms, "nccl_ranks": world if world > 1 else 0,
+                               "bucket_bytes": int(bucket._buf.numel() * 4), "loss": loss_val, "scaling": "weak"}
+        del tfeat, net, head, bucket
+
     # ---- end to end with host buffers -------------------------------------------------------------------------
     host_feats = [torch.empty((B, shp.in_channels, *shp.grid_hw), dtype=torch.float32).pin_memory() for _ in range(2)]
     for hf, f in zip(host_feats, feats):
@@ -464,6 +583,7 @@ def main_ours(args):
                                         "boxes) for %d images: 539,136 B read + 471,744 B written per image" % Bd},
             "clocks": clocks,
         }
+        line.update(extra)
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if gpu_ref is not None:
@@ -486,6 +606,9 @@ def main():
     ap.add_argument("--decode-batch", type=int, default=1024, help="images of the stand-alone decode/NMS roofline measurement")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: one e2e step only (the JSON line is then not a bench result)")
     ap.add_argument("--e2e-chunk", type=int, default=5, help="images per H2D/compute pipeline group of the e2e call")
+    ap.add_argument("--skip-extra", action="store_true", help="skip the configs[2], [3], [4] measurements (profiling aid)")
+    ap.add_argument("--config3-images", type=int, default=2048, help="BASELINE configs[2]: images sharded over the ranks")
+    ap.add_argument("--stress-batch", type=int, default=64, help="BASELINE configs[4]: images per GPU (512 over 8 GPUs)")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON result.  Libraries print there too (NCCL's "NCCL version" banner
     # under NCCL_DEBUG=VERSION is a C printf), so file descriptor 1 is pointed at stderr for the whole run and the

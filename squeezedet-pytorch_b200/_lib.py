@@ -126,6 +126,10 @@ class Workspace:
             self._bufs[key] = buf
         return buf
 
+    def clear(self):
+        """Drop every scratch buffer (after a one-off large call; the next call re-allocates what it needs)."""
+        self._bufs.clear()
+
 
 _tls = threading.local()
 

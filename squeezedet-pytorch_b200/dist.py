@@ -88,6 +88,7 @@ class GradBucket:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         self._n_early, self._pending, self._early_work = len(early), 0, None
+        self._early_ids = {id(p) for p in early}
         for p in early:
             p.register_post_accumulate_grad_hook(self._early_ready)
 
@@ -101,6 +102,21 @@ class GradBucket:
         self._pending -= 1
         if self._pending == 0 and self._distributed():
             self._early_work = dist.all_reduce(self.flat[:self.early_numel], op=dist.ReduceOp.SUM, async_op=True)
+
+    def take_early(self, grads):
+        """Fast path used by the ConvDet backward (model._ConvDetFn): `grads` = {id(param): (param, grad)} for exactly the
+        early parameters, handed over BEFORE the feature gradient is enqueued.  They are added into the bucket and the
+        early all-reduce is launched right away, so on the GPU it runs beside the dgrad GEMM and the backbone backward
+        instead of behind them.  Returns False (nothing taken) when the bucket is not armed or the set does not match;
+        autograd then accumulates the gradients as usual and the hooks launch the collective."""
+        if self._pending <= 0 or set(grads) != self._early_ids or any(g is None for _, g in grads.values()):
+            return False
+        for p, g in grads.values():
+            p.grad.add_(g.view_as(p.grad))
+        self._pending = 0
+        if self._distributed():
+            self._early_work = dist.all_reduce(self.flat[:self.early_numel], op=dist.ReduceOp.SUM, async_op=True)
+        return True
 
     def zero(self):
         """Start of a step: clear the gradients (and the loss / count slots) and arm the early all-reduce."""
@@ -138,7 +154,9 @@ class GradBucket:
 def bucket_for(model):
     """GradBucket of a SqueezeDetWithLoss / SqueezeDetBase-holding module with the ConvDet head as the early segment."""
     base = model.base if hasattr(model, "base") else model
-    return GradBucket(model.parameters(), early=base.convdet.parameters())
+    bucket = GradBucket(model.parameters(), early=base.convdet.parameters())
+    base.grad_sink = bucket
+    return bucket
 
 
 def _batch_images(batch):

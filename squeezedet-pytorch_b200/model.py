@@ -49,29 +49,38 @@ class _ConvDetFn(torch.autograd.Function):
     forward's tcgen05 kernel with swapped roles (ops.convdet_dgrad), the weight gradient on the tcgen05 pixel-contraction
     kernel (ops.convdet_wgrad; Cout <= 80 and an even grid width) or else on the fp32 CUDA-core implicit GEMM of the same
     library, the bias gradient on a cluster reduction.  There is no library (cuDNN / ATen) route: a shape the kernels
-    do not take raises SqdError."""
+    do not take raises SqdError.
+
+    grad_sink (dist.GradBucket or None): when a data-parallel bucket is attached, the weight / bias gradients are
+    computed FIRST, added straight into the bucket's views and their all-reduce is launched before the feature
+    gradient (and with it the whole backbone backward) is even enqueued, so the collective overlaps that work on the
+    GPU ("kick NCCL from the wgrad epilogue").  Autograd then gets None for those two inputs."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, packed, algo, dgrad_packed_fn):
-        ctx.save_for_backward(x, weight)
+    def forward(ctx, x, weight, bias, packed, algo, dgrad_packed_fn, grad_sink=None):
+        ctx.save_for_backward(x, weight, bias)
         ctx.dgrad_packed_fn = dgrad_packed_fn
+        ctx.grad_sink = grad_sink
         return ops.convdet_forward(x, weight, bias, packed=packed, algo=algo)  # (B,gh,gw,Cout)
 
     @staticmethod
     def backward(ctx, g):
-        x, weight = ctx.saved_tensors
+        x, weight, bias = ctx.saved_tensors
         gx = gw = gb = None
         g = g.contiguous()
-        if ctx.needs_input_grad[0]:
-            if weight.shape[1] % 128 != 0:
-                raise SqdError("ConvDet feature gradient: Cin %d is not a multiple of 128 (sqd_convdet_dgrad); detach the "
-                               "features or use a backbone with 128-aligned Fire11 channels" % weight.shape[1])
-            gx = ops.convdet_dgrad(g, weight, ctx.dgrad_packed_fn() if ctx.dgrad_packed_fn else None)
+        if ctx.needs_input_grad[0] and weight.shape[1] % 128 != 0:
+            raise SqdError("ConvDet feature gradient: Cin %d is not a multiple of 128 (sqd_convdet_dgrad); detach the "
+                           "features or use a backbone with 128-aligned Fire11 channels" % weight.shape[1])
         if ctx.needs_input_grad[1]:
             gw = ops.convdet_wgrad(x, g)
         if ctx.needs_input_grad[2]:
             gb = ops.convdet_bias_grad(g)
-        return gx, gw, gb, None, None, None
+        sink = ctx.grad_sink
+        if sink is not None and sink.take_early({id(weight): (weight, gw), id(bias): (bias, gb)}):
+            gw = gb = None      # already in the bucket, their all-reduce is in flight
+        if ctx.needs_input_grad[0]:
+            gx = ops.convdet_dgrad(g, weight, ctx.dgrad_packed_fn() if ctx.dgrad_packed_fn else None)
+        return gx, gw, gb, None, None, None, None
 
 
 class SqueezeDetBase(nn.Module):
@@ -96,6 +105,7 @@ class SqueezeDetBase(nn.Module):
         self._packed_version = None
         self._dgrad_packed = None
         self._dgrad_packed_version = None
+        self.grad_sink = None     # dist.GradBucket of a data-parallel run (dist.bucket_for attaches it)
         self.init_weights()
 
     def init_weights(self):  # squeezedet.py:89-97
@@ -135,7 +145,7 @@ class SqueezeDetBase(nn.Module):
     def head(self, feat):
         """ConvDet + permute/view of squeezedet.py:83-87 on a Fire11 feature map."""
         pred = _ConvDetFn.apply(feat, self.convdet.weight, self.convdet.bias, self.packed_weights(), self.conv_algo,
-                                self.dgrad_packed_weights)
+                                self.dgrad_packed_weights, self.grad_sink)
         return pred.view(-1, self.num_anchors, self.num_classes + 5)
 
     def forward(self, x):

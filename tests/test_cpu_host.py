@@ -178,6 +178,52 @@ for total in (7, 1, 10):
     assert torch.isfinite(bk.flat).all()
     assert torch.allclose(bk.flat, want, rtol=1e-5, atol=1e-6), (total, bk.flat, want)
     assert torch.allclose(loss, l2.mean().detach(), rtol=1e-5), (total, loss, l2.mean())
+# take_early: a head whose backward hands its weight / bias gradients to the bucket BEFORE computing the input gradient
+# (what model._ConvDetFn does): the early all-reduce is launched from inside backward, the result is unchanged
+class HeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, sink):
+        ctx.save_for_backward(x, w, b); ctx.sink = sink
+        return x @ w.t() + b
+    @staticmethod
+    def backward(ctx, g):
+        x, w, b = ctx.saved_tensors
+        gw, gb = g.t() @ x, g.sum(0)
+        order.append("wgrad")
+        if ctx.sink.take_early({id(w): (w, gw), id(b): (b, gb)}):
+            gw = gb = None
+        order.append("dgrad")
+        return g @ w, gw, gb, None
+class EarlyHead(PerImage):
+    def forward(self, batch):
+        l = (HeadFn.apply(torch.relu(self.body(batch["image"])), self.base.convdet.weight, self.base.convdet.bias,
+                          self.base.grad_sink) ** 2).sum(1)
+        return l, {"loss": l}
+order = []
+def spy2(t, *a, **k):
+    order.append("allreduce%d" % t.numel())
+    return orig(t, *a, **k)
+dist.all_reduce = spy2
+torch.manual_seed(9)
+m = EarlyHead()
+bk = sdist.bucket_for(m)
+assert m.base.grad_sink is bk
+full = {"image": torch.randn(9, 8, generator=torch.Generator().manual_seed(3))}
+loss, _ = sdist.train_step(m, sdist.shard_batch(full, rank, world), bk)
+assert order[:3] == ["wgrad", "allreduce%d" % bk.early_numel, "dgrad"], order      # launched between wgrad and dgrad
+assert order.count("allreduce%d" % bk.early_numel) == 1, order
+dist.all_reduce = orig
+m2 = PerImage(); m2.load_state_dict(m.state_dict())
+l2, _ = m2(full)
+l2.mean().backward()
+want = torch.cat([p.grad.flatten() for p in list(m2.base.convdet.parameters()) + list(m2.body.parameters())])
+assert torch.allclose(bk.flat, want, rtol=1e-5, atol=1e-6), (bk.flat, want)
+# not armed (no bucket.zero()): autograd accumulates as usual
+for p_ in m.parameters():
+    p_.grad = None
+lz, _ = m(full)
+lz.mean().backward()
+assert torch.allclose(m.base.convdet.weight.grad, m2.base.convdet.weight.grad, rtol=1e-5, atol=1e-6)
 dist.destroy_process_group()
 print("OK", rank)
 '''
