@@ -107,10 +107,41 @@ def cpu_reference_pass(orc, feat, w, b, anchors, shp):
                                shp.score_thresh)
 
 
-def run_cpu_arm(args, budget_s, warmup, steps):
-    """Times the CPU port (oracle/) on all host cores.  Returns (img/s, dict describing the run)."""
+def make_reference_runner(shp, w, b):
+    """The reference's OWN classes, imported from oracle/_ref (a verbatim copy made by oracle/make_ref.py; absent ->
+    None): SqueezeDet with the backbone replaced by Identity, so SqueezeDetBase.forward's tail (squeezedet.py:79-87),
+    PredictionResolver and SqueezeDet.forward (:109-120,197-206) run on Fire11-shaped input, then Detector.detect
+    (detector.py:20-50: per-image filter with torchvision nms, boxes_postprocess) -- on the CPU, as cfg.device says."""
+    import types
     import torch
-    from oracle import oracle as orc
+    from oracle import make_ref
+    ref = make_ref.load()
+    if ref is None:
+        return None
+    from squeezedet_pytorch_b200 import synth
+    anchors = ref.boxes.generate_anchors(shp.grid_hw, shp.input_hw, synth.KITTI_SEEDS)
+    cfg = types.SimpleNamespace(
+        input_size=shp.input_hw, num_classes=shp.num_classes, anchors=anchors, anchors_per_grid=shp.anchors_per_grid,
+        num_anchors=anchors.shape[0], arch="squeezedet", dropout_prob=0.5, device=torch.device("cpu"),
+        keep_top_k=shp.top_k, nms_thresh=shp.nms_thresh, score_thresh=shp.score_thresh, debug=0, mode="eval",
+        class_loss_weight=1.0, positive_score_loss_weight=3.75, negative_score_loss_weight=100.0, bbox_loss_weight=6.0)
+    net = ref.model.SqueezeDet(cfg)
+    net.base.features = torch.nn.Identity()
+    with torch.no_grad():
+        net.base.convdet.weight.copy_(torch.from_numpy(w))
+        net.base.convdet.bias.copy_(torch.from_numpy(b))
+    det = ref.detector.Detector(net, cfg)
+
+    def run(feat_t):
+        return det.detect({"image": feat_t, "image_meta": {}})
+    return run
+
+
+def run_cpu_arm(args, budget_s, warmup, steps):
+    """Times the reference's CPU implementation of the path on all host cores: the reference's own files (oracle/_ref,
+    kind "reference") when they travelled with the snapshot, else the oracle port (kind "port").
+    Returns a dict describing the run."""
+    import torch
     from squeezedet_pytorch_b200 import synth
     shp = synth.KITTI
     cores = os.cpu_count() or 1
@@ -118,23 +149,35 @@ def run_cpu_arm(args, budget_s, warmup, steps):
     B = args.batch
     feat = synth.features(shp, B, 1234)
     w, b = synth.convdet_params(shp, 4321)
-    anchors = synth.anchor_table(shp)
+    runner = None if args.cpu_port else make_reference_runner(shp, w, b)
+    if runner is not None:
+        feat_t = torch.from_numpy(feat)
+        one = lambda: runner(feat_t)   # noqa: E731
+        kind = "reference"
+        what = ("the reference's own SqueezeDet (Identity backbone) + Detector.detect imported from oracle/_ref "
+                f"(verbatim copy of src/model, src/engine/detector.py, src/utils), torch CPU {cores} threads")
+    else:
+        from oracle import oracle as orc
+        anchors = synth.anchor_table(shp)
+        one = lambda: cpu_reference_pass(orc, feat, w, b, anchors, shp)   # noqa: E731
+        kind = "port"
+        what = f"torch CPU conv2d ({cores} threads) + numpy decode + per-image top-k/NMS (oracle/oracle.py)"
     t0 = time.perf_counter()
-    cpu_reference_pass(orc, feat, w, b, anchors, shp)           # first pass: page-in / thread pool spin-up
+    first = one()                                               # first pass: page-in / thread pool spin-up
     est = time.perf_counter() - t0
+    assert len(first) == B
     warmup = max(1, min(warmup, int(max(1, 0.2 * budget_s / max(est, 1e-3)))))
     steps = max(1, min(steps, int(max(1, 0.8 * budget_s / max(est, 1e-3)))))
     for _ in range(warmup):
-        cpu_reference_pass(orc, feat, w, b, anchors, shp)
+        one()
     times = []
     for _ in range(steps):
         t = time.perf_counter()
-        cpu_reference_pass(orc, feat, w, b, anchors, shp)
+        one()
         times.append(time.perf_counter() - t)
     per_step = float(np.mean(times))
-    info = {"value": B / per_step, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} timed passes (after {warmup} warm-up) over one batch of {B} KITTI-shaped feature maps: "
-                      f"torch CPU conv2d ({cores} threads) + numpy decode + per-image top-k/NMS (oracle/oracle.py)",
+    info = {"value": B / per_step, "unit": "images/s", "cores": cores, "kind": kind,
+            "sample": f"{steps} timed passes (after {warmup} warm-up) over one batch of {B} KITTI-shaped feature maps: " + what,
             "ms_per_step": per_step * 1e3, "steps_run": steps}
     return info
 
@@ -158,8 +201,9 @@ def main_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "KITTI 1248x384 eval-shape head+decode+NMS, batch %d (BASELINE configs[1])" % args.batch,
-                   "note": "reference's CPU implementation of the path, restated (oracle port): the Python reference "
-                           "cannot travel to the GPU box; all host threads"},
+                   "note": "reference's CPU implementation of the path on all host threads: kind 'reference' = the "
+                           "reference's own files from oracle/_ref, kind 'port' = the oracle restatement (when the copy "
+                           "did not travel)"},
         "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": info["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -341,6 +385,9 @@ def main_ours(args):
         barrier()
         return max_over_ranks(a.elapsed_time(b_)) / n
 
+    def use_graph_ok(g):
+        return g["ms_per_step"] is not None
+
     extra = {}
     if not args.skip_extra:
         # configs[2]: 2048 KITTI images sharded by image over the ranks (strong scaling: total work fixed), no collective
@@ -422,24 +469,80 @@ def main_ours(args):
             gt = matcher.dense_targets(*gt_packed)
             return sdist.train_step(head, {"features": tfeat, "gt": gt}, bucket)
 
-        ms_train = timed_steps(train_iter, max(10, min(K, 50)), 5)
+        nt = max(10, min(K, 50))
+        ms_train_eager = timed_steps(train_iter, nt, 5)
         loss_val = float(train_iter(0)[0])
         assert np.isfinite(loss_val), loss_val
         real_distributed = bucket._distributed
         bucket._distributed = lambda: False           # the same step without the collective: the difference is what the
-        ms_train_local = timed_steps(train_iter, max(10, min(K, 50)), 3)   # all-reduce costs the step (its exposed time)
+        ms_train_eager_local = timed_steps(train_iter, nt, 3)   # all-reduce costs the step (its exposed time)
         bucket._distributed = real_distributed
+        # the step as ONE CUDA graph launch (dist.GraphedStep): the eager step is host bound, the replay is not
+        graphed = {"ms_per_step": None, "ms_per_step_without_allreduce": None, "error": None}
+        if not args.no_train_graph:
+            try:
+                g_full = sdist.GraphedStep(lambda: train_iter(0))
+                graphed["ms_per_step"] = timed_steps(lambda _i: g_full(), nt, 3)
+                g_loss = float(g_full()[0])
+                assert abs(g_loss - loss_val) <= 1e-4 * abs(loss_val), (g_loss, loss_val)
+                if world > 1:
+                    bucket._distributed = lambda: False
+                    g_local = sdist.GraphedStep(lambda: train_iter(0))
+                    bucket._distributed = real_distributed
+                    graphed["ms_per_step_without_allreduce"] = timed_steps(lambda _i: g_local(), nt, 3)
+                    del g_local
+                else:
+                    graphed["ms_per_step_without_allreduce"] = graphed["ms_per_step"]
+                del g_full
+            except Exception as e:      # noqa: BLE001 -- report, keep the eager numbers
+                bucket._distributed = real_distributed
+                graphed["error"] = repr(e)[:300]
+                torch.cuda.synchronize()
         ar_ms = None
+        head_only = None
         if world > 1:
             def ar_only(_i):
                 dist.all_reduce(bucket._buf, op=dist.ReduceOp.SUM)
             ar_ms = timed_steps(ar_only, 20, 5)
+            # the same step with a bucket of the ConvDet head alone (497,736 floats): everything this path
+            # produces is reduced beside the dgrad GEMM; what stays exposed in the full bucket is the backbone's segment,
+            # whose gradients come from stock PyTorch after this path's backward
+            if use_graph_ok(graphed):
+                try:
+                    for p_ in net.parameters():
+                        p_.grad = None
+                    hb = sdist.GradBucket(list(net.base.convdet.parameters()), early=list(net.base.convdet.parameters()))
+                    net.base.grad_sink = hb
+
+                    def head_iter(_i):
+                        tfeat.grad = None
+                        gt = matcher.dense_targets(*gt_packed)
+                        return sdist.train_step(head, {"features": tfeat, "gt": gt}, hb)
+                    gh_full = sdist.GraphedStep(lambda: head_iter(0))
+                    t_with = timed_steps(lambda _i: gh_full(), nt, 3)
+                    hb._distributed = lambda: False
+                    gh_local = sdist.GraphedStep(lambda: head_iter(0))
+                    t_without = timed_steps(lambda _i: gh_local(), nt, 3)
+                    head_only = {"bucket_floats": int(hb.flat.numel()), "ms_per_step": t_with,
+                                 "ms_per_step_without_allreduce": t_without, "exposed_allreduce_ms": max(0.0, t_with - t_without)}
+                    del gh_full, gh_local, hb
+                except Exception as e:      # noqa: BLE001
+                    head_only = {"error": repr(e)[:300]}
+                    torch.cuda.synchronize()
+        use_graph = graphed["ms_per_step"] is not None
+        ms_train = graphed["ms_per_step"] if use_graph else ms_train_eager
+        ms_train_local = graphed["ms_per_step_without_allreduce"] if use_graph else ms_train_eager_local
         extra["train_step"] = {"workload": "BASELINE configs[3]: training step of the path at KITTI batch %d per GPU: matcher + targets, "
                                            "ConvDet forward, loss fwd+bwd, native wgrad/bias/dgrad, all-reduce of the flat gradient "
                                            "bucket (%d floats, head segment %d launched before the dgrad GEMM)" % (B, bucket.flat.numel(), bucket.early_numel),
                                "ms_per_step": ms_train, "images_per_s": world * B / (ms_train * 1e-3),
+                               "mode": "one CUDA graph replay per step (dist.GraphedStep)" if use_graph else "eager",
                                "ms_per_step_without_allreduce": ms_train_local,
                                "exposed_allreduce_ms": max(0.0, ms_train - ms_train_local) if world > 1 else 0.0,
+                               "eager": {"ms_per_step": ms_train_eager, "ms_per_step_without_allreduce": ms_train_eager_local,
+                                         "note": "host bound: Python + autograd dispatch of ~40 launches"},
+                               "graph_error": graphed["error"],
+                               "head_only_bucket": head_only,
                                "allreduce_alone_ms": ar_ms, "nccl_ranks": world if world > 1 else 0,
                                "bucket_bytes": int(bucket._buf.numel() * 4), "loss": loss_val, "scaling": "weak"}
         del tfeat, net, head, bucket
@@ -603,10 +706,12 @@ def main():
     ap.add_argument("--batch", type=int, default=20)
     ap.add_argument("--layout", default="nchw", choices=["nchw", "channels_last"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-port", action="store_true", help="CPU arm: time the oracle port even when oracle/_ref is present")
     ap.add_argument("--decode-batch", type=int, default=1024, help="images of the stand-alone decode/NMS roofline measurement")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: one e2e step only (the JSON line is then not a bench result)")
     ap.add_argument("--e2e-chunk", type=int, default=5, help="images per H2D/compute pipeline group of the e2e call")
     ap.add_argument("--skip-extra", action="store_true", help="skip the configs[2], [3], [4] measurements (profiling aid)")
+    ap.add_argument("--no-train-graph", action="store_true", help="time the training step eagerly only")
     ap.add_argument("--config3-images", type=int, default=2048, help="BASELINE configs[2]: images sharded over the ranks")
     ap.add_argument("--stress-batch", type=int, default=64, help="BASELINE configs[4]: images per GPU (512 over 8 GPUs)")
     args = ap.parse_args()

@@ -26,6 +26,8 @@ _vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
 SIGNATURES = {
     "sqd_abi_version": (_i, []),
     "sqd_last_error": (C.c_char_p, []),
+    "sqd_set_option": (_i, [C.c_char_p, _i]),
+    "sqd_get_option": (_i, [C.c_char_p, C.POINTER(C.c_int)]),
     "sqd_convdet_packed_weight_bytes": (_sz, [_i, _i]),
     "sqd_convdet_pack_weights": (_i, [_vp, _i, _i, _vp, _vp]),
     "sqd_convdet_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
@@ -95,6 +97,26 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = load().sqd_last_error().decode("utf-8", "replace")
         raise SqdError(f"{what} failed (code {rc}): {msg}")
+
+
+class option:
+    """Context manager: run a block with a developer option of the library set (sqd_set_option), then restore it.
+    `with _lib.option("SQD_SPLIT_TWO_PASS", 1): ...` -- how the tests select an alternative route."""
+
+    def __init__(self, name, value):
+        self.name, self.value = name.encode(), int(value)
+
+    def __enter__(self):
+        lib = load()
+        old = C.c_int(0)
+        check(lib.sqd_get_option(self.name, C.byref(old)), "sqd_get_option")
+        self.old = old.value
+        check(lib.sqd_set_option(self.name, self.value), "sqd_set_option")
+        return self
+
+    def __exit__(self, *exc):
+        check(load().sqd_set_option(self.name, self.old), "sqd_set_option")
+        return False
 
 
 def ptr(t):

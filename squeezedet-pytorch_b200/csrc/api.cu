@@ -3,6 +3,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 
 // implemented in convdet_simt.cu / convdet_f16.cu
@@ -45,10 +48,57 @@ void sqd_set_error(const char *fmt, ...) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-bool sqd_pdl_enabled() {
-    const char *e = getenv("SQD_NO_PDL");
-    return !(e && atoi(e) != 0);
+// ---- developer options: one table, read from the environment once ---------------------------------------------
+namespace {
+struct OptDef {
+    const char *name;
+    int dflt;
+};
+const OptDef kOptDefs[SQD_OPT_COUNT] = {
+    {"SQD_NO_PDL", 0}, {"SQD_FUSED_SCORE", 0}, {"SQD_SPLIT_TWO_PASS", 0}, {"SQD_SPLIT_CS", 0}, {"SQD_SPLIT_THREADS", 512},
+    {"SQD_SPLIT_ROWS", 0}, {"SQD_DGRAD_PER_SLAB", 0}, {"SQD_DGRAD_BLOCK_SCALES", 0}, {"SQD_WG_SINGLE_TAP", 0}, {"SQD_WG_SYNC", 0},
+    {"SQD_BWD_OLD_PREPASS", 0}, {"SQD_MATCH_SEQUENTIAL", 0}, {"SQD_F16_HALF_TILES", 0}, {"SQD_F16_CHUNK", 3}, {"SQD_F16_DBG", 0},
+    {"SQD_F16_PAIR_STAGES", 4}, {"SQD_F16_A_STAGES", 2}, {"SQD_F16_B_STAGES", 8}, {"SQD_F16_TRACE_CTA", 0}, {"SQD_HEAD_STAGED", 0},
+};
+std::atomic<int> g_opt[SQD_OPT_COUNT];
+std::once_flag g_opt_once;
+void opt_init() {
+    for (int i = 0; i < SQD_OPT_COUNT; ++i) {
+        const char *e = getenv(kOptDefs[i].name);
+        g_opt[i].store(e ? (*e ? atoi(e) : 1) : kOptDefs[i].dflt, std::memory_order_relaxed);
+    }
 }
+int opt_index(const char *name) {
+    if (!name) return -1;
+    for (int i = 0; i < SQD_OPT_COUNT; ++i)
+        if (strcmp(name, kOptDefs[i].name) == 0) return i;
+    return -1;
+}
+}  // namespace
+
+int sqd_opt(SqdOptId id) {
+    std::call_once(g_opt_once, opt_init);
+    return g_opt[id].load(std::memory_order_relaxed);
+}
+
+extern "C" int sqd_set_option(const char *name, int value) {
+    SQD_REQUIRE(name, SQD_E_NULL, "sqd_set_option: NULL name");
+    const int i = opt_index(name);
+    SQD_REQUIRE(i >= 0, SQD_E_UNSUPPORTED, "sqd_set_option: unknown option %s", name ? name : "(null)");
+    std::call_once(g_opt_once, opt_init);
+    g_opt[i].store(value, std::memory_order_relaxed);
+    return SQD_OK;
+}
+
+extern "C" int sqd_get_option(const char *name, int *value) {
+    SQD_REQUIRE(name && value, SQD_E_NULL, "sqd_get_option: NULL pointer");
+    const int i = opt_index(name);
+    SQD_REQUIRE(i >= 0, SQD_E_UNSUPPORTED, "sqd_get_option: unknown option %s", name);
+    *value = sqd_opt(static_cast<SqdOptId>(i));
+    return SQD_OK;
+}
+
+bool sqd_pdl_enabled() { return sqd_opt(SQD_OPT_NO_PDL) == 0; }
 
 extern "C" int sqd_abi_version(void) { return SQD_ABI_VERSION; }
 extern "C" const char *sqd_last_error(void) { return g_err; }

@@ -13,6 +13,9 @@ ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libsqdet_b200.so")
 SOURCES = ["api.cu", "io_kernels.cu", "decode.cu", "topk_nms.cu", "matcher.cu", "loss.cu", "convdet_simt.cu", "convdet_f16.cu", "convdet_bwd.cu", "convdet_wgrad_tc.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+# SQD_BUILD_TRACE=1: profiling build with the clock64 pipeline-trace stamps of the tcgen05 kernels compiled in
+# (tools/tc_trace.py); the shipped library has none of it.
+TRACE = ["-DSQD_ENABLE_TRACE"] if os.environ.get("SQD_BUILD_TRACE") else []
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
          "-I", os.path.join(ROOT, "include"), "-I", HERE]
 
@@ -42,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc, *ARCH, *FLAGS, "-Xptxas", "-v" if verbose else "-warn-spills", "-c", s, "-o", o]
+            cmd = [nvcc, *ARCH, *FLAGS, *TRACE, "-Xptxas", "-v" if verbose else "-warn-spills", "-c", s, "-o", o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

@@ -39,6 +39,17 @@ void sqd_set_error(const char *fmt, ...);
         }                                                                                \
     } while (0)
 
+// ---- developer options --------------------------------------------------------------------------
+// Alternative routes (cross-checked bit for bit by the tests) and tuning knobs.  One table, filled ONCE from the
+// environment on first use and changed afterwards only through sqd_set_option(); no entry point calls getenv().
+enum SqdOptId {
+    SQD_OPT_NO_PDL, SQD_OPT_FUSED_SCORE, SQD_OPT_SPLIT_TWO_PASS, SQD_OPT_SPLIT_CS, SQD_OPT_SPLIT_THREADS, SQD_OPT_SPLIT_ROWS,
+    SQD_OPT_DGRAD_PER_SLAB, SQD_OPT_DGRAD_BLOCK_SCALES, SQD_OPT_WG_SINGLE_TAP, SQD_OPT_WG_SYNC, SQD_OPT_BWD_OLD_PREPASS,
+    SQD_OPT_MATCH_SEQUENTIAL, SQD_OPT_F16_HALF_TILES, SQD_OPT_F16_CHUNK, SQD_OPT_F16_DBG, SQD_OPT_F16_PAIR_STAGES,
+    SQD_OPT_F16_A_STAGES, SQD_OPT_F16_B_STAGES, SQD_OPT_F16_TRACE_CTA, SQD_OPT_HEAD_STAGED, SQD_OPT_COUNT
+};
+int sqd_opt(SqdOptId id);
+
 static inline bool sqd_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- arithmetic that must round exactly like the reference's separate torch / numpy ops -------

@@ -381,7 +381,7 @@ extern "C" int sqd_convdet_dgrad_pack_weights(const float *d_weight, int cout, i
 // caller; image stride ncb >= ceil(cout / 64)): the scale granularity of both the dgrad planes and the wgrad G^T copies.
 int sqd_gpred_absmax(const float *d_gpred, int batch, int P, int cout, int ncb, unsigned *amax_bits, cudaStream_t st,
                      int per_image) {
-    if (cout % 4 == 0 && cout <= 128 && ncb <= 2 && (per_image || !getenv("SQD_BWD_OLD_PREPASS"))) {
+    if (cout % 4 == 0 && cout <= 128 && ncb <= 2 && (per_image || !sqd_opt(SQD_OPT_BWD_OLD_PREPASS))) {
         gpred_absmax_flat_kernel<<<dim3(16, batch), 256, 0, st>>>(reinterpret_cast<const float4 *>(d_gpred), P * (cout / 4),
                                                                  cout / 4, ncb, amax_bits, per_image);
         SQD_LAUNCH_CHECK("gpred_absmax_flat_kernel");
@@ -413,7 +413,7 @@ extern "C" int sqd_convdet_dgrad(const float *d_gpred, const void *d_dgrad_packe
     // ONE scale per image for G when the flat max kernel applies (72 channels = 2 blocks): a tile of the dgrad GEMM is
     // then a single TMEM chunk (one drain of the 384-column accumulator per tile instead of two).  fp16 keeps 11
     // significant bits down to 2^-27 of the image maximum, so a per-block scale buys nothing for a gradient tensor.
-    const int image_scales = (cout % 4 == 0 && cout <= 128 && ncb == 2 && !getenv("SQD_DGRAD_BLOCK_SCALES")) ? 1 : 0;
+    const int image_scales = (cout % 4 == 0 && cout <= 128 && ncb == 2 && !sqd_opt(SQD_OPT_DGRAD_BLOCK_SCALES)) ? 1 : 0;
     char *ws = static_cast<char *>(d_workspace);
     // 1. G -> zero-padded fp16 planes with per-(image, block) scales (G is 1/10 of the features: two small passes)
     char *planes = ws + w.planes_off;
@@ -439,7 +439,7 @@ extern "C" int sqd_convdet_dgrad(const float *d_gpred, const void *d_dgrad_packe
     // writes feature channels [slab*128, +128).  (Six launches of one slab each spend most of their time in prologue,
     // pipeline fill and the last tile's epilogue: 2 tiles per CTA pair.)
     const size_t slab_bytes = align256(sqd_f16_packed_bytes(kSlab, kp));
-    if (getenv("SQD_DGRAD_PER_SLAB")) {
+    if (sqd_opt(SQD_OPT_DGRAD_PER_SLAB)) {
         for (int s = 0; s < ns; ++s) {
             int rc = sqd_convdet_f16_pair(reinterpret_cast<const float *>(planes), SQD_LAYOUT_SPLIT_NHWC,
                                           static_cast<const char *>(d_dgrad_packed) + (size_t)s * slab_bytes, nullptr, batch, kp, gh,
@@ -459,7 +459,7 @@ extern "C" int sqd_convdet_bias_grad(const float *d_gpred, int batch, int gh, in
     SQD_REQUIRE(d_gpred && d_gbias, SQD_E_NULL, "sqd_convdet_bias_grad: NULL pointer");
     SQD_REQUIRE(batch >= 0 && gh > 0 && gw > 0 && cout >= 1, SQD_E_SHAPE, "sqd_convdet_bias_grad: bad shape");
     const size_t rows = (size_t)batch * gh * gw;
-    if (cout % 4 == 0 && sqd_aligned16(d_gpred) && !getenv("SQD_BWD_OLD_PREPASS")) {
+    if (cout % 4 == 0 && sqd_aligned16(d_gpred) && !sqd_opt(SQD_OPT_BWD_OLD_PREPASS)) {
         const int qpp = cout / 4, groups = (qpp + kBgQuads - 1) / kBgQuads;
         bias_grad_cluster_kernel<<<groups * kBgCluster, kBgThreads, 0, static_cast<cudaStream_t>(stream)>>>(
             reinterpret_cast<const float4 *>(d_gpred), rows, qpp, d_gbias);

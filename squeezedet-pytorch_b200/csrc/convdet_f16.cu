@@ -436,8 +436,12 @@ struct UnitIter {
     __device__ __forceinline__ void next(const F16Params &p);
 };
 
+#ifdef SQD_ENABLE_TRACE
 #define SQD_TRACE(slot, i) \
     do { if (p.trace && cta == p.trace_cta && lane == 0 && (i) < 512) p.trace[(i) * 32 + (slot)] = clock64(); } while (0)
+#else
+#define SQD_TRACE(slot, i) do { } while (0)
+#endif
 
 struct Ring {  // stage index + phase bit of a circular buffer of n stages
     int s;
@@ -911,11 +915,16 @@ struct PairIterT {
     }
 };
 
+#ifdef SQD_ENABLE_TRACE
 #define SQD_TRACE2(slot, i) \
     do { if (p.trace && cta == p.trace_cta && lane == 0 && (i) < 512) p.trace[(i) * 32 + (slot)] = clock64(); } while (0)
 // kernel phases (thread 0 of the traced CTA): row 511 of the trace buffer
 #define SQD_TRACE_PH(slot) \
     do { if (p.trace && blockIdx.x == (unsigned)p.trace_cta && threadIdx.x == 0) p.trace[511 * 32 + (slot)] = clock64(); } while (0)
+#else
+#define SQD_TRACE2(slot, i) do { } while (0)
+#define SQD_TRACE_PH(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ bool pair_wait_warp(uint64_t *bar, uint32_t parity, volatile int *abort_flag, bool spin) {
     return spin ? mbar_spin_warp(bar, parity, abort_flag) : mbar_wait_warp(bar, parity, abort_flag);
@@ -1434,11 +1443,6 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int env_int(const char *name, int dflt) {
-    const char *e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-
 int npad_of(int cout) { return (cout + 15) / 16 * 16; }
 // output channels per CTA of a pair (see pack_weights_f16_kernel / convdet_f16_pair_kernel)
 int pair_hr_of(int cout) {
@@ -1449,7 +1453,7 @@ int pair_hr_of(int cout) {
 
 
 int a_stages_for(int npad) {
-    int s = env_int("SQD_F16_A_STAGES", 2);
+    int s = sqd_opt(SQD_OPT_F16_A_STAGES);
     (void)npad;
     return s < 1 ? 1 : (s > 4 ? 4 : s);
 }
@@ -1458,7 +1462,7 @@ int b_stages_for(int npad) {
     const size_t stage = (size_t)2 * npad * kBlockK * 2;
     size_t s = (kSmemLimit - 1024 /*align*/ - kCtrlBytes - (size_t)a_stages_for(npad) * kAStageBytes) / stage;
     if (s > 8) s = 8;
-    const int cap = env_int("SQD_F16_B_STAGES", 8);
+    const int cap = sqd_opt(SQD_OPT_F16_B_STAGES);
     if ((int)s > cap && cap >= 1) s = cap;
     return (int)s;
 }
@@ -1533,7 +1537,7 @@ int pair_stages_for(int n1h) {
     const size_t stage = (size_t)kAStageBytes + (size_t)3 * n1h * kBlockK * 2;
     size_t s = (kSmemLimit - 1024 - kCtrlBytes) / stage;
     if (s > 4) s = 4;
-    const int cap = env_int("SQD_F16_PAIR_STAGES", 4);
+    const int cap = sqd_opt(SQD_OPT_F16_PAIR_STAGES);
     if ((int)s > cap && cap >= 1) s = cap;
     return (int)s;
 }
@@ -1650,21 +1654,21 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
     // which cuts the latency of a batch-1 call from 60 to 51 us.  Not the default: as long as every pair owns whole
     // tiles (up to 74 tiles = 4 KITTI images per launch) the fp32 summation order of a cell does not depend on how a
     // batch is chunked, and the host-buffer entry point relies on that to return bit-identical results for any chunk size.
-    if (2 * p.pair_tiles <= max_pairs && (cin / kBlockK) % 2 == 0 && env_int("SQD_F16_HALF_TILES", 0)) {
+    if (2 * p.pair_tiles <= max_pairs && (cin / kBlockK) % 2 == 0 && sqd_opt(SQD_OPT_F16_HALF_TILES)) {
         npairs = 2 * p.pair_tiles;
         upp = p.upt / 2;
     }
     p.units_per_pair = (int)upp;
     p.stages = pair_stages_for(n1h);
     SQD_REQUIRE(p.stages >= 2, SQD_E_SHAPE, "convdet (tcgen05): shared memory too small for two stages");
-    p.chunk_units = env_int("SQD_F16_CHUNK", 3);   // one 64-channel block (3 dx units) per TMEM chunk
+    p.chunk_units = sqd_opt(SQD_OPT_F16_CHUNK);   // one 64-channel block (3 dx units) per TMEM chunk
     if (p.chunk_units < 1) p.chunk_units = 1;
     p.chunk_blk = 3;
     if (image_scales && p.upt <= 6) {              // every block of an image shares one scale: a whole tile per chunk
         p.chunk_blk = p.upt;
         p.chunk_units = p.upt;
     }
-    p.dbg = env_int("SQD_F16_DBG", 0);
+    p.dbg = sqd_opt(SQD_OPT_F16_DBG);
     p.bias = d_bias;
     p.amax_bits = reinterpret_cast<const unsigned *>(planes);
     p.whdr = static_cast<const PackedHeader *>(d_packed);
@@ -1673,8 +1677,10 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
     p.flags = reinterpret_cast<int *>(ws + w.flags_off);
     p.status = reinterpret_cast<int *>(ws);
     p.trace = nullptr;
-    p.trace_cta = env_int("SQD_F16_TRACE_CTA", 0);
+    p.trace_cta = sqd_opt(SQD_OPT_F16_TRACE_CTA);
+#ifdef SQD_ENABLE_TRACE   // profiling builds only (SQD_BUILD_TRACE=1 python csrc/build.py): device address of a clock64 stamp buffer
     if (const char *e = getenv("SQD_F16_TRACE")) p.trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
+#endif
     const int grid = 2 * npairs;
     p.cand.count = nullptr;
     p.cand.keys = nullptr;
@@ -1685,7 +1691,7 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
         *emit->done = 0;
         const int nf = emit->num_classes + 5;
         const bool shape_ok = cout % nf == 0 && ((emit->num_classes == 3 && npad == 80) || (emit->num_classes == 8 && npad == 128));
-        if (shape_ok && env_int("SQD_FUSED_SCORE", 0)) {
+        if (shape_ok && sqd_opt(SQD_OPT_FUSED_SCORE)) {
             p.cand = emit->cand;
             p.score_thr = emit->score_thr;
             p.anchors_per_cell = cout / nf;
@@ -1715,10 +1721,10 @@ namespace {
 // cluster size for the one-pass NCHW split: the smallest that lets >= 3 CTAs share an SM (<= 72 KB each), else the
 // smallest that fits at all; 0 = shape not eligible (two-pass fallback)
 int split_cluster_size(int P, size_t *smem_out, int *nq4p_out) {
-    if (P % 4 != 0 || env_int("SQD_SPLIT_TWO_PASS", 0)) return 0;
+    if (P % 4 != 0 || sqd_opt(SQD_OPT_SPLIT_TWO_PASS)) return 0;
     const int n4 = P / 4;
     int pick = 0;
-    const int force = env_int("SQD_SPLIT_CS", 0);
+    const int force = sqd_opt(SQD_OPT_SPLIT_CS);
     for (int pass = 0; pass < 2 && !pick; ++pass)
         for (int cs = 1; cs <= kSplitMaxCluster; cs <<= 1) {
             if (cs > n4) break;
@@ -1776,7 +1782,7 @@ int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, 
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        const int threads = env_int("SQD_SPLIT_THREADS", 512), rows = env_int("SQD_SPLIT_ROWS", 0);
+        const int threads = sqd_opt(SQD_OPT_SPLIT_THREADS), rows = sqd_opt(SQD_OPT_SPLIT_ROWS);
         cudaError_t e = cudaErrorInvalidValue;
 #define SQD_SPLIT_LAUNCH(T, R)                                                                                              \
     do {                                                                                                                    \
@@ -1896,7 +1902,7 @@ int sqd_convdet_f16(const float *d_feat, int layout, const void *d_packed, const
     p.units_per_cta = (int)upc;
     p.a_stages = a_stages_for(npad);
     p.b_stages = b_stages_for(npad);
-    p.dbg = env_int("SQD_F16_DBG", 0);
+    p.dbg = sqd_opt(SQD_OPT_F16_DBG);
     p.bias = d_bias;
     p.amax_bits = reinterpret_cast<const unsigned *>(planes);
     p.whdr = static_cast<const PackedHeader *>(d_packed);
@@ -1905,8 +1911,10 @@ int sqd_convdet_f16(const float *d_feat, int layout, const void *d_packed, const
     p.flags = flags;
     p.status = status;
     p.trace = nullptr;
-    p.trace_cta = env_int("SQD_F16_TRACE_CTA", 0);
+    p.trace_cta = sqd_opt(SQD_OPT_F16_TRACE_CTA);
+#ifdef SQD_ENABLE_TRACE   // profiling builds only (SQD_BUILD_TRACE=1 python csrc/build.py): device address of a clock64 stamp buffer
     if (const char *e = getenv("SQD_F16_TRACE")) p.trace = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
+#endif
     switch (npad / 16) {
         case 1: return launch_f16<16>(maps, p, grid, st);
         case 2: return launch_f16<32>(maps, p, grid, st);

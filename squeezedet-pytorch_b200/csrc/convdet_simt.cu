@@ -1,7 +1,7 @@
 // a1 (validation yardstick): ConvDet 3x3 head as a CUDA-core fp32 FMA implicit GEMM.
 // Reference: SqueezeDetBase.convdet + permute/view, src/model/squeezedet.py:73-75,83-87.
 //
-// This is NOT the production head (that is convdet_tc.cu: tcgen05 / TMEM / TMA, 3xTF32).  It exists
+// This is NOT the production head (that is convdet_f16.cu / convdet_fused.cu: tcgen05 / TMEM / TMA, fp16x3).  It exists
 // so that the tensor-core kernel can be checked on the GPU at full size against an independent
 // fp32 evaluation of the same contraction (plain fmaf accumulation, k = tap-major, channel-minor),
 // and it accepts NCHW features directly.  GEMM view: M = B*gh*gw cells, N = Cout, K = 9*Cin.

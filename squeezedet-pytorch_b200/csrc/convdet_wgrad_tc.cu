@@ -652,8 +652,7 @@ int gwp_of(int gw) { return (gw + 1 + 7) & ~7; }   // at least one zero pad colu
 
 // debug aid (SQD_WG_SYNC=1): synchronise after every stage so that a faulting kernel is named
 int stage_check(const char *what, cudaStream_t st) {
-    const char *e = getenv("SQD_WG_SYNC");
-    if (!e || atoi(e) == 0) return SQD_OK;
+    if (!sqd_opt(SQD_OPT_WG_SYNC)) return SQD_OK;
     cudaError_t err = cudaStreamSynchronize(st);
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) {
@@ -672,7 +671,7 @@ WgWs wg_ws(int batch, int cin, int gh, int gw) {
     const int gwp = gwp_of(gw);
     const int tiles = batch * ((gh * gwp + kPixTile - 1) / kPixTile);
     // slices: three waves of work items (channel block x taps), at least ~8 pixel tiles each
-    const int items = ((cin + kMTile - 1) / kMTile) * (getenv("SQD_WG_SINGLE_TAP") ? 9 : 3);
+    const int items = ((cin + kMTile - 1) / kMTile) * (sqd_opt(SQD_OPT_WG_SINGLE_TAP) ? 9 : 3);
     int ns = (3 * SQD_SM_COUNT) / items;   // <= 3 full waves of one CTA per SM (a 4th, nearly empty wave costs a full wave time)
     if (ns > tiles / 8) ns = tiles / 8;
     if (ns < 1) ns = 1;
@@ -726,7 +725,7 @@ extern "C" int sqd_convdet_wgrad_tc(const float *d_feat_nchw, const float *d_gpr
     // 1. operands: pixel-major fp16 planes
     int rc = SQD_OK;
     SQD_REQUIRE(gw % 2 == 0, SQD_E_SHAPE, "sqd_convdet_wgrad_tc: grid width %d must be even", gw);
-    if (kXsChan * gh * (gwp / 8) <= kXsItems * kXsThreads && !getenv("SQD_BWD_OLD_PREPASS")) {
+    if (kXsChan * gh * (gwp / 8) <= kXsItems * kXsThreads && !sqd_opt(SQD_OPT_BWD_OLD_PREPASS)) {
         split_nchw_rows_cluster_kernel<<<(unsigned)(batch * ncb * kXsCluster), kXsThreads, 0, st>>>(
             d_feat_nchw, cin, gh, gw, gwp, amax_x, reinterpret_cast<uint4 *>(x1), reinterpret_cast<uint4 *>(x2));
         SQD_LAUNCH_CHECK("split_nchw_rows_cluster_kernel");
@@ -779,7 +778,7 @@ extern "C" int sqd_convdet_wgrad_tc(const float *d_feat_nchw, const float *d_gpr
     p.amax_g = amax_g;
     p.partial = reinterpret_cast<float *>(ws + w.partial_off);
     p.status = reinterpret_cast<int *>(ws + w.status_off);
-    if (!getenv("SQD_WG_SINGLE_TAP")) {
+    if (!sqd_opt(SQD_OPT_WG_SINGLE_TAP)) {
         // three row shifts per CTA: a third of the feature-tile traffic
         const size_t smem3 = 1024 + (size_t)kStages3 * kStage3Bytes + 1024;
         SQD_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));

@@ -382,7 +382,7 @@ extern "C" int sqd_match_anchors(const float *d_gt_boxes, const int32_t *d_gt_co
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, match_kernel, reinterpret_cast<const float4 *>(d_gt_boxes), d_gt_count, gmax,
                                        d_anchors64, num_anchors, d_anchor_idx, reinterpret_cast<float4 *>(d_deltas), cs,
-                                       getenv("SQD_MATCH_SEQUENTIAL") ? 1 : 0);
+                                       sqd_opt(SQD_OPT_MATCH_SEQUENTIAL) ? 1 : 0);
     if (e != cudaSuccess) {
         sqd_set_error("launch of match_kernel failed: %s", cudaGetErrorString(e));
         return (int)e;

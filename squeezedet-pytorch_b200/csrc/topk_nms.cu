@@ -16,7 +16,8 @@
 //     keys, no sort) and the threshold raised.  After the first cut almost nothing passes (expected
 //     k*ln(A/2048) more candidates).  Only the final k survivors are sorted (by ranking).
 //  2. The k survivors (sorted) get their boxes; a k x k same-class IoU bitmask is built with one
-//     ballot per 32 pairs; one warp runs the sequential greedy sweep over the mask rows.
+//     ballot per 32 pairs; greedy NMS is then solved block by block (32 candidates) as a fixed point of
+//     word' = ballot(pre & (own & word) == 0): no k-step serial chain, typically 2-4 rounds per block.
 //  3. Kept rows with score > thresh are emitted class-ascending / score-descending.
 // The running threshold starts at the score threshold (exact, see score_floor_key), so on real inputs only a few
 // hundred anchors per image ever enter the candidate buffer and mid-scan compactions do not happen.

@@ -192,3 +192,32 @@ def train_step(model, batch, bucket, optimizer=None, grad_norm=None):
     if optimizer is not None:
         optimizer.step()
     return (bucket.loss_slot / bucket.count_slot).reshape(()), stats
+
+
+class GraphedStep:
+    """One training step as a CUDA graph: `fn()` (e.g. `lambda: train_step(model, batch, bucket)`) is run a few times on
+    a side stream, captured once -- forward, native backward, the bucket's NCCL all-reduces and the normalisation are
+    all stream work -- and replayed with ONE launch per step.  The eager step of the head path is host bound (about
+    forty kernel launches, three of them collectives, behind Python and autograd dispatch); the replay runs at the
+    speed of its kernels and the all-reduce of the head segment overlaps the dgrad GEMM as captured.
+
+    Contract of CUDA graphs: every tensor `fn` reads must keep its address -- feed new data with `.copy_()` into the
+    tensors `fn` closed over -- and `fn` must not synchronise with the host.  The value `fn` returned during capture
+    (`.result`) is refreshed by every replay."""
+
+    def __init__(self, fn, warmup=3):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = fn()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.result

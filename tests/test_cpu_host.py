@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/sqdet_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared          # the ctypes table covers the whole header
-    assert lib.sqd_abi_version() == 3
+    assert lib.sqd_abi_version() == 4
 
 
 def test_size_queries_need_no_gpu():
@@ -247,6 +247,25 @@ def test_gloo_world_size_2_shard_and_gradient_allreduce(tmp_path):
         assert "OK" in o
 
 
+def test_option_table_is_set_through_the_abi_not_the_environment(monkeypatch):
+    """Developer options: seeded from the environment once, then only sqd_set_option changes them (no getenv per call)."""
+    import ctypes as C
+    from squeezedet_pytorch_b200 import _lib
+    lib = _lib.load()
+    v = C.c_int(-7)
+    assert lib.sqd_get_option(b"SQD_SPLIT_TWO_PASS", C.byref(v)) == 0 and v.value == 0
+    monkeypatch.setenv("SQD_SPLIT_TWO_PASS", "1")            # too late: the table was filled on first use
+    assert lib.sqd_get_option(b"SQD_SPLIT_TWO_PASS", C.byref(v)) == 0 and v.value == 0
+    with _lib.option("SQD_SPLIT_TWO_PASS", 1):
+        assert lib.sqd_get_option(b"SQD_SPLIT_TWO_PASS", C.byref(v)) == 0 and v.value == 1
+    assert lib.sqd_get_option(b"SQD_SPLIT_TWO_PASS", C.byref(v)) == 0 and v.value == 0
+    assert lib.sqd_set_option(b"SQD_NO_SUCH_OPTION", 1) == -5 and lib.sqd_last_error().startswith(b"sqd_set_option")
+    assert lib.sqd_set_option(None, 1) == -1 and lib.sqd_get_option(b"SQD_NO_PDL", None) == -1
+    # the shipped library carries no trace hook and never reads the environment per call
+    blob = open(_lib.LIB_PATH, "rb").read()
+    assert b"SQD_F16_TRACE\x00" not in blob
+
+
 def _abi_call(lib, name, ptr_value, int_value, size_value=0):
     """Call an int-returning entry point with every pointer = ptr_value, every int = int_value, doubles 0.5."""
     import ctypes as C
@@ -276,7 +295,8 @@ def test_abi_rejects_bad_arguments_before_touching_the_device():
     import ctypes as C
     from squeezedet_pytorch_b200 import _lib
     lib = _lib.load()
-    compute = [n for n, (res, args) in _lib.SIGNATURES.items() if res is C.c_int and args]
+    compute = [n for n, (res, args) in _lib.SIGNATURES.items()
+               if res is C.c_int and args and n not in ("sqd_set_option", "sqd_get_option")]
     assert len(compute) >= 20
     for name in compute:
         rc, msg = _abi_call(lib, name, None, 1)

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import oracle as orc
-from squeezedet_pytorch_b200 import synth
+from squeezedet_pytorch_b200 import _lib, synth
 from conftest import split_ragged
 
 pytestmark = pytest.mark.gpu
@@ -342,9 +342,8 @@ def test_epilogue_candidates_equal_scan_of_pred(ops, monkeypatch, name, batch, s
     w, b = dev(w), dev(b)
     a32 = dev(synth.anchor_table(shp).astype(np.float32))
     args = (a32, shp.anchors_per_grid, shp.num_classes, shp.input_hw, shp.top_k, shp.nms_thresh, thr)
-    monkeypatch.setenv("SQD_FUSED_SCORE", "1")
-    fused = ops.head_detect(feat, w, b, *args)
-    monkeypatch.delenv("SQD_FUSED_SCORE", raising=False)
+    with _lib.option("SQD_FUSED_SCORE", 1):
+        fused = ops.head_detect(feat, w, b, *args)
     scanned = ops.head_detect(feat, w, b, *args)
     pred = ops.convdet_forward(feat, w, b, num_fields=shp.num_fields, check_status=True)
     staged = ops.detect_from_pred(pred, a32, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh, thr, two_phase=False)
@@ -361,11 +360,9 @@ def test_one_pass_split_equals_two_pass(ops, monkeypatch, name, batch):
     shp = {x.name: x for x in (synth.TINY, synth.KITTI, synth.STRESS)}[name]
     feat, (w, b) = dev(synth.features(shp, batch, 51)), synth.convdet_params(shp, 52)
     w, b = dev(w), dev(b)
-    monkeypatch.delenv("SQD_SPLIT_TWO_PASS", raising=False)
     one = ops.convdet_forward(feat, w, b, check_status=True)
-    monkeypatch.setenv("SQD_SPLIT_TWO_PASS", "1")
-    two = ops.convdet_forward(feat, w, b, check_status=True)
-    monkeypatch.delenv("SQD_SPLIT_TWO_PASS", raising=False)
+    with _lib.option("SQD_SPLIT_TWO_PASS", 1):
+        two = ops.convdet_forward(feat, w, b, check_status=True)
     assert torch.equal(one, two)
     cl = ops.convdet_forward(feat.contiguous(memory_format=torch.channels_last), w, b, check_status=True)
     assert torch.equal(one, cl)   # channels_last input: same per-(image, block) scales, same planes
@@ -398,11 +395,8 @@ def test_convdet_dgrad_and_bias_grad(ops, name, batch):
     gx32, _, gb32 = orc.convdet_backward(feat, w, g)
     gx64, _, gb64 = orc.convdet_backward(feat, w, g, dtype=np.float64)
     got = ops.convdet_dgrad(dev(g), dev(w))
-    os.environ["SQD_DGRAD_PER_SLAB"] = "1"       # six launches of one 128-channel slab each: same products; tiles that are
-    try:                                         # split between CTA pairs are cut elsewhere, so the last fp32 add may differ
-        per_slab = ops.convdet_dgrad(dev(g), dev(w))
-    finally:
-        del os.environ["SQD_DGRAD_PER_SLAB"]
+    with _lib.option("SQD_DGRAD_PER_SLAB", 1):   # six launches of one 128-channel slab each: same products; tiles that are
+        per_slab = ops.convdet_dgrad(dev(g), dev(w))   # split between CTA pairs are cut elsewhere, so the last fp32 add may differ
     assert torch.allclose(got, per_slab, rtol=1e-5, atol=2e-5 * float(per_slab.abs().mean()))   # both within 1.3e-5 of float64
     assert torch.equal(got, ops.convdet_dgrad(dev(g), dev(w)))      # and each schedule is deterministic
     assert got.shape == (batch, shp.in_channels, *shp.grid_hw)
@@ -415,11 +409,8 @@ def test_convdet_dgrad_and_bias_grad(ops, name, batch):
     # default: one G scale per image, a whole tile (54 chained MMA pairs) per TMEM chunk -- 10 % faster, the tensor core's
     # truncating accumulation shows a little more; with per-block scales and per-block chunks it is fp32-grade
     assert e_ours < 2.5e-5
-    os.environ["SQD_DGRAD_BLOCK_SCALES"] = "1"
-    try:
+    with _lib.option("SQD_DGRAD_BLOCK_SCALES", 1):
         blk = ops.convdet_dgrad(dev(g), dev(w)).cpu().numpy()
-    finally:
-        del os.environ["SQD_DGRAD_BLOCK_SCALES"]
     e_blk = np.abs(blk - gx64).max() / scale
     print(f"dgrad with per-block scales: max {e_blk:.2e}")
     np.testing.assert_allclose(blk, gx32, rtol=1e-4, atol=1e-4 * scale)
@@ -433,24 +424,17 @@ def test_convdet_dgrad_and_bias_grad(ops, name, batch):
     wscale = np.abs(gw64).mean()
     e_ref = np.abs(gw32 - gw64).max() / wscale
     for tc in (False, True, "single-tap"):   # fp32 CUDA-core kernel, tcgen05 f16x3 (3 taps per CTA), tcgen05 (1 tap per CTA)
-        if tc == "single-tap":
-            os.environ["SQD_WG_SINGLE_TAP"] = "1"
-        try:
+        with _lib.option("SQD_WG_SINGLE_TAP", 1 if tc == "single-tap" else 0):
             gw1 = ops.convdet_wgrad(dev(feat), dev(g), tensor_cores=bool(tc), check_status=True)
             gw2 = ops.convdet_wgrad(dev(feat), dev(g), tensor_cores=bool(tc), check_status=True)
-        finally:
-            os.environ.pop("SQD_WG_SINGLE_TAP", None)
         assert torch.equal(gw1, gw2)
         if tc is True:
             # the one-pass pre-passes (cluster X split, flat max|G|, cluster bias sums) against the kernels they replaced:
             # same scales and planes -> the same gradient bit for bit; the bias sums only differ in summation order
-            os.environ["SQD_BWD_OLD_PREPASS"] = "1"
-            try:
+            with _lib.option("SQD_BWD_OLD_PREPASS", 1):
                 gw_old = ops.convdet_wgrad(dev(feat), dev(g), tensor_cores=True, check_status=True)
                 gb_old = ops.convdet_bias_grad(dev(g))
                 gx_old = ops.convdet_dgrad(dev(g), dev(w))
-            finally:
-                del os.environ["SQD_BWD_OLD_PREPASS"]
             assert torch.equal(gw1, gw_old)
             assert torch.equal(gx_old.cpu(), torch.from_numpy(got))
             assert torch.allclose(gb_old.cpu(), torch.from_numpy(gb), rtol=1e-6, atol=1e-6 * float(np.abs(gb64).max()))

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import oracle as orc
-from squeezedet_pytorch_b200 import synth
+from squeezedet_pytorch_b200 import _lib, synth
 from conftest import split_ragged
 
 pytestmark = pytest.mark.gpu
@@ -611,11 +611,9 @@ def test_matcher_batched_rounds_equal_sequential(monkeypatch):
             bx = np.concatenate([bx] * 4)[:70]                                  # more than two rounds of 32
         boxes_l.append(np.ascontiguousarray(bx, dtype=np.float32))
     gb, _, gc = m.pack(boxes_l)
-    monkeypatch.delenv("SQD_MATCH_SEQUENTIAL", raising=False)
     idx_b, del_b = m.match(gb, gc)
-    monkeypatch.setenv("SQD_MATCH_SEQUENTIAL", "1")
-    idx_s, del_s = m.match(gb, gc)
-    monkeypatch.delenv("SQD_MATCH_SEQUENTIAL", raising=False)
+    with _lib.option("SQD_MATCH_SEQUENTIAL", 1):
+        idx_s, del_s = m.match(gb, gc)
     assert torch.equal(idx_b, idx_s) and torch.equal(del_b, del_s)
     for i, bx in enumerate(boxes_l):
         exp_del, exp_idx = orc.match_anchors(bx, anchors)
