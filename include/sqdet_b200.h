@@ -72,7 +72,7 @@ SQD_API const char *sqd_last_error(void);
 
 /* Developer options: alternative routes through the library (each cross-checked bit for bit against the default route
  * by tests/) and tuning knobs, named like the environment variable that seeds them -- e.g. "SQD_SPLIT_TWO_PASS",
- * "SQD_MATCH_SEQUENTIAL", "SQD_NO_PDL", "SQD_HEAD_STAGED".  The table is filled from the environment ONCE, on first use;
+ * "SQD_MATCH_SEQUENTIAL", "SQD_NO_PDL", "SQD_HEAD_ONE_KERNEL".  The table is filled from the environment ONCE, on first use;
  * afterwards it changes only through sqd_set_option().  No reference counterpart (the reference has no such switches);
  * unknown names return SQD_E_UNSUPPORTED, a NULL name SQD_E_NULL. */
 SQD_API int sqd_set_option(const char *name, int value);

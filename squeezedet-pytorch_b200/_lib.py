@@ -12,7 +12,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsqdet_b200.so")
+# SQD_LIB_PATH: developer override (the profiling build libsqdet_b200_trace.so made with SQD_BUILD_TRACE=1)
+LIB_PATH = os.environ.get("SQD_LIB_PATH") or os.path.join(_HERE, "libsqdet_b200.so")
 
 LAYOUT_NCHW, LAYOUT_NHWC, LAYOUT_SPLIT_NHWC = 0, 1, 2
 CONV_TCGEN05_F16X3, CONV_SIMT_FP32, CONV_TCGEN05_F16X3_1CTA = 0, 1, 2

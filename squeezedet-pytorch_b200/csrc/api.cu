@@ -36,6 +36,10 @@ int sqd_detect_check_args(const char *fn, const void *d_pred, const void *d_anch
                           const void *score, const void *box);
 int sqd_convdet_f16(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
                     int gh, int gw, int cout, float *d_pred, void *d_workspace, cudaStream_t st);
+// implemented in convdet_fused.cu: the one-kernel path (fp32 NCHW features -> pred, operands converted inside the GEMM)
+bool sqd_convdet_fused_eligible(int layout, int batch, int cin, int gh, int gw, int cout);
+int sqd_convdet_fused(const float *d_feat, const void *d_packed, const float *d_bias, int batch, int cin, int gh, int gw,
+                      int cout, float *d_pred, void *d_workspace, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
 
@@ -58,7 +62,7 @@ const OptDef kOptDefs[SQD_OPT_COUNT] = {
     {"SQD_NO_PDL", 0}, {"SQD_FUSED_SCORE", 0}, {"SQD_SPLIT_TWO_PASS", 0}, {"SQD_SPLIT_CS", 0}, {"SQD_SPLIT_THREADS", 512},
     {"SQD_SPLIT_ROWS", 0}, {"SQD_DGRAD_PER_SLAB", 0}, {"SQD_DGRAD_BLOCK_SCALES", 0}, {"SQD_WG_SINGLE_TAP", 0}, {"SQD_WG_SYNC", 0},
     {"SQD_BWD_OLD_PREPASS", 0}, {"SQD_MATCH_SEQUENTIAL", 0}, {"SQD_F16_HALF_TILES", 0}, {"SQD_F16_CHUNK", 3}, {"SQD_F16_DBG", 0},
-    {"SQD_F16_PAIR_STAGES", 4}, {"SQD_F16_A_STAGES", 2}, {"SQD_F16_B_STAGES", 8}, {"SQD_F16_TRACE_CTA", 0}, {"SQD_HEAD_STAGED", 0},
+    {"SQD_F16_PAIR_STAGES", 4}, {"SQD_F16_A_STAGES", 2}, {"SQD_F16_B_STAGES", 8}, {"SQD_F16_TRACE_CTA", 0}, {"SQD_HEAD_ONE_KERNEL", 0},
 };
 std::atomic<int> g_opt[SQD_OPT_COUNT];
 std::once_flag g_opt_once;
@@ -146,6 +150,13 @@ static int convdet_forward_impl(const float *d_feat, int layout, const void *d_p
     SQD_REQUIRE(algo == SQD_CONV_TCGEN05_F16X3 || algo == SQD_CONV_TCGEN05_F16X3_1CTA, SQD_E_UNSUPPORTED,
                 "sqd_convdet_forward: unknown algo %d", algo);
     SQD_REQUIRE(d_packed, SQD_E_NULL, "sqd_convdet_forward: tcgen05 algorithm needs packed weights");
+    // Opt-in route (SQD_HEAD_ONE_KERNEL=1): max pass + ONE GEMM kernel that converts the fp32 features itself (no fp16
+    // planes in HBM, A patch produced once per (tile, block)).  Parity-checked against the default route by the tests;
+    // MEASURED slower than pre-pass + GEMM at KITTI B = 20 (136 vs 132 us, profiles/r02_one_kernel_convdet.txt: register
+    // loads through the LSU cannot stream 74 KB per block and SM), so it is not the default.
+    if (algo == SQD_CONV_TCGEN05_F16X3 && sqd_opt(SQD_OPT_HEAD_ONE_KERNEL) && !(emit && sqd_opt(SQD_OPT_FUSED_SCORE)) &&
+        sqd_convdet_fused_eligible(layout, batch, cin, gh, gw, cout))
+        return sqd_convdet_fused(d_feat, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
     if (algo == SQD_CONV_TCGEN05_F16X3)
         return sqd_convdet_f16_pair(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st, emit, 0, 0, 1, 0, 0);
     return sqd_convdet_f16(d_feat, layout, d_packed, d_bias, batch, cin, gh, gw, cout, d_pred, d_workspace, st);
@@ -294,13 +305,21 @@ extern "C" int sqd_head_detect_profile(const float *d_feat, int layout, const vo
     for (int i = 0; i < 4; ++i) SQD_CUDA(cudaEventCreate(&ev[i]));
     int rc = SQD_OK;
     SQD_CUDA(cudaEventRecord(ev[0], st));
-    rc = sqd_convdet_split_features(d_feat, layout, batch, cin, gh, gw, planes, stream);
-    if (rc == SQD_OK) {
+    if (sqd_opt(SQD_OPT_HEAD_ONE_KERNEL) && sqd_convdet_fused_eligible(layout, batch, cin, gh, gw, cout)) {
+        // one-kernel route: there is no pre-pass (stage 0 = 0 ms), the GEMM reads the fp32 features itself
         SQD_CUDA(cudaEventRecord(ev[1], st));
-        rc = head_detect_impl(static_cast<const float *>(planes), SQD_LAYOUT_SPLIT_NHWC, d_packed, nullptr, d_bias, d_anchors,
-                              batch, cin, gh, gw, anchors_per_grid, num_classes, input_h, input_w, top_k, nms_thresh,
-                              score_thresh, d_count, d_out_anchor, d_out_class, d_out_score, d_out_box, d_workspace,
-                              fused_bytes, SQD_CONV_TCGEN05_F16X3, stream, ev + 2);
+        rc = head_detect_impl(d_feat, layout, d_packed, nullptr, d_bias, d_anchors, batch, cin, gh, gw, anchors_per_grid,
+                              num_classes, input_h, input_w, top_k, nms_thresh, score_thresh, d_count, d_out_anchor,
+                              d_out_class, d_out_score, d_out_box, d_workspace, workspace_bytes, SQD_CONV_TCGEN05_F16X3, stream, ev + 2);
+    } else {
+        rc = sqd_convdet_split_features(d_feat, layout, batch, cin, gh, gw, planes, stream);
+        if (rc == SQD_OK) {
+            SQD_CUDA(cudaEventRecord(ev[1], st));
+            rc = head_detect_impl(static_cast<const float *>(planes), SQD_LAYOUT_SPLIT_NHWC, d_packed, nullptr, d_bias, d_anchors,
+                                  batch, cin, gh, gw, anchors_per_grid, num_classes, input_h, input_w, top_k, nms_thresh,
+                                  score_thresh, d_count, d_out_anchor, d_out_class, d_out_score, d_out_box, d_workspace,
+                                  fused_bytes, SQD_CONV_TCGEN05_F16X3, stream, ev + 2);
+        }
     }
     if (rc == SQD_OK) {
         SQD_CUDA(cudaStreamSynchronize(st));

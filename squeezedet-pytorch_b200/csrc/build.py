@@ -10,8 +10,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
-LIB = os.path.join(PKG, "libsqdet_b200.so")
-SOURCES = ["api.cu", "io_kernels.cu", "decode.cu", "topk_nms.cu", "matcher.cu", "loss.cu", "convdet_simt.cu", "convdet_f16.cu", "convdet_bwd.cu", "convdet_wgrad_tc.cu"]
+LIB = os.path.join(PKG, "libsqdet_b200_trace.so" if os.environ.get("SQD_BUILD_TRACE") else "libsqdet_b200.so")
+SOURCES = ["api.cu", "io_kernels.cu", "decode.cu", "topk_nms.cu", "matcher.cu", "loss.cu", "convdet_simt.cu", "convdet_f16.cu", "convdet_fused.cu", "convdet_bwd.cu", "convdet_wgrad_tc.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # SQD_BUILD_TRACE=1: profiling build with the clock64 pipeline-trace stamps of the tcgen05 kernels compiled in
 # (tools/tc_trace.py); the shipped library has none of it.
@@ -36,7 +36,7 @@ def _stale(target, deps):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build_trace" if TRACE else "build")
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(HERE, "common.cuh"), os.path.join(HERE, "tc_ptx.cuh"), os.path.join(ROOT, "include", "sqdet_b200.h"), __file__]
     objs, procs = [], []

@@ -103,6 +103,7 @@ __device__ __forceinline__ void split_f16(float xs, __half &h1, __half &h2) {
 __global__ void __launch_bounds__(256) absmax_kernel(const float4 *__restrict__ in, size_t n4, unsigned *__restrict__ amax_bits) {
     const float4 *src = in + (size_t)blockIdx.y * n4;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    sqd_pdl_trigger();   // a GEMM launched behind this kernel as a programmatic dependent may set up while it runs
     float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + 3 * stride < n4; i += 4 * stride) {  // four independent 16-byte loads in flight per thread

@@ -563,3 +563,51 @@ def test_no_library_fallback_and_stale_weight_guards(ops):
     assert torch.allclose(got.cpu().double(), ref, rtol=1e-4, atol=1e-5)
     with pytest.raises(SqdError):
         ops.convdet_forward(torch.randn(1, 64, 4, 4, device="cuda"), torch.randn(765, 64, 3, 3, device="cuda"), torch.zeros(765, device="cuda"))
+
+
+@pytest.mark.parametrize("name,batch", [("tiny_160x96", 1), ("tiny_160x96", 5), ("kitti_1248x384", 1), ("kitti_1248x384", 7)])
+def test_one_kernel_route_vs_reference_golden_and_staged(ops, name, batch):
+    """csrc/convdet_fused.cu (opt-in, SQD_HEAD_ONE_KERNEL=1): max pass + ONE GEMM kernel that converts the fp32 NCHW features
+    itself (pixel-flat tiles, all nine taps through descriptor row offsets of one operand patch, relay-warp proxy fence).
+    Same scales and the same two-term split as the staged route, different MMA order: pred within fp32 rounding of the
+    staged route and of the oracle's conv, bit-deterministic, and the same kept detections end to end."""
+    shp = {x.name: x for x in (synth.TINY, synth.KITTI)}[name]
+    feat, (w, b) = synth.features(shp, batch, 91), synth.convdet_params(shp, 92)
+    fd, wd, bd = dev(feat), dev(w), dev(b)
+    staged = ops.convdet_forward(fd, wd, bd, check_status=True)
+    with _lib.option("SQD_HEAD_ONE_KERNEL", 1):
+        one = ops.convdet_forward(fd, wd, bd, check_status=True)
+        again = ops.convdet_forward(fd, wd, bd, check_status=True)
+    assert torch.equal(one, again)
+    assert not torch.equal(one, torch.zeros_like(one))
+    ref = orc.convdet_forward(feat, w, b, shp.num_anchors, shp.num_fields).reshape(one.shape)
+    np.testing.assert_allclose(one.cpu().numpy(), ref, rtol=1e-4, atol=2e-5)
+    assert float((one - staged).abs().max()) < 1e-5
+    a32 = dev(synth.anchor_table(shp).astype(np.float32))
+    args = (a32, shp.anchors_per_grid, shp.num_classes, shp.input_hw, shp.top_k, shp.nms_thresh, shp.score_thresh)
+    det_s = ops.head_detect(fd, wd, bd, *args)
+    with _lib.option("SQD_HEAD_ONE_KERNEL", 1):
+        det_o = ops.head_detect(fd, wd, bd, *args)
+    det_o.check_status()
+    expect = orc.detect_filtered(ref.reshape(batch, shp.num_anchors, shp.num_fields), synth.anchor_table(shp), shp.input_hw,
+                                 shp.num_classes, shp.top_k, shp.nms_thresh, shp.score_thresh)
+    for row, exp in zip(det_o.to_list(), expect):
+        got = row["anchor_idx"].numpy() if row is not None else np.zeros((0,), np.int64)
+        assert np.array_equal(got, exp["anchor_idx"])
+    assert torch.equal(det_o.count, det_s.count) and torch.equal(det_o.anchor, det_s.anchor)
+
+
+def test_one_kernel_route_full_batch_golden(ops):
+    """The one-kernel route on the reference-generated KITTI B = 20 fixture (BASELINE configs[1]): kept indices exact."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "head_e2e_kitti_1248x384_b20.npz"))
+    shp, batch, seed = synth.KITTI, int(g["batch"]), int(g["seed"])
+    feat, (w, b) = synth.features(shp, batch, seed), synth.convdet_params(shp, seed + 1)
+    a32 = dev(synth.anchor_table(shp).astype(np.float32))
+    with _lib.option("SQD_HEAD_ONE_KERNEL", 1):
+        det = ops.head_detect(dev(feat), dev(w), dev(b), a32, shp.anchors_per_grid, shp.num_classes, shp.input_hw, shp.top_k,
+                              shp.nms_thresh, shp.score_thresh)
+    rows = det.to_list()
+    kept = split_ragged(g["kept_count"], g["kept_anchor"])
+    for i in range(batch):
+        got = rows[i]["anchor_idx"].numpy() if rows[i] is not None else np.zeros((0,), np.int64)
+        assert np.array_equal(got, kept[i]), i
