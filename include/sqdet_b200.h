@@ -190,6 +190,12 @@ SQD_API int sqd_head_detect_profile(const float *d_feat, int layout, const void 
 #define SQD_HOST_NO_STAGING_FENCE 1
 SQD_API size_t sqd_head_detect_host_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int top_k, int layout,
                                                     int algo, int chunk_images);
+/* Layout of ONE host block mirroring the device-side result block of sqd_head_detect_host: offsets5 = byte offsets of
+ * (count, anchor, class, score, box), *total = its size.  Passing views of such a (pinned) block as the five host output
+ * pointers lets the call return its detections with a single device-to-host copy.  Host-side helper, no reference
+ * counterpart (the reference copies every kept tensor separately: src/engine/detector.py:37). */
+SQD_API int sqd_head_detect_host_result_layout(int batch, int top_k, size_t *offsets5, size_t *total);
+
 SQD_API int sqd_head_detect_host(const float *h_feat, int layout, const void *d_packed, const float *d_weight,
                                  const float *d_bias, const float *d_anchors, int batch, int cin, int gh, int gw,
                                  int anchors_per_grid, int num_classes, int input_h, int input_w, int top_k,

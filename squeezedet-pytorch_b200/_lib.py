@@ -48,6 +48,7 @@ SIGNATURES = {
     "sqd_head_detect_profile": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _d,
                                      _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, C.POINTER(C.c_float)]),
     "sqd_head_detect_host_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "sqd_head_detect_host_result_layout": (_i, [_i, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "sqd_head_detect_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _d,
                                   _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _i]),
     "sqd_match_anchors": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),

@@ -348,12 +348,53 @@ HostWs host_ws_layout(int batch, int cin, int gh, int gw, int cout, int top_k, i
     return w;
 }
 int clamp_chunk(int batch, int chunk) { return chunk <= 0 || chunk > batch ? batch : chunk; }
+
+// Cross-stream ordering events of sqd_head_detect_host: a few per (host thread, device), created once and re-recorded.
+// Safe: cudaStreamWaitEvent binds to the record that is current when it is CALLED, a later re-record does not move it.
+struct EventRing {
+    static constexpr int kN = 4;
+    cudaEvent_t ev[kN] = {nullptr, nullptr, nullptr, nullptr};
+    int device = -1, next = 0;
+};
+int host_event(cudaEvent_t *out) {
+    static thread_local EventRing rings[16];
+    int dev = 0;
+    SQD_CUDA(cudaGetDevice(&dev));
+    EventRing &r = rings[dev & 15];
+    if (r.device != dev) {           // first use on this device by this thread (or a colliding device id: rebuild)
+        for (int i = 0; i < EventRing::kN; ++i) {
+            if (r.ev[i]) cudaEventDestroy(r.ev[i]);
+            SQD_CUDA(cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming));
+        }
+        r.device = dev;
+        r.next = 0;
+    }
+    *out = r.ev[r.next];
+    r.next = (r.next + 1) % EventRing::kN;
+    return SQD_OK;
+}
 }  // namespace
 
 extern "C" size_t sqd_head_detect_host_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int top_k, int layout,
                                                        int algo, int chunk_images) {
     if (batch <= 0 || cin <= 0 || gh <= 0 || gw <= 0 || cout <= 0 || top_k <= 0) return 256;
     return host_ws_layout(batch, cin, gh, gw, cout, top_k, layout, algo, clamp_chunk(batch, chunk_images)).total;
+}
+
+// Byte offsets of the five result arrays (count, anchor, class, score, box) inside ONE host block of *total bytes that
+// mirrors the device-side result block: a caller that passes views of such a block to sqd_head_detect_host gets its
+// detections with a single device-to-host copy instead of five.
+extern "C" int sqd_head_detect_host_result_layout(int batch, int top_k, size_t *offsets5, size_t *total) {
+    SQD_REQUIRE(offsets5 && total, SQD_E_NULL, "sqd_head_detect_host_result_layout: NULL pointer");
+    SQD_REQUIRE(batch >= 1 && top_k >= 1, SQD_E_SHAPE, "sqd_head_detect_host_result_layout: bad shape");
+    const HostWs w = host_ws_layout(batch, 64, 1, 1, 6, top_k, SQD_LAYOUT_NCHW, SQD_CONV_TCGEN05_F16X3, 1);
+    offsets5[0] = 0;
+    offsets5[1] = w.anchor_off - w.count_off;
+    offsets5[2] = w.cls_off - w.count_off;
+    offsets5[3] = w.score_off - w.count_off;
+    offsets5[4] = w.box_off - w.count_off;
+    *total = w.fused_off - w.count_off;
+    return SQD_OK;
 }
 
 extern "C" int sqd_head_detect_host(const float *h_feat, int layout, const void *d_packed, const float *d_weight,
@@ -392,10 +433,9 @@ extern "C" int sqd_head_detect_host(const float *h_feat, int layout, const void 
     cudaEvent_t ev = nullptr;
     if (cst != st && !(flags & SQD_HOST_NO_STAGING_FENCE)) {
         // the staging buffer may still be read by kernels of the previous call on `stream`
-        SQD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        if (int rc_ev = host_event(&ev)) return rc_ev;
         SQD_CUDA(cudaEventRecord(ev, st));
         SQD_CUDA(cudaStreamWaitEvent(cst, ev, 0));
-        SQD_CUDA(cudaEventDestroy(ev));
     }
     int rc = SQD_OK;
     for (int c = 0; c < nchunks && rc == SQD_OK; ++c) {
@@ -403,10 +443,9 @@ extern "C" int sqd_head_detect_host(const float *h_feat, int layout, const void 
         SQD_CUDA(cudaMemcpyAsync(d_feat + b0 * img_elems, h_feat + b0 * img_elems, nb * img_elems * sizeof(float),
                                  cudaMemcpyHostToDevice, cst));
         if (cst != st) {
-            SQD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            if (int rc_ev = host_event(&ev)) return rc_ev;
             SQD_CUDA(cudaEventRecord(ev, cst));
             SQD_CUDA(cudaStreamWaitEvent(st, ev, 0));
-            SQD_CUDA(cudaEventDestroy(ev));  // released by the driver once the recorded work has completed
         }
         rc = sqd_head_detect_fused(d_feat + b0 * img_elems, layout, d_packed, d_weight, d_bias, d_anchors, nb, cin, gh, gw,
                                    anchors_per_grid, num_classes, input_h, input_w, top_k, nms_thresh, score_thresh,
@@ -415,6 +454,18 @@ extern "C" int sqd_head_detect_host(const float *h_feat, int layout, const void 
                                    workspace_bytes - w.fused_off, algo, stream);
     }
     if (rc) return rc;
+    {   // one D2H when the caller's five buffers are views of ONE block laid out like the device block
+        // (sqd_head_detect_host_result_layout): the usual case for the Python wrapper's HostDetections
+        const char *h0 = reinterpret_cast<const char *>(h_count);
+        const bool mirrored = reinterpret_cast<const char *>(h_out_anchor) - h0 == (ptrdiff_t)(w.anchor_off - w.count_off) &&
+                              reinterpret_cast<const char *>(h_out_class) - h0 == (ptrdiff_t)(w.cls_off - w.count_off) &&
+                              reinterpret_cast<const char *>(h_out_score) - h0 == (ptrdiff_t)(w.score_off - w.count_off) &&
+                              reinterpret_cast<const char *>(h_out_box) - h0 == (ptrdiff_t)(w.box_off - w.count_off);
+        if (mirrored) {
+            SQD_CUDA(cudaMemcpyAsync(h_count, d_count, w.fused_off - w.count_off, cudaMemcpyDeviceToHost, st));
+            return SQD_OK;
+        }
+    }
     SQD_CUDA(cudaMemcpyAsync(h_count, d_count, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SQD_CUDA(cudaMemcpyAsync(h_out_anchor, d_anchor, (size_t)batch * top_k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SQD_CUDA(cudaMemcpyAsync(h_out_class, d_cls, (size_t)batch * top_k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -22,6 +22,8 @@
 // The running threshold starts at the score threshold (exact, see score_floor_key), so on real inputs only a few
 // hundred anchors per image ever enter the candidate buffer and mid-scan compactions do not happen.
 // Algorithmic HBM bytes per image: A*(C+5)*4 (fused) or A*4 (+ a few KB of gathers) for the dense form.
+#include <stdlib.h>
+
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -39,6 +41,15 @@ static_assert(2 * kThreads >= SQD_MAX_TOPK, "the emit phase handles two candidat
 static_assert(kCap / 2 >= SQD_MAX_TOPK, "rank_sort uses the upper half of the buffer as its destination");
 
 typedef sqd_u64 u64;
+
+// Profiling builds (SQD_BUILD_TRACE=1): clock64 stamps of the tail kernel's phases, image SQD_TAIL_TRACE_IMG, 16 slots
+#ifdef SQD_ENABLE_TRACE
+__device__ long long *g_tail_trace = nullptr;
+__device__ int g_tail_trace_img = 0;
+#define TAIL_STAMP(slot) do { if (g_tail_trace && (int)blockIdx.x == g_tail_trace_img && threadIdx.x == 0) g_tail_trace[slot] = clock64(); } while (0)
+#else
+#define TAIL_STAMP(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ unsigned order_bits(float s) { return sqd_order_bits(s); }
 __device__ __forceinline__ u64 make_key(float score, int anchor, int cls) { return sqd_make_key(score, anchor, cls); }
@@ -254,14 +265,13 @@ __device__ void nms_and_emit(const Src &src, Shared &sh, unsigned char *dyn, int
         sarea[i] = fmul(fsub(b.z, b.x), fsub(b.w, b.y));  // torchvision: (x2-x1)*(y2-y1), no +1
     }
     __syncthreads();
+    TAIL_STAMP(4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = kThreads >> 5;
-    for (int item = warp; item < m * wpr; item += nwarp) {
-        const int i = item / wpr, w = item - i * wpr;
-        if ((w << 5) >= i) {  // no j < i in this word (warp-uniform)
-            if (lane == 0) col[item] = 0u;
-            continue;
-        }
+    // One (candidate i, 32-candidate word w) item per warp step, lanes = the j of the word.  Four items are evaluated
+    // together (independent dependency chains: the IEEE division is ~40 dependent instructions), the division only runs
+    // for lanes whose boxes intersect at all (inter > 0: otherwise the quotient is 0 or NaN and cannot exceed a threshold >= 0).
+    auto suppress_bits = [&](int i, int w) -> unsigned {
         const int j = (w << 5) + lane;
         bool sup = false;
         if (j < i && key_class(sh.buf[j]) == key_class(sh.buf[i])) {
@@ -269,13 +279,30 @@ __device__ void nms_and_emit(const Src &src, Shared &sh, unsigned char *dyn, int
             const float iw = fmaxf(0.f, fsub(fminf(a.z, b.z), fmaxf(a.x, b.x)));
             const float ih = fmaxf(0.f, fsub(fminf(a.w, b.w), fmaxf(a.y, b.y)));
             const float inter = fmul(iw, ih);
-            const float iou = fdiv(inter, fsub(fadd(sarea[i], sarea[j]), inter));
-            sup = iou > nms_thr_f;  // false for NaN (0/0 of zero-area boxes), like the reference
+            if (inter > 0.f || nms_thr_f < 0.f) {   // (a negative threshold is met by iou == 0 too)
+                const float iou = fdiv(inter, fsub(fadd(sarea[i], sarea[j]), inter));
+                sup = iou > nms_thr_f;  // false for NaN, like the reference
+            }
         }
-        const unsigned bits = __ballot_sync(0xffffffffu, sup);
-        if (lane == 0) col[item] = bits;
+        return __ballot_sync(0xffffffffu, sup);
+    };
+    const int items = m * wpr;
+    for (int base = warp * 4; base < items; base += nwarp * 4) {
+        unsigned bits[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int item = base + u;
+            bits[u] = 0u;
+            if (item < items) {
+                const int i = wpr == 2 ? item >> 1 : item / wpr, w = item - i * wpr;
+                if ((w << 5) < i) bits[u] = suppress_bits(i, w);   // else: no j < i in this word (warp-uniform)
+            }
+        }
+        const unsigned mine = lane == 0 ? bits[0] : lane == 1 ? bits[1] : lane == 2 ? bits[2] : bits[3];
+        if (lane < 4 && base + lane < items) col[base + lane] = mine;
     }
     __syncthreads();
+    TAIL_STAMP(5);
 
     if (warp == 0) {
         for (int t = 0; (t << 5) < m; ++t) {
@@ -294,6 +321,7 @@ __device__ void nms_and_emit(const Src &src, Shared &sh, unsigned char *dyn, int
         }
     }
     __syncthreads();
+    TAIL_STAMP(6);
 
     // emit: class ascending, then descending score (== position) inside a class
     unsigned mine[2];
@@ -327,6 +355,7 @@ __device__ void nms_and_emit(const Src &src, Shared &sh, unsigned char *dyn, int
         o.score[r] = 0.f;
         o.box[r] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    TAIL_STAMP(7);
     (void)num_classes;
 }
 
@@ -545,6 +574,7 @@ __device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, in
             }
         }
     };
+    TAIL_STAMP(10);
     unsigned lo = order_bits(score_thr_f) + 1u, hi = 0xFFFFFFFFu;  // undecided score-bit range (inclusive)
     int above = 0;                                                 // keys with score bits > hi: selected for sure
     const unsigned top = order_bits(1.0f);                         // scores are probabilities: <= 1
@@ -554,11 +584,13 @@ __device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, in
     for (int level = 0; level < 4; ++level) {
         for (int i = threadIdx.x; i < kBins; i += kThreads) hist[i] = 0;
         __syncthreads();
+        if (level == 0) TAIL_STAMP(11);
         for_each_key([&](u64 key) {
             const unsigned sb = (unsigned)(key >> 32);
             if (sb >= lo && sb <= hi) atomicAdd(&hist[min((sb - lo) >> shift, (unsigned)(kBins - 1))], 1);
         });
         __syncthreads();
+        if (level == 0) TAIL_STAMP(12);
         int c[kPerThread], own = 0;
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) {
@@ -591,6 +623,7 @@ __device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, in
             }
         }
         __syncthreads();
+        if (level == 0) TAIL_STAMP(13);
         const int tb = s_tb;
         const unsigned lo_new = lo + ((unsigned)tb << shift);
         const int above_new = above + s_above_add;
@@ -621,7 +654,9 @@ __global__ void __launch_bounds__(kThreads) detect_from_candidates_kernel(SqdCan
     __shared__ Shared sh;
     extern __shared__ __align__(16) unsigned char dyn[];
     const int img = blockIdx.x;
+    TAIL_STAMP(0);
     sqd_pdl_wait();      // candidate lists and pred are complete and visible
+    TAIL_STAMP(1);
     const int n = min(cand.count[img], cand.stride);
     const u64 *keys = cand.keys + (size_t)img * cand.stride;
     FromPred<0> src;
@@ -646,6 +681,7 @@ __global__ void __launch_bounds__(kThreads) detect_from_candidates_kernel(SqdCan
         have = n <= 16 * kThreads ? hist_select_collect<true>(sh, keys, n, k, score_thr_f)
                                   : hist_select_collect<false>(sh, keys, n, k, score_thr_f);
     }
+    TAIL_STAMP(2);
     if (have) {
         rank_sort(sh);  // descending: the first k entries are the top-k
         if (threadIdx.x == 0 && sh.count > k) sh.count = k;
@@ -673,6 +709,13 @@ __global__ void __launch_bounds__(kThreads) detect_from_candidates_kernel(SqdCan
         select_topk(sh, k);
         rank_sort(sh);
     }
+    TAIL_STAMP(3);
+#ifdef SQD_ENABLE_TRACE
+    if (g_tail_trace && (int)blockIdx.x == g_tail_trace_img && threadIdx.x == 0) {
+        g_tail_trace[8] = n;
+        g_tail_trace[9] = sh.count;
+    }
+#endif
     nms_and_emit(src, sh, dyn, k, C, nms_thr_f, score_thr_f, o, img);
 }
 
@@ -807,6 +850,15 @@ int sqd_detect_from_candidates(SqdCand cand, const float *d_pred, const float *d
     const size_t smem = dyn_smem_bytes(top_k);
     int rc = opt_in_smem(detect_from_candidates_kernel, smem);
     if (rc) return rc;
+#ifdef SQD_ENABLE_TRACE
+    {
+        long long *tp = nullptr;
+        if (const char *e = getenv("SQD_TAIL_TRACE")) tp = reinterpret_cast<long long *>(strtoull(e, nullptr, 0));
+        const int ti = getenv("SQD_TAIL_TRACE_IMG") ? atoi(getenv("SQD_TAIL_TRACE_IMG")) : 0;
+        cudaMemcpyToSymbolAsync(g_tail_trace, &tp, sizeof(tp), 0, cudaMemcpyHostToDevice, st);
+        cudaMemcpyToSymbolAsync(g_tail_trace_img, &ti, sizeof(ti), 0, cudaMemcpyHostToDevice, st);
+    }
+#endif
     // always a dependent launch: its predecessor on the stream is the scan (or the GEMM whose epilogue scored)
     cudaError_t e = sqd_launch_dependent(detect_from_candidates_kernel, dim3(batch), dim3(kThreads), smem, st, true, cand, d_pred,
                                          reinterpret_cast<const float4 *>(d_anchors), num_anchors, num_classes,

@@ -281,11 +281,20 @@ class HostDetections:
     """Pinned host buffers for head_detect_host (same fields as Detections)."""
 
     def __init__(self, batch, top_k):
-        self.count = torch.empty((batch,), dtype=torch.int32).pin_memory()
-        self.anchor = torch.empty((batch, top_k), dtype=torch.int32).pin_memory()
-        self.cls = torch.empty((batch, top_k), dtype=torch.int32).pin_memory()
-        self.score = torch.empty((batch, top_k), dtype=torch.float32).pin_memory()
-        self.box = torch.empty((batch, top_k, 4), dtype=torch.float32).pin_memory()
+        # ONE pinned block laid out like the device-side result block, the five fields are views of it: the call then
+        # brings a batch's detections back with a single device-to-host copy (sqd_head_detect_host_result_layout)
+        offs, total = (C.c_size_t * 5)(), C.c_size_t(0)
+        check(load().sqd_head_detect_host_result_layout(int(batch), int(top_k), offs, C.byref(total)),
+              "sqd_head_detect_host_result_layout")
+        self.block = torch.empty((int(total.value),), dtype=torch.uint8).pin_memory()
+
+        def view(i, n, dtype, shape):
+            return self.block[offs[i]:offs[i] + n * 4].view(dtype).view(shape)
+        self.count = view(0, batch, torch.int32, (batch,))
+        self.anchor = view(1, batch * top_k, torch.int32, (batch, top_k))
+        self.cls = view(2, batch * top_k, torch.int32, (batch, top_k))
+        self.score = view(3, batch * top_k, torch.float32, (batch, top_k))
+        self.box = view(4, batch * top_k * 4, torch.float32, (batch, top_k, 4))
         self.ready = None     # CUDA event of the call that last wrote these buffers (head_detect_host(sync=False))
 
     def wait(self):
