@@ -593,6 +593,29 @@ def main_ours(args):
     barrier()
     t_e2e = max_over_ranks(t_e2e * 1e3) * 1e-3
     e2e_value = world * B * Ke / t_e2e
+    # the floor under e2e: the SAME pinned buffers streamed to the device by bare cudaMemcpyAsync calls, all ranks at once,
+    # no kernels, no result copies -- what the host / PCIe side of this box can deliver to N GPUs concurrently
+    copy_floor = None
+    if not args.skip_e2e:
+        dst = torch.empty_like(host_feats[0], device=dev)
+        cs = torch.cuda.Stream(device=dev)
+        for i in range(2):
+            with torch.cuda.stream(cs):
+                dst.copy_(host_feats[i % 2], non_blocking=True)
+        cs.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(cs):
+            for i in range(Ke):
+                dst.copy_(host_feats[i % 2], non_blocking=True)
+        cs.synchronize()
+        t_copy = time.perf_counter() - t0
+        barrier()
+        t_copy = max_over_ranks(t_copy * 1e3) * 1e-3
+        copy_floor = {"images_per_s": world * B * Ke / t_copy, "gb_per_s": world * h2d * Ke / t_copy / 1e9,
+                      "note": "bare pinned H2D copies of the step's features on all %d rank(s) at once (no kernels): the ceiling "
+                              "of any host-buffer path on this box" % world}
+        del dst
     if sampler.ok:
         sampler.stop()
 
@@ -647,7 +670,8 @@ def main_ours(args):
                                      "scaled operands on tcgen05, fp32 accumulate), fp32-grade: rms 9e-7 vs float64"},
             "per_gpu": value / world,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "note": "sqd_head_detect_host: pinned host features -> H2D in groups of %d images overlapped with the kernels "
+                    "steps": Ke, "bare_h2d_copy_floor": copy_floor,
+                    "frac_of_copy_floor": (e2e_value / copy_floor["images_per_s"]) if copy_floor else None, "note": "sqd_head_detect_host: pinned host features -> H2D in groups of %d images overlapped with the kernels "
                             "-> D2H of the detections; serving loop with two slots: step i+1 is issued before step i's "
                             "result is waited for and read on the host, every step's result is read" % args.e2e_chunk},
             "gpu_launches": 4 * K,

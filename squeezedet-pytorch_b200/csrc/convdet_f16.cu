@@ -937,8 +937,11 @@ __device__ __forceinline__ bool pair_wait_warp(uint64_t *bar, uint32_t parity, v
 // that follows never scans pred.
 // PK: the last 64-channel block is only partly filled (p.ksteps_last valid 16-channel K steps; the rest is zero padding,
 // e.g. the 72 -> 128 padded gradient channels of the dgrad GEMM): its all-zero K steps are not issued.
+constexpr int kScorerWarp0 = kThreads2 / 32;                  // CS > 0: four scorer warps follow the six pipeline warps
+__host__ __device__ constexpr int pair_threads(int cs) { return kThreads2 + (cs > 0 ? 128 : 0); }
+
 template <int NPAD, int CS, bool PK = false, int HR = NPAD / 2, bool K3 = (NPAD >= 96)>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair_threads(CS), 1)
 convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                         const __grid_constant__ CUtensorMap map_b, const PairParams p) {
     // This CTA's half of one tap is [w1: HR rows | w2: HR rows] for its HR output channels.  MMA1 = A1 x all 2*HR rows
@@ -973,6 +976,10 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
     volatile int *abort_flag = reinterpret_cast<volatile int *>(tmem_slot + 1);
     float *s_bias = reinterpret_cast<float *>(tmem_slot + 2);  // NPAD floats
+    // CS > 0: accumulate warp q hands every finished tile to scorer warp q through a two-entry ring
+    uint64_t *sc_full = reinterpret_cast<uint64_t *>(ctrl + 768);   // [4][2] tile record written, pred rows stored
+    uint64_t *sc_empty = sc_full + 8;                               // [4][2] record consumed
+    int *sc_rec = reinterpret_cast<int *>(sc_empty + 8);            // [4][2][4] {image (-1: no more tiles), tile x, tile y, -}
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x;
@@ -1011,6 +1018,11 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
             mbar_init(tfull + b, 1);
             mbar_init(tempty + b, 8);  // 4 accumulate warps x 2 CTAs
         }
+        if (CS > 0)
+            for (int b = 0; b < 8; ++b) {
+                mbar_init(sc_full + b, 1);
+                mbar_init(sc_empty + b, 1);
+            }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -1019,7 +1031,7 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
         tma_prefetch_desc(&map_a2);
         tma_prefetch_desc(&map_b);
     }
-    for (int i = threadIdx.x; i < NPAD; i += kThreads2) s_bias[i] = (i < p.cout && p.bias) ? __ldg(p.bias + i) : 0.f;
+    for (int i = threadIdx.x; i < NPAD; i += pair_threads(CS)) s_bias[i] = (i < p.cout && p.bias) ? __ldg(p.bias + i) : 0.f;
     SQD_TRACE_PH(1);
     if (warp == kWarpMma2) tmem_alloc_2cta(tmem_slot, kTmemCols);
     tc_fence_before();
@@ -1139,7 +1151,7 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
         // All MMAs of this pair are issued: let the kernel behind us (the scan) be scheduled while the last chunks drain
         // and the epilogue runs.  (Triggering at kernel start parks its CTAs next to ours for the whole GEMM: +5 %.)
         sqd_pdl_trigger();
-    } else {
+    } else if (warp < kScorerWarp0) {
         // ===== accumulate + epilogue warps (both CTAs, each on its own 128 TMEM lanes) =====
         const int q = warp & 3;
         const int row = q * 32 + lane;
@@ -1148,95 +1160,25 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
         float acc[NPAD];
         int seg_r0 = 0, chunk = 0, in_chunk = 0;
         PairIter it;
-        // ---- fused score epilogue, software pipelined (CS > 0 and a candidate sink only) ---------------------------
-        // Scoring the 9 anchors of a cell costs ~0.5 us per anchor of dependent exp/div latency; done in one go
-        // after a tile it keeps these warps away from the TMEM accumulators for longer than the two buffers cover
-        // and stalls the tensor pipe (measured +13 %).  Instead the finished tile becomes "pending" and ONE anchor per
-        // thread is scored after each chunk drain, in the time the warp would otherwise wait for the next chunk:
-        // the four scoring logits are read back from the pred row this thread just stored (L2 hit), the warp
-        // appends its candidates with one atomic whose result is only consumed at the next step.
-        constexpr int kNF = (CS > 0 ? CS : 1) + 5;
+        // ---- fused score epilogue (CS > 0 and a candidate sink only): every finished tile is handed to scorer warp q, which
+        // scores the cells this warp just stored while this warp goes on draining TMEM (see the scorer branch below)
         const bool emit = CS > 0 && p.cand.count != nullptr;
-        const sqd_u64 floor_key = sqd_score_floor_key(p.score_thr);
-        const float *pend_row = nullptr;   // this thread's cell of the pending tile (nullptr: outside the image)
-        int pend_k = 1 << 30, pend_img = 0, pend_a0 = 0;      // pend_k >= anchors_per_cell: nothing pending (warp-uniform)
-        sqd_u64 prev_key = 0ull;
-        int prev_off = -1, prev_base = 0, prev_img = 0;
-        bool prev_any = false;                                  // warp-uniform: a step's append is waiting to be retired
-        auto score_step = [&]() {
-            if (prev_any) {   // retire the previous step: its atomic has had a whole chunk period to return
-                const int base = __shfl_sync(0xffffffffu, prev_base, 0);
-                if (prev_off >= 0 && base + prev_off < p.cand.stride)
-                    p.cand.keys[(size_t)prev_img * p.cand.stride + base + prev_off] = prev_key;
-                prev_any = false;
+        int n_handed = 0;
+        auto hand_over = [&](int img, int tx, int ty) {
+            const int slot = n_handed & 1;
+            const uint32_t ph = (uint32_t)(n_handed >> 1) & 1u;
+            if (!mbar_wait_warp(sc_empty + q * 2 + slot, ph ^ 1u, abort_flag)) {
+                if (lane == 0) atomicCAS(p.status, 0, 10);
+                return;
             }
-            if (pend_k >= p.anchors_per_cell) return;
-            float f[(CS > 0 ? CS : 1) + 1];
-            if (pend_row != nullptr) {
-                const float *src = pend_row + pend_k * kNF;
-                if (CS == 3) {
-                    const float4 v = __ldcg(reinterpret_cast<const float4 *>(src));
-                    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j <= CS; ++j) f[j] = __ldcg(src + j);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j <= CS; ++j) f[j] = 0.f;
+            __threadfence();       // this lane's pred stores are visible before the record is
+            __syncwarp();
+            if (lane == 0) {
+                int *rec = sc_rec + (q * 2 + slot) * 4;
+                rec[0] = img; rec[1] = tx; rec[2] = ty;
+                mbar_arrive(sc_full + q * 2 + slot);
             }
-            float scv = 0.f;
-            int cl = 0;
-            const bool cand_ok = sqd_score_candidate<(CS > 0 ? CS : 1)>(f, CS, p.score_thr, scv, cl);
-            const sqd_u64 key = sqd_make_key(scv, pend_a0 + pend_k, cl);
-            const bool pass = pend_row != nullptr && cand_ok && key > floor_key;
-            const unsigned b = __ballot_sync(0xffffffffu, pass);
-            if (b) {
-                if (lane == 0) prev_base = atomicAdd(p.cand.count + pend_img, __popc(b));
-                prev_off = pass ? __popc(b & ((1u << lane) - 1u)) : -1;
-                prev_key = key;
-                prev_img = pend_img;
-                prev_any = true;
-            }
-            ++pend_k;
-        };
-        // Everything still pending at once (the CTA's last tile, or a segment too short to hide the previous tile):
-        // independent anchors give the scheduler ILP and the warp appends with ONE atomic.
-        auto flush_pending = [&]() {
-            constexpr int KMAX = NPAD / kNF;
-            if (prev_any) {
-                const int base = __shfl_sync(0xffffffffu, prev_base, 0);
-                if (prev_off >= 0 && base + prev_off < p.cand.stride)
-                    p.cand.keys[(size_t)prev_img * p.cand.stride + base + prev_off] = prev_key;
-                prev_any = false;
-            }
-            if (pend_k >= p.anchors_per_cell) return;
-            bool pass[KMAX];
-            sqd_u64 key[KMAX];
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                const bool want = k >= pend_k && k < p.anchors_per_cell && pend_row != nullptr;
-                float f[(CS > 0 ? CS : 1) + 1];
-#pragma unroll
-                for (int j = 0; j <= CS; ++j) f[j] = 0.f;
-                if (want) {
-                    const float *src = pend_row + k * kNF;
-                    if (CS == 3) {
-                        const float4 v = __ldcg(reinterpret_cast<const float4 *>(src));
-                        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j <= CS; ++j) f[j] = __ldcg(src + j);
-                    }
-                }
-                float scv = 0.f;
-                int cl = 0;
-                const bool cand_ok = sqd_score_candidate<(CS > 0 ? CS : 1)>(f, CS, p.score_thr, scv, cl);
-                key[k] = sqd_make_key(scv, pend_a0 + k, cl);
-                pass[k] = want && cand_ok && key[k] > floor_key;
-            }
-            sqd_cand_append_warp<KMAX>(p.cand, pend_img, pass, key);
-            pend_k = 1 << 30;
+            ++n_handed;
         };
         for (int i = 0; i < n_units; ++i) {
             if (i == 0 || i == sc.main_len) it.seek(sc.unit(i), tile_offset, p); else it.next(p);
@@ -1304,10 +1246,6 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                 else mbar_arrive_cluster(tempty + buf, 0);
             }
             if (warp == kWarpAcc2) SQD_TRACE2(12, i);
-            if (emit) {
-                __syncwarp();
-                score_step();   // one anchor of the pending tile per chunk period
-            }
 
             const bool seg_end = (i == n_units - 1) || (r == p.upt - 1) || (i == sc.main_len - 1);
             if (!seg_end) continue;
@@ -1396,20 +1334,61 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                         if (n < p.cout) out[n] = acc[n];
                 }
             }
-            if (emit) {
-                __syncwarp();
-                flush_pending();   // a previous tile not fully scored yet (short segments)
-                if (it.img < p.batch) {   // ghost tiles have nothing to score (warp-uniform)
-                    pend_row = inb ? p.pred + (((size_t)it.img * p.gh + y) * p.gw + x) * p.out_stride : nullptr;
-                    pend_img = it.img;
-                    pend_a0 = (y * p.gw + x) * p.anchors_per_cell;
-                    pend_k = 0;
-                }
-            }
+            if (emit && it.img < p.batch) hand_over(it.img, it.tx, it.ty);   // ghost tiles have nothing to score (warp-uniform)
         }
-        if (emit) {   // the CTA's last tile: nothing left to hide behind
-            __syncwarp();
-            flush_pending();
+        if (emit) hand_over(-1, 0, 0);   // no more tiles: the scorer warp leaves
+    } else if (CS > 0 && warp >= kScorerWarp0) {
+        // ===== scorer warps (CS > 0): class softmax x confidence sigmoid, first-max argmax (the same sqd_score_candidate every
+        // filter kernel uses) on the fp32 logits of a finished tile, read back from the pred rows accumulate warp q stored
+        // (L2 hits); anchors above the score threshold go to the image's candidate list with ONE atomic per warp and tile.
+        // These warps are off the TMEM drain path: a tile period is ~58 k cycles, scoring its 9 x 32 anchors takes a few k.
+        constexpr int kNF = CS + 5, KMAX = NPAD / kNF;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const sqd_u64 floor_key = sqd_score_floor_key(p.score_thr);
+        if (p.cand.count != nullptr) {
+            for (int n = 0;; ++n) {
+                const int slot = n & 1;
+                const uint32_t ph = (uint32_t)(n >> 1) & 1u;
+                if (!mbar_wait_warp(sc_full + q * 2 + slot, ph, abort_flag)) {
+                    if (lane == 0) atomicCAS(p.status, 0, 11);
+                    break;
+                }
+                const int *rec = sc_rec + (q * 2 + slot) * 4;
+                const int img = rec[0], tx = rec[1], ty = rec[2];
+                if (img < 0) break;
+                const int x = tx * kTileX + row % kTileX, y = ty * kTileY + row / kTileX;
+                const bool inb = y < p.gh && x < p.gw;
+                const float *cell = p.pred + (((size_t)img * p.gh + y) * p.gw + x) * p.out_stride;
+                const int a0 = (y * p.gw + x) * p.anchors_per_cell;
+                bool pass[KMAX];
+                sqd_u64 key[KMAX];
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+                    const bool want = inb && k < p.anchors_per_cell;
+                    float f[CS + 1];
+#pragma unroll
+                    for (int j = 0; j <= CS; ++j) f[j] = 0.f;
+                    if (want) {
+                        const float *src = cell + k * kNF;
+                        if (CS == 3) {
+                            const float4 v = __ldcg(reinterpret_cast<const float4 *>(src));
+                            f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j <= CS; ++j) f[j] = __ldcg(src + j);
+                        }
+                    }
+                    float scv = 0.f;
+                    int cl = 0;
+                    const bool cand_ok = sqd_score_candidate<CS>(f, CS, p.score_thr, scv, cl);
+                    key[k] = sqd_make_key(scv, a0 + k, cl);
+                    pass[k] = want && cand_ok && key[k] > floor_key;
+                }
+                sqd_cand_append_warp<KMAX>(p.cand, img, pass, key);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sc_empty + q * 2 + slot);
+            }
         }
     }
     SQD_TRACE_PH(5);     // the producer warp is through (thread 0 is its lane 0)
@@ -1549,7 +1528,7 @@ int launch_pair(const CUtensorMap *maps, const PairParams &p, int grid, cudaStre
     SQD_REQUIRE(smem <= kSmemLimit, SQD_E_SHAPE, "convdet (tcgen05): shared memory budget exceeded (%zu bytes)", smem);
     SQD_CUDA(cudaFuncSetAttribute(convdet_f16_pair_kernel<NPAD, CS, PK, HR, K3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // dependent launch when the pre-pass kernel directly precedes it on the stream (p.pdl)
-    cudaError_t e = sqd_launch_dependent(convdet_f16_pair_kernel<NPAD, CS, PK, HR, K3>, dim3(grid), dim3(kThreads2), smem, st, p.pdl != 0,
+    cudaError_t e = sqd_launch_dependent(convdet_f16_pair_kernel<NPAD, CS, PK, HR, K3>, dim3(grid), dim3(pair_threads(CS)), smem, st, p.pdl != 0,
                                          maps[0], maps[1], maps[2], p);
     if (e != cudaSuccess) {
         sqd_set_error("launch of convdet_f16_pair_kernel failed: %s", cudaGetErrorString(e));

@@ -66,11 +66,13 @@ class GradBucket:
     the backbone's backward still runs; `allreduce_sum` / `allreduce_mean` then reduce the rest and wait for both.  The
     result is the same as one all-reduce of the whole buffer.
 
-    Two trailing slots ride along with the last segment (no extra collective, no host sync): `loss_slot` (this rank's
-    SUM of per-image losses) and `count_slot` (this rank's image count).  After the all-reduce they hold the global
-    loss sum and the global batch size, and `allreduce_sum(normalize=True)` divides the gradients by that count on the
-    device -- the reference's whole-batch `loss.mean()` (trainer.py:43) for ANY split of the batch, uneven or with
-    empty shards.  Every rank issues the same sequence of collectives whether or not its hooks fired."""
+    Two leading slots ride along with the FIRST segment (no extra collective, no host sync): `loss_slot` (this rank's
+    SUM of per-image losses -- known before backward starts) and `count_slot` (this rank's image count).  After the
+    all-reduce they hold the global loss sum and the global batch size, and `allreduce_sum(normalize=True)` divides the
+    gradients by that count on the device -- the reference's whole-batch `loss.mean()` (trainer.py:43) for ANY split
+    of the batch, uneven or with empty shards.  Travelling with the early segment they are reduced beside the dgrad
+    GEMM; a bucket that holds only the head then has no collective left after backward.  Every rank issues the same
+    sequence of collectives whether or not its hooks fired."""
 
     def __init__(self, params, early=()):
         early = [p for p in early if p.requires_grad]
@@ -79,10 +81,12 @@ class GradBucket:
         self.early_numel = sum(p.numel() for p in early)
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else "cpu"
-        self._buf = torch.zeros(total + 2, dtype=torch.float32, device=dev)
-        self.flat = self._buf[:total]                   # the gradients
-        self.loss_slot = self._buf[total:total + 1]
-        self.count_slot = self._buf[total + 1:total + 2]
+        self._buf = torch.zeros(total + 4, dtype=torch.float32, device=dev)   # [loss, count, 0, 0 | gradients]: 16-byte aligned
+        self.loss_slot = self._buf[0:1]
+        self.count_slot = self._buf[1:2]
+        self.flat = self._buf[4:]                       # the gradients
+        self._early_seg = self._buf[:4 + self.early_numel]      # slots + head gradients: the first all-reduce
+        self._rest_seg = self._buf[4 + self.early_numel:]       # everything else (may be empty)
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
@@ -101,7 +105,7 @@ class GradBucket:
             return                  # not armed (zero() was not called for this step) or already launched
         self._pending -= 1
         if self._pending == 0 and self._distributed():
-            self._early_work = dist.all_reduce(self.flat[:self.early_numel], op=dist.ReduceOp.SUM, async_op=True)
+            self._early_work = dist.all_reduce(self._early_seg, op=dist.ReduceOp.SUM, async_op=True)
 
     def take_early(self, grads):
         """Fast path used by the ConvDet backward (model._ConvDetFn): `grads` = {id(param): (param, grad)} for exactly the
@@ -115,7 +119,7 @@ class GradBucket:
             p.grad.add_(g.view_as(p.grad))
         self._pending = 0
         if self._distributed():
-            self._early_work = dist.all_reduce(self.flat[:self.early_numel], op=dist.ReduceOp.SUM, async_op=True)
+            self._early_work = dist.all_reduce(self._early_seg, op=dist.ReduceOp.SUM, async_op=True)
         return True
 
     def zero(self):
@@ -130,10 +134,13 @@ class GradBucket:
             armed = self._pending > 0 or self._early_work is not None
             if self._n_early and armed:
                 if self._early_work is None:    # the hooks never fired (empty shard: no backward): same collectives anyway
-                    self._early_work = dist.all_reduce(self.flat[:self.early_numel], op=dist.ReduceOp.SUM, async_op=True)
-                work = dist.all_reduce(self._buf[self.early_numel:], op=dist.ReduceOp.SUM, async_op=True)
+                    self._early_work = dist.all_reduce(self._early_seg, op=dist.ReduceOp.SUM, async_op=True)
+                work = None
+                if self._rest_seg.numel() > 0:
+                    work = dist.all_reduce(self._rest_seg, op=dist.ReduceOp.SUM, async_op=True)
                 self._early_work.wait()
-                work.wait()
+                if work is not None:
+                    work.wait()
                 self._early_work = None
             else:
                 dist.all_reduce(self._buf, op=dist.ReduceOp.SUM)
@@ -179,13 +186,13 @@ def train_step(model, batch, bucket, optimizer=None, grad_norm=None):
     Returns (mean loss over the global batch as a 0-d device tensor, this shard's per-image statistics dict or {})."""
     bucket.zero()
     n_local = _batch_images(batch)
+    bucket.count_slot.fill_(float(n_local))
     stats = {}
     if n_local > 0:
         loss, stats = model(batch)
         loss_sum = loss.sum()
+        bucket.loss_slot.copy_(loss_sum.detach().reshape(1))    # before backward: the slots travel with the early segment
         loss_sum.backward()         # the head's all-reduce is launched from inside, as soon as its gradients exist
-        bucket.loss_slot.copy_(loss_sum.detach().reshape(1))
-    bucket.count_slot.fill_(float(n_local))
     bucket.allreduce_sum(normalize=True)
     if grad_norm:
         torch.nn.utils.clip_grad_norm_(bucket.params, grad_norm)
