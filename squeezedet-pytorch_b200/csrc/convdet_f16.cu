@@ -841,6 +841,7 @@ struct PairParams {
     int trace_cta;
     int out_stride;      // floats between consecutive cells of the output (== cout for pred; Cin for the dgrad slabs)
     int pdl;             // host only: launch as a programmatic dependent of the pre-pass kernel
+    int a_bufs;          // AO kernels: operand buffers (whole (tile, block) patches) in front of the weight stages
     int ksteps_last;     // PK kernels: valid 16-channel K steps of the last channel block (1..4)
     // PK kernels (the dgrad GEMM): `slabs` weight matrices share the same input planes; the tile space is slab-major,
     // tiles_per_slab (even) tiles per slab; slab s uses the weights of map_b's 3rd coordinate s (header `slab_stride`
@@ -937,11 +938,35 @@ __device__ __forceinline__ bool pair_wait_warp(uint64_t *bar, uint32_t parity, v
 // that follows never scans pred.
 // PK: the last 64-channel block is only partly filled (p.ksteps_last valid 16-channel K steps; the rest is zero padding,
 // e.g. the 72 -> 128 padded gradient channels of the dgrad GEMM): its all-zero K steps are not issued.
-constexpr int kScorerWarp0 = kThreads2 / 32;                  // CS > 0: four scorer warps follow the six pipeline warps
-__host__ __device__ constexpr int pair_threads(int cs) { return kThreads2 + (cs > 0 ? 128 : 0); }
+// AO ("A once"): the operand patch of a (tile, channel block) is fetched ONCE instead of once per dx tap.  The TMA box is
+// {64 ch, 10 y, 18 x} on a tensor map whose dimension order is (channel, y, x, image), so the patch lands x-major / y-minor:
+// row = px*10 + py.  An 8-row swizzle atom is then one tile COLUMN (8 consecutive y of one x), atoms follow each other at a
+// uniform 10 rows (SBO = 1280 B), and tap (dy, dx) is the same patch read from row dx*10 + dy on -- legal because the tensor
+// core derives the 128-byte swizzle phase from absolute address bits (profiles/r01_umma_row_offset_microtest.txt), at the
+// aligned rate (tools/micro/umma_rate_shift.cu).  M row m of a tile = cell (y0 + m % 8, x0 + m / 8).  46 KB per (tile, block)
+// instead of 3 x 41 KB: the kernel is bound by the shared-memory port (profiles/r02_one_kernel_convdet.txt), and this takes
+// 77 KB of TMA writes per block off it.  A ring of whole-block operand buffers + the usual ring of weight stages.
+constexpr int kAoY = kTileY + 2, kAoX = kTileX + 2;
+constexpr int kAoBoxBytes = kAoX * kAoY * kBlockK * 2;                     // 23040: what one TMA box delivers
+constexpr int kAoPlaneBytes = (kAoBoxBytes + 1023) / 1024 * 1024;          // 23552: swizzle-atom aligned
+constexpr int kAoBufBytes = 2 * kAoPlaneBytes;
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 
-template <int NPAD, int CS, bool PK = false, int HR = NPAD / 2, bool K3 = (NPAD >= 96)>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair_threads(CS), 1)
+constexpr int kScorerWarp0 = kThreads2 / 32;                  // CS > 0: four scorer warps follow the six pipeline warps
+// AO kernels: one more warp, the operand-patch producer (its waits for a free operand buffer must not hold up the
+// weight-stage refills of the other producer warp)
+__host__ __device__ constexpr int pair_threads(int cs, bool ao = false) { return kThreads2 + (cs > 0 ? 128 : 0) + (ao ? 32 : 0); }
+
+template <int NPAD, int CS, bool PK = false, int HR = NPAD / 2, bool K3 = (NPAD >= 96), bool AO = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair_threads(CS, AO), 1)
 convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                         const __grid_constant__ CUtensorMap map_b, const PairParams p) {
     // This CTA's half of one tap is [w1: HR rows | w2: HR rows] for its HR output channels.  MMA1 = A1 x all 2*HR rows
@@ -950,7 +975,9 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
     constexpr int N1H = 2 * HR, N2H = (HR + 7) / 8 * 8;
     static_assert(HR % 4 == 0 && 2 * HR <= NPAD && N2H <= N1H, "pair layout");
     constexpr int kBTapBytes = N1H * kBlockK * 2;           // multiple of 1024: N1H is a multiple of 8
-    constexpr int kStageBytes = kAStageBytes + 3 * kBTapBytes;
+    static_assert(!AO || (CS == 0 && !PK), "the A-once layout is built for the plain forward kernel");
+    constexpr int kBOff = AO ? 0 : kAStageBytes;            // the three weight tiles inside a stage
+    constexpr int kStageBytes = kBOff + 3 * kBTapBytes;
     // K3 (Npad >= 96: the stress shape's 117 channels, the dgrad GEMM's 128): THREE MMAs of N = 2*HR per K step instead --
     // A1 x w1 -> main columns, A1 x w2 and A2 x w1 -> the SAME cross columns (both carry the 2^-11 scale).  Same tensor
     // time in the linear regime of the MMA rate (N >= 96: 128 + 64 = 3 x 64 cycles), but 4*HR accumulator columns instead
@@ -968,6 +995,8 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int S = p.stages;
+    uint8_t *a_ring = smem;                                 // AO: p.a_bufs whole-block operand buffers in front of the stages
+    if (AO) smem += (size_t)p.a_bufs * kAoBufBytes;
     uint8_t *ctrl = smem + (size_t)S * kStageBytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(ctrl);   // [4]
     uint64_t *sfree = full + 4;                            // [4]
@@ -977,6 +1006,8 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
     volatile int *abort_flag = reinterpret_cast<volatile int *>(tmem_slot + 1);
     float *s_bias = reinterpret_cast<float *>(tmem_slot + 2);  // NPAD floats
     // CS > 0: accumulate warp q hands every finished tile to scorer warp q through a two-entry ring
+    uint64_t *afull = reinterpret_cast<uint64_t *>(ctrl + 768);     // AO (never with CS > 0): [4] leader: both CTAs' patch landed
+    uint64_t *afree = afull + 4;                                    //                         [4] both: its MMAs completed
     uint64_t *sc_full = reinterpret_cast<uint64_t *>(ctrl + 768);   // [4][2] tile record written, pred rows stored
     uint64_t *sc_empty = sc_full + 8;                               // [4][2] record consumed
     int *sc_rec = reinterpret_cast<int *>(sc_empty + 8);            // [4][2][4] {image (-1: no more tiles), tile x, tile y, -}
@@ -1023,6 +1054,11 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                 mbar_init(sc_full + b, 1);
                 mbar_init(sc_empty + b, 1);
             }
+        if (AO)
+            for (int b = 0; b < 4; ++b) {
+                mbar_init(afull + b, 1);
+                mbar_init(afree + b, 1);
+            }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -1031,7 +1067,7 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
         tma_prefetch_desc(&map_a2);
         tma_prefetch_desc(&map_b);
     }
-    for (int i = threadIdx.x; i < NPAD; i += pair_threads(CS)) s_bias[i] = (i < p.cout && p.bias) ? __ldg(p.bias + i) : 0.f;
+    for (int i = threadIdx.x; i < NPAD; i += pair_threads(CS, AO)) s_bias[i] = (i < p.cout && p.bias) ? __ldg(p.bias + i) : 0.f;
     SQD_TRACE_PH(1);
     if (warp == kWarpMma2) tmem_alloc_2cta(tmem_slot, kTmemCols);
     tc_fence_before();
@@ -1060,9 +1096,9 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
             if (elect_one_sync()) {
                 uint8_t *st = smem + (size_t)rs.s * kStageBytes;
                 const int x = it.tx * kTileX + it.dxi - 1, y = it.ty * kTileY - 1;
-                const int bytes = ((p.dbg & 2) ? 0 : kAStageBytes) + ((p.dbg & 4) ? 0 : 3 * kBTapBytes);
+                const int bytes = ((p.dbg & 2) || AO ? 0 : kAStageBytes) + ((p.dbg & 4) ? 0 : 3 * kBTapBytes);
                 if (rank == 0) mbar_arrive_expect_tx(full + rs.s, 2 * bytes);  // both CTAs' bytes
-                if (!(p.dbg & 2)) {   // ghost tile: image index == batch -> out of bounds -> zeros
+                if (!AO && !(p.dbg & 2)) {   // ghost tile: image index == batch -> out of bounds -> zeros
                     tma_load_4d_2cta(&map_a1, full + rs.s, st, it.cb * kBlockK, x, y, it.img);
                     tma_load_4d_2cta(&map_a2, full + rs.s, st + kPlaneBytes, it.cb * kBlockK, x, y, it.img);
                 }
@@ -1071,10 +1107,10 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
 #pragma unroll
                     for (int dyi = 0; dyi < 3; ++dyi) {
                         if (PK)
-                            tma_load_3d_2cta(&map_b, full + rs.s, st + kAStageBytes + dyi * kBTapBytes,
+                            tma_load_3d_2cta(&map_b, full + rs.s, st + kBOff + dyi * kBTapBytes,
                                              (dyi * 3 + it.dxi) * p.cin + it.cb * kBlockK, (int)rank * N1H, slab);
                         else
-                            tma_load_2d_2cta(&map_b, full + rs.s, st + kAStageBytes + dyi * kBTapBytes,
+                            tma_load_2d_2cta(&map_b, full + rs.s, st + kBOff + dyi * kBTapBytes,
                                              (dyi * 3 + it.dxi) * p.cin + it.cb * kBlockK, (int)rank * N1H);
                     }
                 }
@@ -1082,24 +1118,54 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
             __syncwarp();
             rs.advance(S);
         }
+    } else if (AO && warp == kScorerWarp0) {
+        // ===== AO operand producer: the patch of this CTA's tile, fetched by the first unit of every (tile, block) group
+        // of the pair's sequence (a group is cut where the sequence is: at its start, its end and at the main / tail seam) =====
+        PairIter it;
+        Ring ra{0, 0};
+        for (int i = 0; i < n_units; ++i) {
+            if (i == 0 || i == sc.main_len) it.seek(sc.unit(i), tile_offset, p); else it.next(p);
+            if (!(it.dxi == 0 || i == 0 || i == sc.main_len)) continue;
+            if (!pair_wait_warp(afree + ra.s, ra.ph ^ 1u, abort_flag, spin)) {
+                if (lane == 0) atomicCAS(p.status, 0, 12);
+                break;
+            }
+            if (elect_one_sync()) {
+                uint8_t *ab = a_ring + (size_t)ra.s * kAoBufBytes;
+                if (rank == 0) mbar_arrive_expect_tx(afull + ra.s, (p.dbg & 2) ? 0 : 4 * kAoBoxBytes);   // 2 planes x 2 CTAs
+                if (!(p.dbg & 2)) {   // map dimension order (channel, y, x, image); out of bounds (padding, ghost tile) -> zeros
+                    const int x = it.tx * kTileX - 1, y = it.ty * kTileY - 1;
+                    tma_load_4d_2cta(&map_a1, afull + ra.s, ab, it.cb * kBlockK, y, x, it.img);
+                    tma_load_4d_2cta(&map_a2, afull + ra.s, ab + kAoPlaneBytes, it.cb * kBlockK, y, x, it.img);
+                }
+            }
+            __syncwarp();
+            ra.advance(p.a_bufs);
+        }
     } else if (warp == kWarpMma2) {
         if (rank == 0) {
             // ===== MMA issuer (leader CTA): 24 M=256 MMAs per unit; converged warp, one elected lane issues =====
-            Ring rs{0, 0};
+            Ring rs{0, 0}, ra{0, 0};
             int chunk = 0, in_chunk = 0;  // a chunk = up to p.chunk_units consecutive units of one segment in one accumulator
             PairIter it;
             for (int i = 0; i < n_units; ++i) {
                 if (i == 0 || i == sc.main_len) it.seek(sc.unit(i), tile_offset, p); else it.next(p);
+                const bool a_first = AO && (it.dxi == 0 || i == 0 || i == sc.main_len);
+                const bool a_last = AO && (it.dxi == 2 || i == n_units - 1 || i == sc.main_len - 1);
                 const int buf = kAccBufs == 2 ? (chunk & 1) : 0;
                 const uint32_t acc_ph = kAccBufs == 2 ? ((uint32_t)(chunk >> 1) & 1u) : ((uint32_t)chunk & 1u);
-                if (in_chunk == 0) {
+                if (in_chunk == 0 && !(p.dbg & 128)) {   // dbg 128 / 64: timing experiments (skip the accumulator / operand waits)
                     if (!pair_wait_warp(tempty + buf, acc_ph ^ 1u, abort_flag, spin)) {
                         if (lane == 0) atomicCAS(p.status, 0, 4);
                         break;
                     }
                 }
                 SQD_TRACE2(2, i);
-                if (!pair_wait_warp(full + rs.s, rs.ph, abort_flag, spin)) {
+                if (a_first && !(p.dbg & 64) && !pair_wait_warp(afull + ra.s, ra.ph, abort_flag, spin)) {
+                    if (lane == 0) atomicCAS(p.status, 0, 13);
+                    break;
+                }
+                if (!(p.dbg & 64) && !pair_wait_warp(full + rs.s, rs.ph, abort_flag, spin)) {
                     if (lane == 0) atomicCAS(p.status, 0, 2);
                     break;
                 }
@@ -1107,17 +1173,22 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                 tc_fence_after();
                 const uint32_t d1 = tmem_base + (uint32_t)buf * kAccCols, d2 = d1 + 2 * N1H;
                 const uint32_t st = smem_u32(smem + (size_t)rs.s * kStageBytes);
+                const uint32_t ab = smem_u32(a_ring + (size_t)ra.s * kAoBufBytes) + (uint32_t)(it.dxi * kAoY) * 128u;   // AO: tap column
                 const bool chunk_end = sc.chunk_ends(i, it.r, in_chunk, p.chunk_units);
                 const int nks = (PK && it.cb == p.cin / kBlockK - 1) ? p.ksteps_last : kBlockK / kUmmaK;
                 if (elect_one_sync()) {
                     if (!(p.dbg & 1)) {
 #pragma unroll
                         for (int dyi = 0; dyi < 3; ++dyi) {
-                            const uint64_t a1 = umma_desc_sw128(st + dyi * kDyBytes);
-                            const uint64_t a2 = umma_desc_sw128(st + kPlaneBytes + dyi * kDyBytes);
-                            const uint64_t b = umma_desc_sw128(st + kAStageBytes + dyi * kBTapBytes);
+                            // dbg 32 (timing experiment, wrong results): atom-aligned taps and SBO = 1024 on the AO buffers
+                            const uint32_t ab_t = (p.dbg & 32) ? (ab & ~1023u) + dyi * 1024 : ab + dyi * 128;
+                            const uint32_t sbo_t = (p.dbg & 32) ? 1024 : kAoY * 128;
+                            const uint64_t a1 = AO ? umma_desc_sw128_sbo(ab_t, sbo_t) : umma_desc_sw128(st + dyi * kDyBytes);
+                            const uint64_t a2 = AO ? umma_desc_sw128_sbo(ab_t + kAoPlaneBytes, sbo_t)
+                                                   : umma_desc_sw128(st + kPlaneBytes + dyi * kDyBytes);
+                            const uint64_t b = umma_desc_sw128(st + kBOff + dyi * kBTapBytes);
                             const uint64_t bw1 = b;   // the w1 rows come first
-                            const uint64_t bw2 = umma_desc_sw128(st + kAStageBytes + dyi * kBTapBytes + HR * kBlockK * 2);
+                            const uint64_t bw2 = umma_desc_sw128(st + kBOff + dyi * kBTapBytes + HR * kBlockK * 2);
 #pragma unroll
                             for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
                                 if (PK && ks >= nks) continue;
@@ -1135,11 +1206,13 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                         }
                     }
                     umma_commit_2cta(sfree + rs.s, 3);                  // stage reusable in both CTAs
+                    if (a_last) umma_commit_2cta(afree + ra.s, 3);      // operand buffer reusable in both CTAs
                     if (chunk_end) umma_commit_2cta(tfull + buf, 3);    // chunk complete (both CTAs' accumulate warps)
                 }
                 __syncwarp();
                 SQD_TRACE2(10, i);
                 rs.advance(S);
+                if (a_last) ra.advance(p.a_bufs);
                 if (chunk_end) {
                     ++chunk;
                     in_chunk = 0;
@@ -1243,7 +1316,8 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
             __syncwarp();
             if (lane == 0) {
                 if (rank == 0) mbar_arrive(tempty + buf);
-                else mbar_arrive_cluster(tempty + buf, 0);
+                else if (p.dbg & 16) mbar_arrive_cluster(tempty + buf, 0);
+                else mbar_arrive_remote(tempty + buf, 0);   // TMEM reads are ordered by wait::ld + the tcgen05 fence above
             }
             if (warp == kWarpAcc2) SQD_TRACE2(12, i);
 
@@ -1285,7 +1359,7 @@ convdet_f16_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid
                 continue;
             }
             // whole tile in registers: x 1/(s_a*s_w), + bias -> pred   (ghost tile: img == batch, nothing stored)
-            const int x = it.tx * kTileX + row % kTileX, y = it.ty * kTileY + row / kTileX;
+            const int x = it.tx * kTileX + (AO ? row / kTileY : row % kTileX), y = it.ty * kTileY + (AO ? row % kTileY : row / kTileX);
             const bool inb = it.img < p.batch && y < p.gh && x < p.gw;
             const int slab = it.slab;
             // the feature scales were divided out chunk by chunk; the weight scale belongs to the slab
@@ -1522,13 +1596,23 @@ int pair_stages_for(int n1h) {
     return (int)s;
 }
 
-template <int NPAD, int CS = 0, bool PK = false, int HR = NPAD / 2, bool K3 = (NPAD >= 96)>
+// A-once layout (AO kernels): the largest operand-buffer count (<= 3) that leaves room for three weight stages
+int ao_bufs_for(int n1h) {
+    const size_t avail = kSmemLimit - 1024 - kCtrlBytes - (size_t)3 * 3 * n1h * kBlockK * 2;
+    size_t n = avail / kAoBufBytes;
+    const int cap = sqd_opt(SQD_OPT_F16_AO_BUFS);   // 2: a buffer is refilled a whole block (three units) ahead of its use
+    if ((int)n > cap && cap >= 2) n = cap;
+    return n > 3 ? 3 : (int)n;
+}
+
+template <int NPAD, int CS = 0, bool PK = false, int HR = NPAD / 2, bool K3 = (NPAD >= 96), bool AO = false>
 int launch_pair(const CUtensorMap *maps, const PairParams &p, int grid, cudaStream_t st) {
-    const size_t smem = 1024 + (size_t)p.stages * (kAStageBytes + 3 * 2 * HR * kBlockK * 2) + kCtrlBytes + (PK ? kEpiStageBytes : 0);
+    const size_t smem = AO ? 1024 + (size_t)p.a_bufs * kAoBufBytes + (size_t)p.stages * (3 * 2 * HR * kBlockK * 2) + kCtrlBytes
+                           : 1024 + (size_t)p.stages * (kAStageBytes + 3 * 2 * HR * kBlockK * 2) + kCtrlBytes + (PK ? kEpiStageBytes : 0);
     SQD_REQUIRE(smem <= kSmemLimit, SQD_E_SHAPE, "convdet (tcgen05): shared memory budget exceeded (%zu bytes)", smem);
-    SQD_CUDA(cudaFuncSetAttribute(convdet_f16_pair_kernel<NPAD, CS, PK, HR, K3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SQD_CUDA(cudaFuncSetAttribute(convdet_f16_pair_kernel<NPAD, CS, PK, HR, K3, AO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // dependent launch when the pre-pass kernel directly precedes it on the stream (p.pdl)
-    cudaError_t e = sqd_launch_dependent(convdet_f16_pair_kernel<NPAD, CS, PK, HR, K3>, dim3(grid), dim3(pair_threads(CS)), smem, st, p.pdl != 0,
+    cudaError_t e = sqd_launch_dependent(convdet_f16_pair_kernel<NPAD, CS, PK, HR, K3, AO>, dim3(grid), dim3(pair_threads(CS, AO)), smem, st, p.pdl != 0,
                                          maps[0], maps[1], maps[2], p);
     if (e != cudaSuccess) {
         sqd_set_error("launch of convdet_f16_pair_kernel failed: %s", cudaGetErrorString(e));
@@ -1569,11 +1653,22 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
     }
     const PlaneLayout pl = plane_layout(batch, cin, gh, gw);
 
+    if (slabs < 1) slabs = 1;
+    const bool multi = (slabs > 1 || (ksteps_last >= 1 && ksteps_last < 4)) && npad == 128;
+    // A-once operand layout (one patch fetch per (tile, block), see kAoY): the plain forward kernel of the two-MMA scheme
+    const bool fused_score = emit && sqd_opt(SQD_OPT_FUSED_SCORE);
+    const bool ao = !multi && !fused_score && npad <= 80 && ao_bufs_for(n1h) >= 2 && sqd_opt(SQD_OPT_F16_A_ONCE);
     alignas(64) CUtensorMap maps[3];
     for (int i = 0; i < 2; ++i) {
-        const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)gw, (cuuint64_t)gh, (cuuint64_t)batch};
-        const cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)gw * cin * 2, (cuuint64_t)gh * gw * cin * 2};
-        const cuuint32_t box[4] = {kBlockK, kTileX, kPatchY, 1};
+        // AO: dimension order (channel, y, x, image), so that the box lands x-major / y-minor in shared memory
+        const cuuint64_t dims_xy[4] = {(cuuint64_t)cin, (cuuint64_t)gw, (cuuint64_t)gh, (cuuint64_t)batch};
+        const cuuint64_t strides_xy[3] = {(cuuint64_t)cin * 2, (cuuint64_t)gw * cin * 2, (cuuint64_t)gh * gw * cin * 2};
+        const cuuint32_t box_xy[4] = {kBlockK, kTileX, kPatchY, 1};
+        const cuuint64_t dims_yx[4] = {(cuuint64_t)cin, (cuuint64_t)gh, (cuuint64_t)gw, (cuuint64_t)batch};
+        const cuuint64_t strides_yx[3] = {(cuuint64_t)gw * cin * 2, (cuuint64_t)cin * 2, (cuuint64_t)gh * gw * cin * 2};
+        const cuuint32_t box_yx[4] = {kBlockK, kAoY, kAoX, 1};
+        const cuuint64_t *dims = ao ? dims_yx : dims_xy, *strides = ao ? strides_yx : strides_xy;
+        const cuuint32_t *box = ao ? box_yx : box_xy;
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         void *base = const_cast<char *>(planes + (i == 0 ? pl.p1_off : pl.p2_off));
         CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
@@ -1581,10 +1676,8 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SQD_REQUIRE(r == CUDA_SUCCESS, SQD_E_DRIVER, "cuTensorMapEncodeTiled(features) failed: CUresult %d", (int)r);
     }
-    if (slabs < 1) slabs = 1;
-    // the dgrad GEMM (PK kernel): several weight matrices over the same planes in one launch and / or a partly filled last
-    // channel block; it addresses the weights through a 3-D map {k, row, slab}
-    const bool multi = (slabs > 1 || (ksteps_last >= 1 && ksteps_last < 4)) && npad == 128;
+    // the dgrad GEMM (PK kernel, `multi`): several weight matrices over the same planes in one launch and / or a partly
+    // filled last channel block; it addresses the weights through a 3-D map {k, row, slab}
     SQD_REQUIRE(slabs == 1 || multi, SQD_E_UNSUPPORTED, "convdet (tcgen05): multi-slab launches need Cout == 128 per slab");
     if (slabs == 1) slab_stride = 0;
     {
@@ -1640,6 +1733,15 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
     }
     p.units_per_pair = (int)upp;
     p.stages = pair_stages_for(n1h);
+    p.a_bufs = 0;
+    if (ao) {
+        p.a_bufs = ao_bufs_for(n1h);
+        const size_t left = kSmemLimit - 1024 - kCtrlBytes - (size_t)p.a_bufs * kAoBufBytes;
+        int sb = (int)(left / ((size_t)3 * n1h * kBlockK * 2));
+        const int cap = sqd_opt(SQD_OPT_F16_PAIR_STAGES);
+        p.stages = sb > 4 ? 4 : sb;
+        if (p.stages > cap && cap >= 2) p.stages = cap;
+    }
     SQD_REQUIRE(p.stages >= 2, SQD_E_SHAPE, "convdet (tcgen05): shared memory too small for two stages");
     p.chunk_units = sqd_opt(SQD_OPT_F16_CHUNK);   // one 64-channel block (3 dx units) per TMEM chunk
     if (p.chunk_units < 1) p.chunk_units = 1;
@@ -1682,6 +1784,16 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
     }
     if (multi) return launch_pair<128, 0, true>(maps, p, grid, st);   // the dgrad GEMM
     p.ksteps_last = 4;
+    if (ao) {
+        switch (npad / 16) {
+            case 1: return launch_pair<16, 0, false, 8, false, true>(maps, p, grid, st);
+            case 2: return launch_pair<32, 0, false, 16, false, true>(maps, p, grid, st);
+            case 3: return launch_pair<48, 0, false, 24, false, true>(maps, p, grid, st);
+            case 4: return launch_pair<64, 0, false, 32, false, true>(maps, p, grid, st);
+            case 5: return n1h == 72 ? launch_pair<80, 0, false, 36, false, true>(maps, p, grid, st)
+                                     : launch_pair<80, 0, false, 40, false, true>(maps, p, grid, st);
+        }
+    }
     switch (npad / 16) {
         case 1: return launch_pair<16>(maps, p, grid, st);
         case 2: return launch_pair<32>(maps, p, grid, st);

@@ -185,6 +185,15 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t rank
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// Same, with the default (.release at CTA scope) semantics -- the form cutlass::arch::ClusterBarrier::arrive(cta_id) uses for
+// its accumulator pipeline.  Enough when the data the barrier guards is not ordinary memory (TMEM reads ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync): a cluster-scope release also waits for the thread's outstanding
+// global stores, which costs the pair's second CTA on every accumulator hand-back.
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t *dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
                  : "memory");

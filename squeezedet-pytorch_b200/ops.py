@@ -232,8 +232,11 @@ def detect_from_pred(pred, anchors_f32, input_hw, num_classes, top_k, nms_thresh
 
 
 def head_detect(feat, weight, bias, anchors_f32, anchors_per_grid, num_classes, input_hw, top_k, nms_thresh,
-                score_thresh, packed=None, algo=CONV_TCGEN05_F16X3, out: Detections = None) -> Detections:
-    """Fire11 features -> final detections (ConvDet + decode + top-k + NMS) through one ABI call."""
+                score_thresh, packed=None, algo=CONV_TCGEN05_F16X3, out: Detections = None, slot=None) -> Detections:
+    """Fire11 features -> final detections (ConvDet + decode + top-k + NMS) through one ABI call.
+
+    `slot` (serving loops): calls issued on DIFFERENT streams must not share a workspace; give each stream its own slot
+    number and its own `out`."""
     lib = load()
     layout, x = feature_layout(feat)
     B, cin, gh, gw = x.shape
@@ -244,7 +247,7 @@ def head_detect(feat, weight, bias, anchors_f32, anchors_per_grid, num_classes, 
     if algo != CONV_SIMT_FP32 and packed is None:
         packed = pack_convdet_weights(w)
     nbytes = lib.sqd_head_detect_workspace_bytes(B, cin, gh, gw, cout, layout, algo)
-    ws = workspace().get("head_detect", nbytes, x.device)
+    ws = workspace().get("head_detect" if slot is None else "head_detect/%d" % slot, nbytes, x.device)
     det = out if out is not None else _alloc_detections(B, top_k, x.device)
     if algo != CONV_SIMT_FP32 and B > 0:
         off = lib.sqd_head_detect_status_offset(B, gh, gw, cout)

@@ -368,6 +368,22 @@ def test_one_pass_split_equals_two_pass(ops, monkeypatch, name, batch):
     assert torch.equal(one, cl)   # channels_last input: same per-(image, block) scales, same planes
 
 
+@pytest.mark.parametrize("name,batch", [("tiny_160x96", 3), ("kitti_1248x384", 1), ("kitti_1248x384", 7)])
+def test_a_once_operand_layout_is_bit_identical(ops, name, batch):
+    """Opt-in SQD_F16_A_ONCE=1 (convdet_f16_pair_kernel<..., AO>): the operand patch of a (tile, channel block) is
+    fetched once as a {64 ch, 10 y, 18 x} box that lands x-major in shared memory, and the nine taps are descriptor row
+    offsets into it.  Same products in the same order: pred is bit-identical to the default three-fetch layout.
+    (Measured slower, profiles/r02_a_once_operand.txt, hence opt-in.)"""
+    shp = {x.name: x for x in (synth.TINY, synth.KITTI)}[name]
+    feat, (w, b) = dev(synth.features(shp, batch, 61)), synth.convdet_params(shp, 62)
+    w, b = dev(w), dev(b)
+    base = ops.convdet_forward(feat, w, b, check_status=True)
+    with _lib.option("SQD_F16_A_ONCE", 1):
+        ao = ops.convdet_forward(feat, w, b, check_status=True)
+    assert torch.equal(base, ao)
+    assert not torch.equal(ao, torch.zeros_like(ao))
+
+
 def test_split_grid_not_multiple_of_four(ops):
     """6 x 11 grid (P = 66, not a multiple of 4): the one-pass kernel is not eligible; scales differ wildly between
     channel blocks and images (1e-6 ... 1e4) and the result still matches the fp32 SIMT kernel."""

@@ -36,10 +36,13 @@ NAMES = ["A_issue", "B_issue0", "m_tmem_ok", "m_a_ok", "m_b0_ok", "m_b0_iss", "m
          "m_end", "acc_start", "acc_done"]
 for setting in (sys.argv[1:] or [""]):
     keys = []
+    saved = {}
     for kv in filter(None, setting.split(",")):
         k, v = kv.split("=")
-        os.environ[k] = v
-        keys.append(k)
+        old = C.c_int(0)
+        lib.sqd_get_option(k.encode(), C.byref(old))
+        saved[k] = old.value
+        lib.sqd_set_option(k.encode(), int(v))   # the option table is read from the environment only once
     for _ in range(3):
         gemm()
     trace = torch.zeros((512, 32), dtype=torch.int64, device=dev)
@@ -49,6 +52,14 @@ for setting in (sys.argv[1:] or [""]):
     del os.environ["SQD_F16_TRACE"]
     t = trace.cpu().numpy()
     n = int((t[:, 10] > 0).sum())
+    ce = t[:511, 12] > 0                      # units that closed a chunk (accumulate-warp stamps)
+    if ce.sum() > 2:
+        dr = (t[:511, 12] - t[:511, 11])[ce]
+        print(f"==== {setting or 'default'}: accumulate warp 0 of the traced CTA: {int(ce.sum())} chunks, drain {dr[1:-1].mean():.0f} cycles (min {dr.min()}, max {dr.max()})")
+    if n == 0:
+        for k, v in saved.items():
+            lib.sqd_set_option(k.encode(), v)
+        continue
     t0 = t[0, 0]
     print(f"==== {setting or 'default'}: {n} units traced")
     ph = t[511, :8]
@@ -67,8 +78,8 @@ for setting in (sys.argv[1:] or [""]):
               "acc: tfull seen after m_end %.0f, drain %.0f | tempty seen by mma(i+2) after acc_done(i) %.0f" % (
                   np.diff(t[:n, 10]).mean(), float((t[m, 2] - t[1:n - 3, 10]).mean()), d(3, 2), d(10, 3), d(3, 0), d(11, 10), d(12, 11),
                   float((t[4:n, 2] - t[2:n - 2, 12]).mean())))
-        for k in keys:
-            del os.environ[k]
+        for k, v in saved.items():
+            lib.sqd_set_option(k.encode(), v)
         continue
     print("period (m_end to m_end): mean %.0f median %.0f" % (np.diff(t[:n, 10]).mean(), np.median(np.diff(t[:n, 10]))))
     print("mma: wait tmem_empty %.0f | wait a_full %.0f | per dy: wait b_full %.0f %.0f %.0f, issue %.0f %.0f %.0f | tail commits %.0f | loop back %.0f" % (
@@ -79,5 +90,5 @@ for setting in (sys.argv[1:] or [""]):
     print("acc: start after m_end %.0f | drain duration %.0f | idle between drains %.0f" % (
         (t[m, 11] - t[m, 10]).mean(), (t[m, 12] - t[m, 11]).mean(), (t[3:n - 1, 11] - t[m, 12]).mean()))
     print("A issue lead over m_a_ok %.0f | B issue(dy0) lead over m_b0_ok %.0f" % ((t[m, 3] - t[m, 0]).mean(), (t[m, 4] - t[m, 1]).mean()))
-    for k in keys:
-        del os.environ[k]
+    for k, v in saved.items():
+        lib.sqd_set_option(k.encode(), v)
