@@ -36,8 +36,32 @@ METRIC = "images/sec head+decode+NMS @1248x384 (whole job; per-GPU = value / n_g
 FLOP_PER_IMAGE = 2 * 1872 * 72 * 6912          # 1,863,254,016
 PRED_BYTES_PER_IMAGE = 16848 * 8 * 4           # 539,136
 FEAT_BYTES_PER_IMAGE = 768 * 24 * 78 * 4       # 5,750,784
-NCU_CONVDET_TRAFFIC_B20 = 125986560 + 5881088  # bytes per launch at B = 20 (ncu --set full capture, profiles/r01_ncu_b20_final2.txt)
+NCU_STEP_PROFILE = "profiles/r02_ncu_b20.txt"                  # ncu --set full of the four step kernels at B = 20
+NCU_DECODE_PROFILE = "profiles/r02_ncu_decode_nms_b1024.txt"   # ... of scan / tail / dense decode on 1024 images
 DENSE_BYTES_PER_IMAGE = 16848 * (8 + 4 + 16)   # 471,744 (int64 id, score, box)
+
+
+def ncu_traffic(profile, *kernels):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the named kernels, read from a committed
+    `tools/ncu_summary.py full` text summary of one `ncu --set full` capture; None if the file or a kernel is missing.
+    (Nothing is profiled during the bench run: ncu cannot run inside the timed process.)"""
+    path = os.path.join(ROOT, profile)
+    if not os.path.exists(path):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, cur, seen = 0.0, None, set()
+    for ln in open(path):
+        if ln.startswith("=="):
+            cur = next((k for k in kernels if k in ln), None)
+            if cur in seen:      # first launch of each kernel only
+                cur = None
+            elif cur:
+                seen.add(cur)
+        elif cur:
+            parts = ln.split()
+            if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and parts[2] in unit:
+                total += float(parts[1]) * unit[parts[2]]
+    return int(total) if len(seen) == len(kernels) else None
 
 
 def load_peaks():
@@ -216,6 +240,116 @@ def main_reference(args):
 # ----------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------
+def demo_config(args, dev, ops, synth):
+    """BASELINE configs[0] on the GPU (and, when oracle/_ref travelled, the reference's own demo pipeline on the CPU)."""
+    import torch
+    from squeezedet_pytorch_b200 import config as sqd_config
+    from squeezedet_pytorch_b200.detector import Detector
+    from squeezedet_pytorch_b200.model import SqueezeDet
+    shp = synth.KITTI
+    gpath = os.path.join(ROOT, "tests", "golden", "demo_kitti_samples.npz")
+    if os.path.exists(gpath):
+        g = np.load(gpath, allow_pickle=False)
+        rgb, what = g["image_0"], "the reference's sample image %s (375x1242 uint8)" % str(g["ids"][0])
+    else:
+        rgb, what = np.random.RandomState(3).randint(0, 256, size=(375, 1242, 3)).astype(np.uint8), "synthetic 375x1242 uint8 image"
+    h0, w0 = rgb.shape[:2]
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        cfg = sqd_config.kitti_config(device=dev)
+        model = SqueezeDet(cfg)
+        model.load_state_dict(synth.demo_state_dict(model, shp, 2024))
+        det = Detector(model, cfg)
+        host = torch.from_numpy(rgb).pin_memory()
+        scales = torch.tensor([[shp.input_hw[0] / h0, shp.input_hw[1] / w0]], dtype=torch.float32)
+        meta = {"image_id": ["demo"], "orig_size": torch.tensor([[h0, w0, 3]], dtype=torch.int32), "scales": scales}
+        mean, std = cfg.rgb_mean.reshape(3), cfg.rgb_std.reshape(3)
+
+        def one():
+            x = ops.preprocess_images(host.to(dev, non_blocking=True)[None], mean, std, shp.input_hw)
+            return det.detect({"image": x, "image_meta": meta})[0]
+        for _ in range(5):
+            res = one()
+        n = 40
+        t0 = time.perf_counter()
+        for _ in range(n):
+            res = one()                 # ends with the device-to-host copy of the detections: a blocking call
+        ms = (time.perf_counter() - t0) / n * 1e3
+        # stage split with events (one more pass)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        stage = np.zeros(3)
+        for _ in range(10):
+            ev[0].record()
+            x = ops.preprocess_images(host.to(dev, non_blocking=True)[None], mean, std, shp.input_hw)
+            ev[1].record()
+            with torch.no_grad():
+                feat = model.base.features(x)
+            ev[2].record()
+            ops.head_detect(feat, model.base.convdet.weight, model.base.convdet.bias, model.resolver._anchors_on(feat.device),
+                            cfg.anchors_per_grid, cfg.num_classes, cfg.input_size, cfg.keep_top_k, cfg.nms_thresh,
+                            cfg.score_thresh, packed=model.base.packed_weights())
+            ev[3].record()
+            torch.cuda.synchronize()
+            stage += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(3)]) / 10
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    out = {"workload": "BASELINE configs[0]: demo, batch 1: " + what + " on the host -> preprocess -> SqueezeDet backbone (stock "
+                       "PyTorch / cuDNN fp32) -> ConvDet + decode + top-64 + NMS + boxes_postprocess -> result dict on the host; "
+                       "seeded weights (the bundled checkpoint is not in the image)",
+           "ms_per_image": ms, "images_per_s": 1e3 / ms, "kept": int(len(res.get("class_ids", []))),
+           "stage_ms": {"h2d_preprocess": float(stage[0]), "backbone_stock_pytorch": float(stage[1]),
+                        "path_head_decode_nms": float(stage[2])}}
+    if not args.no_cpu_baseline:
+        out["reference_cpu"] = demo_reference_cpu(rgb, synth)
+    return out
+
+
+def demo_reference_cpu(rgb, synth):
+    """The reference's own demo pipeline on the host cores for the same image: utils.image whiten / resize,
+    model.squeezedet.SqueezeDet (backbone included) and engine.detector.Detector.detect, imported from oracle/_ref."""
+    import types
+    import torch
+    from oracle import make_ref
+    ref = make_ref.load()
+    if ref is None:
+        return {"unavailable": "oracle/_ref did not travel with the snapshot"}
+    import importlib
+    rimg = importlib.import_module("utils.image")
+    shp = synth.KITTI
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    anchors = ref.boxes.generate_anchors(shp.grid_hw, shp.input_hw, synth.KITTI_SEEDS)
+    cfg = types.SimpleNamespace(
+        input_size=shp.input_hw, num_classes=shp.num_classes, anchors=anchors, anchors_per_grid=shp.anchors_per_grid,
+        num_anchors=anchors.shape[0], arch="squeezedet", dropout_prob=0.5, device=torch.device("cpu"),
+        keep_top_k=shp.top_k, nms_thresh=shp.nms_thresh, score_thresh=shp.score_thresh, debug=0, mode="eval",
+        class_loss_weight=1.0, positive_score_loss_weight=3.75, negative_score_loss_weight=100.0, bbox_loss_weight=6.0)
+    net = ref.model.SqueezeDet(cfg)
+    net.load_state_dict(synth.demo_state_dict(net, shp, 2024))
+    det = ref.detector.Detector(net, cfg)
+    mean = np.array([93.877, 98.801, 95.923], dtype=np.float32).reshape(1, 1, 3)
+    std = np.array([78.782, 80.130, 81.200], dtype=np.float32).reshape(1, 1, 3)
+
+    def one():
+        image = rgb.astype(np.float32)
+        meta = {"image_id": "demo", "orig_size": np.array(image.shape, dtype=np.int32)}
+        image, meta = rimg.whiten(image, meta, mean=mean, std=std)
+        image, meta, _ = rimg.resize(image, meta, shp.input_hw)
+        x = torch.from_numpy(image.transpose(2, 0, 1)).unsqueeze(0)
+        bmeta = {k: torch.from_numpy(v).unsqueeze(0) if isinstance(v, np.ndarray) else [v] for k, v in meta.items()}
+        return det.detect({"image": x, "image_meta": bmeta})[0]
+    one()
+    times = []
+    for _ in range(5):
+        t = time.perf_counter()
+        res = one()
+        times.append(time.perf_counter() - t)
+    return {"ms_per_image": float(np.mean(times)) * 1e3, "images_per_s": 1.0 / float(np.mean(times)), "cores": cores,
+            "kind": "reference", "kept": int(len(res.get("class_ids", []))),
+            "sample": "5 timed images (after 1 warm-up), the reference's whiten/resize + SqueezeDet + Detector.detect on CPU"}
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -478,6 +612,14 @@ def main_ours(args):
         ops.workspace().clear()
         torch.cuda.empty_cache()
 
+        # configs[0]: the demo (demo.py:17-52), batch 1 per image: uint8 image on the HOST -> H2D -> sqd_preprocess (whiten
+        # + resize) -> the stock backbone (cuDNN fp32, TF32 off; out of scope, timed because the demo runs it) -> the path
+        # (sqd_head_detect_fused + sqd_boxes_postprocess behind Detector.detect) -> the reference's result dict on the host.
+        if rank == 0:
+            extra["config1_demo"] = demo_config(args, dev, ops, synth)
+            ops.workspace().clear()
+            torch.cuda.empty_cache()
+
         # configs[3]: the training step of the path, batch 20 per GPU: anchor matching + dense targets (a10-a13), ConvDet
         # forward (a1), loss forward + analytic backward (a14-a16), native wgrad / bias grad / dgrad (8f.2) and the NCCL
         # all-reduce of the flat gradient bucket (8e row 2; the full model's 2,082,120 floats, the head's segment launched
@@ -727,14 +869,16 @@ def main_ours(args):
                                  "score_candidates_kernel<3>", "detect_from_candidates_kernel"],
             "kernel_ms": kern,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops"], "traffic": NCU_CONVDET_TRAFFIC_B20 if B == 20 else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, "
-                                           "profiles/r01_ncu_b20_final2.txt (B = 20 only)",
+                         "frac": achieved / peaks["tflops"], "traffic": ncu_traffic(NCU_STEP_PROFILE, "convdet_f16_pair_kernel") if B == 20 else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, parsed at run time from "
+                                           "the committed ncu --set full summary %s (B = 20 only; ncu flushes L2 before the "
+                                           "launch, so this is the cold-cache figure: algorithmic bytes are 115.0 MB of planes "
+                                           "+ 2.0 MB weights + 10.8 MB pred)" % NCU_STEP_PROFILE,
                          "kernel": "convdet_f16_pair_kernel<80,0,false,36>",
                          "peak_source": peaks["source"] + ", dense bf16 burst",
                          "launch_ms": kern["convdet_alone_ms"],
                          "launch_ms_source": "CUDA events around back-to-back launches of the GEMM kernel on pre-split planes "
-                                             "(3 rotating sets > L2); ncu launch list: profiles/r01_launches_b20_final2.txt",
+                                             "(3 rotating sets > L2); ncu launch list: profiles/r02_launches_b20.txt",
                          "in_step": {"launch_ms": kern["convdet_ms"], "achieved": achieved_in_step,
                                      "frac": achieved_in_step / peaks["tflops"],
                                      "note": "between the stage events of sqd_head_detect_profile: the events serialise the "
@@ -744,7 +888,9 @@ def main_ours(args):
                                  "fp32-level accuracy, so frac <= 0.31 by construction"},
             "roofline_decode_nms": {"bound": "hbm", "achieved": Bd * PRED_BYTES_PER_IMAGE / det_s / 1e9,
                                     "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                    "frac": Bd * PRED_BYTES_PER_IMAGE / det_s / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                    "frac": Bd * PRED_BYTES_PER_IMAGE / det_s / 1e9 / peaks["hbm_gbs"],
+                                    "traffic": ncu_traffic(NCU_DECODE_PROFILE, "score_candidates_kernel", "detect_from_candidates_kernel") if Bd == 1024 else None,
+                                    "traffic_source": NCU_DECODE_PROFILE + " (scan 94.1 us at 5.86 TB/s = 0.90 of peak, tail 39.2 us)",
                                     "kernel": "score_candidates_kernel<3> + detect_from_candidates_kernel",
                                     "images_per_s": Bd / det_s,
                                     "note": "sqd_detect_from_pred (scan + per-image tail: the two kernels the fused step runs "
@@ -753,7 +899,8 @@ def main_ours(args):
             "roofline_decode": {"bound": "hbm", "achieved": Bd * (PRED_BYTES_PER_IMAGE + DENSE_BYTES_PER_IMAGE) / dec_s / 1e9,
                                 "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                 "frac": Bd * (PRED_BYTES_PER_IMAGE + DENSE_BYTES_PER_IMAGE) / dec_s / 1e9 / peaks["hbm_gbs"],
-                                "traffic": None, "kernel": "decode_kernel<3>",
+                                "traffic": ncu_traffic(NCU_DECODE_PROFILE, "decode_kernel") if Bd == 1024 else None,
+                                "traffic_source": NCU_DECODE_PROFILE, "kernel": "decode_kernel<3>",
                                 "note": "sqd_decode_scores: the dense SqueezeDet.forward contract (class_ids i64, scores, "
                                         "boxes) for %d images: 539,136 B read + 471,744 B written per image" % Bd},
             "clocks": clocks,

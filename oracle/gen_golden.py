@@ -485,11 +485,59 @@ def gen_preprocess():
     save("preprocess", n=np.array(len(cases)), mean=mean.reshape(3), std=std.reshape(3), **arrays)
 
 
+def gen_demo():
+    """BASELINE configs[0] (demo.py:17-52, batch 1 per sample image): sample PNG -> BaseDataset.preprocess ->
+    SqueezeDet (backbone + head, seeded weights: the checkpoint is absent) -> Detector.detect, all reference code on CPU.
+    Stored: the two sample images themselves (uint8, so the GPU box can run the same pipeline), the reference's
+    detections in original-image coordinates and a strided sample of its Fire11 features."""
+    import cv2
+    _, rb = _ref_kitti_module()
+    shp = synth.KITTI
+    cfg = ref_cfg(shp)
+    cfg.class_names = ("Car", "Pedestrian", "Cyclist")
+    model = ref_model.SqueezeDet(cfg)
+    seed = 2024
+    model.load_state_dict(synth.demo_state_dict(model, shp, seed))
+    det = ref_detector.Detector(model, cfg)
+    mean = np.array([93.877, 98.801, 95.923], dtype=np.float32).reshape(1, 1, 3)   # kitti.py:17-18
+    std = np.array([78.782, 80.130, 81.200], dtype=np.float32).reshape(1, 1, 3)
+    fake = types.SimpleNamespace(cfg=types.SimpleNamespace(drift_prob=0.0, flip_prob=0.0, forbid_resize=False),
+                                 phase="val", rgb_mean=mean, rgb_std=std, input_size=shp.input_hw)
+    arrays = {}
+    ids = ("000061", "004615")
+    for i, image_id in enumerate(ids):
+        path = os.path.join(REF, "data", "samples", "kitti", "testing", "image_2", image_id + ".png")
+        rgb = np.ascontiguousarray(cv2.imread(path)[:, :, ::-1])               # skimage.io.imread order (RGB), uint8
+        image = rgb.astype(np.float32)                                         # demo.py:39
+        meta = {"image_id": image_id, "orig_size": np.array(image.shape, dtype=np.int32)}
+        image, meta, _ = rb.BaseDataset.preprocess(fake, image, meta, None)
+        x = torch.from_numpy(image.transpose(2, 0, 1)).unsqueeze(0)
+        bmeta = {k: torch.from_numpy(v).unsqueeze(0) if isinstance(v, np.ndarray) else [v] for k, v in meta.items()}
+        with torch.no_grad():
+            feat = model.base.features(x)
+            res = det.detect({"image": x, "image_meta": bmeta})[0]
+            dense = model({"image": x})
+            kept = tracked_filter(det, {k: v[0] for k, v in dense.items()})
+        k_anchor, k_cls, k_score, _ = kept
+        assert np.array_equal(k_cls, res["class_ids"]) and np.array_equal(k_score, res["scores"])
+        arrays[f"image_{i}"] = rgb
+        arrays[f"class_ids_{i}"] = res["class_ids"].astype(np.int64)
+        arrays[f"scores_{i}"] = res["scores"].astype(np.float32)
+        arrays[f"boxes_{i}"] = res["boxes"].astype(np.float32)
+        arrays[f"anchor_{i}"] = k_anchor
+        arrays[f"scales_{i}"] = meta["scales"]
+        arrays[f"feat_sample_{i}"] = feat[0, ::37, ::5, ::7].numpy().copy()
+        arrays[f"feat_absmax_{i}"] = np.array(float(feat.abs().max()))
+        print(image_id, rgb.shape, "kept", len(res["class_ids"]), "feat max", float(feat.abs().max()),
+              "score range", float(res["scores"].min()), float(res["scores"].max()))
+    save("demo_kitti_samples", n=np.array(len(ids)), seed=np.array(seed), ids=np.array(ids), **arrays)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["anchors", "decode_filter", "nms", "matcher", "matcher_fallback", "loss", "head_e2e",
-                             "head_e2e_full", "nonfinite", "postprocess", "kitti_results", "preprocess"]
+                             "head_e2e_full", "nonfinite", "postprocess", "kitti_results", "preprocess", "demo"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

@@ -180,3 +180,30 @@ def nonfinite_pred(shape: Shape, seed: int, anchors=None) -> np.ndarray:
     pred[3, top[3][1], C] = -np.inf         # confidence logit -inf: sigmoid 0
     pred[4, top[4][2], C - 1] = np.nan      # a single NaN class logit
     return pred
+
+
+def demo_state_dict(model, shape: Shape, seed: int):
+    """Seeded weights for a whole SqueezeDet (backbone + ConvDet), keyed like `model.state_dict()` -- the reference's class
+    and ours share the key names (utils/model.py:5-40).  The bundled checkpoint is absent and the reference's
+    own init (std 0.005 / 0.002, squeezedet.py:89-97) collapses the Fire11 features to ~0, so the backbone convs get
+    He-scaled normals (numpy RandomState, independent of torch's generator), zero biases, and the head gets
+    convdet_params(): O(1) features, logits of std ~1, real detections.  Returns {name: torch tensor}."""
+    import torch
+    rs = np.random.RandomState(seed)
+    out = {}
+    for name, t in model.state_dict().items():
+        shp = tuple(t.shape)
+        if name.endswith("convdet.weight") or name.endswith("convdet.bias"):
+            continue
+        if len(shp) == 4:
+            fan_in = shp[1] * shp[2] * shp[3]
+            out[name] = torch.from_numpy((rs.standard_normal(shp) * np.sqrt(2.0 / fan_in)).astype(np.float32))
+        else:
+            out[name] = torch.zeros(shp, dtype=t.dtype)
+    w, b = convdet_params(shape, seed + 1)
+    for name in model.state_dict():
+        if name.endswith("convdet.weight"):
+            out[name] = torch.from_numpy(w)
+        elif name.endswith("convdet.bias"):
+            out[name] = torch.from_numpy(b)
+    return out
