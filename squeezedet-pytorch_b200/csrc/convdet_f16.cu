@@ -1810,14 +1810,17 @@ int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, 
 size_t sqd_f16_split_bytes(int batch, int cin, int gh, int gw) { return plane_layout(batch, cin, gh, gw).total; }
 
 namespace {
-// cluster size for the one-pass NCHW split: the smallest that lets >= 3 CTAs share an SM (<= 72 KB each), else the
-// smallest that fits at all; 0 = shape not eligible (two-pass fallback)
+// cluster size for the one-pass NCHW split: the smallest that lets >= 3 CTAs share an SM (<= 72 KB each); 0 = shape not
+// eligible (two-pass fallback).  A slab that needs more than 72 KB per CTA even at the largest cluster (the stress grid:
+// 64 x 7488 floats = 120 KB per CTA at 16) would run ONE CTA per SM, whose load / barrier / store phases then have nothing
+// to overlap with: measured 1.010 ms for the one-pass kernel against 0.655 ms for max pass + split pass at 64 stress
+// images (tools/shape_bench.py), so such shapes take the two passes.  SQD_SPLIT_CS forces a size (up to 200 KB per CTA).
 int split_cluster_size(int P, size_t *smem_out, int *nq4p_out) {
     if (P % 4 != 0 || sqd_opt(SQD_OPT_SPLIT_TWO_PASS)) return 0;
     const int n4 = P / 4;
     int pick = 0;
     const int force = sqd_opt(SQD_OPT_SPLIT_CS);
-    for (int pass = 0; pass < 2 && !pick; ++pass)
+    for (int pass = 0; pass < (force ? 2 : 1) && !pick; ++pass)
         for (int cs = 1; cs <= kSplitMaxCluster; cs <<= 1) {
             if (cs > n4) break;
             if (force && cs != force) continue;

@@ -360,10 +360,12 @@ def test_one_pass_split_equals_two_pass(ops, monkeypatch, name, batch):
     shp = {x.name: x for x in (synth.TINY, synth.KITTI, synth.STRESS)}[name]
     feat, (w, b) = dev(synth.features(shp, batch, 51)), synth.convdet_params(shp, 52)
     w, b = dev(w), dev(b)
-    one = ops.convdet_forward(feat, w, b, check_status=True)
+    with _lib.option("SQD_SPLIT_CS", 16 if name.startswith("stress") else 0):   # stress: one pass only when forced
+        one = ops.convdet_forward(feat, w, b, check_status=True)
     with _lib.option("SQD_SPLIT_TWO_PASS", 1):
         two = ops.convdet_forward(feat, w, b, check_status=True)
     assert torch.equal(one, two)
+    assert torch.equal(one, ops.convdet_forward(feat, w, b, check_status=True))   # whatever the default picks
     cl = ops.convdet_forward(feat.contiguous(memory_format=torch.channels_last), w, b, check_status=True)
     assert torch.equal(one, cl)   # channels_last input: same per-(image, block) scales, same planes
 
