@@ -116,8 +116,9 @@ struct Shared {
 // selected bin is needed in full.  Keys are unique (the anchor index is part of the key), so exactly k keys
 // satisfy key >= sel_lo.  Keys live in registers during the passes (kCap / kThreads per thread); the survivors
 // are written back unsorted, and the running threshold becomes sel_lo - 1.  All threads must call.
+template <int T = kThreads>
 __device__ void select_topk(Shared &sh, int k) {
-    constexpr int kPer = kCap / kThreads;
+    constexpr int kPer = kCap / T;
     __syncthreads();
     const int cnt = min(sh.count, kCap);
     if (cnt <= k) {           // nothing to cut (uniform)
@@ -128,14 +129,14 @@ __device__ void select_topk(Shared &sh, int k) {
     u64 my[kPer];
 #pragma unroll
     for (int i = 0; i < kPer; ++i) {
-        const int idx = threadIdx.x + i * kThreads;
+        const int idx = threadIdx.x + i * T;
         my[i] = idx < cnt ? sh.buf[idx] : 0ull;  // 0 is below every real key (score bits of a finite float are never 0)
     }
     const int lane = threadIdx.x & 31;
     u64 prefix = 0ull;
     int need = k, shift = 56;
     for (; shift >= 0; shift -= 8) {
-        if (threadIdx.x < 256) sh.hist[threadIdx.x] = 0;
+        for (int i = threadIdx.x; i < 256; i += T) sh.hist[i] = 0;
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
@@ -198,17 +199,18 @@ __device__ void select_topk(Shared &sh, int k) {
 
 // Sort the (<= k <= kCap/2) survivors in descending order by ranking: rank(i) = #{j : key_j > key_i}.
 // k*k/kThreads comparisons per thread (8 for k = 64); keys are unique so ranks are a permutation.
+template <int T = kThreads>
 __device__ void rank_sort(Shared &sh) {
     const int m = sh.count;
     u64 *out = sh.buf + kCap / 2;
-    for (int i = threadIdx.x; i < m; i += kThreads) {
+    for (int i = threadIdx.x; i < m; i += T) {
         const u64 key = sh.buf[i];
         int rank = 0;
         for (int j = 0; j < m; ++j) rank += sh.buf[j] > key ? 1 : 0;
         out[rank] = key;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < m; i += kThreads) sh.buf[i] = out[i];
+    for (int i = threadIdx.x; i < m; i += T) sh.buf[i] = out[i];
     __syncthreads();
 }
 
@@ -248,7 +250,7 @@ struct FilterOut {
 //    word' = ballot(pre & (own & word) == 0) to its fixed point -- after r rounds the first r lanes are final, and a
 //    fixed point satisfies the defining recurrence, whose solution is unique.  Typically 2-4 rounds per block.
 //  * output position = rank of (class, index) among the kept rows: class ascending / score descending.
-template <class Src>
+template <class Src, int T = kThreads>
 __device__ void nms_and_emit(const Src &src, Shared &sh, unsigned char *dyn, int k, int num_classes, float nms_thr_f,
                              float score_thr_f, const FilterOut &o, int img) {
     const int m = sh.count;
@@ -259,7 +261,7 @@ __device__ void nms_and_emit(const Src &src, Shared &sh, unsigned char *dyn, int
     unsigned *okey = col + (size_t)k * wpr;
     unsigned *keepw = okey + k;
 
-    for (int i = threadIdx.x; i < m; i += kThreads) {
+    for (int i = threadIdx.x; i < m; i += T) {
         const float4 b = src.box(key_anchor(sh.buf[i]));
         sbox[i] = b;
         sarea[i] = fmul(fsub(b.z, b.x), fsub(b.w, b.y));  // torchvision: (x2-x1)*(y2-y1), no +1
@@ -267,7 +269,7 @@ __device__ void nms_and_emit(const Src &src, Shared &sh, unsigned char *dyn, int
     __syncthreads();
     TAIL_STAMP(4);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = kThreads >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = T >> 5;
     // One (candidate i, 32-candidate word w) item per warp step, lanes = the j of the word.  Four items are evaluated
     // together (independent dependency chains: the IEEE division is ~40 dependent instructions), the division only runs
     // for lanes whose boxes intersect at all (inter > 0: otherwise the quotient is 0 or NaN and cannot exceed a threshold >= 0).
@@ -324,11 +326,12 @@ __device__ void nms_and_emit(const Src &src, Shared &sh, unsigned char *dyn, int
     TAIL_STAMP(6);
 
     // emit: class ascending, then descending score (== position) inside a class
-    unsigned mine[2];
+    constexpr int kEmitPer = (SQD_MAX_TOPK + T - 1) / T;   // candidates per thread (m <= k <= SQD_MAX_TOPK)
+    unsigned mine[kEmitPer];
     int n_valid = 0;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int t = threadIdx.x + h * kThreads;
+    for (int h = 0; h < kEmitPer; ++h) {
+        const int t = threadIdx.x + h * T;
         bool v = false;
         if (t < m) v = ((keepw[t >> 5] >> (t & 31)) & 1u) && key_score(sh.buf[t]) > score_thr_f;
         mine[h] = v ? ((unsigned)key_class(sh.buf[t]) << 16) | (unsigned)t : 0xFFFFFFFFu;
@@ -336,8 +339,8 @@ __device__ void nms_and_emit(const Src &src, Shared &sh, unsigned char *dyn, int
         n_valid += __syncthreads_count(v);
     }
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int t = threadIdx.x + h * kThreads;
+    for (int h = 0; h < kEmitPer; ++h) {
+        const int t = threadIdx.x + h * T;
         if (mine[h] == 0xFFFFFFFFu) continue;
         int pos = 0;
         for (int u = 0; u < m; ++u) pos += okey[u] < mine[h] ? 1 : 0;
@@ -348,7 +351,7 @@ __device__ void nms_and_emit(const Src &src, Shared &sh, unsigned char *dyn, int
         o.box[r] = sbox[t];
     }
     if (threadIdx.x == 0) o.count[img] = n_valid;
-    for (int t = n_valid + threadIdx.x; t < k; t += kThreads) {  // deterministic padding rows
+    for (int t = n_valid + threadIdx.x; t < k; t += T) {  // deterministic padding rows
         const size_t r = (size_t)img * k + t;
         o.anchor[r] = -1;
         o.cls[r] = -1;
@@ -537,20 +540,20 @@ __global__ void __launch_bounds__(kScanThreads) score_candidates_kernel(const fl
 // at or above the threshold bin fit the sort buffer; those are then collected (unordered) into sh.buf.  Typical lists
 // (thousands of distinct scores) need ONE level: histogram pass + collect pass.  Returns false (nothing collected) if
 // even single-score bins overflow the buffer (massive exact ties): the caller then uses the running-threshold loop.
-template <bool kInRegs>
+template <bool kInRegs, int T = kThreads>
 __device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, int n, int k, float score_thr_f) {
-    constexpr int kBins = 2048, kPerThread = kBins / kThreads;
+    constexpr int kBins = 2048, kPerThread = kBins / T;
     constexpr int kCollectCap = kCap / 2;
     constexpr int kHold = 16;  // keys per thread kept in registers when the list has <= kHold*kThreads entries
     int *hist = reinterpret_cast<int *>(sh.buf + kCap / 2);  // upper half of the key buffer: free until the sort
-    __shared__ int s_wtot[kThreads / 32];
+    __shared__ int s_wtot[T / 32];
     __shared__ int s_tb, s_above_add, s_tb_cnt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64 my[kInRegs ? kHold : 1];
     if (kInRegs) {  // ONE pass over the list, all loads in flight together; 0 = no key (never a real key)
 #pragma unroll
         for (int u = 0; u < kHold; ++u) {
-            const int i = threadIdx.x + u * kThreads;
+            const int i = threadIdx.x + u * T;
             my[u] = i < n ? __ldcg(keys + i) : 0ull;
         }
     }
@@ -561,11 +564,11 @@ __device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, in
             for (int u = 0; u < kHold; ++u)
                 if (my[u] != 0ull) fn(my[u]);
         } else {
-            for (int base = 0; base < n; base += 8 * kThreads) {
+            for (int base = 0; base < n; base += 8 * T) {
                 u64 t[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int i = base + u * kThreads + threadIdx.x;
+                    const int i = base + u * T + threadIdx.x;
                     t[u] = i < n ? __ldcg(keys + i) : 0ull;
                 }
 #pragma unroll
@@ -582,7 +585,7 @@ __device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, in
     int shift = 0;
     while ((span >> shift) >= (unsigned)kBins) ++shift;
     for (int level = 0; level < 4; ++level) {
-        for (int i = threadIdx.x; i < kBins; i += kThreads) hist[i] = 0;
+        for (int i = threadIdx.x; i < kBins; i += T) hist[i] = 0;
         __syncthreads();
         if (level == 0) TAIL_STAMP(11);
         for_each_key([&](u64 key) {
@@ -606,7 +609,7 @@ __device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, in
         if (lane == 0) s_wtot[warp] = suf;
         __syncthreads();
         int higher = 0;
-        for (int w = warp + 1; w < kThreads / 32; ++w) higher += s_wtot[w];
+        for (int w = warp + 1; w < T / 32; ++w) higher += s_wtot[w];
         const int incl = suf + higher, excl = incl - own;  // keys in bins of threads >= / > this one
         const int need = k - above;
         if (excl < need && need <= incl) {  // exactly one thread: the range holds at least `need` keys
@@ -647,10 +650,15 @@ __device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, in
 }
 
 // Phase 2: one CTA per image over its candidate list (a few hundred keys on real inputs; at most A).
-__global__ void __launch_bounds__(kThreads) detect_from_candidates_kernel(SqdCand cand, const float *pred,
-                                                                          const float4 *anchors, int A, int C, float wmax,
-                                                                          float hmax, int k, float nms_thr_f,
-                                                                          float score_thr_f, FilterOut o) {
+// T threads per CTA: 512 for small batches (the shortest latency chain per image), 128 for large ones -- the kernel is a
+// chain of short barrier-separated phases, so what a full GPU needs is MANY resident CTAs (8 per SM at 128 threads
+// against 2 at 512: 1024 images in one wave instead of 3.5).
+template <int T>
+__global__ void __launch_bounds__(T) detect_from_candidates_kernel(SqdCand cand, const float *pred,
+                                                                   const float4 *anchors, int A, int C, float wmax,
+                                                                   float hmax, int k, float nms_thr_f,
+                                                                   float score_thr_f, FilterOut o) {
+    constexpr int kRoundT = T * kUnroll;
     __shared__ Shared sh;
     extern __shared__ __align__(16) unsigned char dyn[];
     const int img = blockIdx.x;
@@ -673,29 +681,29 @@ __global__ void __launch_bounds__(kThreads) detect_from_candidates_kernel(SqdCan
     bool have = false;
     if (n <= max(k + 192, 256) && n <= kCap / 2) {
         // short list: sort it directly
-        for (int i = threadIdx.x; i < n; i += kThreads) sh.buf[i] = __ldcg(keys + i);
+        for (int i = threadIdx.x; i < n; i += T) sh.buf[i] = __ldcg(keys + i);
         if (threadIdx.x == 0) sh.count = n;
         __syncthreads();
         have = true;
     } else {
-        have = n <= 16 * kThreads ? hist_select_collect<true>(sh, keys, n, k, score_thr_f)
-                                  : hist_select_collect<false>(sh, keys, n, k, score_thr_f);
+        have = n <= 16 * T ? hist_select_collect<true, T>(sh, keys, n, k, score_thr_f)
+                           : hist_select_collect<false, T>(sh, keys, n, k, score_thr_f);
     }
     TAIL_STAMP(2);
     if (have) {
-        rank_sort(sh);  // descending: the first k entries are the top-k
+        rank_sort<T>(sh);  // descending: the first k entries are the top-k
         if (threadIdx.x == 0 && sh.count > k) sh.count = k;
         __syncthreads();
     } else {
         // fallback (massive exact score ties): running-threshold scan with exact radix selects
         if (threadIdx.x == 0) sh.count = 0;
         __syncthreads();
-        for (int base = 0; base < n; base += kRound) {
+        for (int base = 0; base < n; base += kRoundT) {
             const u64 thr = sh.thresh;
             u64 kk[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const int i = base + u * kThreads + threadIdx.x;
+                const int i = base + u * T + threadIdx.x;
                 kk[u] = i < n ? __ldcg(keys + i) : 0ull;
             }
 #pragma unroll
@@ -704,10 +712,10 @@ __global__ void __launch_bounds__(kThreads) detect_from_candidates_kernel(SqdCan
                     const int pos = atomicAdd(&sh.count, 1);
                     if (pos < kCap) sh.buf[pos] = kk[u];
                 }
-            if (__syncthreads_or(*(volatile int *)&sh.count > kCap - kRound)) select_topk(sh, k);
+            if (__syncthreads_or(*(volatile int *)&sh.count > kCap - kRoundT)) select_topk<T>(sh, k);
         }
-        select_topk(sh, k);
-        rank_sort(sh);
+        select_topk<T>(sh, k);
+        rank_sort<T>(sh);
     }
     TAIL_STAMP(3);
 #ifdef SQD_ENABLE_TRACE
@@ -716,7 +724,7 @@ __global__ void __launch_bounds__(kThreads) detect_from_candidates_kernel(SqdCan
         g_tail_trace[9] = sh.count;
     }
 #endif
-    nms_and_emit(src, sh, dyn, k, C, nms_thr_f, score_thr_f, o, img);
+    nms_and_emit<FromPred<0>, T>(src, sh, dyn, k, C, nms_thr_f, score_thr_f, o, img);
 }
 
 size_t dyn_smem_bytes(int k) {
@@ -848,7 +856,12 @@ int sqd_detect_from_candidates(SqdCand cand, const float *d_pred, const float *d
                                float *d_out_score, float *d_out_box, cudaStream_t st) {
     FilterOut o{d_count, d_out_anchor, d_out_class, d_out_score, reinterpret_cast<float4 *>(d_out_box)};
     const size_t smem = dyn_smem_bytes(top_k);
-    int rc = opt_in_smem(detect_from_candidates_kernel, smem);
+    // large batches: 128-thread CTAs, 8 per SM, so that every image's tail is resident at once (SQD_TAIL_THREADS forces)
+    const int tail_opt = sqd_opt(SQD_OPT_TAIL_THREADS);
+    // (measured, KITTI clustered pred: 1024 images 115.4 us with 128 threads vs 127.5 with 512; 256 images 53.5 vs 41.8 --
+    // up to two waves of 512-thread CTAs are the shorter chain)
+    const bool small_cta = tail_opt ? tail_opt == 128 : batch > 4 * SQD_SM_COUNT;
+    int rc = small_cta ? opt_in_smem(detect_from_candidates_kernel<128>, smem) : opt_in_smem(detect_from_candidates_kernel<kThreads>, smem);
     if (rc) return rc;
 #ifdef SQD_ENABLE_TRACE
     {
@@ -860,10 +873,13 @@ int sqd_detect_from_candidates(SqdCand cand, const float *d_pred, const float *d
     }
 #endif
     // always a dependent launch: its predecessor on the stream is the scan (or the GEMM whose epilogue scored)
-    cudaError_t e = sqd_launch_dependent(detect_from_candidates_kernel, dim3(batch), dim3(kThreads), smem, st, true, cand, d_pred,
-                                         reinterpret_cast<const float4 *>(d_anchors), num_anchors, num_classes,
-                                         (float)(input_w - 1), (float)(input_h - 1), top_k, float_at_or_below(nms_thresh),
-                                         (float)score_thresh, o);
+    const float4 *anc = reinterpret_cast<const float4 *>(d_anchors);
+    const float wmax = (float)(input_w - 1), hmax = (float)(input_h - 1), nthr = float_at_or_below(nms_thresh);
+    cudaError_t e = small_cta
+        ? sqd_launch_dependent(detect_from_candidates_kernel<128>, dim3(batch), dim3(128), smem, st, true, cand, d_pred, anc,
+                               num_anchors, num_classes, wmax, hmax, top_k, nthr, (float)score_thresh, o)
+        : sqd_launch_dependent(detect_from_candidates_kernel<kThreads>, dim3(batch), dim3(kThreads), smem, st, true, cand, d_pred,
+                               anc, num_anchors, num_classes, wmax, hmax, top_k, nthr, (float)score_thresh, o);
     if (e != cudaSuccess) {
         sqd_set_error("launch of detect_from_candidates_kernel failed: %s", cudaGetErrorString(e));
         return (int)e;

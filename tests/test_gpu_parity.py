@@ -187,6 +187,31 @@ def test_detect_two_phase_equals_clustered(ops, name, batch, score_thresh):
     assert int(two.count.sum()) > 0
 
 
+@pytest.mark.parametrize("name,batch", [("tiny_160x96", 5), ("kitti_1248x384", 597), ("stress_2496x768", 3)])
+@pytest.mark.parametrize("score_thresh", [None, -1.0])
+def test_tail_cta_size_does_not_change_results(ops, name, batch, score_thresh):
+    """The per-image tail runs in 512-thread CTAs for small batches and in 128-thread CTAs (8 per SM) above 592 images
+    (KITTI x 597 takes the small CTA by default); SQD_TAIL_THREADS forces either.  Same results, including the lists of
+    A candidates that score_thresh -1 produces (histogram select from L2 re-reads, running-threshold fallback)."""
+    shp = SHAPES[name]
+    thr = shp.score_thresh if score_thresh is None else score_thresh
+    if batch > 100 and score_thresh is not None:
+        batch = 40
+    a64, a32 = anchors_dev(shp)
+    base = synth.clustered_pred(shp, min(batch, 16), 407, anchors=a64)
+    dp = dev(base).repeat((batch + 15) // 16, 1, 1)[:batch].contiguous()
+    args = (dp, a32, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh, thr)
+    default = ops.detect_from_pred(*args, two_phase=True)
+    with _lib.option("SQD_TAIL_THREADS", 128):
+        small = ops.detect_from_pred(*args, two_phase=True)
+    with _lib.option("SQD_TAIL_THREADS", 512):
+        big = ops.detect_from_pred(*args, two_phase=True)
+    for f in ("count", "anchor", "cls", "score", "box"):
+        assert torch.equal(getattr(small, f), getattr(big, f)), f
+        assert torch.equal(getattr(default, f), getattr(big, f)), f
+    assert int(big.count.sum()) > 0
+
+
 def test_detect_two_phase_generic_class_count(ops):
     """A class count without a specialised kernel (C = 5) goes through the generic staged scan."""
     shp = synth.Shape("c5", (96, 160), 5, 16)
@@ -530,9 +555,12 @@ def test_filter_ties_and_max_sizes(ops, C, k, A, levels):
     one = ops.detect_from_pred(dp, a32, shp.input_hw, C, k, nms, thr, two_phase=False)
     dense = ops.decode_scores(dp, a32, shp.input_hw, C)
     unf = ops.topk_nms(dense["class_ids"], dense["scores"], dense["boxes"], C, k, nms, thr)
+    with _lib.option("SQD_TAIL_THREADS", 128):     # the 128-thread tail CTA large batches use
+        small = ops.detect_from_pred(dp, a32, shp.input_hw, C, k, nms, thr, two_phase=True)
     for f in ("count", "anchor", "cls", "score", "box"):
         assert torch.equal(getattr(two, f), getattr(one, f)), f
         assert torch.equal(getattr(two, f), getattr(unf, f)), f
+        assert torch.equal(getattr(two, f), getattr(small, f)), f
     ids, sc, bx = (dense[x].cpu().numpy() for x in ("class_ids", "scores", "boxes"))
     expect = [orc.filter_image(ids[b], sc[b], bx[b], C, k, nms, thr) for b in range(B)]
     _check_rows(dets_to_lists(two), expect, exact_values=True)
