@@ -271,37 +271,74 @@ __device__ void nms_and_emit(const Src &src, Shared &sh, unsigned char *dyn, int
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = T >> 5;
     // One (candidate i, 32-candidate word w) item per warp step, lanes = the j of the word.  Four items are evaluated
-    // together (independent dependency chains: the IEEE division is ~40 dependent instructions), the division only runs
-    // for lanes whose boxes intersect at all (inter > 0: otherwise the quotient is 0 or NaN and cannot exceed a threshold >= 0).
-    auto suppress_bits = [&](int i, int w) -> unsigned {
-        const int j = (w << 5) + lane;
-        bool sup = false;
-        if (j < i && key_class(sh.buf[j]) == key_class(sh.buf[i])) {
-            const float4 a = sbox[i], b = sbox[j];
-            const float iw = fmaxf(0.f, fsub(fminf(a.z, b.z), fmaxf(a.x, b.x)));
-            const float ih = fmaxf(0.f, fsub(fminf(a.w, b.w), fmaxf(a.y, b.y)));
-            const float inter = fmul(iw, ih);
-            if (inter > 0.f || nms_thr_f < 0.f) {   // (a negative threshold is met by iou == 0 too)
-                const float iou = fdiv(inter, fsub(fadd(sarea[i], sarea[j]), inter));
-                sup = iou > nms_thr_f;  // false for NaN, like the reference
-            }
-        }
-        return __ballot_sync(0xffffffffu, sup);
-    };
-    const int items = m * wpr;
-    for (int base = warp * 4; base < items; base += nwarp * 4) {
-        unsigned bits[4];
+    // together (independent dependency chains), and only lanes whose boxes intersect at all are tested (inter > 0:
+    // otherwise the quotient is 0 or NaN and cannot exceed a threshold >= 0).
+    // The reference's test is RN32(inter / uni) > thr (torchvision: float division, strict >).  For 0 <= thr and a finite
+    // positive divisor that is decided WITHOUT the ~40-instruction IEEE division: with thr+ the next float above thr,
+    //   RN32(q) > thr  <=>  RN32(q) >= thr+  <=>  q > mid, or q == mid and the tie rounds to thr+ (its mantissa is even),
+    // mid = (thr + thr+)/2, and q vs mid is inter vs mid*uni -- exact in double (25 x 24 significant bits).  With
+    // inter > 0 the only divisor the product form gets wrong is a negative one (quotient < 0 <= thr: never suppresses;
+    // uni is never -0 here): uni == 0 -> +inf > thr, uni == +inf -> 0, NaN -> false all come out right, and inter == inf
+    // makes uni -inf or NaN.  Negative (or absurdly large) thresholds take the division.
+    const float thr_up = __uint_as_float(__float_as_uint(nms_thr_f) + 1u);
+    const bool fast_ok = nms_thr_f >= 0.f && nms_thr_f < 1e30f;
+    const double thr_mid = 0.5 * ((double)nms_thr_f + (double)thr_up);
+    const bool tie_up = (__float_as_uint(thr_up) & 1u) == 0u;
+    // Word by word: a lane keeps candidate j = 32w + lane of the word (box, area, class) in registers and the warp walks
+    // the candidates i >= 32w it owns (every nwarp-th), four at a time.  Branch free -- invalid lanes are masked at the
+    // end -- so the four items' shared-memory loads and arithmetic overlap; the division path is taken by a warp only if
+    // one of its lanes needs it.  Item (i, w) with 32w == i has no j < i and writes 0 (the sweep reads it as `own`).
+    for (int w = 0; (w << 5) < m; ++w) {
+        const int j = (w << 5) + lane, jc = min(j, m - 1);
+        const float4 bj = sbox[jc];
+        const float aj = sarea[jc];
+        const int cj = key_class(sh.buf[jc]);
+        for (int i0 = (w << 5) + warp; i0 < m; i0 += 4 * nwarp) {
+            unsigned bits[4];
+            if (fast_ok) {   // uniform.  Bitwise (not short-circuit) logic: no branches, the four chains interleave
+                float4 a[4];
+                float ai[4];
+                int ci[4], ii[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int item = base + u;
-            bits[u] = 0u;
-            if (item < items) {
-                const int i = wpr == 2 ? item >> 1 : item / wpr, w = item - i * wpr;
-                if ((w << 5) < i) bits[u] = suppress_bits(i, w);   // else: no j < i in this word (warp-uniform)
+                for (int u = 0; u < 4; ++u) {
+                    ii[u] = min(i0 + u * nwarp, m - 1);
+                    a[u] = sbox[ii[u]];
+                    ai[u] = sarea[ii[u]];
+                    ci[u] = key_class(sh.buf[ii[u]]);
+                }
+                bool sup[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float iw = fmaxf(0.f, fsub(fminf(a[u].z, bj.z), fmaxf(a[u].x, bj.x)));
+                    const float ih = fmaxf(0.f, fsub(fminf(a[u].w, bj.w), fmaxf(a[u].y, bj.y)));
+                    const float inter = fmul(iw, ih);
+                    const float uni = fsub(fadd(ai[u], aj), inter);
+                    const double prod = thr_mid * (double)uni, di = (double)inter;
+                    const bool cmp = tie_up ? di >= prod : di > prod;
+                    sup[u] = (j < ii[u]) & (cj == ci[u]) & (inter > 0.f) & !(uni < 0.f) & cmp;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) bits[u] = __ballot_sync(0xffffffffu, sup[u]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = min(i0 + u * nwarp, m - 1);
+                    const float4 a = sbox[i];
+                    const float iw = fmaxf(0.f, fsub(fminf(a.z, bj.z), fmaxf(a.x, bj.x)));
+                    const float ih = fmaxf(0.f, fsub(fminf(a.w, bj.w), fmaxf(a.y, bj.y)));
+                    const float inter = fmul(iw, ih);
+                    const float uni = fsub(fadd(sarea[i], aj), inter);
+                    const bool same = j < i && cj == key_class(sh.buf[i]);
+                    const bool sup = same && (inter > 0.f || nms_thr_f < 0.f) && fdiv(inter, uni) > nms_thr_f;  // false for NaN
+                    bits[u] = __ballot_sync(0xffffffffu, sup);
+                }
+            }
+            if (lane < 4) {
+                const int i = i0 + lane * nwarp;
+                const unsigned mine = lane == 0 ? bits[0] : lane == 1 ? bits[1] : lane == 2 ? bits[2] : bits[3];
+                if (i < m) col[i * wpr + w] = mine;
             }
         }
-        const unsigned mine = lane == 0 ? bits[0] : lane == 1 ? bits[1] : lane == 2 ? bits[2] : bits[3];
-        if (lane < 4 && base + lane < items) col[base + lane] = mine;
     }
     __syncthreads();
     TAIL_STAMP(5);
@@ -546,6 +583,9 @@ __device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, in
     constexpr int kCollectCap = kCap / 2;
     constexpr int kHold = 16;  // keys per thread kept in registers when the list has <= kHold*kThreads entries
     int *hist = reinterpret_cast<int *>(sh.buf + kCap / 2);  // upper half of the key buffer: free until the sort
+    // bin b lives at hist[b ^ ((b >> 5) & 31)]: thread t reads its kPerThread CONSECUTIVE bins one per step, which without
+    // the swizzle is a 16-way (128 threads) / 4-way (512 threads) bank conflict per step; with it every step is conflict free
+    auto hpos = [](unsigned b) { return b ^ ((b >> 5) & 31u); };
     __shared__ int s_wtot[T / 32];
     __shared__ int s_tb, s_above_add, s_tb_cnt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -590,14 +630,14 @@ __device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, in
         if (level == 0) TAIL_STAMP(11);
         for_each_key([&](u64 key) {
             const unsigned sb = (unsigned)(key >> 32);
-            if (sb >= lo && sb <= hi) atomicAdd(&hist[min((sb - lo) >> shift, (unsigned)(kBins - 1))], 1);
+            if (sb >= lo && sb <= hi) atomicAdd(&hist[hpos(min((sb - lo) >> shift, (unsigned)(kBins - 1)))], 1);
         });
         __syncthreads();
         if (level == 0) TAIL_STAMP(12);
         int c[kPerThread], own = 0;
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) {
-            c[j] = hist[threadIdx.x * kPerThread + j];
+            c[j] = hist[hpos(threadIdx.x * kPerThread + j)];
             own += c[j];
         }
         int suf = own;  // inclusive suffix sum over the lanes >= this one
@@ -654,7 +694,7 @@ __device__ bool hist_select_collect(Shared &sh, const u64 *__restrict__ keys, in
 // chain of short barrier-separated phases, so what a full GPU needs is MANY resident CTAs (8 per SM at 128 threads
 // against 2 at 512: 1024 images in one wave instead of 3.5).
 template <int T>
-__global__ void __launch_bounds__(T) detect_from_candidates_kernel(SqdCand cand, const float *pred,
+__global__ void __launch_bounds__(T, T == 128 ? 8 : 1) detect_from_candidates_kernel(SqdCand cand, const float *pred,
                                                                    const float4 *anchors, int A, int C, float wmax,
                                                                    float hmax, int k, float nms_thr_f,
                                                                    float score_thr_f, FilterOut o) {

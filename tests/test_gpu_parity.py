@@ -791,3 +791,30 @@ def test_demo_samples_vs_reference_golden(ops, golden):
             assert len(res["class_ids"]) > 10
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+@pytest.mark.parametrize("thresh", [0.5, 0.25, 1.0 / 3.0, 0.4, 0.2, 0.0, 0.75, float(np.float32(1.0 / 3.0)),
+                                    float(np.nextafter(np.float32(0.5), np.float32(0))), 1.0, 2.0, -0.1])
+def test_nms_threshold_boundary_is_exact(ops, thresh):
+    """The tail decides `float(inter / union) > thresh` without the division (inter vs mid * union in double, see
+    nms_and_emit).  Boxes on a small integer lattice make thousands of pairs whose IoU is EXACTLY a small rational --
+    1/2, 1/3, 2/5, 1/4 ... -- so thresholds on, just below and just above such values, 0, 1, > 1 and negative ones must
+    all reproduce the reference arithmetic (oracle.nms = torchvision's CPU rules, pinned by nms_torchvision.npz); rows
+    with zero-area, inverted and infinite boxes take the division path."""
+    rs = np.random.RandomState(int(abs(thresh) * 1000) + 5)
+    B, A, k = 6, 400, 256
+    xy = rs.randint(0, 6, size=(B, A, 2)).astype(np.float32)
+    wh = rs.randint(1, 7, size=(B, A, 2)).astype(np.float32)
+    boxes = np.concatenate([xy, xy + wh], axis=2)
+    boxes[0, :30, 2:] = boxes[0, :30, :2]                       # zero-area boxes (0/0 -> NaN: never suppress)
+    boxes[1, :20, [0, 2]] = boxes[1, :20, [2, 0]]               # inverted boxes (negative areas)
+    boxes[2, :10, 2] = np.inf                                   # infinite extent
+    boxes[3] *= np.float32(1e-20)                               # tiny areas: products in the denormal range
+    boxes[4] *= np.float32(3e18)                                # huge areas: area sums overflow to inf
+    scores = rs.permutation(B * A).reshape(B, A).astype(np.float32) / (B * A) * 0.5 + 0.4    # distinct
+    ids = np.zeros((B, A), dtype=np.int64)
+    out = ops.topk_nms(dev(ids), dev(scores), dev(boxes), 1, k, thresh, 0.05)
+    for b in range(B):
+        exp = orc.filter_image(ids[b], scores[b], boxes[b], 1, k, thresh, 0.05)
+        n = int(out.count[b])
+        assert np.array_equal(out.anchor[b, :n].cpu().numpy(), exp["anchor_idx"]), (thresh, b)
