@@ -639,7 +639,25 @@ def main_ours(args):
                 self.base, self.loss = full.base, full.loss
 
             def forward(self, batch):
-                return self.loss(self.base.head(batch["features"]), batch["gt"])
+                pred = self.base.head(batch["features"])
+                gt = batch["gt"]
+                if isinstance(gt, tuple):      # (dense targets built on a side stream, the event that marks them ready)
+                    gt, ready = gt
+                    torch.cuda.current_stream(dev).wait_event(ready)
+                return self.loss(pred, gt)
+
+        class _FeatureGradSink(torch.autograd.Function):
+            """Stands where the backbone's backward would: takes the feature gradient the dgrad GEMM wrote (channels_last
+            memory) and ends the graph there.  Without it `tfeat` is a leaf and autograd's AccumulateGrad re-lays the
+            115 MB gradient out as NCHW -- a 137 us strided copy per step (tools/train_profile.py) that belongs to neither
+            the path nor a real training step, where the gradient goes on into the backbone."""
+            @staticmethod
+            def forward(ctx, x):
+                return x.view_as(x)
+
+            @staticmethod
+            def backward(ctx, g):
+                return None
 
         head = HeadWithLoss(net)
         bucket = sdist.bucket_for(net)
@@ -648,10 +666,24 @@ def main_ours(args):
         gt_packed = matcher.pack(list(box_l), list(cls_l))
         tfeat = feats[0].detach().clone().requires_grad_(True)
 
+        # The reference builds the targets in DataLoader workers, i.e. beside the GPU work (datasets/base.py:52-76); here
+        # the matcher (80 us, a latency chain on 160 CTAs) runs on a side stream beside the ConvDet forward and the loss
+        # waits for its event -- inside the CUDA graph that is a fork / join.
+        side = torch.cuda.Stream(device=dev)
+
+        def targets_on_side_stream():
+            cur = torch.cuda.current_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                gt = matcher.dense_targets(*gt_packed)
+                ready = torch.cuda.Event()
+                ready.record(side)
+            gt.record_stream(cur)
+            return gt, ready
+
         def train_iter(_i):
             tfeat.grad = None
-            gt = matcher.dense_targets(*gt_packed)
-            return sdist.train_step(head, {"features": tfeat, "gt": gt}, bucket)
+            return sdist.train_step(head, {"features": _FeatureGradSink.apply(tfeat), "gt": targets_on_side_stream()}, bucket)
 
         nt = max(10, min(K, 50))
         ms_train_eager = timed_steps(train_iter, nt, 5)
@@ -700,8 +732,7 @@ def main_ours(args):
 
                     def head_iter(_i):
                         tfeat.grad = None
-                        gt = matcher.dense_targets(*gt_packed)
-                        return sdist.train_step(head, {"features": tfeat, "gt": gt}, hb)
+                        return sdist.train_step(head, {"features": _FeatureGradSink.apply(tfeat), "gt": targets_on_side_stream()}, hb)
                     gh_full = sdist.GraphedStep(lambda: head_iter(0))
                     t_with = timed_steps(lambda _i: gh_full(), nt, 3)
                     hb._distributed = lambda: False
@@ -716,8 +747,9 @@ def main_ours(args):
         use_graph = graphed["ms_per_step"] is not None
         ms_train = graphed["ms_per_step"] if use_graph else ms_train_eager
         ms_train_local = graphed["ms_per_step_without_allreduce"] if use_graph else ms_train_eager_local
-        extra["train_step"] = {"workload": "BASELINE configs[3]: training step of the path at KITTI batch %d per GPU: matcher + targets, "
-                                           "ConvDet forward, loss fwd+bwd, native wgrad/bias/dgrad, all-reduce of the flat gradient "
+        extra["train_step"] = {"workload": "BASELINE configs[3]: training step of the path at KITTI batch %d per GPU: matcher + targets (side "
+                                           "stream, beside the forward), ConvDet forward, loss fwd+bwd, native wgrad/bias/dgrad (feature "
+                                           "gradient handed over as channels_last memory), all-reduce of the flat gradient "
                                            "bucket (%d floats, head segment %d launched before the dgrad GEMM)" % (B, bucket.flat.numel(), bucket.early_numel),
                                "ms_per_step": ms_train, "images_per_s": world * B / (ms_train * 1e-3),
                                "mode": "one CUDA graph replay per step (dist.GraphedStep)" if use_graph else "eager",

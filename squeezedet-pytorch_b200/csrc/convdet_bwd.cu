@@ -18,6 +18,8 @@
 
 size_t sqd_f16_packed_bytes(int cout, int cin);
 int sqd_f16_pack_weights(const float *d_weight, int cout, int cin, void *d_packed, cudaStream_t st);
+int sqd_f16_pack_dgrad_slabs(const float *d_weight, int cout, int cin, int slab_rows, int kp, int nslabs, void *d_packed,
+                             size_t slab_bytes, float *d_scratch, cudaStream_t st);
 size_t sqd_f16_split_bytes(int batch, int cin, int gh, int gw);
 size_t sqd_f16_workspace_bytes(int batch, int cin, int gh, int gw, int cout, int layout);
 int sqd_convdet_f16_pair(const float *d_feat, int layout, const void *d_packed, const float *d_bias, int batch, int cin,
@@ -367,6 +369,9 @@ extern "C" int sqd_convdet_dgrad_pack_weights(const float *d_weight, int cout, i
     const int kp = kpad_of(cout), ns = nslab_of(cin);
     const size_t slab_bytes = align256(sqd_f16_packed_bytes(kSlab, kp));
     char *base = static_cast<char *>(d_packed);
+    if (!sqd_opt(SQD_OPT_DGRAD_PACK_LOOP))   // default: every slab in two launches, straight from W (same bytes)
+        return sqd_f16_pack_dgrad_slabs(d_weight, cout, cin, kSlab, kp, ns, d_packed, slab_bytes,
+                                        reinterpret_cast<float *>(base + (size_t)ns * slab_bytes), st);
     float *tmp = reinterpret_cast<float *>(base + (size_t)ns * slab_bytes);
     for (int s = 0; s < ns; ++s) {
         flip_transpose_weights_kernel<<<SQD_SM_COUNT, 256, 0, st>>>(d_weight, cout, cin, kp, s, tmp);

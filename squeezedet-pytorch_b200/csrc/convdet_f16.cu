@@ -1586,6 +1586,88 @@ int sqd_f16_pack_weights(const float *d_weight, int cout, int cin, void *d_packe
     return SQD_OK;
 }
 
+// ---- the dgrad GEMM's weight slabs, all of them in TWO launches ---------------------------------------------------------
+// Slab s is the packed form (header + both fp16 layouts, exactly what sqd_f16_pack_weights writes) of the flipped /
+// transposed matrix W2_s (slab_rows, kp, 3, 3), W2_s[j][n][t] = W[n][s*slab_rows + j][8 - t], zero outside W.  Built
+// slab by slab that is a transpose kernel, a memset, a max kernel and a pack kernel per slab -- 24 launches of a few
+// microseconds each for the KITTI head, 70 us of a training step that re-packs after every optimizer step; here one block
+// per slab reduces max|W| of its channels straight from W and one grid packs every slab from W.  Same bytes.
+namespace {
+constexpr int kSlabMaxBlocks = 24;   // blocks per slab of the max kernel; their partial maxima go through `partial`
+__global__ void __launch_bounds__(256) dgrad_slab_absmax_kernel(const float *__restrict__ w, int cout, int cin, int slab_rows,
+                                                                float *__restrict__ partial) {
+    const int s = blockIdx.y;
+    const int c0 = s * slab_rows, nc = min(slab_rows, cin - c0), run = nc * 9;   // per output channel: one contiguous run
+    float m = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cout * run; i += gridDim.x * blockDim.x) {
+        const int n = i / run, r = i - n * run;
+        m = fmaxf(m, fabsf(w[((size_t)n * cin + c0) * 9 + r]));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float s_m[8];
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i) m = fmaxf(m, s_m[i]);
+        partial[s * kSlabMaxBlocks + blockIdx.x] = m;
+    }
+}
+
+__global__ void pack_dgrad_slabs_kernel(const float *__restrict__ w, int cout, int cin, int slab_rows, int kp, int npad, int hr,
+                                        char *base, size_t slab_bytes, const float *__restrict__ partial) {
+    const int s = blockIdx.y;
+    PackedHeader *hdr = reinterpret_cast<PackedHeader *>(base + (size_t)s * slab_bytes);
+    const size_t ktot = (size_t)9 * kp, total = (size_t)npad * ktot;
+    __half *mat = reinterpret_cast<__half *>(base + (size_t)s * slab_bytes + kHeaderBytes), *mat2 = mat + 2 * total;
+    float amax = 0.f;
+    for (int i = 0; i < kSlabMaxBlocks; ++i) amax = fmaxf(amax, __ldg(partial + s * kSlabMaxBlocks + i));
+    const float sc = pow2_scale_for(amax);
+    if (blockIdx.x == 0) {   // the header: every byte, like the memset + field writes of sqd_f16_pack_weights
+        if (threadIdx.x < kHeaderBytes / 4) reinterpret_cast<unsigned *>(hdr)[threadIdx.x] = 0u;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            hdr->amax_bits = __float_as_uint(amax);
+            hdr->scale = sc;
+            hdr->inv_scale = 1.f / sc;
+            hdr->npad = npad;
+            hdr->cin = kp;
+            hdr->hr = hr;
+        }
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / ktot);                       // row of the slab: feature channel s*slab_rows + n
+        const size_t k = i % ktot;
+        const int tap = (int)(k / kp), c = (int)(k % kp);    // c: gradient (output) channel, padded to kp
+        const int fc = s * slab_rows + n;
+        float v = 0.f;
+        if (n < slab_rows && c < cout && fc < cin) v = w[((size_t)c * cin + fc) * 9 + (8 - tap)];
+        __half h1, h2;
+        split_f16(v * sc, h1, h2);
+        mat[i] = h2;
+        mat[total + i] = h1;
+        if (n < 2 * hr) {
+            const int r = n / hr, j = n - r * hr;
+            mat2[((size_t)(r * 2 * hr + j)) * ktot + k] = h1;
+            mat2[((size_t)(r * 2 * hr + hr + j)) * ktot + k] = h2;
+        }
+    }
+}
+}  // namespace
+
+// d_scratch: at least nslabs * 24 floats (the caller passes the scratch matrix behind the slabs)
+int sqd_f16_pack_dgrad_slabs(const float *d_weight, int cout, int cin, int slab_rows, int kp, int nslabs, void *d_packed,
+                             size_t slab_bytes, float *d_scratch, cudaStream_t st) {
+    SQD_REQUIRE(kp % kBlockK == 0 && slab_rows >= 1 && slab_rows <= 128, SQD_E_SHAPE, "dgrad weight slabs: bad shape");
+    char *base = static_cast<char *>(d_packed);
+    dgrad_slab_absmax_kernel<<<dim3(kSlabMaxBlocks, nslabs), 256, 0, st>>>(d_weight, cout, cin, slab_rows, d_scratch);
+    SQD_LAUNCH_CHECK("dgrad_slab_absmax_kernel");
+    pack_dgrad_slabs_kernel<<<dim3(SQD_SM_COUNT, nslabs), 256, 0, st>>>(d_weight, cout, cin, slab_rows, kp, npad_of(slab_rows),
+                                                                         pair_hr_of(slab_rows), base, slab_bytes, d_scratch);
+    SQD_LAUNCH_CHECK("pack_dgrad_slabs_kernel");
+    return SQD_OK;
+}
+
 namespace {
 int pair_stages_for(int n1h) {
     const size_t stage = (size_t)kAStageBytes + (size_t)3 * n1h * kBlockK * 2;

@@ -386,6 +386,25 @@ def test_a_once_operand_layout_is_bit_identical(ops, name, batch):
     assert not torch.equal(ao, torch.zeros_like(ao))
 
 
+@pytest.mark.parametrize("cout,cin", [(72, 768), (117, 768), (24, 128), (50, 192), (8, 64)])
+def test_dgrad_weight_slabs_two_launches_equal_slab_loop(ops, cout, cin):
+    """sqd_convdet_dgrad_pack_weights: all slabs in two launches straight from W (default) against the slab-by-slab
+    transpose / memset / max / pack loop (SQD_DGRAD_PACK_LOOP=1): byte-identical slabs (the trailing scratch matrix of the
+    loop route is not part of the format)."""
+    from squeezedet_pytorch_b200 import _lib as L
+    rs = np.random.RandomState(cout * 1000 + cin)
+    w = dev((rs.standard_normal((cout, cin, 3, 3)) * 10.0 ** rs.uniform(-3, 3)).astype(np.float32))
+    new = ops.pack_convdet_dgrad_weights(w)
+    with L.option("SQD_DGRAD_PACK_LOOP", 1):
+        old = ops.pack_convdet_dgrad_weights(w)
+    kp = (cout + 63) // 64 * 64
+    nslab = (cin + 127) // 128
+    scratch = (128 * kp * 9 * 4 + 255) // 256 * 256
+    n = new.numel() - scratch
+    assert n > 0 and n % nslab == 0
+    assert torch.equal(new[:n], old[:n])
+
+
 def test_split_grid_not_multiple_of_four(ops):
     """6 x 11 grid (P = 66, not a multiple of 4): the one-pass kernel is not eligible; scales differ wildly between
     channel blocks and images (1e-6 ... 1e4) and the result still matches the fp32 SIMT kernel."""
