@@ -42,23 +42,58 @@ class Detector(object):
         self.model = model.to(cfg.device)
         self.model.eval()
         self.cfg = cfg
+        # cfg.cuda_graph = True: backbone + path of a batch shape are captured once into a CUDA graph and replayed --
+        # the batch-1 demo (demo.py:17-52) is launch bound in the stock backbone (~60 small kernels, 1.8 ms eager)
+        self.use_graph = bool(getattr(cfg, "cuda_graph", False))
+        self._graphs = {}
 
     # -- the fast path: features -> final detections, one host crossing ------------------------------
     @torch.no_grad()
     def detect_batch(self, batch, postprocess=True):
         """Device-side result for a batch {'image': (B,3,H,W)} (+ optional 'image_meta'):
         (Detections with the boxes still in network-input coordinates, (B,10) postprocess records or None)."""
-        cfg = self.cfg
-        base = self.model.base
-        feat = base.features(batch["image"])
-        anchors = self.model.resolver._anchors_on(feat.device)
-        det = ops.head_detect(feat, base.convdet.weight, base.convdet.bias, anchors, cfg.anchors_per_grid,
-                              cfg.num_classes, cfg.input_size, cfg.keep_top_k, cfg.nms_thresh, cfg.score_thresh,
-                              packed=base.packed_weights(), algo=base.conv_algo)
+        image = batch["image"]
+        det = self._detect_graphed(image) if self.use_graph and image.is_cuda else self._detect_eager(image)
         meta = None
         if postprocess and "image_meta" in batch and batch["image_meta"]:
-            meta = torch.from_numpy(_meta_record(batch["image_meta"], det.count.shape[0])).to(feat.device)
+            meta = torch.from_numpy(_meta_record(batch["image_meta"], det.count.shape[0])).to(image.device)
         return det, meta
+
+    def _detect_eager(self, image, out=None):
+        cfg, base = self.cfg, self.model.base
+        feat = base.features(image)
+        anchors = self.model.resolver._anchors_on(feat.device)
+        return ops.head_detect(feat, base.convdet.weight, base.convdet.bias, anchors, cfg.anchors_per_grid,
+                               cfg.num_classes, cfg.input_size, cfg.keep_top_k, cfg.nms_thresh, cfg.score_thresh,
+                               packed=base.packed_weights(), algo=base.conv_algo, out=out)
+
+    def _detect_graphed(self, image):
+        """One CUDA graph per (input shape, weight version): replay = copy the batch into the graph's input buffer + one
+        launch.  The returned Detections are the graph's own output block: valid until the next call with this shape."""
+        w = self.model.base.convdet.weight
+        key = (tuple(image.shape), image.dtype, str(image.device), w._version, w.data_ptr())
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= 8:            # stale shapes / weight versions
+                self._graphs.clear()
+            static_in = torch.empty_like(image)
+            static_in.copy_(image)
+            det = ops._alloc_detections(image.shape[0], self.cfg.keep_top_k, image.device)
+            cur = torch.cuda.current_stream(image.device)
+            side = torch.cuda.Stream(device=image.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(3):                # cuDNN algorithm selection, workspaces, packed weights: before capture
+                    self._detect_eager(static_in, out=det)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._detect_eager(static_in, out=det)
+            entry = self._graphs[key] = (graph, static_in, det)
+        graph, static_in, det = entry
+        static_in.copy_(image)
+        graph.replay()
+        return det
 
     @torch.no_grad()
     def detect_packed(self, batch):

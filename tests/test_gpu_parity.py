@@ -761,6 +761,7 @@ def test_demo_samples_vs_reference_golden(ops, golden):
         model = SqueezeDet(cfg)
         model.load_state_dict(synth.demo_state_dict(model, shp, int(g["seed"])))
         det = Detector(model, cfg)
+        det_graph = Detector(model, sqd_config.kitti_config(device="cuda", cuda_graph=True))
         a64 = synth.anchor_table(shp)
         for i in range(int(g["n"])):
             rgb = g[f"image_{i}"]
@@ -782,8 +783,12 @@ def test_demo_samples_vs_reference_golden(ops, golden):
             exp = orc.detect_filtered(pred, a64, shp.input_hw, shp.num_classes, shp.top_k, shp.nms_thresh, shp.score_thresh)[0]
             n = int(raw.count[0])
             assert np.array_equal(raw.anchor[0, :n].cpu().numpy(), exp["anchor_idx"])
-            # (2) end to end against the reference's Detector.detect
+            # (2) end to end against the reference's Detector.detect -- eager and as a replayed CUDA graph (cfg.cuda_graph)
+            gres = det_graph.detect({"image": x, "image_meta": meta})[0]
+            gres = det_graph.detect({"image": x, "image_meta": meta})[0]      # second call: a replay
             res = det.detect({"image": x, "image_meta": meta})[0]
+            for f in ("class_ids", "scores", "boxes"):
+                assert np.array_equal(res[f], gres[f]), f
             assert np.array_equal(res["class_ids"], g[f"class_ids_{i}"])
             assert np.array_equal(raw.anchor[0, :n].cpu().numpy(), g[f"anchor_{i}"])
             np.testing.assert_allclose(res["scores"], g[f"scores_{i}"], rtol=1e-3)
