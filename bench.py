@@ -132,7 +132,7 @@ def cpu_reference_pass(orc, feat, w, b, anchors, shp):
                                shp.score_thresh)
 
 
-def make_reference_runner(shp, w, b):
+def make_reference_runner(shp, w, b, device="cpu"):
     """The reference's OWN classes, imported from oracle/_ref (a verbatim copy made by oracle/make_ref.py; absent ->
     None): SqueezeDet with the backbone replaced by Identity, so SqueezeDetBase.forward's tail (squeezedet.py:79-87),
     PredictionResolver and SqueezeDet.forward (:109-120,197-206) run on Fire11-shaped input, then Detector.detect
@@ -147,7 +147,7 @@ def make_reference_runner(shp, w, b):
     anchors = ref.boxes.generate_anchors(shp.grid_hw, shp.input_hw, synth.KITTI_SEEDS)
     cfg = types.SimpleNamespace(
         input_size=shp.input_hw, num_classes=shp.num_classes, anchors=anchors, anchors_per_grid=shp.anchors_per_grid,
-        num_anchors=anchors.shape[0], arch="squeezedet", dropout_prob=0.5, device=torch.device("cpu"),
+        num_anchors=anchors.shape[0], arch="squeezedet", dropout_prob=0.5, device=torch.device(device),
         keep_top_k=shp.top_k, nms_thresh=shp.nms_thresh, score_thresh=shp.score_thresh, debug=0, mode="eval",
         class_loss_weight=1.0, positive_score_loss_weight=3.75, negative_score_loss_weight=100.0, bbox_loss_weight=6.0)
     net = ref.model.SqueezeDet(cfg)
@@ -862,6 +862,21 @@ def main_ours(args):
         a_cpu = torch.from_numpy(synth.anchor_table(shp).astype(np.float32))[None]
         run_ref = lambda f: torch_port.detect(f, weight, bias, a_cpu, shp.num_classes, shp.input_hw, shp.top_k,  # noqa: E731
                                               shp.nms_thresh, shp.score_thresh)
+        gpu_kind = ("port of the reference's PyTorch CUDA path (oracle/torch_port.py): cuDNN fp32 conv + ATen decode + "
+                    "per-image argsort / torchvision.ops.nms loop with its host syncs")
+        try:    # the reference's OWN classes on the GPU when oracle/_ref travelled: cfg.device = cuda, nothing else changed
+            ref_gpu = make_reference_runner(shp, w_np, b_np, device=str(dev))
+        except Exception as e:      # noqa: BLE001 -- e.g. torchvision without CUDA ops: keep the port
+            ref_gpu = None
+            print("reference classes on the GPU unavailable: %r" % (e,), file=sys.stderr)
+        if ref_gpu is not None:
+            with torch.no_grad():
+                first = ref_gpu(feats[0])
+            assert len(first) == B
+            run_ref = ref_gpu
+            gpu_kind = ("reference: the reference's own SqueezeDet (Identity backbone) + Detector.detect from oracle/_ref "
+                        "with cfg.device = cuda (cuDNN fp32 conv, ATen decode kernels, per-image argsort / torchvision nms "
+                        "loop with its host syncs and per-image .cpu() copies)")
         for i in range(2):
             run_ref(feats[i % R])
         torch.cuda.synchronize()
@@ -872,8 +887,7 @@ def main_ours(args):
             nref += 1
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / nref
-        gpu_ref = {"value": B / dt, "unit": "images/s", "kind": "port of the reference's PyTorch CUDA path (oracle/torch_port.py): "
-                   "cuDNN fp32 conv + ATen decode + per-image argsort / torchvision.ops.nms loop with its host syncs",
+        gpu_ref = {"value": B / dt, "unit": "images/s", "kind": gpu_kind,
                    "sample": "%d passes over one batch of %d resident feature maps, wall clock" % (nref, B),
                    "ms_per_step": dt * 1e3}
 
