@@ -16,7 +16,8 @@
 //     keys, no sort) and the threshold raised.  After the first cut almost nothing passes (expected
 //     k*ln(A/2048) more candidates).  Only the final k survivors are sorted (by ranking).
 //  2. The k survivors (sorted) get their boxes; a k x k same-class IoU bitmask is built with one
-//     ballot per 32 pairs; greedy NMS is then solved block by block (32 candidates) as a fixed point of
+//     ballot per 32 pairs (the reference's `float(inter/union) > thresh` decided exactly WITHOUT the division, see
+//     nms_and_emit); greedy NMS is then solved block by block (32 candidates) as a fixed point of
 //     word' = ballot(pre & (own & word) == 0): no k-step serial chain, typically 2-4 rounds per block.
 //  3. Kept rows with score > thresh are emitted class-ascending / score-descending.
 // The running threshold starts at the score threshold (exact, see score_floor_key), so on real inputs only a few
@@ -37,7 +38,7 @@ constexpr int kUnroll = 2;
 constexpr int kRound = kThreads * kUnroll;  // anchors consumed per round
 constexpr int kCap = 2048;                  // candidate buffer entries (>= SQD_MAX_TOPK + kRound)
 static_assert(kCap >= SQD_MAX_TOPK + kRound, "candidate buffer too small");
-static_assert(2 * kThreads >= SQD_MAX_TOPK, "the emit phase handles two candidates per thread");
+static_assert(SQD_MAX_TOPK <= kCap / 2, "the emit phase handles ceil(SQD_MAX_TOPK / T) candidates per thread, T = 128 or 512");
 static_assert(kCap / 2 >= SQD_MAX_TOPK, "rank_sort uses the upper half of the buffer as its destination");
 
 typedef sqd_u64 u64;
