@@ -397,27 +397,23 @@ def main_ours(args):
     # batch 20 the tail runs on 20 of 148 SMs).  Every step does all of its work; only the order of independent steps'
     # kernels on the GPU changes (tools/two_slot_bench.py: 148 -> 137 us per step; three slots are slower).
     S = max(1, args.slots)
-    slot_streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
-    slot_dets = [ops._alloc_detections(B, shp.top_k, dev) for _ in range(S)]
+    loop = ops.HeadDetectLoop(weight, bias, anchors, shp.anchors_per_grid, shp.num_classes, shp.input_hw, shp.top_k,
+                              shp.nms_thresh, shp.score_thresh, slots=S, packed=packed)
 
     def slot_step(i):
-        with torch.cuda.stream(slot_streams[i % S]):
-            ops.head_detect(feats[i % R], weight, bias, anchors, shp.anchors_per_grid, shp.num_classes, shp.input_hw,
-                            shp.top_k, shp.nms_thresh, shp.score_thresh, packed=packed, out=slot_dets[i % S], slot=i % S)
+        return loop.submit(feats[i % R])
 
     def timed_slot_loop(n):
-        """n steps over the slots between two events on the current stream (which the slot streams fork from / join)."""
+        """n steps through the serving loop between two events on the current stream (the slots fork from / join it)."""
         main = torch.cuda.current_stream(dev)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(main)
-        for s_ in slot_streams:
-            s_.wait_event(a)
+        last = None
         for i in range(n):
-            slot_step(i)
-        for s_ in slot_streams:
-            main.wait_stream(s_)
+            last = slot_step(i)
+        loop.join()
         b.record(main)
-        return a, b
+        return a, b, last
 
     def barrier():
         if world > 1:
@@ -454,7 +450,7 @@ def main_ours(args):
     torch.cuda.synchronize()
     barrier()
     t_wall0 = time.perf_counter()
-    e0, e1 = timed_slot_loop(K)
+    e0, e1, last_det = timed_slot_loop(K)
     torch.cuda.synchronize()
     t_wall1 = time.perf_counter()
     barrier()
@@ -462,7 +458,7 @@ def main_ours(args):
     step(K - 1)   # the slot that ran step K-1 holds the same detections as the single-stream call
     torch.cuda.synchronize()
     for f in ("count", "anchor", "cls", "score", "box"):
-        assert torch.equal(getattr(slot_dets[(K - 1) % S], f), getattr(det, f)), f
+        assert torch.equal(getattr(last_det, f), getattr(det, f)), f
     if sampler.ok and len([s for s in sampler.samples if t_wall0 <= s[0] <= t_wall1]) < 5:
         # timed region too short for NVML: keep the identical load running (untimed) until enough samples exist
         t_extra0 = time.perf_counter()

@@ -260,6 +260,55 @@ def head_detect(feat, weight, bias, anchors_f32, anchors_per_grid, num_classes, 
     return det
 
 
+class HeadDetectLoop:
+    """Device-resident serving loop over `slots` independent slots (stream + workspace + output block each).
+
+    Consecutive batches are independent, so two of them may be in flight: the feature pre-pass of batch i+1 then runs on
+    the SMs that the per-image tail of batch i leaves idle (batch 20: 20 of 148 SMs) -- +8-10 % images/s over issuing
+    every call on one stream; three slots are slower (tools/two_slot_bench.py).  Every batch runs all of its kernels.
+
+        loop = HeadDetectLoop(weight, bias, anchors, anchors_per_grid, num_classes, input_hw, top_k, nms, thr)
+        for feat in batches:
+            det = loop.submit(feat)      # enqueues; `det` is the slot's output block, valid once its stream has run
+            ...                          # consume det on loop.stream_of(det) (or after loop.join()) before the slot
+        loop.join()                      # comes round again `slots` submissions later
+
+    `submit` makes the slot's stream wait for the caller's current stream (the features are ready there) and `join`
+    makes the caller's stream wait for every slot."""
+
+    def __init__(self, weight, bias, anchors_f32, anchors_per_grid, num_classes, input_hw, top_k, nms_thresh, score_thresh,
+                 slots=2, packed=None, algo=CONV_TCGEN05_F16X3):
+        self.args = (weight, bias, anchors_f32, anchors_per_grid, num_classes, input_hw, top_k, nms_thresh, score_thresh)
+        self.packed, self.algo, self.top_k = packed, algo, top_k
+        dev = weight.device
+        self.device = dev
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, int(slots)))]
+        self.dets = [None] * len(self.streams)
+        self.i = 0
+        if packed is None and resolve_conv_algo(algo, weight.shape[1], weight.shape[0]) != CONV_SIMT_FP32:
+            self.packed = pack_convdet_weights(weight.detach().contiguous())
+
+    def submit(self, feat) -> Detections:
+        s = self.i % len(self.streams)
+        self.i += 1
+        st = self.streams[s]
+        st.wait_stream(torch.cuda.current_stream(self.device))
+        if self.dets[s] is None or self.dets[s].count.shape[0] != feat.shape[0]:
+            self.dets[s] = _alloc_detections(feat.shape[0], self.top_k, self.device)
+        with torch.cuda.stream(st):
+            head_detect(feat, *self.args, packed=self.packed, algo=self.algo, out=self.dets[s], slot=s)
+        feat.record_stream(st)
+        return self.dets[s]
+
+    def stream_of(self, det):
+        return self.streams[next(i for i, d in enumerate(self.dets) if d is det)]
+
+    def join(self):
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            cur.wait_stream(st)
+
+
 def head_detect_profile(feat, bias, anchors_f32, anchors_per_grid, num_classes, input_hw, top_k, nms_thresh,
                         score_thresh, packed, out: Detections = None):
     """Diagnostic twin of head_detect: same kernels, returns (Detections, [split_ms, convdet_ms, filter_ms]) measured

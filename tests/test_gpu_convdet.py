@@ -648,3 +648,28 @@ def test_one_kernel_route_full_batch_golden(ops):
     for i in range(batch):
         got = rows[i]["anchor_idx"].numpy() if rows[i] is not None else np.zeros((0,), np.int64)
         assert np.array_equal(got, kept[i]), i
+
+
+@pytest.mark.parametrize("slots", [1, 2, 3])
+def test_head_detect_loop_equals_single_calls(ops, slots):
+    """ops.HeadDetectLoop: batches alternate over `slots` (stream + workspace + output block each) and may overlap on the
+    GPU; every batch must return exactly what a plain head_detect call returns, whatever was in flight beside it."""
+    shp = synth.KITTI
+    w, b = synth.convdet_params(shp, 32)
+    wd, bd = dev(w), dev(b)
+    a32 = dev(synth.anchor_table(shp).astype(np.float32))
+    args = (a32, shp.anchors_per_grid, shp.num_classes, shp.input_hw, shp.top_k, shp.nms_thresh, shp.score_thresh)
+    feats = [dev(synth.features(shp, 3, 300 + i)) for i in range(7)]
+    expect = [ops.head_detect(f, wd, bd, *args) for f in feats]
+    loop = ops.HeadDetectLoop(wd, bd, *args, slots=slots)
+    got = []
+    for f in feats:
+        det = loop.submit(f)
+        with torch.cuda.stream(loop.stream_of(det)):      # consume on the slot's stream before the slot comes round again
+            got.append(ops.Detections(*(getattr(det, n).clone() for n in ("count", "anchor", "cls", "score", "box"))))
+    loop.join()
+    torch.cuda.synchronize()
+    for e, g in zip(expect, got):
+        for n in ("count", "anchor", "cls", "score", "box"):
+            assert torch.equal(getattr(e, n), getattr(g, n)), n
+    assert int(expect[0].count.sum()) > 0
