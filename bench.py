@@ -948,7 +948,7 @@ def main_ours(args):
                                     "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": Bd * PRED_BYTES_PER_IMAGE / det_s / 1e9 / peaks["hbm_gbs"],
                                     "traffic": ncu_traffic(NCU_DECODE_PROFILE, "score_candidates_kernel", "detect_from_candidates_kernel") if Bd == 1024 else None,
-                                    "traffic_source": NCU_DECODE_PROFILE + " (scan 94.1 us at 5.86 TB/s = 0.90 of peak, tail 39.2 us)",
+                                    "traffic_source": NCU_DECODE_PROFILE + " (cold-cache ncu run: scan 93.2 us at 5.9 TB/s = 0.91 of peak, 128-thread tail 21.6 us)",
                                     "kernel": "score_candidates_kernel<3> + detect_from_candidates_kernel",
                                     "images_per_s": Bd / det_s,
                                     "note": "sqd_detect_from_pred (scan + per-image tail: the two kernels the fused step runs "
