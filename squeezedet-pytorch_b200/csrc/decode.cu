@@ -37,24 +37,26 @@ __global__ void __launch_bounds__(kThreads) decode_kernel(DecodeArgs a) {
     const long long g0 = (long long)blockIdx.x * kThreads;
     const int n = (int)min((long long)kThreads, a.total - g0);
     const float *src = a.pred + g0 * NF;
-    const int count = n * NF;
-    {
-        const int nvec = count >> 2;  // slab start is 16-byte aligned: kThreads*NF*4 is a multiple of 16
-        const float4 *src4 = reinterpret_cast<const float4 *>(src);
-        float4 *dst4 = reinterpret_cast<float4 *>(slab);
-        for (int i = threadIdx.x; i < nvec; i += kThreads) dst4[i] = ld_stream_f4(src4 + i);
-        for (int i = (nvec << 2) + threadIdx.x; i < count; i += kThreads) slab[i] = src[i];
-    }
-    __syncthreads();
-    if ((int)threadIdx.x >= n) return;
-
     float f[SQD_CMAX(CS) + 5];
     if (CS == 3) {
-        const float4 *row = reinterpret_cast<const float4 *>(slab + threadIdx.x * 8);
-        const float4 lo = row[0], hi = row[1];
+        // 32-byte rows: a thread reads its own row with two 16-byte loads (a warp covers 1 KB contiguous; the second
+        // load of a 32-byte sector hits L1) -- no shared-memory round trip, no block barrier
+        if ((int)threadIdx.x >= n) return;
+        const float4 *row = reinterpret_cast<const float4 *>(src) + 2 * threadIdx.x;
+        const float4 lo = __ldg(row), hi = __ldg(row + 1);
         f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w;
         f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
     } else {
+        const int count = n * NF;
+        {
+            const int nvec = count >> 2;  // slab start is 16-byte aligned: kThreads*NF*4 is a multiple of 16
+            const float4 *src4 = reinterpret_cast<const float4 *>(src);
+            float4 *dst4 = reinterpret_cast<float4 *>(slab);
+            for (int i = threadIdx.x; i < nvec; i += kThreads) dst4[i] = ld_stream_f4(src4 + i);
+            for (int i = (nvec << 2) + threadIdx.x; i < count; i += kThreads) slab[i] = src[i];
+        }
+        __syncthreads();
+        if ((int)threadIdx.x >= n) return;
 #pragma unroll
         for (int j = 0; j < SQD_CMAX(CS) + 5; ++j)
             if (j < NF) f[j] = slab[threadIdx.x * NF + j];
@@ -134,7 +136,7 @@ extern "C" int sqd_decode_scores(const float *d_pred, const float *d_anchors, in
     const size_t smem = (size_t)kThreads * (num_classes + 5) * sizeof(float);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (num_classes == 3)
-        decode_kernel<3><<<(unsigned)blocks, kThreads, smem, st>>>(a);
+        decode_kernel<3><<<(unsigned)blocks, kThreads, 0, st>>>(a);
     else if (num_classes == 8)
         decode_kernel<8><<<(unsigned)blocks, kThreads, smem, st>>>(a);
     else
