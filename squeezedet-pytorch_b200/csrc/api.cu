@@ -63,7 +63,7 @@ const OptDef kOptDefs[SQD_OPT_COUNT] = {
     {"SQD_SPLIT_ROWS", 0}, {"SQD_DGRAD_PER_SLAB", 0}, {"SQD_DGRAD_BLOCK_SCALES", 0}, {"SQD_WG_SINGLE_TAP", 0}, {"SQD_WG_SYNC", 0},
     {"SQD_BWD_OLD_PREPASS", 0}, {"SQD_MATCH_SEQUENTIAL", 0}, {"SQD_F16_HALF_TILES", 0}, {"SQD_F16_CHUNK", 3}, {"SQD_F16_DBG", 0},
     {"SQD_F16_PAIR_STAGES", 4}, {"SQD_F16_A_STAGES", 2}, {"SQD_F16_B_STAGES", 8}, {"SQD_F16_TRACE_CTA", 0}, {"SQD_HEAD_ONE_KERNEL", 0},
-    {"SQD_F16_A_ONCE", 0}, {"SQD_F16_AO_BUFS", 2}, {"SQD_TAIL_THREADS", 0}, {"SQD_DGRAD_PACK_LOOP", 0},
+    {"SQD_F16_A_ONCE", 0}, {"SQD_F16_AO_BUFS", 2}, {"SQD_TAIL_THREADS", 0}, {"SQD_DGRAD_PACK_LOOP", 0}, {"SQD_SPLIT_REGS", 0},
 };
 std::atomic<int> g_opt[SQD_OPT_COUNT];
 std::once_flag g_opt_once;

@@ -46,7 +46,7 @@ enum SqdOptId {
     SQD_OPT_NO_PDL, SQD_OPT_FUSED_SCORE, SQD_OPT_SPLIT_TWO_PASS, SQD_OPT_SPLIT_CS, SQD_OPT_SPLIT_THREADS, SQD_OPT_SPLIT_ROWS,
     SQD_OPT_DGRAD_PER_SLAB, SQD_OPT_DGRAD_BLOCK_SCALES, SQD_OPT_WG_SINGLE_TAP, SQD_OPT_WG_SYNC, SQD_OPT_BWD_OLD_PREPASS,
     SQD_OPT_MATCH_SEQUENTIAL, SQD_OPT_F16_HALF_TILES, SQD_OPT_F16_CHUNK, SQD_OPT_F16_DBG, SQD_OPT_F16_PAIR_STAGES,
-    SQD_OPT_F16_A_STAGES, SQD_OPT_F16_B_STAGES, SQD_OPT_F16_TRACE_CTA, SQD_OPT_HEAD_ONE_KERNEL, SQD_OPT_F16_A_ONCE, SQD_OPT_F16_AO_BUFS, SQD_OPT_TAIL_THREADS, SQD_OPT_DGRAD_PACK_LOOP, SQD_OPT_COUNT
+    SQD_OPT_F16_A_STAGES, SQD_OPT_F16_B_STAGES, SQD_OPT_F16_TRACE_CTA, SQD_OPT_HEAD_ONE_KERNEL, SQD_OPT_F16_A_ONCE, SQD_OPT_F16_AO_BUFS, SQD_OPT_TAIL_THREADS, SQD_OPT_DGRAD_PACK_LOOP, SQD_OPT_SPLIT_REGS, SQD_OPT_COUNT
 };
 int sqd_opt(SqdOptId id);
 

@@ -320,6 +320,108 @@ __global__ void __launch_bounds__(kSplitThreads) split_nchw_cluster_kernel(const
     }
 }
 
+// ONE-PASS NCHW split, register resident (opt-in SQD_SPLIT_REGS=1, for slabs of at most 8 x 64 float4 columns: P <= 2048;
+// bit-identical planes, MEASURED SLOWER than the shared-memory kernel below: step 156.0 vs 147.2 us at KITTI B = 20 -- 128
+// registers x 256 threads leave two CTAs = 16 warps per SM to hide the shuffle / convert chain; with the rows stored
+// straight from registers, 32 lines per store instruction, it was 184.6 us.  profiles/r02_prepass_register_resident.txt).
+// Same decomposition -- a cluster of 8 CTAs per (image, 64-channel block) slab, CTA r the float4 columns
+// [r*n4/8, (r+1)*n4/8) -- but nothing goes through shared memory: a thread issues ALL 16 of its 16-byte loads up front
+// (channels 4s + cl, s = 0..15, of one column: 64 KB in flight per CTA), the block maximum goes round the cluster, and the
+// NCHW -> NHWC transposition is a 4 x 4 register transpose per load step among the four lanes of a column (two rounds of
+// two shuffles).  A lane ends up with all 64 channels of ONE cell = the 128-byte row of that cell in each plane, which it
+// writes with 16-byte stores.  No staging tile, no block barrier besides the cluster's; planes bit-identical to the
+// shared-memory kernel's (same scale, same split arithmetic).
+constexpr int kRsThreads = 256, kRsCluster = 8;
+__global__ void __cluster_dims__(kRsCluster, 1, 1) __launch_bounds__(kRsThreads, 2)
+split_nchw_regs_cluster_kernel(const float *__restrict__ in, uint4 *__restrict__ p1, uint4 *__restrict__ p2, int cin, int P,
+                               unsigned *__restrict__ amax_bits) {
+    __shared__ float s_red[kRsThreads / 32];
+    __shared__ unsigned s_cmax[kRsCluster];
+    namespace cgx = cooperative_groups;
+    cgx::cluster_group cluster = cgx::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int slab = blockIdx.x / kRsCluster, ncb = cin >> 6;
+    const int b = slab / ncb, cb = slab - b * ncb, c0 = cb << 6;
+    const int n4 = P >> 2;
+    const int q4b = (rank * n4) / kRsCluster, q4e = ((rank + 1) * n4) / kRsCluster;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ci = lane >> 2, cl = lane & 3;               // column within the warp's group of 8, channel within a quad
+    const int chunk = q4b + warp * 8 + ci;
+    const bool valid = chunk < q4e;
+    const float4 *src = reinterpret_cast<const float4 *>(in + ((size_t)b * cin + c0) * P) + chunk;
+    sqd_pdl_trigger();   // the GEMM behind this kernel may be scheduled as SMs drain; it waits for this grid to complete
+
+    float4 v[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s)
+        v[s] = valid ? ld_stream_f4(src + (size_t)(4 * s + cl) * n4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float m = 0.f;
+#pragma unroll
+    for (int s = 0; s < 16; ++s)
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v[s].x), fabsf(v[s].y))), fmaxf(fabsf(v[s].z), fabsf(v[s].w)));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < kRsThreads / 32 ? s_red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((int)threadIdx.x < kRsCluster) cluster.map_shared_rank(s_cmax, threadIdx.x)[rank] = __float_as_uint(m);
+    }
+    cluster.sync();  // every CTA's maximum has landed in every CTA's s_cmax
+    unsigned mb = 0u;
+#pragma unroll
+    for (int r = 0; r < kRsCluster; ++r) mb = max(mb, s_cmax[r]);
+    if (rank == 0 && threadIdx.x == 0) amax_bits[slab] = mb;
+    const float sc = pow2_scale_for(__uint_as_float(mb));
+
+    // transpose + split: after step s this lane holds channels 4s..4s+3 of cell 4*chunk + cl
+    const bool hi2 = (cl & 2) != 0, hi1 = (cl & 1) != 0;
+    uint2 w1[16], w2[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const float4 t = v[s];
+        // round 1 (partner cl ^ 2): swap the off-diagonal 2 x 2 blocks
+        const float r0 = __shfl_xor_sync(0xffffffffu, hi2 ? t.x : t.z, 2), r1 = __shfl_xor_sync(0xffffffffu, hi2 ? t.y : t.w, 2);
+        const float ax = hi2 ? r0 : t.x, ay = hi2 ? r1 : t.y, az = hi2 ? t.z : r0, aw = hi2 ? t.w : r1;
+        // round 2 (partner cl ^ 1): transpose inside the 2 x 2 blocks
+        const float q0 = __shfl_xor_sync(0xffffffffu, hi1 ? ax : ay, 1), q1 = __shfl_xor_sync(0xffffffffu, hi1 ? az : aw, 1);
+        const float x0 = (hi1 ? q0 : ax) * sc, x1 = (hi1 ? ay : q0) * sc, x2 = (hi1 ? q1 : az) * sc, x3 = (hi1 ? aw : q1) * sc;
+        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn((x0 - f01.x) * kLoScale, (x1 - f01.y) * kLoScale);
+        const __half2 l23 = __floats2half2_rn((x2 - f23.x) * kLoScale, (x3 - f23.y) * kLoScale);
+        w1[s].x = *reinterpret_cast<const unsigned *>(&h01);
+        w1[s].y = *reinterpret_cast<const unsigned *>(&h23);
+        w2[s].x = *reinterpret_cast<const unsigned *>(&l01);
+        w2[s].y = *reinterpret_cast<const unsigned *>(&l23);
+    }
+    // Lane L now holds cell L of the warp's 32 cells (4*ci + cl == lane): a 128-byte row per plane.  Written directly that
+    // is 32 different lines per store instruction (measured: the whole kernel 88 us); instead the rows pass through a
+    // warp-private staging tile (pitch 144 B: conflict-free both ways, __syncwarp only) and leave as 4 cells x 128
+    // contiguous bytes per instruction.
+    __shared__ uint4 s_stage[kRsThreads / 32][32 * 9];
+    uint4 *stg = s_stage[warp];
+    const int pr0 = lane >> 3, piece = lane & 7;
+    const size_t cell0 = (size_t)b * P + 4 * (size_t)(q4b + warp * 8);
+#pragma unroll
+    for (int plane = 0; plane < 2; ++plane) {
+        uint4 *dst = plane == 0 ? p1 : p2;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            stg[lane * 9 + j] = plane == 0 ? make_uint4(w1[2 * j].x, w1[2 * j].y, w1[2 * j + 1].x, w1[2 * j + 1].y)
+                                           : make_uint4(w2[2 * j].x, w2[2 * j].y, w2[2 * j + 1].x, w2[2 * j + 1].y);
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int pr = 4 * t + pr0;                                   // cell of the warp: column pr >> 2, pixel pr & 3
+            if (q4b + warp * 8 + (pr >> 2) < q4e) dst[(((cell0 + pr) * cin + c0) >> 3) + piece] = stg[pr * 9 + piece];
+        }
+    }
+}
+
 __global__ void weight_absmax_kernel(const float *__restrict__ w, size_t n, PackedHeader *hdr) {
     float m = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -1946,6 +2048,14 @@ int sqd_f16_split_features(const float *d_feat, int layout, int batch, int cin, 
     size_t smem = 0;
     int nq4p = 0;
     const int cs = split_cluster_size(P, &smem, &nq4p);
+    if (cs > 0 && sqd_opt(SQD_OPT_SPLIT_REGS) && P % 4 == 0 && (P / 4 + kRsCluster - 1) / kRsCluster <= 8 * (kRsThreads / 32) &&
+        !sqd_opt(SQD_OPT_SPLIT_CS)) {
+        // register-resident one-pass kernel: a CTA covers at most 64 float4 columns (8 warps x 8)
+        split_nchw_regs_cluster_kernel<<<(unsigned)((size_t)batch * ncb * kRsCluster), kRsThreads, 0, st>>>(
+            d_feat, reinterpret_cast<uint4 *>(p1), reinterpret_cast<uint4 *>(p2), cin, P, amax);
+        SQD_LAUNCH_CHECK("split_nchw_regs_cluster_kernel");
+        return SQD_OK;
+    }
     if (cs > 0) {
         // one pass: a cluster per (image, channel block) slab
         cudaLaunchConfig_t cfg = {};

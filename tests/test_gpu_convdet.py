@@ -366,6 +366,8 @@ def test_one_pass_split_equals_two_pass(ops, monkeypatch, name, batch):
         two = ops.convdet_forward(feat, w, b, check_status=True)
     assert torch.equal(one, two)
     assert torch.equal(one, ops.convdet_forward(feat, w, b, check_status=True))   # whatever the default picks
+    with _lib.option("SQD_SPLIT_REGS", 1):      # opt-in register-resident one-pass kernel (shuffle transposes): same planes
+        assert torch.equal(one, ops.convdet_forward(feat, w, b, check_status=True))
     cl = ops.convdet_forward(feat.contiguous(memory_format=torch.channels_last), w, b, check_status=True)
     assert torch.equal(one, cl)   # channels_last input: same per-(image, block) scales, same planes
 
