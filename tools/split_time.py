@@ -1,5 +1,5 @@
-"""Times the feature pre-pass (sqd_convdet_split_features) alone for a few kernel configurations (env switches are read
-per call).  usage: python tools/split_time.py [batch]"""
+"""Times the feature pre-pass (sqd_convdet_split_features) alone for a few kernel configurations (selected through
+sqd_set_option: the option table is read from the environment only once).  usage: python tools/split_time.py [batch]"""
 import ctypes as C
 import os
 import sys
@@ -20,10 +20,12 @@ st = _lib.stream_ptr(dev)
 nbytes = feats[0].numel() * 8
 
 
+DEFAULTS = {"SQD_SPLIT_TWO_PASS": 0, "SQD_SPLIT_CS": 0, "SQD_SPLIT_THREADS": 512, "SQD_SPLIT_ROWS": 0, "SQD_SPLIT_REGS": 0}
+
+
 def run(tag, env):
-    for k in ("SQD_SPLIT_TWO_PASS", "SQD_SPLIT_CS", "SQD_SPLIT_THREADS", "SQD_SPLIT_ROWS"):
-        os.environ.pop(k, None)
-    os.environ.update(env)
+    for k, v in {**DEFAULTS, **{k: int(v) for k, v in env.items()}}.items():
+        _lib.check(lib.sqd_set_option(k.encode(), int(v)), "sqd_set_option")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n = 30
     for i in range(n + 5):
@@ -37,6 +39,8 @@ def run(tag, env):
     print(f"{tag:40s} {us:8.1f} us  {nbytes / us / 1e6:6.2f} TB/s (read+write)")
 
 
+run("default (one-pass cluster kernel, shared tile)", {})
+run("register-resident one-pass (SQD_SPLIT_REGS)", {"SQD_SPLIT_REGS": "1"})
 run("two-pass (absmax + split)", {"SQD_SPLIT_TWO_PASS": "1"})
 for cs in (8, 16):
     for th in (256, 512, 1024):
