@@ -762,6 +762,10 @@ def main_ours(args):
                                "mode": "one CUDA graph replay per step (dist.GraphedStep)" if use_graph else "eager",
                                "ms_per_step_without_allreduce": ms_train_local,
                                "exposed_allreduce_ms": max(0.0, ms_train - ms_train_local) if world > 1 else 0.0,
+                               "exposed_allreduce_ms_head_bucket": (head_only or {}).get("exposed_allreduce_ms") if world > 1 else 0.0,
+                               "exposed_note": "full-model bucket: the backbone's 1.58 M floats are reduced after this path's backward and "
+                                               "have nothing to overlap with in this bench (the backbone's own backward is out of scope); "
+                                               "the head's 497,736 floats -- every gradient this path produces -- are reduced beside the dgrad GEMM",
                                "eager": {"ms_per_step": ms_train_eager, "ms_per_step_without_allreduce": ms_train_eager_local,
                                          "note": "host bound: Python + autograd dispatch of ~40 launches"},
                                "graph_error": graphed["error"],
