@@ -10,12 +10,15 @@ maps (BASELINE.json configs[1]: KITTI 1248x384 eval shape, batch 20 per GPU, 78x
 3 classes, top-64, NMS 0.4).  With N>1 every rank runs its own batch-20 slice (images are
 independent: no collective on the inference path; weak scaling); time = max over ranks.
 
-  value     images/s, inputs resident in HBM, K steps between two CUDA events, the steps alternating over
-            two slots (stream + workspace + output block); `single_stream` = the same on one stream
+  value     images/s, inputs resident in HBM, K steps between two CUDA events, issued through ops.HeadDetectLoop
+            (two slots: stream + workspace + output block each, steps alternate); `single_stream` = one stream
   e2e       images/s through the same public call with HOST (pinned) buffers: H2D of the step's
-            features and D2H of its detections inside the timed region
-  roofline  ConvDet tcgen05 kernel (the dominant launch): algorithmic FLOPs / event-timed duration
-  cpu_baseline / --impl reference: the CPU oracle port of the reference path on the host cores
+            features and D2H of its detections inside the timed region; bare_h2d_copy_floor beside it
+  roofline  ConvDet tcgen05 kernel (the dominant launch): algorithmic FLOPs / event-timed duration; traffic parsed
+            from the committed ncu summary under profiles/
+  cpu_baseline / --impl reference: the reference's OWN files (oracle/_ref, copied by oracle/make_ref.py) on the
+            host cores; the oracle port only if that copy did not travel
+  config1_demo / config3 / train_step / config5_stress: the other BASELINE.json configurations
 """
 from __future__ import annotations
 
