@@ -675,3 +675,35 @@ def test_head_detect_loop_equals_single_calls(ops, slots):
         for n in ("count", "anchor", "cls", "score", "box"):
             assert torch.equal(getattr(e, n), getattr(g, n)), n
     assert int(expect[0].count.sum()) > 0
+
+
+def test_detector_graph_follows_weight_updates_and_shapes(ops):
+    """Detector(cfg.cuda_graph=True) keys its captured graphs on the input shape and the weight version: after an in-place
+    weight update or with another batch size it must return what the eager detector returns, never a stale replay."""
+    from squeezedet_pytorch_b200 import config as sqd_config
+    from squeezedet_pytorch_b200.detector import Detector
+    from squeezedet_pytorch_b200.model import SqueezeDet
+    shp = synth.TINY
+    cfg_e = sqd_config.make_config(shp, device="cuda")
+    cfg_g = sqd_config.make_config(shp, device="cuda", cuda_graph=True)
+    model = SqueezeDet(cfg_e)
+    model.load_state_dict(synth.demo_state_dict(model, shp, 7))
+    eager, graphed = Detector(model, cfg_e), Detector(model, cfg_g)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+
+    def same(batch):
+        x = torch.randn((batch, 3, *shp.input_hw), generator=gen, device="cuda")
+        a, _ = eager.detect_batch({"image": x})
+        a = [getattr(a, f).clone() for f in ("count", "anchor", "cls", "score", "box")]
+        for _ in range(2):                       # capture, then a replay
+            g, _ = graphed.detect_batch({"image": x})
+            for u, f in zip(a, ("count", "anchor", "cls", "score", "box")):
+                assert torch.equal(u, getattr(g, f)), f
+        return int(a[0].sum())
+    kept = same(2)
+    kept += same(3)                              # another shape: its own graph
+    with torch.no_grad():
+        model.base.convdet.weight.mul_(1.5)      # in-place update bumps the version: re-packed weights, new graph
+        model.base.convdet.bias.add_(0.25)
+    kept += same(2)
+    assert kept > 0
